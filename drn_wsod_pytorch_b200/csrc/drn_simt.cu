@@ -1,0 +1,472 @@
+// fp32 / bandwidth kernels of the DRN-WSOD hot path: fused normalise+first conv, SIMT implicit-GEMM
+// conv/linear (exact-fp32 mode), 2x2 max-pool, ROIPool (+objectness scaling), dtype casts.
+// sm_100a only.  See include/drn_b200.h for the contract of every entry point.
+#include "common.cuh"
+#include <float.h>
+
+namespace drn {
+
+static thread_local char g_err[512];
+char* err_buf() { return g_err; }
+int set_err(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// a1+a2: (img - mean)/std fused into the 3x3, Cin=3 first convolution (stride 1 or 2, pad 1).
+// One thread = one output pixel x 16 output channels; 4 adjacent threads cover the 64-channel row
+// of a pixel so the NHWC store is a contiguous 256 B (fp32) / 128 B (bf16) per pixel.
+// ------------------------------------------------------------------------------------------
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+conv3x3_c3_kernel(const float* __restrict__ img, int H, int W, int Hp, int Wp, float m0, float m1, float m2, float s0,
+                  float s1, float s2, const float* __restrict__ wp, const float* __restrict__ scale,
+                  const float* __restrict__ bias, int Cout, int stride, int relu, int Ho, int Wo,
+                  OutT* __restrict__ out) {
+  extern __shared__ float sw[];  // [27][Cout]
+  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) sw[i] = wp[i];
+  __syncthreads();
+  const int groups = Cout >> 4;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long pix = gid / groups;
+  const int cg = (int)(gid % groups);
+  if (pix >= (long long)Ho * Wo) return;
+  const int oh = (int)(pix / Wo), ow = (int)(pix % Wo);
+  const float mean[3] = {m0, m1, m2};
+  const float stdv[3] = {s0, s1, s2};
+  float x[27];
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int ih = oh * stride - 1 + kh, iw = ow * stride - 1 + kw;
+      // (ih, iw) outside the valid H x W image but inside the Hp x Wp canvas is ImageList zero padding
+      const bool inb = (ih >= 0) && (ih < H) && (iw >= 0) && (iw < W);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float v = 0.f;
+        if (inb) v = __fdiv_rn(__fsub_rn(__ldg(img + ((long long)c * H + ih) * W + iw), mean[c]), stdv[c]);
+        x[(kh * 3 + kw) * 3 + c] = v;
+      }
+    }
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  const float* wrow = sw + cg * 16;
+#pragma unroll
+  for (int k = 0; k < 27; ++k) {
+    const float4* w4 = reinterpret_cast<const float4*>(wrow + k * Cout);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 wv = w4[q];
+      acc[q * 4 + 0] = fmaf(x[k], wv.x, acc[q * 4 + 0]);
+      acc[q * 4 + 1] = fmaf(x[k], wv.y, acc[q * 4 + 1]);
+      acc[q * 4 + 2] = fmaf(x[k], wv.z, acc[q * 4 + 2]);
+      acc[q * 4 + 3] = fmaf(x[k], wv.w, acc[q * 4 + 3]);
+    }
+  }
+  OutT* o = out + pix * Cout + cg * 16;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int c = cg * 16 + j;
+    float v = acc[j];
+    if (scale) v = v * __ldg(scale + c);
+    v += __ldg(bias + c);
+    if (relu) v = fmaxf(v, 0.f);
+    if constexpr (sizeof(OutT) == 4) o[j] = v; else o[j] = __float2bfloat16(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// SIMT fp32 implicit GEMM: out[m][n] = act(sum_k A[m][k] * Wt[k][n] * scale[n] + bias[n] + res[m][n])
+// m = output pixel (NHWC, stride 1, "same" padding), k = (kh, kw, cin), n = cout.
+// Tile 128(m) x 64(n) x 16(k), 128 threads, 8x8 register tile, register-staged double buffering.
+// ------------------------------------------------------------------------------------------
+constexpr int CBM = 128, CBN = 64, CBK = 16, CPAD = 4;
+
+__global__ void __launch_bounds__(128)
+conv_igemm_f32_kernel(const float* __restrict__ in, int N, int H, int W, int Cin,
+                      const float* __restrict__ wt, int ksize, int dil,
+                      const float* __restrict__ scale, const float* __restrict__ bias,
+                      const float* __restrict__ residual, int relu, float* __restrict__ out, int Cout,
+                      int ldo) {
+  __shared__ __align__(16) float As[2][CBK][CBM + CPAD];
+  __shared__ __align__(16) float Bs[2][CBK][CBN];
+  const int tid = threadIdx.x;
+  const long long M = (long long)N * H * W;
+  const long long m0 = (long long)blockIdx.x * CBM;
+  const int n0 = blockIdx.y * CBN;
+  const int KT = (ksize * ksize * Cin) / CBK;
+  const int half = ksize >> 1;
+
+  // A-load assignment: this thread loads float4 #kq of the 16-wide k slab of 4 pixels.
+  const int kq = tid & 3;
+  int ph[4], pw[4];
+  long long pbase[4];
+  bool pval[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + (tid >> 2) + 32 * i;
+    pval[i] = m < M;
+    const long long mm = pval[i] ? m : 0;
+    const int w_ = (int)(mm % W);
+    const int h_ = (int)((mm / W) % H);
+    ph[i] = h_;
+    pw[i] = w_;
+    pbase[i] = mm * Cin;  // offset of (n,h,w,0)
+  }
+  // B-load assignment: 2 float4 per thread.
+  const int bk0 = tid >> 4, bn4 = (tid & 15) * 4;
+
+  float4 ra[4], rb[2];
+  auto load_tile = [&](int kt) {
+    const int kk = kt * CBK;
+    const int tap = kk / Cin;
+    const int c0 = kk - tap * Cin + kq * 4;
+    const int dh = (tap / ksize - half) * dil, dw = (tap % ksize - half) * dil;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int ih = ph[i] + dh, iw = pw[i] + dw;
+      const bool ok = pval[i] && ih >= 0 && ih < H && iw >= 0 && iw < W;
+      ra[i] = ok ? __ldg(reinterpret_cast<const float4*>(in + pbase[i] + ((long long)dh * W + dw) * Cin + c0))
+                 : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      rb[i] = __ldg(reinterpret_cast<const float4*>(wt + (long long)(kk + bk0 + 8 * i) * Cout + n0 + bn4));
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int ml = (tid >> 2) + 32 * i;
+      As[buf][kq * 4 + 0][ml] = ra[i].x;
+      As[buf][kq * 4 + 1][ml] = ra[i].y;
+      As[buf][kq * 4 + 2][ml] = ra[i].z;
+      As[buf][kq * 4 + 3][ml] = ra[i].w;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) *reinterpret_cast<float4*>(&Bs[buf][bk0 + 8 * i][bn4]) = rb[i];
+  };
+
+  const int ty = tid >> 3, tx = tid & 7;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  load_tile(0);
+  store_tile(0);
+  __syncthreads();
+  for (int kt = 0; kt < KT; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < KT) load_tile(kt + 1);
+#pragma unroll
+    for (int k = 0; k < CBK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][32 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < KT) store_tile(buf ^ 1);
+    __syncthreads();
+  }
+
+  // epilogue
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= M) continue;
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh) {
+      const int n = n0 + jh * 32 + tx * 4;
+      float4 v = make_float4(acc[i][jh * 4 + 0], acc[i][jh * 4 + 1], acc[i][jh * 4 + 2], acc[i][jh * 4 + 3]);
+      if (scale) {
+        const float4 s = __ldg(reinterpret_cast<const float4*>(scale + n));
+        v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
+      }
+      if (bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n));
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+      }
+      if (residual) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(residual + m * Cout + n));
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+      }
+      if (relu) {
+        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+      }
+      *reinterpret_cast<float4*>(out + m * ldo + n) = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// MaxPool2d(2, stride s, pad 0) on NHWC; one thread = one output pixel x 16-byte channel vector.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 max4(float4 a, float4 b) {
+  return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+__device__ __forceinline__ uint4 max8bf(uint4 a, uint4 b) {
+  uint4 r;
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+maxpool2x2_kernel(const void* __restrict__ in_, int N, int H, int W, int C, int s, int Ho, int Wo,
+                  void* __restrict__ out_) {
+  const int vec = BF16 ? 8 : 4;
+  const int CV = C / vec;
+  const long long total = (long long)N * Ho * Wo * CV;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int cv = (int)(gid % CV);
+  long long p = gid / CV;
+  const int ow = (int)(p % Wo); p /= Wo;
+  const int oh = (int)(p % Ho);
+  const int n = (int)(p / Ho);
+  const long long base = (((long long)n * H + oh * s) * W + ow * s) * CV + cv;
+  const long long rs = (long long)W * CV;
+  if constexpr (BF16) {
+    const uint4* in = reinterpret_cast<const uint4*>(in_);
+    uint4 v = max8bf(max8bf(__ldg(in + base), __ldg(in + base + CV)),
+                     max8bf(__ldg(in + base + rs), __ldg(in + base + rs + CV)));
+    reinterpret_cast<uint4*>(out_)[gid] = v;
+  } else {
+    const float4* in = reinterpret_cast<const float4*>(in_);
+    float4 v = max4(max4(__ldg(in + base), __ldg(in + base + CV)),
+                    max4(__ldg(in + base + rs), __ldg(in + base + rs + CV)));
+    reinterpret_cast<float4*>(out_)[gid] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// a7+a8: ROIPool 7x7 (torchvision semantics) x (objectness+1).
+// grid = (R, 7): one CTA per (proposal, bin row); threads stride over 16-byte channel vectors so
+// every load/store is a coalesced 512 B per warp; the conv5 map stays L2-resident (<= 134 MB bf16
+// only at cfg 5; 19-75 MB otherwise) and the R x 49 x C output is the only HBM stream.
+// ------------------------------------------------------------------------------------------
+struct RoiBins {
+  int hs, he;
+  int ws[7], we[7];
+};
+
+__device__ __forceinline__ void roi_geometry(const float* __restrict__ box, float scale, int h, int w,
+                                             int ph, RoiBins& g) {
+  // torchvision roi_pool: C round() (half away from zero) on scaled coords, +1 extents, floor/ceil
+  // bin edges, clamp to the map.  All arithmetic fp32, single roundings (no contraction).
+  const int sw = (int)roundf(__fmul_rn(box[0], scale));
+  const int sh = (int)roundf(__fmul_rn(box[1], scale));
+  const int ew = (int)roundf(__fmul_rn(box[2], scale));
+  const int eh = (int)roundf(__fmul_rn(box[3], scale));
+  const int rw = max(ew - sw + 1, 1), rh = max(eh - sh + 1, 1);
+  const float bh = __fdiv_rn((float)rh, 7.f), bw = __fdiv_rn((float)rw, 7.f);
+  g.hs = min(max((int)floorf(__fmul_rn((float)ph, bh)) + sh, 0), h);
+  g.he = min(max((int)ceilf(__fmul_rn((float)(ph + 1), bh)) + sh, 0), h);
+#pragma unroll
+  for (int p = 0; p < 7; ++p) {
+    g.ws[p] = min(max((int)floorf(__fmul_rn((float)p, bw)) + sw, 0), w);
+    g.we[p] = min(max((int)ceilf(__fmul_rn((float)(p + 1), bw)) + sw, 0), w);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+roipool_f32_kernel(const float* __restrict__ feat, int h, int w, int C, const float* __restrict__ boxes,
+                   const float* __restrict__ obj, float scale, float* __restrict__ out) {
+  const int r = blockIdx.x, ph = blockIdx.y;
+  RoiBins g;
+  roi_geometry(boxes + 4 * (long long)r, scale, h, w, ph, g);
+  const float mul = obj ? __fadd_rn(__ldg(obj + r), 1.f) : 1.f;
+  const int CV = C >> 2;
+  const float4* f4 = reinterpret_cast<const float4*>(feat);
+  float4* o4 = reinterpret_cast<float4*>(out + ((long long)r * 49 + ph * 7) * C);
+  for (int cv = threadIdx.x; cv < CV; cv += blockDim.x) {
+#pragma unroll 1
+    for (int pw = 0; pw < 7; ++pw) {
+      const int ws = g.ws[pw], we = g.we[pw];
+      const bool empty = (g.he <= g.hs) || (we <= ws);
+      float4 m = empty ? make_float4(0.f, 0.f, 0.f, 0.f)
+                       : make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+      for (int y = g.hs; y < g.he; ++y) {
+        const float4* row = f4 + ((long long)y * w) * CV + cv;
+#pragma unroll 4
+        for (int x = ws; x < we; ++x) {
+          const float4 v = __ldg(row + (long long)x * CV);
+          if (v.x > m.x) m.x = v.x;
+          if (v.y > m.y) m.y = v.y;
+          if (v.z > m.z) m.z = v.z;
+          if (v.w > m.w) m.w = v.w;
+        }
+      }
+      m.x = __fmul_rn(m.x, mul); m.y = __fmul_rn(m.y, mul);
+      m.z = __fmul_rn(m.z, mul); m.w = __fmul_rn(m.w, mul);
+      __stcs(o4 + (long long)pw * CV + cv, m);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+roipool_bf16_kernel(const uint4* __restrict__ f8, int h, int w, int C, const float* __restrict__ boxes,
+                    const float* __restrict__ obj, float scale, uint4* __restrict__ out) {
+  const int r = blockIdx.x, ph = blockIdx.y;
+  RoiBins g;
+  roi_geometry(boxes + 4 * (long long)r, scale, h, w, ph, g);
+  const float mul = obj ? __fadd_rn(__ldg(obj + r), 1.f) : 1.f;
+  const int CV = C >> 3;
+  uint4* o8 = out + ((long long)r * 49 + ph * 7) * CV;
+  const __nv_bfloat16 lowest = __ushort_as_bfloat16((unsigned short)0xFF7F);  // most negative finite bf16
+  for (int cv = threadIdx.x; cv < CV; cv += blockDim.x) {
+#pragma unroll 1
+    for (int pw = 0; pw < 7; ++pw) {
+      const int ws = g.ws[pw], we = g.we[pw];
+      const bool empty = (g.he <= g.hs) || (we <= ws);
+      __nv_bfloat162 m[4];
+      const __nv_bfloat16 init = empty ? __float2bfloat16(0.f) : lowest;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) m[i] = __halves2bfloat162(init, init);
+      for (int y = g.hs; y < g.he; ++y) {
+        const uint4* row = f8 + ((long long)y * w) * CV + cv;
+#pragma unroll 4
+        for (int x = ws; x < we; ++x) {
+          const uint4 v = __ldg(row + (long long)x * CV);
+          const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) m[i] = __hmax2(m[i], pv[i]);
+        }
+      }
+      uint4 o;
+      __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(m[i]);
+        po[i] = __floats2bfloat162_rn(__fmul_rn(f.x, mul), __fmul_rn(f.y, mul));
+      }
+      __stcs(o8 + (long long)pw * CV + cv, o);
+    }
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16(in[i]);
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(in[i]);
+}
+
+}  // namespace drn
+
+using namespace drn;
+
+extern "C" {
+
+int drn_version(void) { return 100; }
+const char* drn_last_error(void) { return drn::err_buf(); }
+
+int drn_conv3x3_c3_fwd(const float* img, int H, int W, int Hp, int Wp, const float* mean3, const float* std3,
+                       const float* w_packed, const float* scale, const float* bias, int Cout,
+                       int stride, int relu, void* out, int out_dtype, drn_stream_t stream) {
+  DRN_CHECK_ARG(img && mean3 && std3 && w_packed && bias && out, "conv3x3_c3: null pointer");
+  DRN_CHECK_ARG(Cout % 16 == 0 && Cout <= 256, "conv3x3_c3: Cout=%d must be a multiple of 16, <=256", Cout);
+  DRN_CHECK_ARG(stride == 1 || stride == 2, "conv3x3_c3: stride %d", stride);
+  DRN_CHECK_ARG(H > 0 && W > 0 && Hp >= H && Wp >= W, "conv3x3_c3: bad image/canvas size %dx%d in %dx%d", H, W, Hp, Wp);
+  const int Ho = (Hp + 2 - 3) / stride + 1, Wo = (Wp + 2 - 3) / stride + 1;
+  const long long threads = (long long)Ho * Wo * (Cout / 16);
+  const int grid = (int)((threads + 255) / 256);
+  const size_t smem = 27 * Cout * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype == DRN_F32)
+    conv3x3_c3_kernel<float><<<grid, 256, smem, st>>>(img, H, W, Hp, Wp, mean3[0], mean3[1], mean3[2], std3[0],
+        std3[1], std3[2], w_packed, scale, bias, Cout, stride, relu, Ho, Wo, (float*)out);
+  else
+    conv3x3_c3_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(img, H, W, Hp, Wp, mean3[0], mean3[1], mean3[2],
+        std3[0], std3[1], std3[2], w_packed, scale, bias, Cout, stride, relu, Ho, Wo, (__nv_bfloat16*)out);
+  DRN_CHECK_LAUNCH("conv3x3_c3");
+  return 0;
+}
+
+int drn_conv_igemm_f32(const float* in, int N, int H, int W, int Cin, const float* w, int ksize,
+                       int dilation, const float* scale, const float* bias, const float* residual,
+                       int relu, float* out, int Cout, int ldo, drn_stream_t stream) {
+  DRN_CHECK_ARG(in && w && out, "conv_igemm_f32: null pointer");
+  DRN_CHECK_ARG(ksize == 1 || ksize == 3, "conv_igemm_f32: ksize %d", ksize);
+  DRN_CHECK_ARG(Cin % 16 == 0, "conv_igemm_f32: Cin=%d must be a multiple of 16", Cin);
+  DRN_CHECK_ARG(Cout % 64 == 0, "conv_igemm_f32: Cout=%d must be a multiple of 64", Cout);
+  DRN_CHECK_ARG(ldo >= Cout && ldo % 4 == 0, "conv_igemm_f32: ldo=%d", ldo);
+  const long long M = (long long)N * H * W;
+  if (M == 0) return 0;
+  dim3 grid((unsigned)((M + CBM - 1) / CBM), Cout / CBN);
+  conv_igemm_f32_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(in, N, H, W, Cin, w, ksize, dilation,
+      scale, bias, residual, relu, out, Cout, ldo);
+  DRN_CHECK_LAUNCH("conv_igemm_f32");
+  return 0;
+}
+
+int drn_maxpool2x2_nhwc(const void* in, int N, int H, int W, int C, int stride, int dtype, void* out,
+                        drn_stream_t stream) {
+  DRN_CHECK_ARG(in && out, "maxpool: null pointer");
+  DRN_CHECK_ARG(stride == 1 || stride == 2, "maxpool: stride %d", stride);
+  DRN_CHECK_ARG(H >= 2 && W >= 2, "maxpool: map %dx%d too small", H, W);
+  const int vec = dtype == DRN_BF16 ? 8 : 4;
+  DRN_CHECK_ARG(C % vec == 0, "maxpool: C=%d not a multiple of %d", C, vec);
+  const int Ho = (H - 2) / stride + 1, Wo = (W - 2) / stride + 1;
+  const long long total = (long long)N * Ho * Wo * (C / vec);
+  const int grid = (int)((total + 255) / 256);
+  if (dtype == DRN_BF16)
+    maxpool2x2_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(in, N, H, W, C, stride, Ho, Wo, out);
+  else
+    maxpool2x2_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(in, N, H, W, C, stride, Ho, Wo, out);
+  DRN_CHECK_LAUNCH("maxpool2x2");
+  return 0;
+}
+
+int drn_roipool_fwd(const void* feat, int h, int w, int C, const float* boxes, const float* objectness,
+                    int R, float spatial_scale, int dtype, void* out, drn_stream_t stream) {
+  DRN_CHECK_ARG(feat && out && (boxes || R == 0), "roipool: null pointer");
+  DRN_CHECK_ARG(h > 0 && w > 0, "roipool: empty feature map");
+  if (R == 0) return 0;
+  dim3 grid(R, 7);
+  if (dtype == DRN_BF16) {
+    DRN_CHECK_ARG(C % 8 == 0, "roipool: C=%d not a multiple of 8", C);
+    roipool_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)feat, h, w, C, boxes,
+        objectness, spatial_scale, (uint4*)out);
+  } else {
+    DRN_CHECK_ARG(C % 4 == 0, "roipool: C=%d not a multiple of 4", C);
+    roipool_f32_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const float*)feat, h, w, C, boxes,
+        objectness, spatial_scale, (float*)out);
+  }
+  DRN_CHECK_LAUNCH("roipool");
+  return 0;
+}
+
+int drn_cast_f32_to_bf16(const float* in, void* out, int64_t n, drn_stream_t stream) {
+  if (n == 0) return 0;
+  cast_f32_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out, n);
+  DRN_CHECK_LAUNCH("cast_f32_to_bf16");
+  return 0;
+}
+int drn_cast_bf16_to_f32(const void* in, float* out, int64_t n, drn_stream_t stream) {
+  if (n == 0) return 0;
+  cast_bf16_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, out, n);
+  DRN_CHECK_LAUNCH("cast_bf16_to_f32");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,853 @@
+"""Host-side mirror of the reference's plugin interface for the hot path.
+
+Same registry names, constructor signatures, config keys and `state_dict` keys as
+projects/WSL/wsl/modeling/{meta_arch/rcnn.py, backbone/{resnet_ws,vgg}.py,
+roi_heads/{box_head,fast_rcnn,roi_heads,roi_heads_wsddn,roi_heads_oicr}.py}; the modules only
+hold parameters and orchestration -- every arithmetic step is a C-ABI call into libdrn_b200.so
+(ops.py).  Derived weight layouts (NHWC filters, folded FrozenBN, fc6 K-permutation, concatenated
+heads, bf16 copies) are caches refreshed whenever the source parameters change.
+
+Forward only (losses are device scalars, not autograd-connected): the backward of the trainable
+tail is SURVEY.md §8f row 1.
+"""
+import os
+from collections import namedtuple
+from typing import Dict, List, Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from .config import precision_of
+from .registry import BACKBONE_REGISTRY, META_ARCH_REGISTRY, ROI_BOX_HEAD_REGISTRY, ROI_HEADS_REGISTRY
+from .structures import Boxes, ImageList, Instances, detector_postprocess
+
+ShapeSpec = namedtuple("ShapeSpec", ["channels", "height", "width", "stride"], defaults=(None, None, None, None))
+
+
+def _event_storage():
+    """The reference logs scalars through detectron2's global EventStorage
+    (detectron2/utils/events.py:16-25).  Use it when we run inside such a process; otherwise
+    logging is a no-op (and costs no device sync)."""
+    try:
+        from detectron2.utils.events import get_event_storage  # type: ignore
+
+        return get_event_storage()
+    except Exception:
+        return None
+
+
+def _versions(tensors):
+    return tuple((t.data_ptr(), t._version, t.device) for t in tensors if t is not None)
+
+
+# ------------------------------------------------------------------------------------------------
+# layers (parameter holders with the reference's names)
+# ------------------------------------------------------------------------------------------------
+class FrozenBatchNorm2d(nn.Module):
+    """Buffers of detectron2/layers/batch_norm.py:14-65 (eps 1e-5); folded into the conv epilogue."""
+
+    def __init__(self, num_features, eps=1e-5):
+        super().__init__()
+        self.num_features = num_features
+        self.eps = eps
+        self.register_buffer("weight", torch.ones(num_features))
+        self.register_buffer("bias", torch.zeros(num_features))
+        self.register_buffer("running_mean", torch.zeros(num_features))
+        self.register_buffer("running_var", torch.ones(num_features) - eps)
+
+
+class Conv2d(nn.Module):
+    """Parameters of detectron2/layers/wrappers.py:41-99 Conv2d (+ optional `.norm`)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, dilation=1, bias=False, norm=None):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride, self.dilation = kernel_size, stride, dilation
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels, kernel_size, kernel_size))
+        nn.init.kaiming_normal_(self.weight, mode="fan_out", nonlinearity="relu")  # c2_msra_fill
+        self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
+        self.norm = norm
+        self._cache = {}
+
+    def packed(self, precision):
+        """Derived kernel operands: filter in (kh,kw,cin) K order, FrozenBN folded to scale/bias."""
+        src = [self.weight, self.bias]
+        if self.norm is not None:
+            src += [self.norm.weight, self.norm.bias, self.norm.running_mean, self.norm.running_var]
+        key = (precision, _versions(src))
+        hit = self._cache.get(precision)
+        if hit is not None and hit["key"] == key:
+            return hit
+        with torch.no_grad():
+            w = self.weight.detach().float()
+            cout = w.shape[0]
+            if self.norm is not None:
+                scale = self.norm.weight * (self.norm.running_var + self.norm.eps).rsqrt()
+                bias = self.norm.bias - self.norm.running_mean * scale
+                scale, bias = scale.float().contiguous(), bias.float().contiguous()
+            else:
+                scale = None
+                bias = (self.bias.detach().float() if self.bias is not None else torch.zeros(cout, device=w.device)).contiguous()
+            if self.in_channels == 3 or precision == "fp32":
+                wp = w.permute(2, 3, 1, 0).reshape(-1, cout).contiguous()  # [(kh,kw,cin)][cout]
+            else:
+                wp = w.permute(0, 2, 3, 1).reshape(cout, -1).contiguous().to(torch.bfloat16)  # [cout][(kh,kw,cin)]
+        hit = {"key": key, "w": wp, "scale": scale, "bias": bias, "cout": cout}
+        self._cache[precision] = hit
+        return hit
+
+
+class Linear(nn.Linear):
+    """nn.Linear parameters + cached kernel layouts (optionally with fc6's (c,ph,pw)->(ph,pw,c) K permutation)."""
+
+    def packed(self, precision, permute_c49=None, pad_to=64):
+        key = (precision, permute_c49, _versions([self.weight, self.bias]))
+        hit = getattr(self, "_cache", {}).get((precision, permute_c49))
+        if hit is not None and hit["key"] == key:
+            return hit
+        hit = dict(pack_linear([self.weight], [self.bias], precision, permute_c49, pad_to), key=key)
+        if not hasattr(self, "_cache"):
+            self._cache = {}
+        self._cache[(precision, permute_c49)] = hit
+        return hit
+
+
+def pack_linear(weights, biases, precision, permute_c49=None, pad_to=64):
+    """Concatenate [N_i, K] weights along N, zero-pad N to a multiple of `pad_to`, lay out for the kernels."""
+    with torch.no_grad():
+        w = torch.cat([x.detach().float() for x in weights], dim=0)
+        b = torch.cat([x.detach().float() for x in biases], dim=0)
+        n, k = w.shape
+        if permute_c49 is not None:  # reference flattens pooled features as (c, ph, pw); ROIPool writes (ph, pw, c)
+            c = permute_c49
+            w = w.view(n, c, k // c).permute(0, 2, 1).reshape(n, k)
+        npad = (n + pad_to - 1) // pad_to * pad_to
+        if npad != n:
+            w = torch.cat([w, w.new_zeros(npad - n, k)], dim=0)
+            b = torch.cat([b, b.new_zeros(npad - n)], dim=0)
+        if precision == "fp32":
+            wp = w.t().contiguous()  # [K][N]
+        else:
+            wp = w.contiguous().to(torch.bfloat16)  # [N][K]
+    return {"w": wp, "scale": None, "bias": b.contiguous(), "cout": npad, "n": n}
+
+
+def run_conv(conv: Conv2d, x, precision, relu, residual=None):
+    p = conv.packed(precision)
+    if precision == "fp32":
+        return ops.conv_f32(x, p, conv.kernel_size, conv.dilation, relu, residual)
+    return ops.conv_bf16_tc(x, p, conv.kernel_size, conv.dilation, relu, residual)
+
+
+def run_linear(x2d, packed, precision, relu, out_dtype=None):
+    """x2d: [M, K] -> [M, Npad] through the same implicit-GEMM kernels (a linear layer is a 1x1 conv
+    over an M x 1 'image')."""
+    M, K = x2d.shape
+    x4 = x2d.view(1, M, 1, K)
+    if precision == "fp32":
+        y = ops.conv_f32(x4, packed, 1, 1, relu)
+    else:
+        y = ops.conv_bf16_tc(x4, packed, 1, 1, relu, out_dtype=out_dtype or torch.bfloat16)
+    return y.view(M, packed["cout"])
+
+
+# ------------------------------------------------------------------------------------------------
+# backbones
+# ------------------------------------------------------------------------------------------------
+class _Block(nn.Module):
+    def freeze(self):
+        for p in self.parameters():
+            p.requires_grad = False
+        return self
+
+
+class BasicStem(_Block):
+    """projects/WSL/wsl/modeling/backbone/resnet_ws.py:357-416."""
+
+    def __init__(self, in_channels=3, out_channels=64):
+        super().__init__()
+        self.stride = 4
+        self.out_channels = out_channels
+        self.conv1 = Conv2d(in_channels, out_channels, 3, stride=2, norm=FrozenBatchNorm2d(out_channels))
+        self.conv2 = Conv2d(out_channels, out_channels, 3, norm=FrozenBatchNorm2d(out_channels))
+        self.conv3 = Conv2d(out_channels, out_channels, 3, norm=FrozenBatchNorm2d(out_channels))
+
+
+class BasicBlock(_Block):
+    """resnet_ws.py:32-112 (all convs stride 1; `stride` only sets the trailing max-pool)."""
+
+    def __init__(self, in_channels, out_channels, stride=1, dilation=1, has_pool=False):
+        super().__init__()
+        self.stride, self.has_pool, self.out_channels = stride, has_pool, out_channels
+        self.shortcut = (
+            Conv2d(in_channels, out_channels, 1, norm=FrozenBatchNorm2d(out_channels)) if in_channels != out_channels else None
+        )
+        self.conv1 = Conv2d(in_channels, out_channels, 3, dilation=dilation, norm=FrozenBatchNorm2d(out_channels))
+        self.conv2 = Conv2d(out_channels, out_channels, 3, dilation=dilation, norm=FrozenBatchNorm2d(out_channels))
+
+    def run(self, x, precision):
+        out = run_conv(self.conv1, x, precision, relu=True)
+        sc = run_conv(self.shortcut, x, precision, relu=False) if self.shortcut is not None else x
+        out = run_conv(self.conv2, out, precision, relu=True, residual=sc)
+        return ops.maxpool2x2(out, self.stride) if self.has_pool else out
+
+
+class BottleneckBlock(_Block):
+    """resnet_ws.py:115-237."""
+
+    def __init__(self, in_channels, out_channels, bottleneck_channels, stride=1, dilation=1, has_pool=False):
+        super().__init__()
+        self.stride, self.has_pool, self.out_channels = stride, has_pool, out_channels
+        self.shortcut = (
+            Conv2d(in_channels, out_channels, 1, norm=FrozenBatchNorm2d(out_channels)) if in_channels != out_channels else None
+        )
+        self.conv1 = Conv2d(in_channels, bottleneck_channels, 1, norm=FrozenBatchNorm2d(bottleneck_channels))
+        self.conv2 = Conv2d(bottleneck_channels, bottleneck_channels, 3, dilation=dilation,
+                            norm=FrozenBatchNorm2d(bottleneck_channels))
+        self.conv3 = Conv2d(bottleneck_channels, out_channels, 1, norm=FrozenBatchNorm2d(out_channels))
+
+    def run(self, x, precision):
+        out = run_conv(self.conv1, x, precision, relu=True)
+        out = run_conv(self.conv2, out, precision, relu=True)
+        sc = run_conv(self.shortcut, x, precision, relu=False) if self.shortcut is not None else x
+        out = run_conv(self.conv3, out, precision, relu=True, residual=sc)
+        return ops.maxpool2x2(out, self.stride) if self.has_pool else out
+
+
+class PlainBlock(_Block):
+    """projects/WSL/wsl/modeling/backbone/vgg.py:35-111."""
+
+    def __init__(self, in_channels, out_channels, num_conv, dilation=1, stride=1, has_pool=False):
+        super().__init__()
+        self.num_conv, self.stride, self.has_pool, self.out_channels = num_conv, stride, has_pool, out_channels
+        for i in range(num_conv):
+            setattr(self, f"conv{i + 1}", Conv2d(in_channels if i == 0 else out_channels, out_channels, 3,
+                                                 dilation=dilation, bias=True))
+
+    def run(self, x, precision, skip_first=False):
+        for i in range(1 if skip_first else 0, self.num_conv):
+            x = run_conv(getattr(self, f"conv{i + 1}"), x, precision, relu=True)
+        return ops.maxpool2x2(x, self.stride) if self.has_pool else x
+
+
+class Backbone(nn.Module):
+    """Interface of detectron2/modeling/backbone/backbone.py:10-53."""
+
+    size_divisibility = 0
+
+    def output_shape(self):
+        return {
+            n: ShapeSpec(channels=self._out_feature_channels[n], stride=self._out_feature_strides[n])
+            for n in self._out_features
+        }
+
+    def _act_dtype(self):
+        return torch.float32 if self.precision == "fp32" else torch.bfloat16
+
+    def forward(self, x):
+        """x: N x 3 x H x W fp32, already normalised (reference interface).  Returns
+        {name: N x C x h x w} whose memory is channels-last (the NHWC buffer the kernels wrote)."""
+        assert x.dim() == 4 and x.shape[1] == 3, f"backbone takes (N, 3, H, W); got {tuple(x.shape)}"
+        outs = [self.forward_image(x[i].contiguous(), (x.shape[2], x.shape[3]), (0.0, 0.0, 0.0), (1.0, 1.0, 1.0))
+                for i in range(x.shape[0])]
+        return {self._out_features[0]: torch.cat(outs, dim=0).permute(0, 3, 1, 2)}
+
+
+class ResNetWS(Backbone):
+    """projects/WSL/wsl/modeling/backbone/resnet_ws.py:419-534 (+ builder :616-703)."""
+
+    def __init__(self, stem, stages, out_features, precision):
+        super().__init__()
+        self.precision = precision
+        self.stem = stem
+        self._out_feature_strides, self._out_feature_channels = {"stem": 4}, {"stem": stem.out_channels}
+        self.stage_names = []
+        stride = 4
+        for i, blocks in enumerate(stages):
+            name = f"res{i + 2}"
+            self.add_module(name, nn.Sequential(*blocks))
+            self.stage_names.append(name)
+            for b in blocks:
+                stride *= b.stride
+            self._out_feature_strides[name] = stride
+            self._out_feature_channels[name] = blocks[-1].out_channels
+        self._out_features = list(out_features)
+        assert len(self._out_features) == 1 and self._out_features[0] == self.stage_names[-1], (
+            "the B200 path returns the last stage only (WSL configs use OUT_FEATURES: ['res5'])")
+
+    def freeze(self, freeze_at=0):
+        if freeze_at >= 1:
+            self.stem.freeze()
+        for idx, name in enumerate(self.stage_names, start=2):
+            if freeze_at >= idx:
+                for block in getattr(self, name).children():
+                    block.freeze()
+        return self
+
+    def forward_image(self, img_chw, canvas_hw, mean, std):
+        """One raw image (3xHxW fp32) on a zero canvas -> [1,h,w,C] NHWC; normalisation is fused into conv1."""
+        pr = self.precision
+        x = ops.first_conv(img_chw, canvas_hw, mean, std, self.stem.conv1.packed(pr), stride=2, out_dtype=self._act_dtype())
+        x = run_conv(self.stem.conv2, x, pr, relu=True)
+        x = run_conv(self.stem.conv3, x, pr, relu=True)
+        x = ops.maxpool2x2(x, 2)
+        for name in self.stage_names:
+            for block in getattr(self, name).children():
+                x = block.run(x, pr)
+        return x
+
+
+class VGG16(Backbone):
+    """projects/WSL/wsl/modeling/backbone/vgg.py:114-231."""
+
+    def __init__(self, conv5_dilation, freeze_at, precision):
+        super().__init__()
+        self.precision = precision
+        d2 = conv5_dilation == 2
+        spec = [("plain1", 3, 64, 2, 1, 2, True), ("plain2", 64, 128, 2, 1, 2, True), ("plain3", 128, 256, 3, 1, 2, True),
+                ("plain4", 256, 512, 3, 1, 1 if d2 else 2, True), ("plain5", 512, 512, 3, conv5_dilation, 1, False)]
+        strides = [2, 4, 8, 8 if d2 else 16, 8 if d2 else 16]
+        self._out_feature_strides, self._out_feature_channels = {}, {}
+        self.stage_names = []
+        for i, (name, cin, cout, nconv, dil, stride, pool) in enumerate(spec):
+            block = PlainBlock(cin, cout, nconv, dilation=dil, stride=stride, has_pool=pool)
+            self.add_module(name, nn.Sequential(block))
+            self.stage_names.append(name)
+            self._out_feature_strides[name] = strides[i]
+            self._out_feature_channels[name] = cout
+            if freeze_at >= i + 1:
+                block.freeze()
+        self._out_features = ["plain5"]
+
+    def forward_image(self, img_chw, canvas_hw, mean, std):
+        pr = self.precision
+        first = self.plain1[0]
+        x = ops.first_conv(img_chw, canvas_hw, mean, std, first.conv1.packed(pr), stride=1, out_dtype=self._act_dtype())
+        x = first.run(x, pr, skip_first=True)
+        for name in self.stage_names[1:]:
+            x = getattr(self, name)[0].run(x, pr)
+        return x
+
+
+@BACKBONE_REGISTRY.register()
+def build_ws_resnet_backbone(cfg, input_shape=None):
+    """Same schedule as resnet_ws.py:616-703: all convs stride 1, MaxPool2d(2) after the last block of
+    res2 (stride 2) and res3 (stride 2, or 1 when RES5_DILATION == 2), res4/res5 dilated."""
+    r = cfg.MODEL.RESNETS
+    depth, dil = r.DEPTH, r.RES5_DILATION
+    assert dil in (1, 2), f"res5_dilation cannot be {dil}."
+    assert not any(r.DEFORM_ON_PER_STAGE), "deformable stages are outside the hot path (SURVEY.md §2 row 23)"
+    assert r.NUM_GROUPS == 1, "grouped 3x3 convs are not used by the WSL configs"
+    assert r.NORM == "FrozenBN", "the hot path folds FrozenBN into the conv epilogue (WSL configs use FrozenBN)"
+    nblocks = {18: [2, 2, 2, 2], 34: [3, 4, 6, 3], 50: [3, 4, 6, 3], 101: [3, 4, 23, 3], 152: [3, 8, 36, 3]}[depth]
+    basic = depth in (18, 34)
+    in_ch, out_ch = r.STEM_OUT_CHANNELS, r.RES2_OUT_CHANNELS
+    if basic:
+        assert out_ch == 64, "Must set MODEL.RESNETS.RES2_OUT_CHANNELS = 64 for R18/R34"
+    bott = r.NUM_GROUPS * r.WIDTH_PER_GROUP
+    out_stage = max({"res2": 2, "res3": 3, "res4": 4, "res5": 5}[f] for f in r.OUT_FEATURES)
+    stages = []
+    for idx, stage_idx in enumerate(range(2, out_stage + 1)):
+        dilation = dil if stage_idx in (4, 5) else 1
+        first_stride = 2 if idx == 0 or (stage_idx == 3 and dil == 1) else 1
+        has_pool = stage_idx in (2, 3)
+        blocks = []
+        for b in range(nblocks[idx]):
+            last = b == nblocks[idx] - 1
+            kw = dict(stride=first_stride if last else 1, dilation=dilation, has_pool=has_pool and last)
+            blocks.append(BasicBlock(in_ch, out_ch, **kw) if basic else BottleneckBlock(in_ch, out_ch, bott, **kw))
+            in_ch = out_ch
+        out_ch *= 2
+        bott *= 2
+        stages.append(blocks)
+    stem = BasicStem(3 if input_shape is None else input_shape.channels, r.STEM_OUT_CHANNELS)
+    return ResNetWS(stem, stages, r.OUT_FEATURES, precision_of(cfg)).freeze(cfg.MODEL.BACKBONE.FREEZE_AT)
+
+
+@BACKBONE_REGISTRY.register()
+def build_vgg_backbone(cfg, input_shape=None):
+    assert cfg.MODEL.VGG.DEPTH == 16, "only VGG16 exists in the reference (vgg.py:238-241)"
+    return VGG16(cfg.MODEL.VGG.CONV5_DILATION, cfg.MODEL.BACKBONE.FREEZE_AT, precision_of(cfg))
+
+
+# ------------------------------------------------------------------------------------------------
+# ROI heads
+# ------------------------------------------------------------------------------------------------
+@ROI_BOX_HEAD_REGISTRY.register()
+class DiscriminativeAdaptionNeck(nn.Module):
+    """projects/WSL/wsl/modeling/roi_heads/box_head.py:19-103 with NUM_CONV == 0 (all WSL configs)."""
+
+    def __init__(self, cfg, input_shape):
+        super().__init__()
+        assert cfg.MODEL.ROI_BOX_HEAD.NUM_CONV == 0, "conv layers in the DAN neck are not used by any WSL config"
+        self.in_channels = input_shape.channels
+        size = input_shape.channels * (input_shape.height or 1) * (input_shape.width or 1)
+        self.fcs = []
+        for k, dim in enumerate(cfg.MODEL.ROI_BOX_HEAD.DAN_DIM):
+            fc = Linear(size, dim)
+            nn.init.normal_(fc.weight, std=0.005)
+            nn.init.constant_(fc.bias, 0.1)
+            self.add_module(f"fc{k + 1}", fc)
+            self.fcs.append(fc)
+            size = dim
+        self._output_size = size
+        self.precision = precision_of(cfg)
+        self._seed = 0
+
+    @property
+    def output_shape(self):
+        return ShapeSpec(channels=self._output_size)
+
+    def run(self, pooled2d, bin_major):
+        """pooled2d: [R, 49*C] (bin-major from the fused ROIPool) or [R, C*49] (reference order)."""
+        x = pooled2d
+        for i, fc in enumerate(self.fcs):
+            perm = self.in_channels if (i == 0 and bin_major) else None
+            x = run_linear(x, fc.packed(self.precision, permute_c49=perm), self.precision, relu=True)
+            if self.training:  # box_head.py:90
+                self._seed += 1
+                ops.dropout_(x, 0.5, self._seed)
+        return x
+
+    def forward(self, x):
+        if x.dim() > 2:
+            x = torch.flatten(x, start_dim=1)
+        x = x.contiguous()
+        if self.precision != "fp32" and x.dtype != torch.bfloat16:
+            x = ops.to_bf16(x)
+        return self.run(x, bin_major=False)
+
+
+class _OutputLayers(nn.Module):
+    def _common(self, cfg, input_shape):
+        self.in_size = input_shape.channels * (input_shape.width or 1) * (input_shape.height or 1)
+        self.num_classes = cfg.MODEL.ROI_HEADS.NUM_CLASSES
+        self.cls_agnostic = cfg.MODEL.ROI_BOX_HEAD.CLS_AGNOSTIC_BBOX_REG
+        self.num_bbox_reg_classes = 1 if self.cls_agnostic else self.num_classes
+        self.bbox_w = tuple(cfg.MODEL.ROI_BOX_HEAD.BBOX_REG_WEIGHTS)
+        self.box_dim = len(self.bbox_w)
+        self.smooth_l1_beta = cfg.MODEL.ROI_BOX_HEAD.SMOOTH_L1_BETA
+        self.test_score_thresh = cfg.MODEL.ROI_HEADS.SCORE_THRESH_TEST
+        self.test_nms_thresh = cfg.MODEL.ROI_HEADS.NMS_THRESH_TEST
+        self.test_topk_per_image = cfg.TEST.DETECTIONS_PER_IMAGE
+        self.loss_weight = {"loss_box_reg": cfg.MODEL.ROI_BOX_HEAD.BBOX_REG_LOSS_WEIGHT}
+        self.mean_loss = cfg.WSL.MEAN_LOSS
+        assert cfg.MODEL.ROI_BOX_HEAD.BBOX_REG_LOSS_TYPE == "smooth_l1", "only smooth_l1 box loss is on the hot path"
+
+
+class WSDDNOutputLayers(_OutputLayers):
+    """Parameters of projects/WSL/wsl/modeling/roi_heads/fast_rcnn.py:400-491 (cls, det)."""
+
+    def __init__(self, cfg, input_shape):
+        super().__init__()
+        self._common(cfg, input_shape)
+        self.cls = Linear(self.in_size, self.num_classes)
+        self.det = Linear(self.in_size, self.num_classes)
+        for l in (self.cls, self.det):
+            nn.init.xavier_uniform_(l.weight)
+            nn.init.constant_(l.bias, 0)
+
+
+class OICROutputLayers(_OutputLayers):
+    """Parameters of fast_rcnn.py:1243-1361 (cls_score, bbox_pred)."""
+
+    def __init__(self, cfg, input_shape, refine_k):
+        super().__init__()
+        self._common(cfg, input_shape)
+        self.refine_k = refine_k
+        self.refine_reg = list(cfg.WSL.REFINE_REG)
+        self.cls_score = Linear(self.in_size, self.num_classes + 1)
+        self.bbox_pred = Linear(self.in_size, self.num_bbox_reg_classes * self.box_dim)
+        nn.init.normal_(self.cls_score.weight, std=0.01)
+        nn.init.normal_(self.bbox_pred.weight, std=0.001)
+        for l in (self.cls_score, self.bbox_pred):
+            nn.init.constant_(l.bias, 0)
+
+
+def fast_rcnn_inference_single_image(all_boxes, all_scores, image_shape, score_thresh, nms_thresh, topk, inst_cls, box_cls):
+    """Tail of fast_rcnn.py:88-141: finite filter, drop bg column, clip, threshold, per-class NMS, top-k.
+    (Kept on torch/torchvision ops: SURVEY.md §8f row 2 'next'.)"""
+    import torchvision
+
+    boxes, scores = all_boxes, all_scores
+    valid = torch.isfinite(boxes).all(dim=1) & torch.isfinite(scores).all(dim=1)
+    if not valid.all():
+        boxes, scores = boxes[valid], scores[valid]
+    scores = scores[:, :-1]
+    nreg = boxes.shape[1] // 4
+    b = box_cls(boxes.reshape(-1, 4).clone())
+    b.clip(image_shape)
+    boxes = b.tensor.view(-1, nreg, 4)
+    mask = scores > score_thresh
+    inds = mask.nonzero()
+    boxes = boxes[inds[:, 0], 0] if nreg == 1 else boxes[mask]
+    scores = scores[mask]
+    keep = torchvision.ops.batched_nms(boxes.float(), scores, inds[:, 1], nms_thresh)
+    if topk >= 0:
+        keep = keep[:topk]
+    res = inst_cls(image_shape)
+    res.pred_boxes = box_cls(boxes[keep])
+    res.scores = scores[keep]
+    res.pred_classes = inds[keep, 1]
+    return res, inds[keep, 0]
+
+
+class _WSLROIHeads(nn.Module):
+    """Shared machinery of WSDDNROIHeads / OICRROIHeads (roi_heads.py:156-212, roi_heads_oicr.py:50-194)."""
+
+    def __init__(self, cfg, input_shape, with_refinery):
+        super().__init__()
+        m = cfg.MODEL
+        self.num_classes = m.ROI_HEADS.NUM_CLASSES
+        self.batch_size_per_image = m.ROI_HEADS.BATCH_SIZE_PER_IMAGE
+        self.positive_fraction = m.ROI_HEADS.POSITIVE_FRACTION
+        self.proposal_append_gt = m.ROI_HEADS.PROPOSAL_APPEND_GT
+        self.iou_thresholds = list(m.ROI_HEADS.IOU_THRESHOLDS)
+        self.iou_labels = list(m.ROI_HEADS.IOU_LABELS)
+        assert len(self.iou_labels) == len(self.iou_thresholds) + 1 and all(l in (-1, 0, 1) for l in self.iou_labels)
+        self.box_in_features = list(m.ROI_HEADS.IN_FEATURES)
+        assert len(self.box_in_features) == 1, "single-level ROIPool only (WSL configs pool res5/plain5)"
+        assert m.ROI_BOX_HEAD.POOLER_TYPE == "ROIPool", "the hot path implements POOLER_TYPE: ROIPool"
+        assert m.ROI_BOX_HEAD.POOLER_RESOLUTION == 7, "ROIPool kernel is specialised for 7x7 bins"
+        assert not m.MASK_ON and not m.KEYPOINT_ON
+        assert not self.proposal_append_gt, "WSL configs set PROPOSAL_APPEND_GT: False"
+        shape = input_shape[self.box_in_features[0]]
+        self.in_channels = shape.channels
+        self.pooler_scale = 1.0 / shape.stride
+        self.train_on_pred_boxes = m.ROI_BOX_HEAD.TRAIN_ON_PRED_BOXES
+        assert not self.train_on_pred_boxes
+        self.cls_agnostic_bbox_reg = m.ROI_BOX_HEAD.CLS_AGNOSTIC_BBOX_REG
+        self.precision = precision_of(cfg)
+        head_cls = ROI_BOX_HEAD_REGISTRY.get(m.ROI_BOX_HEAD.NAME)
+        self.box_head = head_cls(cfg, ShapeSpec(channels=self.in_channels, height=7, width=7))
+        self.box_predictor = WSDDNOutputLayers(cfg, self.box_head.output_shape)
+        self.refine_K = cfg.WSL.REFINE_NUM if with_refinery else 0
+        self.refine_reg = list(cfg.WSL.REFINE_REG) if with_refinery else []
+        self.box_refinery = []
+        for k in range(self.refine_K):
+            layer = OICROutputLayers(cfg, self.box_head.output_shape, k)
+            self.add_module(f"box_refinery_{k}", layer)
+            self.box_refinery.append(layer)
+        self.iter = 0
+        self.iter_test = 0
+        self.epoch_test = 0
+        self.output_dir, self.vis_test, self.vis_period = cfg.OUTPUT_DIR, cfg.WSL.VIS_TEST, cfg.VIS_PERIOD
+        self._heads_cache = None
+        self._counter = None
+        self.last_trace = None
+        self.keep_trace = False
+
+    # -- derived: one concatenated head matrix [cls | det | cls_score_0.. | bbox_pred_k (reg stages)] ----
+    def _heads_packed(self):
+        K = self.num_classes
+        layers = [self.box_predictor.cls, self.box_predictor.det] + [r.cls_score for r in self.box_refinery]
+        layers += [self.box_refinery[k].bbox_pred for k in range(self.refine_K) if self.refine_reg[k]]
+        key = _versions([p for l in layers for p in (l.weight, l.bias)])
+        if self._heads_cache is not None and self._heads_cache["key"] == key:
+            return self._heads_cache
+        packed = pack_linear([l.weight for l in layers], [l.bias for l in layers], self.precision)
+        offs, o = {}, 0
+        offs["cls"] = o; o += K
+        offs["det"] = o; o += K
+        for k in range(self.refine_K):
+            offs[f"cls_score_{k}"] = o; o += K + 1
+        for k in range(self.refine_K):
+            if self.refine_reg[k]:
+                offs[f"bbox_pred_{k}"] = o; o += self.box_refinery[k].bbox_pred.out_features
+            else:
+                offs[f"bbox_pred_{k}"] = -1
+        packed.update(key=key, offs=offs)
+        self._heads_cache = packed
+        return packed
+
+    def _features_hwc(self, features, i):
+        f = features[self.box_in_features[0]]
+        x = f[i].permute(1, 2, 0)  # [h,w,C]; a no-copy view when the backbone wrote NHWC
+        want = torch.float32 if self.precision == "fp32" else torch.bfloat16
+        if x.dtype != want:
+            x = ops.to_bf16(x.contiguous()) if want == torch.bfloat16 else ops.to_f32(x.contiguous())
+        return x.contiguous()
+
+    def _roi_logits(self, features, proposals, i):
+        """ROIPool x (objectness+1) -> fc6 -> fc7 -> all head logits for image i: [R, ld] fp32."""
+        p = proposals[i]
+        boxes = p.proposal_boxes.tensor.float().contiguous()
+        obj = p.objectness_logits.float().contiguous()
+        pooled = ops.roipool(self._features_hwc(features, i), boxes, obj, self.pooler_scale)
+        feat = self.box_head.run(pooled, bin_major=True)
+        heads = self._heads_packed()
+        logits = run_linear(feat, heads, self.precision, relu=False, out_dtype=torch.float32)
+        return boxes, obj, feat, logits, heads
+
+    def _image_level_gt(self, targets):
+        """roi_heads.py:137-153 (device-side unique; G is read back once per image because it sizes launches)."""
+        K = self.num_classes
+        out = []
+        for t in targets:
+            gt = torch.unique(t.gt_classes, sorted=True).to(torch.int64)
+            oh = torch.zeros((K,), dtype=torch.float32, device=gt.device)
+            oh[gt] = 1.0
+            out.append((gt, oh))
+        self.gt_classes_img = [g for g, _ in out]
+        self.gt_classes_img_int = self.gt_classes_img
+        self.gt_classes_img_oh = torch.stack([o for _, o in out], dim=0) if out else None
+        return out
+
+    def _put_scalars(self, storage, pending):
+        if storage is None:
+            return
+        for name, val in pending:
+            storage.put_scalar(name, float(val))
+
+    def forward(self, images, features, proposals, targets=None):
+        if self.training:
+            assert targets, "'targets' argument is required during training"
+            losses = self._forward_train(features, proposals, targets)
+            self.iter += 1
+            if self.iter_test > 0:
+                self.epoch_test += 1
+            self.iter_test = 0
+            return proposals, losses
+        pred_instances, all_scores, all_boxes = self._forward_eval(features, proposals)
+        self.iter_test += 1
+        return pred_instances, {}, all_scores, all_boxes
+
+    def forward_with_given_boxes(self, features, instances):
+        assert not self.training
+        assert instances[0].has("pred_boxes") and instances[0].has("pred_classes")
+        return instances, [], []
+
+    # -- train ---------------------------------------------------------------------------------------
+    def _forward_train(self, features, proposals, targets):
+        K, N, S = self.num_classes, len(proposals), self.refine_K
+        dev = proposals[0].proposal_boxes.tensor.device
+        storage = _event_storage()
+        img_gt = self._image_level_gt(targets)
+        if self._counter is None or self._counter.device != dev:
+            self._counter = torch.zeros((1,), dtype=torch.int32, device=dev)
+        nloss = 1 + S + sum(self.refine_reg)
+        loss_buf = torch.zeros((N, nloss), dtype=torch.float32, device=dev)
+        stage_stats = [[None] * N for _ in range(S)]
+        label_counts = [[None] * N for _ in range(S + 1)]
+        mil_scale = (1.0 / (N * N)) if self.box_predictor.mean_loss else (1.0 / N)
+        traces = []
+        img_scores = []
+        for i in range(N):
+            boxes, obj, feat, logits, heads = self._roi_logits(features, proposals, i)
+            offs = heads["offs"]
+            gt_int, gt_oh = img_gt[i]
+            tg = targets[i]
+            # labelling against the real GT (roi_heads_oicr.py:266): feeds logging + proposals' gt fields
+            lab0, midx0, cnt0 = ops.label_proposals(boxes, tg.gt_boxes.tensor.float().contiguous(),
+                                                    tg.gt_classes.to(torch.int64).contiguous(), K,
+                                                    self.iou_thresholds, self.iou_labels)
+            label_counts[0][i] = cnt0
+            proposals[i].gt_classes = lab0
+            if len(tg) > 0:
+                proposals[i].gt_boxes = type(tg.gt_boxes)(tg.gt_boxes.tensor[midx0])
+            scores, img_score = ops.wsddn_mil(logits, K, offs["cls"], offs["det"], gt_oh, self.box_predictor.mean_loss,
+                                              mil_scale, loss_buf[i, 0:1])
+            img_scores.append(img_score)
+            tr = {"scores": scores, "img_score": img_score, "logits": logits, "feat": feat, "labels_gt": lab0, "stages": []}
+            prev, prev_ld_deltas, prev_deltas, col = scores, 0, None, 1
+            for k in range(S):
+                bw = self.box_refinery[k].bbox_w
+                pgt_idx, pgt_score, pgt_box, pgt_w = ops.oicr_pgt(prev, boxes, gt_int, img_score, k > 0, prev_deltas,
+                                                                  prev_ld_deltas, self.cls_agnostic_bbox_reg, bw)
+                labels, midx, cnt = ops.label_proposals(boxes, pgt_box, gt_int, K, self.iou_thresholds, self.iou_labels)
+                label_counts[k + 1][i] = cnt
+                probs, stats, weights = ops.oicr_stage(logits, offs[f"cls_score_{k}"], K, labels, midx, pgt_w, 1.0,
+                                                       loss_buf[i, col:col + 1], self._counter)
+                stage_stats[k][i] = stats
+                col += 1
+                if self.refine_reg[k]:
+                    doff = offs[f"bbox_pred_{k}"]
+                    lw = self.box_refinery[k].loss_weight.get("loss_box_reg", 1.0)
+                    ops.oicr_boxreg_loss(logits, doff, K, self.cls_agnostic_bbox_reg, boxes, pgt_box, labels, midx, bw,
+                                         self.box_refinery[k].smooth_l1_beta, lw, loss_buf[i, col:col + 1], self._counter)
+                    col += 1
+                    prev_deltas, prev_ld_deltas = logits[:, doff:], logits.shape[1]
+                else:
+                    prev_deltas, prev_ld_deltas = None, 0
+                prev = probs
+                tr["stages"].append(dict(pgt_idx=pgt_idx, pgt_scores=pgt_score, pgt_boxes=pgt_box, pgt_weights=pgt_w,
+                                         labels=labels, matched=midx, probs=probs, weights=weights))
+            traces.append(tr)
+        self.pred_class_img_logits = torch.stack(img_scores, dim=0)
+        self.last_trace = traces if self.keep_trace else None
+
+        # assemble the loss dict (keys/normalisation of fast_rcnn.py:317-329, :1128-1144, :1146-1211)
+        losses = {}
+        if N == 1:
+            row = loss_buf[0]
+            losses["loss_cls"] = row[0]
+            col = 1
+            for k in range(S):
+                losses[f"loss_cls_r{k}"] = row[col]; col += 1
+                if self.refine_reg[k]:
+                    losses[f"loss_box_reg_r{k}"] = row[col]; col += 1
+        else:
+            losses["loss_cls"] = loss_buf[:, 0].sum()
+            col = 1
+            Rtot = sum(len(p) for p in proposals)
+            for k in range(S):
+                st = torch.stack(stage_stats[k], dim=0)
+                losses[f"loss_cls_r{k}"] = st[:, 4].sum() / st[:, 5].sum(); col += 1
+                if self.refine_reg[k]:
+                    rs = torch.tensor([len(p) for p in proposals], dtype=torch.float32, device=dev)
+                    losses[f"loss_box_reg_r{k}"] = (loss_buf[:, col] * rs).sum() / Rtot; col += 1
+
+        if storage is not None:  # the reference's scalars (roi_heads.py:346-349, roi_heads_oicr.py:345-348, fast_rcnn.py:1098-1126)
+            pend = []
+            for s, suffix in enumerate([""] + [f"_r{k}" for k in range(S)]):
+                c = torch.stack(label_counts[s], 0).float().mean(0).tolist()
+                pend += [("roi_head/num_fg_samples" + suffix, c[0]), ("roi_head/num_bg_samples" + suffix, c[1]),
+                         ("roi_head/num_ig_samples" + suffix, c[2])]
+            obj1 = torch.cat([p.objectness_logits.float() + 1 for p in proposals])
+            pend += [("proposals/objectness_logits+1 mean", obj1.mean()), ("proposals/objectness_logits+1 max", obj1.max()),
+                     ("proposals/objectness_logits+1 min", obj1.min())]
+            Rtot = sum(len(p) for p in proposals)
+            for k in range(S):
+                st = torch.stack(stage_stats[k], 0).sum(0).tolist()
+                pend.append((f"fast_rcnn/cls_accuracy_r{k}", st[0] / max(Rtot, 1)))
+                if st[1] > 0:
+                    pend += [(f"fast_rcnn/fg_cls_accuracy_r{k}", st[2] / st[1]), (f"fast_rcnn/false_negative_r{k}", st[3] / st[1])]
+            self._put_scalars(storage, pend)
+        return losses
+
+    # -- eval ----------------------------------------------------------------------------------------
+    def _forward_eval(self, features, proposals):
+        K, S = self.num_classes, self.refine_K
+        results, all_scores, all_boxes = [], [], []
+        for i in range(len(proposals)):
+            boxes, obj, feat, logits, heads = self._roi_logits(features, proposals, i)
+            offs = heads["offs"]
+            p = proposals[i]
+            if S > 0:
+                bw = self.box_refinery[-1].bbox_w
+                ks = [S - 1] if self.refine_reg[-1] else list(range(S))
+                nreg = 1 if self.cls_agnostic_bbox_reg else K
+                sc, bx = ops.oicr_infer(logits, K, [offs[f"cls_score_{k}"] for k in ks],
+                                        [offs[f"bbox_pred_{k}"] for k in ks], boxes, bw, nreg)
+                layer = self.box_refinery[-1]
+            else:
+                layer = self.box_predictor
+                gt_oh = torch.zeros((K,), dtype=torch.float32, device=boxes.device)
+                dummy = torch.empty((1,), dtype=torch.float32, device=boxes.device)
+                scores, _ = ops.wsddn_mil(logits, K, offs["cls"], offs["det"], gt_oh, True, 1.0, dummy)
+                # fast_rcnn.py:668-687: zero background column; :645-666 boxes = apply_deltas(0, proposals)
+                sc = torch.cat((scores, scores.new_zeros(scores.shape[0], 1)), dim=1)
+                bx = ops.oicr_infer(logits, K, [offs["cls"]], [-1], boxes, layer.bbox_w, K)[1]
+            inst_cls, box_cls = type(p), type(p.proposal_boxes)
+            res, _ = fast_rcnn_inference_single_image(bx, sc, p.image_size, layer.test_score_thresh, layer.test_nms_thresh,
+                                                      layer.test_topk_per_image, inst_cls, box_cls)
+            results.append(res)
+            all_scores.append(sc.unsqueeze(0))
+            all_boxes.append(bx.unsqueeze(0))
+        return results, all_scores, all_boxes
+
+
+@ROI_HEADS_REGISTRY.register()
+class WSDDNROIHeads(_WSLROIHeads):
+    """projects/WSL/wsl/modeling/roi_heads/roi_heads_wsddn.py (box branch)."""
+
+    def __init__(self, cfg, input_shape):
+        super().__init__(cfg, input_shape, with_refinery=False)
+
+
+@ROI_HEADS_REGISTRY.register()
+class OICRROIHeads(_WSLROIHeads):
+    """projects/WSL/wsl/modeling/roi_heads/roi_heads_oicr.py (box branch + refinement loop :365-397)."""
+
+    def __init__(self, cfg, input_shape):
+        super().__init__(cfg, input_shape, with_refinery=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# meta architecture
+# ------------------------------------------------------------------------------------------------
+@META_ARCH_REGISTRY.register()
+class GeneralizedRCNNWSL(nn.Module):
+    """projects/WSL/wsl/modeling/meta_arch/rcnn.py:23-265 with precomputed proposals."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        m = cfg.MODEL
+        self.backbone = BACKBONE_REGISTRY.get(m.BACKBONE.NAME)(cfg, ShapeSpec(channels=len(m.PIXEL_MEAN)))
+        self.proposal_generator = None
+        self.load_proposals = m.LOAD_PROPOSALS
+        self.roi_heads = ROI_HEADS_REGISTRY.get(m.ROI_HEADS.NAME)(cfg, self.backbone.output_shape())
+        self.input_format = cfg.INPUT.FORMAT
+        self.vis_period = cfg.VIS_PERIOD
+        self.register_buffer("pixel_mean", torch.Tensor(list(m.PIXEL_MEAN)).view(-1, 1, 1))
+        self.register_buffer("pixel_std", torch.Tensor(list(m.PIXEL_STD)).view(-1, 1, 1))
+        assert self.pixel_mean.shape == self.pixel_std.shape
+        self.cpg = False
+        self._mean_std_host = None
+
+    @property
+    def device(self):
+        return self.pixel_mean.device
+
+    def _mean_std(self):
+        key = (self.pixel_mean._version, self.pixel_std._version, self.pixel_mean.device)
+        if self._mean_std_host is None or self._mean_std_host[0] != key:
+            self._mean_std_host = (key, self.pixel_mean.flatten().tolist(), self.pixel_std.flatten().tolist())
+        return self._mean_std_host[1], self._mean_std_host[2]
+
+    def preprocess_image(self, batched_inputs):
+        """rcnn.py:242-249.  Normalisation is fused into the first conv, so this only moves the raw
+        images to the device and records the zero-padded canvas ImageList.from_tensors would build."""
+        images = [x["image"].to(self.device, non_blocking=True).float().contiguous() for x in batched_inputs]
+        sizes = [(im.shape[-2], im.shape[-1]) for im in images]
+        canvas = (max(s[0] for s in sizes), max(s[1] for s in sizes))
+        return images, sizes, canvas
+
+    def _features(self, images, canvas):
+        mean, std = self._mean_std()
+        feats = [self.backbone.forward_image(im, canvas, mean, std) for im in images]
+        f = feats[0] if len(feats) == 1 else torch.cat(feats, dim=0)
+        return {self.backbone._out_features[0]: f.permute(0, 3, 1, 2)}
+
+    def forward(self, batched_inputs):
+        if not self.training:
+            return self.inference(batched_inputs)
+        images, sizes, canvas = self.preprocess_image(batched_inputs)
+        gt_instances = [x["instances"].to(self.device) for x in batched_inputs] if "instances" in batched_inputs[0] else None
+        features = self._features(images, canvas)
+        assert self.load_proposals and "proposals" in batched_inputs[0]
+        proposals = [x["proposals"].to(self.device) for x in batched_inputs]
+        _, detector_losses = self.roi_heads(ImageList(None, sizes), features, proposals, gt_instances)
+        losses = {}
+        losses.update(detector_losses)
+        return losses
+
+    def inference(self, batched_inputs, detected_instances=None, do_postprocess=True):
+        assert not self.training
+        images, sizes, canvas = self.preprocess_image(batched_inputs)
+        features = self._features(images, canvas)
+        if detected_instances is None:
+            assert self.load_proposals and "proposals" in batched_inputs[0]
+            proposals = [x["proposals"].to(self.device) for x in batched_inputs]
+            results, _, all_scores, all_boxes = self.roi_heads(ImageList(None, sizes), features, proposals, None)
+        else:
+            detected_instances = [x.to(self.device) for x in detected_instances]
+            results, all_scores, all_boxes = self.roi_heads.forward_with_given_boxes(features, detected_instances)
+        if do_postprocess:
+            return GeneralizedRCNNWSL._postprocess(results, batched_inputs, sizes)
+        return results, all_scores, all_boxes
+
+    @staticmethod
+    def _postprocess(instances, batched_inputs, image_sizes):
+        out = []
+        for res, inp, size in zip(instances, batched_inputs, image_sizes):
+            out.append({"instances": detector_postprocess(res, inp.get("height", size[0]), inp.get("width", size[1]))})
+        return out
+
+
+def build_model(cfg):
+    """detectron2/modeling/meta_arch/build.py:15-23."""
+    model = META_ARCH_REGISTRY.get(cfg.MODEL.META_ARCHITECTURE)(cfg)
+    model.to(torch.device(cfg.MODEL.DEVICE))
+    return model

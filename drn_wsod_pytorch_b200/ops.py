@@ -1,0 +1,168 @@
+"""Thin Python wrappers over the C ABI (one function per entry point of include/drn_b200.h).
+
+Tensors are torch CUDA tensors used purely as device buffers; all arithmetic happens inside
+libdrn_b200.so.  Activations are NHWC.  Nothing here falls back to torch ops.
+"""
+import torch
+
+from . import lib
+from .lib import DRN_BF16, DRN_F32, call, current_stream, fvec, ivec
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return DRN_F32
+    if t.dtype == torch.bfloat16:
+        return DRN_BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _chk(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the B200 path has no CPU fallback")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+
+
+def first_conv(img_chw, canvas_hw, mean, std, packed, stride, relu=True, out_dtype=torch.float32):
+    """Fused (img-mean)/std + 3x3 Cin=3 conv + affine + ReLU.  img_chw: 3xHxW fp32 -> 1xHoxWoxCout."""
+    _chk(img_chw, "image")
+    assert img_chw.dtype == torch.float32 and img_chw.dim() == 3 and img_chw.shape[0] == 3
+    H, W = img_chw.shape[1:]
+    Hp, Wp = canvas_hw
+    Cout = packed["cout"]
+    Ho, Wo = (Hp + 2 - 3) // stride + 1, (Wp + 2 - 3) // stride + 1
+    out = torch.empty((1, Ho, Wo, Cout), device=img_chw.device, dtype=out_dtype)
+    call("drn_conv3x3_c3_fwd", img_chw, H, W, Hp, Wp, fvec(mean), fvec(std), packed["w"], packed["scale"],
+         packed["bias"], Cout, stride, int(relu), out, _dt(out), current_stream())
+    return out
+
+
+def conv_f32(x, packed, ksize, dilation, relu, residual=None, out=None, ldo=None):
+    """SIMT fp32 implicit-GEMM conv / linear.  x: [N,H,W,Cin] fp32 NHWC."""
+    _chk(x, "x")
+    N, H, W, Cin = x.shape
+    Cout = packed["cout"]
+    if out is None:
+        out = torch.empty((N, H, W, Cout), device=x.device, dtype=torch.float32)
+        ldo = Cout
+    call("drn_conv_igemm_f32", x, N, H, W, Cin, packed["w"], ksize, dilation, packed["scale"], packed["bias"],
+         residual, int(relu), out, Cout, ldo, current_stream())
+    return out
+
+
+def conv_bf16_tc(x, packed, ksize, dilation, relu, residual=None, out_dtype=torch.bfloat16):
+    """tcgen05 implicit-GEMM conv / linear.  x: [N,H,W,Cin] bf16 NHWC."""
+    _chk(x, "x")
+    N, H, W, Cin = x.shape
+    Cout = packed["cout"]
+    out = torch.empty((N, H, W, Cout), device=x.device, dtype=out_dtype)
+    call("drn_conv_igemm_bf16_tc", x, N, H, W, Cin, packed["w"], ksize, dilation, packed["scale"], packed["bias"],
+         residual, int(relu), out, _dt(out), Cout, Cout, current_stream())
+    return out
+
+
+def maxpool2x2(x, stride):
+    _chk(x, "x")
+    N, H, W, C = x.shape
+    Ho, Wo = (H - 2) // stride + 1, (W - 2) // stride + 1
+    out = torch.empty((N, Ho, Wo, C), device=x.device, dtype=x.dtype)
+    call("drn_maxpool2x2_nhwc", x, N, H, W, C, stride, _dt(x), out, current_stream())
+    return out
+
+
+def roipool(feat_hwc, boxes, objectness, spatial_scale):
+    """feat_hwc: [h,w,C]; boxes [R,4] fp32; objectness [R] fp32 or None -> [R, 49*C] (bin-major)."""
+    _chk(feat_hwc, "features")
+    _chk(boxes, "boxes")
+    h, w, C = feat_hwc.shape
+    R = boxes.shape[0]
+    out = torch.empty((R, 49 * C), device=feat_hwc.device, dtype=feat_hwc.dtype)
+    call("drn_roipool_fwd", feat_hwc, h, w, C, boxes, objectness, R, float(spatial_scale), _dt(feat_hwc), out,
+         current_stream())
+    return out
+
+
+def dropout_(x, p, seed):
+    call("drn_dropout_inplace", x, x.numel(), _dt(x), float(p), int(seed), current_stream())
+    return x
+
+
+def wsddn_mil(logits, K, cls_off, det_off, gt_onehot, mean_loss, loss_scale, loss_out):
+    R, ld = logits.shape
+    dev = logits.device
+    scores = torch.empty((R, K), device=dev, dtype=torch.float32)
+    img_score = torch.empty((K,), device=dev, dtype=torch.float32)
+    ws = torch.empty((2 * R + K,), device=dev, dtype=torch.float32)
+    call("drn_wsddn_mil_fwd", logits, ld, R, K, cls_off, det_off, gt_onehot, int(mean_loss), float(loss_scale),
+         scores, img_score, loss_out, ws, current_stream())
+    return scores, img_score
+
+
+def oicr_pgt(prev_scores, boxes, gt_classes, img_score, rederive, deltas, ld_deltas, cls_agnostic, bbox_w):
+    R, ld = prev_scores.shape
+    G = gt_classes.numel()
+    dev = prev_scores.device
+    pgt_idx = torch.empty((G,), device=dev, dtype=torch.int64)
+    pgt_score = torch.empty((G,), device=dev, dtype=torch.float32)
+    pgt_box = torch.empty((G, 4), device=dev, dtype=torch.float32)
+    pgt_weight = torch.empty((G,), device=dev, dtype=torch.float32)
+    call("drn_oicr_pgt", prev_scores, ld, R, boxes, gt_classes, G, img_score, int(rederive), deltas, int(ld_deltas),
+         int(cls_agnostic), fvec(bbox_w), pgt_idx, pgt_score, pgt_box, pgt_weight, current_stream())
+    return pgt_idx, pgt_score, pgt_box, pgt_weight
+
+
+def label_proposals(boxes, gt_boxes, gt_classes, K, thresholds, labels_cfg):
+    R = boxes.shape[0]
+    G = 0 if gt_classes is None else gt_classes.numel()
+    dev = boxes.device
+    labels = torch.empty((R,), device=dev, dtype=torch.int64)
+    matched = torch.empty((R,), device=dev, dtype=torch.int64)
+    counts = torch.empty((3,), device=dev, dtype=torch.int32)
+    call("drn_label_proposals", boxes, R, gt_boxes if G else None, gt_classes if G else None, G, K,
+         fvec(thresholds), ivec(labels_cfg), len(thresholds), labels, matched, counts, current_stream())
+    return labels, matched, counts
+
+
+def oicr_stage(logits, col_off, K, labels, matched, pgt_weight, loss_scale, loss_out, counter):
+    R, ld = logits.shape
+    dev = logits.device
+    probs = torch.empty((R, K + 1), device=dev, dtype=torch.float32)
+    stats = torch.empty((6,), device=dev, dtype=torch.float32)
+    weights = torch.empty((R,), device=dev, dtype=torch.float32)
+    nb = (R + 255) // 256
+    part = torch.empty((6 * nb,), device=dev, dtype=torch.float32)
+    call("drn_oicr_stage_fwd", logits, ld, col_off, R, K, labels, matched, pgt_weight, pgt_weight.numel(),
+         float(loss_scale), probs, loss_out, stats, weights, part, counter, current_stream())
+    return probs, stats, weights
+
+
+def oicr_boxreg_loss(logits, col_off, K, cls_agnostic, boxes, pgt_box, labels, matched, bbox_w, beta, loss_scale,
+                     loss_out, counter):
+    R, ld = logits.shape
+    nb = (R + 255) // 256
+    part = torch.empty((nb,), device=logits.device, dtype=torch.float32)
+    call("drn_oicr_boxreg_loss", logits, ld, col_off, R, K, int(cls_agnostic), boxes, pgt_box, labels, matched,
+         fvec(bbox_w), float(beta), float(loss_scale), loss_out, part, counter, current_stream())
+
+
+def oicr_infer(logits, K, col_offs, delta_offs, boxes, bbox_w, nreg):
+    R, ld = logits.shape
+    dev = logits.device
+    all_scores = torch.empty((R, K + 1), device=dev, dtype=torch.float32)
+    all_boxes = torch.empty((R, 4 * nreg), device=dev, dtype=torch.float32)
+    call("drn_oicr_infer", logits, ld, R, K, nreg, len(col_offs), ivec(col_offs), ivec(delta_offs), boxes, fvec(bbox_w),
+         all_scores, all_boxes, current_stream())
+    return all_scores, all_boxes
+
+
+def to_bf16(x):
+    out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    call("drn_cast_f32_to_bf16", x.contiguous(), out, x.numel(), current_stream())
+    return out
+
+
+def to_f32(x):
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    call("drn_cast_bf16_to_f32", x.contiguous(), out, x.numel(), current_stream())
+    return out

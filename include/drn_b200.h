@@ -1,0 +1,160 @@
+/*
+ * drn_b200.h -- C ABI of libdrn_b200.so: the B200 (sm_100a) kernels of the DRN-WSOD
+ * per-image detection hot path.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void*; nothing here synchronises or allocates;
+ *   - return value 0 = OK, non-zero = error; drn_last_error() gives the thread-local message
+ *     (the Python shim raises RuntimeError with it, mirroring the reference's assert/raise style);
+ *   - activations are NHWC ("channels last"); dtype codes: DRN_F32 = 0, DRN_BF16 = 1;
+ *   - "rows" are region proposals (R per image), "classes" K, refinement stages S.
+ *
+ * Each entry point cites the reference code it replaces (paths relative to the reference root;
+ * WSL = projects/WSL/wsl/modeling).
+ */
+#ifndef DRN_B200_H
+#define DRN_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRN_F32 0
+#define DRN_BF16 1
+
+typedef void* drn_stream_t;
+
+int drn_version(void);
+const char* drn_last_error(void);
+
+/* First backbone conv fused with image normalisation.
+ * Replaces WSL/meta_arch/rcnn.py:242-249 (preprocess_image: (img-mean)/std) +
+ * WSL/backbone/resnet_ws.py:363-372,405-407 (stem.conv1 3x3 s2 + FrozenBN + ReLU) or
+ * WSL/backbone/vgg.py:44-54,97-98 (plain1.conv1 3x3 s1 + bias + ReLU).
+ * img: [3][H][W] fp32 (BGR 0..255) placed top-left on a zero Hp x Wp canvas (Hp>=H, Wp>=W: the
+ * padding detectron2/structures/image_list.py:57-119 adds after normalisation);
+ * w_packed: [3*3*3][Cout] fp32, row = (kh*3+kw)*3+cin; scale may be NULL;
+ * out: [Ho][Wo][Cout] with Ho=(Hp+2-3)/stride+1; y = relu(conv*scale[c]+bias[c]). */
+int drn_conv3x3_c3_fwd(const float* img_chw, int H, int W, int Hp, int Wp, const float* mean3_host,
+                       const float* std3_host,
+                       const float* w_packed, const float* scale, const float* bias, int Cout,
+                       int stride, int relu, void* out_nhwc, int out_dtype, drn_stream_t stream);
+
+/* Implicit-GEMM convolution / linear layer, fp32 SIMT (exact-fp32 mode).
+ * Replaces detectron2/layers/wrappers.py:84-99 (Conv2d.forward = conv + norm + activation),
+ * detectron2/layers/batch_norm.py:45-65 (FrozenBatchNorm2d as x*scale+bias), the residual add +
+ * ReLU of WSL/backbone/resnet_ws.py:96-112,217-237 and nn.Linear + ReLU of
+ * WSL/roi_heads/box_head.py:82-91 (a linear layer is the ksize=1, H=rows, W=1 case).
+ * in: [N][H][W][Cin]; w: [ksize*ksize*Cin][Cout] (row = (kh*ksize+kw)*Cin+cin); stride 1,
+ * padding = dilation*(ksize/2); scale may be NULL (=1); residual may be NULL; out: [N][H][W][Cout]
+ * with row pitch ldo >= Cout elements.  Cin % 16 == 0, Cout % 64 == 0. */
+int drn_conv_igemm_f32(const float* in, int N, int H, int W, int Cin, const float* w, int ksize,
+                       int dilation, const float* scale, const float* bias, const float* residual,
+                       int relu, float* out, int Cout, int ldo, drn_stream_t stream);
+
+/* Tensor-core (tcgen05/TMEM/TMA) implicit-GEMM convolution / linear layer, bf16 in, fp32 accumulate.
+ * Same reference lines as drn_conv_igemm_f32.  in: [N][H][W][Cin] bf16; w: [Cout][ksize*ksize*Cin]
+ * bf16 (K-major, K order (kh,kw,cin)); bias/scale fp32 [Cout]; residual bf16 [N][H][W][Cout] or NULL;
+ * out dtype DRN_BF16 or DRN_F32, row pitch ldo elements.  Cin % 64 == 0, Cout % 16 == 0. */
+int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int Cin, const void* w, int ksize,
+                           int dilation, const float* scale, const float* bias, const void* residual,
+                           int relu, void* out, int out_dtype, int Cout, int ldo, drn_stream_t stream);
+
+/* MaxPool2d(kernel 2, stride 1|2, padding 0), NHWC.
+ * Replaces nn.MaxPool2d in WSL/backbone/resnet_ws.py:93-94,110-111,403,415 and vgg.py:93-94,108-109. */
+int drn_maxpool2x2_nhwc(const void* in, int N, int H, int W, int C, int stride, int dtype, void* out,
+                        drn_stream_t stream);
+
+/* ROIPool(7x7, max) fused with the x(objectness+1) scaling.
+ * Replaces detectron2/modeling/poolers.py:191-226 (ROIPooler.forward -> torchvision.ops.RoIPool)
+ * and WSL/roi_heads/roi_heads_oicr.py:342-343 / roi_heads_wsddn.py:285-286.
+ * feat: [h][w][C] (one image); boxes: [R][4] fp32 XYXY image px; objectness: [R] fp32 or NULL;
+ * out: [R][49][C], bin-major ((ph*7+pw)*C + c) -- fc6's weight is permuted to that K order. */
+int drn_roipool_fwd(const void* feat_nhwc, int h, int w, int C, const float* boxes,
+                    const float* objectness, int R, float spatial_scale, int dtype, void* out,
+                    drn_stream_t stream);
+
+/* WSDDN dual-softmax MIL head + image-level BCE.
+ * Replaces WSL/roi_heads/fast_rcnn.py:493-527 (softmax(cls,1)*softmax(det,0)), :689-700
+ * (predict_probs_img: clamp(sum_r)), :317-329 (binary_cross_entropy_loss) for ONE image.
+ * logits: [R][ld] fp32 with cls at columns [cls_off, cls_off+K), det at [det_off, det_off+K);
+ * gt_onehot: [K] fp32; scores out [R][K]; img_score out [K]; loss out [1] =
+ *   (mean_loss ? mean_k : sum_k) BCE(img_score, gt_onehot) * loss_scale  (loss_scale = 1/num_images).
+ * row_ws: [2*R + K] fp32 scratch. */
+int drn_wsddn_mil_fwd(const float* logits, int ld, int R, int K, int cls_off, int det_off,
+                      const float* gt_onehot, int mean_loss, float loss_scale, float* scores,
+                      float* img_score, float* loss, float* row_ws, drn_stream_t stream);
+
+/* Pseudo-ground-truth mining of one OICR stage.
+ * Replaces WSL/roi_heads/roi_heads_oicr.py:491-567 (get_pgt): for each image-level GT class g,
+ * argmax over proposals of prev_scores[:, gt_classes[g]] (ties -> lowest index, NaN wins),
+ * pgt box = that proposal's box (rederive != 0: passed through Box2BoxTransform.apply_deltas with the
+ * given deltas (NULL = zeros), detectron2/modeling/box_regression.py:73-110, as stages k>=1 do via
+ * fast_rcnn.py:1511-1532), weight = img_score[class].
+ * prev_scores: [R][ld_prev]; gt_classes: [G] int64; deltas: row pitch ld_deltas, class c at columns
+ * [4c,4c+4) (or [0,4) if cls_agnostic), or NULL; bbox_w: 4 floats (host).
+ * Outputs: pgt_idx [G] int64, pgt_score [G], pgt_box [G][4], pgt_weight [G]. */
+int drn_oicr_pgt(const float* prev_scores, int ld_prev, int R, const float* boxes,
+                 const int64_t* gt_classes, int G, const float* img_score, int rederive,
+                 const float* deltas, int ld_deltas, int cls_agnostic, const float* bbox_w_host,
+                 int64_t* pgt_idx, float* pgt_score, float* pgt_box, float* pgt_weight,
+                 drn_stream_t stream);
+
+/* Proposal labelling against (pseudo) ground truth.
+ * Replaces WSL/roi_heads/roi_heads.py:255-353 (label_and_sample_proposals; no sampling, :245-246),
+ * detectron2/structures/boxes.py:329-361 (pairwise_iou), detectron2/modeling/matcher.py:61-103.
+ * thresholds_host: nthr floats (ascending, without the -inf/+inf sentinels); labels_host: nthr+1
+ * ints in {-1,0,1}.  Outputs: labels [R] int64 (class, K = background, -1 = ignore),
+ * matched_idx [R] int64, counts [3] int32 = (#fg, #bg, #ignore).  G == 0 -> all background. */
+int drn_label_proposals(const float* boxes, int R, const float* gt_boxes, const int64_t* gt_classes,
+                        int G, int K, const float* thresholds_host, const int* labels_host, int nthr,
+                        int64_t* labels, int64_t* matched_idx, int32_t* counts, drn_stream_t stream);
+
+/* One OICR refinement stage: weighted softmax cross-entropy + next-stage probabilities.
+ * Replaces WSL/roi_heads/roi_heads_oicr.py:381-397, fast_rcnn.py:1089-1096 (weights/valid),
+ * :1128-1144 (weighted CE / #valid), :1098-1126 (_log_accuracy counters), :1561-1575 (softmax).
+ * logits: [R][ld] with this stage's K+1 columns at col_off; labels/matched_idx from
+ * drn_label_proposals; pgt_weight [G].  Outputs: probs [R][K+1]; loss [1]; stats [6] fp32 =
+ * (#accurate, #fg, #fg_accurate, #false_negative, sum_r w*CE, #valid); weights [R] (proposal weights, may be NULL).
+ * part_ws: [6*ceil(R/256)] fp32 scratch, counter: [1] uint32 zero-initialised (self-resetting). */
+int drn_oicr_stage_fwd(const float* logits, int ld, int col_off, int R, int K, const int64_t* labels,
+                       const int64_t* matched_idx, const float* pgt_weight, int G, float loss_scale,
+                       float* probs, float* loss, float* stats, float* weights, float* part_ws,
+                       uint32_t* counter, drn_stream_t stream);
+
+/* Box regression loss of a refinement stage with REFINE_REG[k] (reg/ configs).
+ * Replaces WSL/roi_heads/fast_rcnn.py:1146-1211 with smooth_l1(beta) and
+ * detectron2/modeling/box_regression.py:38-71 (get_deltas).  deltas: [R][ld] at col_off, 4K wide
+ * (or 4 if cls_agnostic); gt box of row r = pgt_box[matched_idx[r]].  loss = sum / R * loss_scale. */
+int drn_oicr_boxreg_loss(const float* deltas, int ld, int col_off, int R, int K, int cls_agnostic,
+                         const float* boxes, const float* pgt_box, const int64_t* labels,
+                         const int64_t* matched_idx, const float* bbox_w_host, float beta,
+                         float loss_scale, float* loss, float* part_ws, uint32_t* counter,
+                         drn_stream_t stream);
+
+/* Inference scores/boxes.
+ * Replaces WSL/roi_heads/fast_rcnn.py:1577-1594 (predict_probs_K: mean of S softmaxes),
+ * :1534-1559 (predict_boxes_K: mean deltas -> apply_deltas) and, for WSDDN heads, :668-687.
+ * logits: [R][ld]; stage s has its K+1 class logits at col_offs_host[s]; delta_offs_host[s] >= 0
+ * gives that stage's 4*nreg deltas (or -1 = zeros); nreg = K, or 1 if class-agnostic regression.
+ * all_scores [R][K+1]; all_boxes [R][4*nreg]. */
+int drn_oicr_infer(const float* logits, int ld, int R, int K, int nreg, int S, const int* col_offs_host,
+                   const int* delta_offs_host, const float* boxes, const float* bbox_w_host,
+                   float* all_scores, float* all_boxes, drn_stream_t stream);
+
+/* Train-mode dropout of the fc6/fc7 activations, in place: x = keep ? x/(1-p) : 0 with a
+ * counter-based RNG keyed by (seed, element index).
+ * Replaces F.dropout(p=0.5) in WSL/roi_heads/box_head.py:90 (mask not comparable to torch's RNG;
+ * parity runs keep the box head in eval mode exactly like the survey's oracle). */
+int drn_dropout_inplace(void* x, int64_t n, int dtype, float p, uint64_t seed, drn_stream_t stream);
+
+/* dtype / layout helpers used by the weight cache (not on the per-image path). */
+int drn_cast_f32_to_bf16(const float* in, void* out, int64_t n, drn_stream_t stream);
+int drn_cast_bf16_to_f32(const void* in, float* out, int64_t n, drn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,88 @@
+"""Shared fixtures for the parity tests: case table, seeded inputs/weights, structure conversion."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import drn_wsod_pytorch_b200 as drn  # noqa: E402
+from drn_wsod_pytorch_b200 import synth  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+# name -> (builtin config, reference YAML (relative to projects/WSL/configs), overrides, [(H, W, R, G, seed)...])
+CASES = {
+    # BASELINE.json configs[0]: the reference's own CPU-runnable plumbing case
+    "wsddn_v16_300": ("wsddn_V_16_DC5_1x", "PascalVOC-Detection/wsddn_V_16_DC5_1x.yaml", [], [(300, 300, 64, 2, 11)]),
+    "oicr_r18_small": ("oicr_WSR_18_DC5_1x", "PascalVOC-Detection/oicr_WSR_18_DC5_1x.yaml", [], [(160, 224, 96, 2, 12)]),
+    "oicr_r50_small": ("oicr_WSR_50_DC5_1x", "PascalVOC-Detection/oicr_WSR_50_DC5_1x.yaml", [], [(128, 192, 64, 1, 13)]),
+    "oicr_v16_small": ("oicr_V_16_DC5_1x", "PascalVOC-Detection/oicr_V_16_DC5_1x.yaml", [], [(128, 160, 64, 3, 14)]),
+    "oicr_r101_coco_small": ("oicr_WSR_101_DC5_1x_coco", "COCO-Detection/oicr_WSR_101_DC5_1x.yaml", [], [(128, 160, 64, 5, 15)]),
+    "oicr_r18_reg": ("oicr_WSR_18_DC5_1x", "PascalVOC-Detection/reg/oicr_WSR_18_DC5_1x.yaml",
+                     ["WSL.REFINE_NUM", 4, "WSL.REFINE_REG", [False, False, False, True]], [(128, 192, 64, 2, 16)]),
+    "oicr_r18_batch2": ("oicr_WSR_18_DC5_1x", "PascalVOC-Detection/oicr_WSR_18_DC5_1x.yaml", [],
+                        [(128, 192, 48, 2, 17), (160, 160, 80, 1, 18)]),
+}
+# overrides that exist only on our side (the reference YAML already carries them)
+OURS_ONLY = {"oicr_r18_reg"}
+
+
+def arch_key(cfg):
+    m = cfg.MODEL
+    if "vgg" in m.BACKBONE.NAME:
+        return f"vgg16_d{m.VGG.CONV5_DILATION}"
+    return f"resnet_ws{m.RESNETS.DEPTH}_d{m.RESNETS.RES5_DILATION}"
+
+
+def case_inputs(case):
+    _, _, _, imgs = CASES[case]
+    K = 80 if "coco" in case else 20
+    return [synth.make_inputs(H, W, R, seed=seed, num_gt=G, num_classes=K) for (H, W, R, G, seed) in imgs]
+
+
+def case_config(case, device="cpu", precision=None):
+    name, _, ov, _ = CASES[case]
+    ov = list(ov) + ["MODEL.DEVICE", device]
+    if precision:
+        ov += ["B200.PRECISION", precision]
+    return drn.builtin_config(name, ov)
+
+
+def case_weights(cfg, model_or_shapes, seed=0):
+    shapes = model_or_shapes if isinstance(model_or_shapes, dict) else synth.state_shapes(model_or_shapes)
+    return synth.make_weights(shapes, seed=seed, calib=synth.load_calib(arch_key(cfg)))
+
+
+def to_batched(inputs, inst_cls, box_cls, device="cpu", train=True):
+    """Our synthetic dicts -> the reference's batched_inputs format (rcnn.py:138-160)."""
+    out = []
+    for inp in inputs:
+        H, W = inp["height"], inp["width"]
+        d = {"image": inp["image"].to(device), "height": H, "width": W}
+        p = inst_cls((H, W))
+        p.proposal_boxes = box_cls(inp["boxes"].clone().to(device))
+        p.objectness_logits = inp["objectness"].clone().to(device)
+        d["proposals"] = p
+        if train:
+            g = inst_cls((H, W))
+            g.gt_boxes = box_cls(inp["gt_boxes"].clone().to(device))
+            g.gt_classes = inp["gt_classes"].clone().to(device)
+            d["instances"] = g
+        out.append(d)
+    return out
+
+
+def load_golden(case):
+    path = os.path.join(GOLDEN_DIR, case + ".npz")
+    z = np.load(path, allow_pickle=False)
+    return {k: z[k] for k in z.files}
+
+
+def rel_err(a, b, floor=1e-6):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / (np.abs(b) + floor))) if a.size else 0.0

@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Benchmark of the DRN-WSOD hot path (BASELINE.json metric: images/sec, WSOD forward+loss,
+one 600x1000 synthetic image + 4 000 (2 000) random proposals per GPU, at 1/2/4/8 B200).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload r50_bf16|r18_fp32|...] [--impl ours|reference]
+
+One step = one train-mode forward+loss of GeneralizedRCNNWSL over one image per GPU (dropout on, as in
+the reference's train mode).  Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# workload -> (builtin config, H, W, R, precision, GMAC per image {conv, fc6, fc7, heads} from BASELINE.md §3)
+WORKLOADS = {
+    "r18_fp32": ("oicr_WSR_18_DC5_1x", 600, 1000, 2000, "fp32", dict(conv=118.0, fc6=205.5, fc7=33.6, heads=0.85)),
+    "r18_bf16": ("oicr_WSR_18_DC5_1x", 600, 1000, 2000, "bf16", dict(conv=118.0, fc6=205.5, fc7=33.6, heads=0.85)),
+    "r50_bf16": ("oicr_WSR_50_DC5_1x", 600, 1000, 4000, "bf16", dict(conv=232.7, fc6=822.1, fc7=33.6, heads=1.7)),
+    "r50_fp32": ("oicr_WSR_50_DC5_1x", 600, 1000, 4000, "fp32", dict(conv=232.7, fc6=822.1, fc7=33.6, heads=1.7)),
+    "v16_bf16": ("oicr_V_16_DC5_1x", 600, 1000, 2000, "bf16", dict(conv=231.9, fc6=205.5, fc7=33.6, heads=0.85)),
+    "r101_coco_bf16": ("oicr_WSR_101_DC5_1x_coco", 800, 1333, 4000, "bf16", dict(conv=723.5, fc6=822.1, fc7=33.6, heads=6.6)),
+}
+DEFAULT_WORKLOAD = os.environ.get("DRN_BENCH_WORKLOAD", "r50_bf16")  # BASELINE.json configs[2]: the 4k-proposal metric
+METRIC = "images/sec (4k proposals/img) WSOD forward+loss"
+# kernels launched per C-ABI call (for the gpu_launches claim)
+LAUNCHES = {"drn_wsddn_mil_fwd": 3, "drn_label_proposals": 2}
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p["bf16_tflops_sustained"],
+                "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc, self.lines, self.index = None, [], index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_batched(inp, device, drn, pinned=False):
+    H, W = inp["height"], inp["width"]
+    t = {k: (v.pin_memory() if pinned and torch.is_tensor(v) else v) for k, v in inp.items()}
+    if device is not None:
+        t = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in t.items()}
+    p = drn.Instances((H, W), proposal_boxes=drn.Boxes(t["boxes"]), objectness_logits=t["objectness"])
+    g = drn.Instances((H, W), gt_boxes=drn.Boxes(t["gt_boxes"]), gt_classes=t["gt_classes"])
+    return [{"image": t["image"], "proposals": p, "instances": g, "height": H, "width": W}]
+
+
+def cpu_reference_step(state, spec, inp, R_sample, threads):
+    """One bounded sample of the reference CPU path (oracle port): full backbone on the full image,
+    ROI stage on the first R_sample proposals; per-image time extrapolated linearly in R for the
+    ROI stage (ROIPool + fc6/fc7 + heads are linear in R).  Returns (est. seconds per full image, parts)."""
+    from oracle import wsl_oracle as O
+
+    torch.set_num_threads(threads)
+    R = inp["boxes"].shape[0]
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        x = O.preprocess_image(inp["image"], spec)
+        fmap = O.backbone_forward(x, state, spec)
+        t1 = time.perf_counter()
+        sub = dict(inp, boxes=inp["boxes"][:R_sample], objectness=inp["objectness"][:R_sample])
+        pooled = O.roi_pool(fmap, sub["boxes"], 1.0 / spec.stride) * (sub["objectness"] + 1).view(-1, 1, 1, 1)
+        t2 = time.perf_counter()
+        feat = O.dan_forward(pooled, state)
+        scores = O.wsddn_scores(feat, state)
+        for k in range(spec.refine_num):
+            pre = f"roi_heads.box_refinery_{k}."
+            torch.softmax(torch.nn.functional.linear(feat, state[pre + "cls_score.weight"], state[pre + "cls_score.bias"]), -1)
+        t3 = time.perf_counter()
+    tb, tp, th = t1 - t0, t2 - t1, t3 - t2
+    est = tb + (tp + th) * (R / R_sample)
+    return est, {"backbone_s": tb, "roipool_s": tp, "fc_heads_s": th, "R_sample": R_sample}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="also print a per-kernel-family time breakdown to stderr")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg_name, H, W, R, precision, gmac = WORKLOADS[args.workload]
+    config = {"workload": f"{cfg_name} {H}x{W} R={R} {precision} (BASELINE.json configs[{2 if 'r50' in args.workload else 1}])"
+              if args.workload in ("r50_bf16", "r18_fp32") else f"{cfg_name} {H}x{W} R={R} {precision}",
+              "images_per_gpu": 1, "proposals_per_image": R, "parallelism": f"dp{world}", "dropout": "on (train mode)",
+              "l2": "no flush: per-step working set (fc6 weights 411 MB + ROI features 0.2-0.8 GB) exceeds the 126 MB L2"}
+
+    import drn_wsod_pytorch_b200 as drn
+    from drn_wsod_pytorch_b200 import synth
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+
+    cfg = drn.builtin_config(cfg_name, ["MODEL.DEVICE", "cpu" if args.impl == "reference" else f"cuda:{local_rank}",
+                                        "B200.PRECISION", precision])
+    threads = os.cpu_count() or 1
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import wsl_oracle as O
+
+        model = drn.build_model(cfg)  # parameter shapes only (CPU); arithmetic below is the oracle's
+        state = dict(helpers.case_weights(cfg, model))
+        spec = O.spec_from_cfg(cfg)
+        inp = synth.make_inputs(H, W, R, seed=0)
+        R_sample = min(R, 250)
+        for _ in range(min(args.warmup, 1)):
+            cpu_reference_step(state, spec, inp, min(R_sample, 50), threads)
+        ests = [cpu_reference_step(state, spec, inp, R_sample, threads) for _ in range(max(1, min(args.steps, 3)))]
+        est = sum(e for e, _ in ests) / len(ests)
+        val = 1.0 / est
+        sample = (f"full backbone on the {H}x{W} image + ROI stage on {R_sample} of {R} proposals, ROI-stage time "
+                  f"scaled x{R / R_sample:.0f} (linear in R); {len(ests)} reps; torch {torch.__version__} CPU ops")
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": "images/sec", "n_gpus": args.gpus,
+                          "steps": len(ests), "warmup": min(args.warmup, 1), "ms_per_step": est * 1e3, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": val, "unit": "images/sec", "cores": threads, "kind": "port", "sample": sample,
+                                           "parts": ests[-1][1]},
+                          "e2e": {"value": val, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return
+
+    # ------------------------------------------------------------------ our arm (B200)
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    from drn_wsod_pytorch_b200 import lib as drn_lib, ops
+
+    model = drn.build_model(cfg)
+    weights = helpers.case_weights(cfg, model)
+    model.load_state_dict({**weights, "pixel_mean": model.pixel_mean, "pixel_std": model.pixel_std}, strict=True)
+    del weights
+    model.train()
+    inp = synth.make_inputs(H, W, R, seed=rank)  # one distinct image per rank (weak scaling)
+    batched_dev = make_batched(inp, dev, drn)
+    host = make_batched(inp, None, drn, pinned=True)[0]
+    loss_keys = None
+
+    # count kernel launches through the C ABI
+    counter = {"n": 0}
+    orig_call = drn_lib.call
+
+    def counting_call(name, *a):
+        counter["n"] += LAUNCHES.get(name, 1)
+        return orig_call(name, *a)
+
+    drn_lib.call = counting_call
+    ops.call = counting_call
+
+    # time the dominant kernel (fc6 GEMM) live, on the launching stream, inside the timed region
+    fc6_events = []
+    fc6_K = 49 * model.roi_heads.in_channels
+    orig_tc, orig_f32 = ops.conv_bf16_tc, ops.conv_f32
+
+    def wrap(fn):
+        def inner(x, packed, ksize, dilation, relu, *a, **k):
+            if ksize == 1 and x.shape[-1] == fc6_K and record["on"]:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = fn(x, packed, ksize, dilation, relu, *a, **k)
+                e1.record()
+                fc6_events.append((e0, e1))
+                return out
+            return fn(x, packed, ksize, dilation, relu, *a, **k)
+        return inner
+
+    record = {"on": False}
+    ops.conv_bf16_tc, ops.conv_f32 = wrap(orig_tc), wrap(orig_f32)
+    import drn_wsod_pytorch_b200.modeling as M  # noqa: F401  (uses ops.* attributes at call time)
+
+    def step(batched):
+        losses = model(batched)
+        vec = torch.stack([losses[k] for k in sorted(losses)])
+        if dist is not None:
+            dist.all_reduce(vec, op=dist.ReduceOp.AVG)  # comm.reduce_dict equivalent (detectron2/utils/comm.py:234-263)
+        return vec, sorted(losses)
+
+    def sync_all():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        vec, loss_keys = step(batched_dev)
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    counter["n"] = 0
+    record["on"] = True
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        vec, _ = step(batched_dev)
+    e1.record()
+    sync_all()
+    record["on"] = False
+    launches = counter["n"]
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = t.item()
+    fc6_ms = sum(a.elapsed_time(b) for a, b in fc6_events) / max(1, len(fc6_events))
+
+    # end-to-end: pinned host inputs -> H2D -> forward+loss -> D2H loss read, every step
+    def e2e_step():
+        d = {"image": host["image"].to(dev, non_blocking=True), "height": H, "width": W,
+             "proposals": host["proposals"].to(dev, non_blocking=True), "instances": host["instances"].to(dev, non_blocking=True)}
+        v, _ = step([d])
+        return v.cpu()
+
+    for _ in range(3):
+        e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        loss_host = e2e_step()
+    sync_all()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
+    if dist is not None:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    h2d = sum(v.numel() * v.element_size() for v in (inp["image"], inp["boxes"], inp["objectness"], inp["gt_boxes"], inp["gt_classes"]))
+    d2h = loss_host.numel() * loss_host.element_size()
+
+    if args.breakdown and rank == 0:
+        fams = {}
+
+        def fam_wrap(name, fn):
+            def inner(*a, **k):
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record(); out = fn(*a, **k); a1.record()
+                fams.setdefault(name, []).append((a0, a1))
+                return out
+            return inner
+
+        saved = {n: getattr(ops, n) for n in ("first_conv", "conv_f32", "conv_bf16_tc", "maxpool2x2", "roipool", "wsddn_mil",
+                                               "oicr_pgt", "label_proposals", "oicr_stage", "dropout_")}
+        for n, f in saved.items():
+            setattr(ops, n, fam_wrap(n, f))
+        step(batched_dev)
+        torch.cuda.synchronize()
+        for n, f in saved.items():
+            setattr(ops, n, f)
+        print("breakdown (ms, 1 step):", {n: round(sum(a.elapsed_time(b) for a, b in ev), 3) for n, ev in fams.items()},
+              file=sys.stderr)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peaks = _peaks()
+    ms_step = ms_total / args.steps
+    value = world * args.steps / (ms_total / 1e3)
+    fc6_tflops = 2 * gmac["fc6"] * 1e9 / (fc6_ms * 1e-3) / 1e12 if fc6_ms > 0 else 0.0
+    total_tflops = 2 * sum(gmac.values()) * 1e9 / (ms_step * 1e-3) / 1e12
+    peak = peaks["bf16_tflops_sustained"]
+    out = {
+        "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic", "config": config,
+        "e2e": {"value": world * args.steps / t_e2e.item(), "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "fc6 GEMM (gemm_tc_kernel)" if precision == "bf16" else "fc6 GEMM (conv_igemm_f32_kernel, SIMT fp32)",
+                     "achieved": fc6_tflops, "peak": peak, "unit": "TFLOP/s", "frac": fc6_tflops / peak,
+                     "peak_source": f"{peaks['src']} cuBLAS bf16 sustained (kernel timed inside a long step)",
+                     "traffic": None, "kernel_ms": fc6_ms, "share_of_step": fc6_ms / ms_step,
+                     "whole_step_tflops": total_tflops, "whole_step_frac": total_tflops / peak},
+        "losses": dict(zip(loss_keys, [round(float(x), 6) for x in vec.tolist()])),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import wsl_oracle as O
+
+        state = dict(helpers.case_weights(cfg, model))
+        spec = O.spec_from_cfg(cfg)
+        cinp = synth.make_inputs(H, W, R, seed=0)
+        R_sample = min(R, 250)
+        cpu_reference_step(state, spec, cinp, 50, threads)
+        est, parts = cpu_reference_step(state, spec, cinp, R_sample, threads)
+        out["cpu_baseline"] = {"value": 1.0 / est, "unit": "images/sec", "cores": threads, "kind": "port",
+                               "sample": f"full backbone on the {H}x{W} image + ROI stage on {R_sample} of {R} proposals, ROI-stage time "
+                                         f"scaled x{R / R_sample:.0f} (linear in R); fp32 torch CPU ops, {threads} threads", "parts": parts}
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

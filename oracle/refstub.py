@@ -302,13 +302,15 @@ def _smooth_l1_loss(input, target, beta, reduction="none"):
 _INSTALLED = False
 
 
-def install():
-    """Install the stubs and import the reference.  Returns (detectron2, wsl)."""
+def install(with_wsl=True):
+    """Install the stubs and import the reference.  Returns (detectron2, wsl).
+    with_wsl=False imports detectron2 only (used to test the registry drop-in, where the B200
+    package registers the WSL names instead of the reference's wsl.modeling)."""
     global _INSTALLED
     if not reference_available():
         raise RuntimeError(f"reference tree not present at {REFERENCE_ROOT}")
     if _INSTALLED:
-        return sys.modules["detectron2"], sys.modules["wsl"]
+        return sys.modules["detectron2"], sys.modules.get("wsl")
 
     _mod("fvcore", __version__="0.1.2")
     _mod("fvcore.common")
@@ -362,6 +364,8 @@ def install():
 
     c = _mod("detectron2._C")
     detectron2._C = c
+    if not with_wsl:
+        return detectron2, None
 
     spec = importlib.util.spec_from_file_location(
         "wsl",

@@ -1,0 +1,272 @@
+"""Per-kernel parity tests of libdrn_b200.so against the CPU oracle (run on the B200: -m gpu).
+Every call goes through the C ABI (drn_wsod_pytorch_b200.ops -> ctypes -> libdrn_b200.so)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import helpers
+from drn_wsod_pytorch_b200 import ops
+from oracle import wsl_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _c_roipool(feat_chw, boxes, scale):
+    path = os.path.join(helpers.ROOT, "oracle", "_build", "libroipool_ref.so")
+    if not os.path.exists(path):
+        import __graft_entry__ as g
+
+        g.build()
+    lib = ctypes.CDLL(path)
+    C, h, w = feat_chw.shape
+    R = boxes.shape[0]
+    out = np.empty((R, C, 7, 7), dtype=np.float32)
+    f = np.ascontiguousarray(feat_chw, dtype=np.float32)
+    b = np.ascontiguousarray(boxes, dtype=np.float32)
+    lib.roipool_ref(f.ctypes.data_as(ctypes.c_void_p), C, h, w, b.ctypes.data_as(ctypes.c_void_p), R,
+                    ctypes.c_float(scale), 7, out.ctypes.data_as(ctypes.c_void_p))
+    return out
+
+
+def _edge_boxes():
+    return [[4, 4, 20, 20], [12, 12, 12, 12], [36, 28, 44, 36], [-100, -100, -50, -50], [5000, 5000, 6000, 6000],
+            [0, 0, 10000, 10000], [4.0, 12.0, 4.0, 100.0], [100, 3.9999, 101, 4.0001], [-30, 10, 40, 60]]
+
+
+@pytest.mark.parametrize("C,h,w,R", [(64, 19, 27, 300), (512, 74, 124, 64), (2048, 18, 18, 32)])
+def test_roipool_fp32_bit_exact(C, h, w, R):
+    rng = np.random.default_rng(C + R)
+    feat = rng.standard_normal((C, h, w)).astype(np.float32)
+    H, W = h * 8, w * 8
+    x0 = rng.uniform(-10, W - 20, R); y0 = rng.uniform(-10, H - 20, R)
+    boxes = np.stack([x0, y0, x0 + rng.uniform(0, W, R), y0 + rng.uniform(0, H, R)], 1).astype(np.float32)
+    boxes = np.concatenate([boxes, np.asarray(_edge_boxes(), dtype=np.float32)], 0)
+    obj = rng.uniform(0, 1, len(boxes)).astype(np.float32)
+    ref = _c_roipool(feat, boxes, 0.125) * (obj + np.float32(1.0))[:, None, None, None]
+    tv = O.roi_pool(torch.from_numpy(feat)[None], torch.from_numpy(boxes), 0.125).numpy() * (obj + np.float32(1.0))[:, None, None, None]
+    assert np.array_equal(ref, tv), "C restatement disagrees with torchvision"
+    f_hwc = torch.from_numpy(feat).permute(1, 2, 0).contiguous().to(DEV)
+    out = ops.roipool(f_hwc, torch.from_numpy(boxes).to(DEV), torch.from_numpy(obj).to(DEV), 0.125)
+    got = out.view(len(boxes), 49, C).permute(0, 2, 1).reshape(len(boxes), C, 7, 7).cpu().numpy()
+    assert np.array_equal(got, ref)  # max-pool is exact; one fp32 multiply by (objectness+1)
+
+
+def test_roipool_bf16_bit_exact():
+    rng = np.random.default_rng(5)
+    C, h, w, R = 256, 37, 50, 200
+    feat = torch.from_numpy(rng.standard_normal((C, h, w)).astype(np.float32)).bfloat16()
+    x0 = rng.uniform(0, 300, R); y0 = rng.uniform(0, 200, R)
+    boxes = np.stack([x0, y0, x0 + rng.uniform(0, 300, R), y0 + rng.uniform(0, 200, R)], 1).astype(np.float32)
+    obj = rng.uniform(0, 1, R).astype(np.float32)
+    pooled = O.roi_pool(feat.float()[None], torch.from_numpy(boxes), 0.125)
+    ref = (pooled * (torch.from_numpy(obj) + 1).view(-1, 1, 1, 1)).bfloat16()
+    out = ops.roipool(feat.permute(1, 2, 0).contiguous().to(DEV), torch.from_numpy(boxes).to(DEV),
+                      torch.from_numpy(obj).to(DEV), 0.125)
+    got = out.view(R, 49, C).permute(0, 2, 1).reshape(R, C, 7, 7).cpu()
+    assert torch.equal(got, ref)
+
+
+def test_roipool_empty_and_constant_properties():
+    f = torch.full((10, 12, 64), 3.5, device=DEV)
+    boxes = torch.tensor([[0.0, 0, 50, 50], [20, 20, 90, 70]], device=DEV)
+    out = ops.roipool(f, boxes, None, 0.125)
+    assert torch.all(out == 3.5)  # max over a constant map is the constant (idempotence)
+    out0 = ops.roipool(f, boxes[:0].contiguous(), None, 0.125)
+    assert out0.shape == (0, 49 * 64)
+
+
+@pytest.mark.parametrize("cin,cout,k,dil,res,relu", [(64, 64, 3, 1, False, True), (64, 128, 3, 2, True, True),
+                                                      (128, 64, 1, 1, True, False), (16, 64, 3, 1, False, False)])
+def test_conv_simt_fp32(cin, cout, k, dil, res, relu):
+    g = torch.Generator().manual_seed(cin * 7 + cout + k + dil)
+    N, H, W = 2, 21, 35
+    x = torch.randn(N, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    scale = torch.rand(cout, generator=g) + 0.5
+    bias = torch.randn(cout, generator=g)
+    r = torch.randn(N, cout, H, W, generator=g) if res else None
+    ref = F.conv2d(x, w, None, padding=dil * (k // 2), dilation=dil) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+    if res:
+        ref = ref + r
+    if relu:
+        ref = F.relu(ref)
+    packed = {"w": w.permute(2, 3, 1, 0).reshape(-1, cout).contiguous().to(DEV), "scale": scale.to(DEV), "bias": bias.to(DEV), "cout": cout}
+    out = ops.conv_f32(x.permute(0, 2, 3, 1).contiguous().to(DEV), packed, k, dil, relu,
+                       r.permute(0, 2, 3, 1).contiguous().to(DEV) if res else None)
+    got = out.permute(0, 3, 1, 2).cpu()
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("stride,canvas", [(2, None), (1, None), (2, (45, 70))])
+def test_first_conv_fused_normalise(stride, canvas):
+    g = torch.Generator().manual_seed(stride)
+    H, W, cout = 37, 61, 64
+    img = torch.rand(3, H, W, generator=g) * 255
+    mean, std = [102.9801, 115.9465, 122.7717], [1.0, 1.0, 1.0]
+    w = torch.randn(cout, 3, 3, 3, generator=g) * 0.1
+    scale = torch.rand(cout, generator=g) + 0.5
+    bias = torch.randn(cout, generator=g)
+    x = (img - torch.tensor(mean).view(3, 1, 1)) / torch.tensor(std).view(3, 1, 1)
+    cv = canvas or (H, W)
+    x = F.pad(x, (0, cv[1] - W, 0, cv[0] - H))
+    ref = F.relu(F.conv2d(x[None], w, None, stride=stride, padding=1) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1))
+    packed = {"w": w.permute(2, 3, 1, 0).reshape(-1, cout).contiguous().to(DEV), "scale": scale.to(DEV), "bias": bias.to(DEV), "cout": cout}
+    out = ops.first_conv(img.to(DEV), cv, mean, std, packed, stride)
+    torch.testing.assert_close(out.permute(0, 3, 1, 2).cpu(), ref, rtol=1e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize("stride,dtype", [(2, torch.float32), (1, torch.float32), (1, torch.bfloat16), (2, torch.bfloat16)])
+def test_maxpool_exact(stride, dtype):
+    x = torch.randn(2, 64, 23, 31, generator=torch.Generator().manual_seed(1)).to(dtype)
+    ref = F.max_pool2d(x.float(), 2, stride).to(dtype)
+    out = ops.maxpool2x2(x.permute(0, 2, 3, 1).contiguous().to(DEV), stride)
+    assert torch.equal(out.permute(0, 3, 1, 2).cpu(), ref)
+
+
+# ------------------------------------------------------------------ tcgen05 path
+def _bf16_ref_gemm(a, w, scale, bias, res, relu):
+    y = a.float() @ w.float().t()
+    if scale is not None:
+        y = y * scale
+    y = y + bias
+    if res is not None:
+        y = y + res.float()
+    return F.relu(y) if relu else y
+
+
+@pytest.mark.parametrize("M,K,N,relu,res,f32out", [(128, 64, 64, False, False, True), (300, 256, 128, True, False, False),
+                                                    (2000, 1024, 512, True, True, False), (77, 128, 104, False, False, True),
+                                                    (1000, 4096, 128, False, False, True)])
+def test_tc_gemm_bf16(M, K, N, relu, res, f32out):
+    g = torch.Generator().manual_seed(M + K + N)
+    a = (torch.randn(M, K, generator=g)).bfloat16()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16()
+    scale = torch.rand(N, generator=g) + 0.5
+    bias = torch.randn(N, generator=g)
+    r = torch.randn(M, N, generator=g).bfloat16() if res else None
+    ref = _bf16_ref_gemm(a, w, scale, bias, r, relu)
+    packed = {"w": w.to(DEV), "scale": scale.to(DEV), "bias": bias.to(DEV), "cout": N}
+    out = ops.conv_bf16_tc(a.view(1, M, 1, K).to(DEV), packed, 1, 1, relu, r.view(1, M, 1, N).to(DEV) if res else None,
+                           out_dtype=torch.float32 if f32out else torch.bfloat16)
+    got = out.view(M, N).float().cpu()
+    # bf16 operands, fp32 accumulation: only summation order (and the bf16 output rounding) differ
+    torch.testing.assert_close(got, ref, rtol=1e-2 if not f32out else 2e-3, atol=1e-2 if not f32out else 2e-3)
+
+
+@pytest.mark.parametrize("cin,cout,dil,H,W,res", [(64, 64, 1, 16, 32, False), (128, 256, 2, 21, 35, True), (64, 128, 1, 74, 124, False),
+                                                   (256, 64, 2, 9, 17, True)])
+def test_tc_conv3x3_bf16(cin, cout, dil, H, W, res):
+    g = torch.Generator().manual_seed(cin + cout + dil + H)
+    N = 2
+    x = torch.randn(N, cin, H, W, generator=g).bfloat16()
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / (9 * cin) ** 0.5).bfloat16()
+    scale = torch.rand(cout, generator=g) + 0.5
+    bias = torch.randn(cout, generator=g)
+    r = torch.randn(N, cout, H, W, generator=g).bfloat16() if res else None
+    ref = F.conv2d(x.float(), w.float(), None, padding=dil, dilation=dil) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+    if res:
+        ref = ref + r.float()
+    ref = F.relu(ref)
+    packed = {"w": w.permute(0, 2, 3, 1).reshape(cout, -1).contiguous().to(DEV), "scale": scale.to(DEV), "bias": bias.to(DEV), "cout": cout}
+    out = ops.conv_bf16_tc(x.permute(0, 2, 3, 1).contiguous().to(DEV), packed, 3, dil, True,
+                           r.permute(0, 2, 3, 1).contiguous().to(DEV) if res else None)
+    torch.testing.assert_close(out.permute(0, 3, 1, 2).float().cpu(), ref, rtol=1e-2, atol=1e-2)
+
+
+# ------------------------------------------------------------------ heads
+def _rand_logits(R, K, S, seed):
+    g = torch.Generator().manual_seed(seed)
+    ld = ((2 * K + S * (K + 1) + 63) // 64) * 64
+    return torch.randn(R, ld, generator=g) * 2.0, ld
+
+
+@pytest.mark.parametrize("R,K", [(64, 20), (2000, 20), (4000, 80), (1, 20)])
+def test_wsddn_mil(R, K):
+    logits, ld = _rand_logits(R, K, 3, R + K)
+    oh = torch.zeros(K); oh[[3, 7]] = 1
+    s_ref = F.softmax(logits[:, :K], 1) * F.softmax(logits[:, K:2 * K], 0)
+    img_ref = torch.clamp(s_ref.sum(0), 1e-6, 1 - 1e-6)
+    loss_ref = F.binary_cross_entropy(img_ref[None], oh[None], reduction="mean")
+    loss = torch.zeros(1, device=DEV)
+    scores, img = ops.wsddn_mil(logits.to(DEV), K, 0, K, oh.to(DEV), True, 1.0, loss)
+    torch.testing.assert_close(scores.cpu(), s_ref, rtol=1e-4, atol=1e-12)
+    torch.testing.assert_close(img.cpu(), img_ref, rtol=1e-4, atol=1e-9)
+    torch.testing.assert_close(loss.cpu()[0], loss_ref, rtol=1e-5, atol=1e-7)
+
+
+def test_oicr_stage_chain_exact_indices():
+    """pgt argmax (ties -> lowest index), IoU/Matcher labels and the weighted CE against the oracle."""
+    R, K, S = 1500, 20, 3
+    spec = O.Spec(num_classes=K)
+    inp = helpers.synth.make_inputs(600, 1000, R, seed=3, num_gt=3)
+    logits, ld = _rand_logits(R, K, S, 9)
+    boxes = inp["boxes"]
+    gt_int = torch.unique(inp["gt_classes"])
+    scores = F.softmax(logits[:, :K], 1) * F.softmax(logits[:, K:2 * K], 0)
+    scores[5, gt_int[0]] = scores[:, gt_int[0]].max() * 2  # plant an exact tie: rows 5 and 900
+    scores[900, gt_int[0]] = scores[5, gt_int[0]]
+    img = torch.clamp(scores.sum(0, keepdim=True), 1e-6, 1 - 1e-6)
+    d_logits, d_boxes = logits.to(DEV), boxes.to(DEV)
+    counter = torch.zeros(1, dtype=torch.int32, device=DEV)
+    prev_ref, prev_boxes_ref = scores, boxes
+    prev = scores.to(DEV)
+    for k in range(S):
+        idx_r, sc_r, bx_r, w_r = O.get_pgt(prev_ref, prev_boxes_ref, gt_int, img, k, spec)
+        lab_r, mi_r = O.label_proposals(boxes, bx_r, gt_int, spec)
+        col = 2 * K + k * (K + 1)
+        lg = logits[:, col:col + K + 1]
+        loss_r, wts_r = O.oicr_stage_loss(lg, lab_r, torch.index_select(w_r, 0, mi_r))
+        idx, sc, bx, w = ops.oicr_pgt(prev, d_boxes, gt_int.to(DEV), img[0].to(DEV), k > 0, None, 0, False, spec.bbox_reg_weights)
+        lab, mi, cnt = ops.label_proposals(d_boxes, bx, gt_int.to(DEV), K, spec.iou_thresholds, spec.iou_labels)
+        loss = torch.zeros(1, device=DEV)
+        probs, stats, wts = ops.oicr_stage(d_logits, col, K, lab, mi, w, 1.0, loss, counter)
+        assert torch.equal(idx.cpu(), idx_r)
+        if k == 0:
+            assert idx_r[0].item() == 5  # the planted tie resolves to the lowest index
+        assert torch.equal(bx.cpu(), bx_r)  # incl. the re-derived (apply_deltas with zero deltas) boxes of k >= 1
+        assert torch.equal(lab.cpu(), lab_r) and torch.equal(mi.cpu(), mi_r)
+        assert cnt.cpu().tolist() == [int((lab_r < K).sum()), int((lab_r == K).sum()), 0]
+        torch.testing.assert_close(wts.cpu(), wts_r, rtol=0, atol=0)
+        torch.testing.assert_close(loss.cpu()[0], loss_r, rtol=1e-5, atol=1e-8)
+        torch.testing.assert_close(probs.cpu(), F.softmax(lg, -1), rtol=1e-5, atol=1e-9)
+        assert counter.item() == 0
+        prev_ref = F.softmax(lg, -1)
+        prev_boxes_ref = O.apply_deltas(torch.zeros(R, 4 * K), boxes, spec.bbox_reg_weights)
+        prev = probs
+
+
+def test_label_proposals_no_gt_and_ignore_band():
+    boxes = helpers.synth.make_inputs(300, 400, 500, seed=1)["boxes"]
+    lab, mi, cnt = ops.label_proposals(boxes.to(DEV), None, None, 20, [0.5], [0, 1])
+    assert torch.all(lab == 20) and cnt.cpu().tolist() == [0, 500, 0]
+    spec = O.Spec(iou_thresholds=[0.1, 0.5], iou_labels=[-1, 0, 1])
+    gtb = torch.tensor([[10.0, 10, 200, 220], [150, 60, 390, 290]])
+    gtc = torch.tensor([4, 9])
+    lab_r, mi_r = O.label_proposals(boxes, gtb, gtc, spec)
+    lab, mi, cnt = ops.label_proposals(boxes.to(DEV), gtb.to(DEV), gtc.to(DEV), 20, [0.1, 0.5], [-1, 0, 1])
+    assert torch.equal(lab.cpu(), lab_r) and torch.equal(mi.cpu(), mi_r)
+    assert cnt.cpu()[2].item() == int((lab_r == -1).sum()) > 0
+
+
+def test_oicr_infer_mean_softmax():
+    R, K, S = 700, 20, 3
+    logits, ld = _rand_logits(R, K, S, 4)
+    boxes = helpers.synth.make_inputs(300, 400, R, seed=2)["boxes"]
+    cols = [2 * K + k * (K + 1) for k in range(S)]
+    ref = sum(F.softmax(logits[:, c:c + K + 1], -1) for c in cols) / S
+    sc, bx = ops.oicr_infer(logits.to(DEV), K, cols, [-1] * S, boxes.to(DEV), [10.0, 10.0, 5.0, 5.0], K)
+    torch.testing.assert_close(sc.cpu(), ref, rtol=1e-5, atol=1e-9)
+    ref_b = O.apply_deltas(torch.zeros(R, 4 * K), boxes, [10.0, 10.0, 5.0, 5.0])
+    assert torch.equal(bx.cpu(), ref_b)
+
+
+def test_dropout_statistics():
+    x = torch.ones(1 << 20, device=DEV)
+    ops.dropout_(x, 0.5, 123)
+    kept = (x != 0).float().mean().item()
+    assert abs(kept - 0.5) < 5e-3 and torch.all((x == 0) | (x == 2.0))

@@ -1,0 +1,149 @@
+"""CPU-side checks: C-ABI exports, config surface, state_dict compatibility, registry drop-in,
+structures, synthetic-data determinism.  No GPU compute."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+import drn_wsod_pytorch_b200 as drn
+from drn_wsod_pytorch_b200 import lib, synth
+from oracle import refstub
+
+HAVE_REF = refstub.reference_available()
+
+
+def test_cabi_library_exports_every_header_symbol():
+    if not os.path.exists(lib.LIB_PATH):
+        import __graft_entry__ as g
+
+        g.build()
+    handle = ctypes.CDLL(lib.LIB_PATH)
+    syms = lib.header_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(handle, s), f"{s} declared in include/drn_b200.h but not exported"
+    assert set(lib._PROTOS) | {"drn_last_error"} == set(syms), "lib.py prototypes out of sync with the header"
+    handle.drn_version.restype = ctypes.c_int
+    assert handle.drn_version() >= 100
+
+
+def test_cabi_argument_errors_are_reported_not_crashed():
+    handle = lib.load()
+    rc = handle.drn_roipool_fwd(None, 4, 4, 64, None, None, 3, ctypes.c_float(0.125), 0, None, None)
+    assert rc != 0 and b"null pointer" in handle.drn_last_error()
+    with pytest.raises(RuntimeError, match="Cin"):
+        lib.call("drn_conv_igemm_f32", 1, 1, 4, 4, 3, 1, 3, 1, None, None, None, 0, 1, 64, 64, None)
+
+
+def test_product_path_refuses_cpu_tensors():
+    from drn_wsod_pytorch_b200 import ops
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.roipool(torch.zeros(4, 4, 64), torch.zeros(1, 4), None, 0.125)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(helpers.ROOT, "drn_wsod_pytorch_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("no oracle", ""), f"{fn} references oracle/"
+
+
+@pytest.mark.parametrize("case", list(helpers.CASES))
+def test_state_dict_keys_and_builtin_config(case):
+    cfg = helpers.case_config(case)
+    model = drn.build_model(cfg)
+    keys = list(model.state_dict().keys())
+    assert keys[0] == "pixel_mean" and any(k.startswith("roi_heads.box_head.fc1") for k in keys)
+    trainable = {n for n, p in model.named_parameters() if p.requires_grad}
+    assert all(n.startswith("roi_heads.") for n in trainable), "FREEZE_AT: 5 freezes the whole backbone"
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="needs /root/reference")
+def test_reference_yaml_loads_unchanged_and_matches_builtin():
+    base = os.path.join(refstub.WSL_ROOT, "configs")
+    for case, (name, yaml_rel, ov, _) in helpers.CASES.items():
+        cfg = drn.get_cfg().merge_from_file(os.path.join(base, yaml_rel))
+        ours = drn.builtin_config(name, ov)
+        for path in ["MODEL.BACKBONE.NAME", "MODEL.BACKBONE.FREEZE_AT", "MODEL.RESNETS.DEPTH", "MODEL.RESNETS.RES5_DILATION",
+                     "MODEL.RESNETS.RES2_OUT_CHANNELS", "MODEL.VGG.CONV5_DILATION", "MODEL.ROI_HEADS.NAME",
+                     "MODEL.ROI_HEADS.NUM_CLASSES", "MODEL.ROI_HEADS.IN_FEATURES", "MODEL.ROI_HEADS.SCORE_THRESH_TEST",
+                     "MODEL.ROI_HEADS.NMS_THRESH_TEST", "MODEL.ROI_HEADS.PROPOSAL_APPEND_GT", "MODEL.ROI_BOX_HEAD.DAN_DIM",
+                     "MODEL.ROI_BOX_HEAD.POOLER_TYPE", "MODEL.ROI_BOX_HEAD.POOLER_RESOLUTION", "MODEL.PIXEL_MEAN",
+                     "MODEL.LOAD_PROPOSALS", "WSL.REFINE_NUM", "WSL.REFINE_REG", "WSL.MEAN_LOSS", "MODEL.META_ARCHITECTURE"]:
+            a, b = cfg, ours
+            for part in path.split("."):
+                a, b = a[part], b[part]
+            assert list(a) == list(b) if isinstance(a, (list, tuple)) else a == b, (case, path, a, b)
+
+
+_DROPIN = r"""
+import sys
+sys.path.insert(0, {root!r})
+from oracle import refstub
+refstub.install(with_wsl=False)                      # detectron2 only: the reference's wsl.modeling is NOT imported
+import drn_wsod_pytorch_b200 as drn
+drn.register_into_detectron2()
+from detectron2.config import get_cfg
+from detectron2.modeling import build_model
+import importlib.util, os
+spec = importlib.util.spec_from_file_location("wsl_cfg", os.path.join(refstub.WSL_ROOT, "wsl", "config", "defaults.py"))
+m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+cfg = get_cfg(); m.add_wsl_config(cfg)
+cfg.merge_from_file(os.path.join(refstub.WSL_ROOT, "configs", "PascalVOC-Detection/oicr_WSR_18_DC5_1x.yaml"))
+cfg.MODEL.DEVICE = "cpu"
+model = build_model(cfg)                               # the reference's own builder + unchanged YAML
+assert type(model).__module__.startswith("drn_wsod_pytorch_b200"), type(model)
+print("DROPIN_OK", type(model).__name__, len(model.state_dict()))
+"""
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="needs /root/reference")
+def test_registry_drop_in_behind_reference_build_model():
+    out = subprocess.run([sys.executable, "-c", _DROPIN.format(root=helpers.ROOT)], capture_output=True, text=True, timeout=300)
+    assert "DROPIN_OK GeneralizedRCNNWSL 132" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="needs /root/reference")
+def test_state_dict_identical_to_reference_model():
+    cfg_r, ref = refstub.build_reference_model("PascalVOC-Detection/oicr_WSR_50_DC5_1x.yaml", ["MODEL.ROI_BOX_HEAD.DAN_DIM", "[64,64]"])
+    ours = drn.build_model(drn.builtin_config("oicr_WSR_50_DC5_1x", ["MODEL.DEVICE", "cpu", "MODEL.ROI_BOX_HEAD.DAN_DIM", [64, 64]]))
+    a = [(k, tuple(v.shape)) for k, v in ref.state_dict().items()]
+    b = [(k, tuple(v.shape)) for k, v in ours.state_dict().items()]
+    assert a == b
+    ours.load_state_dict(ref.state_dict(), strict=True)  # a reference checkpoint loads as-is
+
+
+def test_structures_surface():
+    b = drn.Boxes(torch.tensor([[0.0, 0, 10, 10], [5, 5, 50, 60]]))
+    assert torch.equal(b.area(), torch.tensor([100.0, 2475.0]))
+    b.clip((40, 30))
+    assert b.tensor[1].tolist() == [5, 5, 30, 40]
+    inst = drn.Instances((40, 30), proposal_boxes=b, objectness_logits=torch.tensor([0.1, 0.2]))
+    assert len(inst) == 2 and inst.has("proposal_boxes") and len(inst[torch.tensor([True, False])]) == 1
+    with pytest.raises(AssertionError):
+        inst.gt_classes = torch.zeros(3)
+    from drn_wsod_pytorch_b200.structures import detector_postprocess
+
+    r = drn.Instances((40, 30), pred_boxes=drn.Boxes(torch.tensor([[0.0, 0, 30, 40], [3, 3, 3, 9]])), scores=torch.tensor([0.9, 0.8]))
+    out = detector_postprocess(r, 80, 60)
+    assert len(out) == 1 and out.pred_boxes.tensor[0].tolist() == [0, 0, 60, 80]
+
+
+def test_synthetic_data_is_deterministic_and_well_formed():
+    a, b = synth.make_inputs(600, 1000, 2000, seed=0), synth.make_inputs(600, 1000, 2000, seed=0)
+    assert torch.equal(a["image"], b["image"]) and torch.equal(a["boxes"], b["boxes"])
+    bx = a["boxes"]
+    assert (bx[:, 2] - bx[:, 0]).min() >= 20 and (bx[:, 3] - bx[:, 1]).min() >= 20
+    assert bx[:, 2].max() <= 1000 and bx[:, 3].max() <= 600 and bx.min() >= 0
+    shapes = {"backbone.stem.conv1.weight": (64, 3, 3, 3), "backbone.stem.conv1.norm.weight": (64,),
+              "roi_heads.box_head.fc1.weight": (16, 128), "roi_heads.box_head.fc1.bias": (16,)}
+    w1, w2 = synth.make_weights(shapes, 3), synth.make_weights(shapes, 3)
+    assert all(torch.equal(w1[k], w2[k]) for k in w1)
+    assert synth.load_calib("resnet_ws18_d2"), "data/calib.json missing"

@@ -439,9 +439,10 @@ int drn_maxpool2x2_nhwc(const void* in, int N, int H, int W, int C, int stride, 
 
 int drn_roipool_fwd(const void* feat, int h, int w, int C, const float* boxes, const float* objectness,
                     int R, float spatial_scale, int dtype, void* out, drn_stream_t stream) {
-  DRN_CHECK_ARG(feat && out && (boxes || R == 0), "roipool: null pointer");
+  DRN_CHECK_ARG(R >= 0, "roipool: R=%d", R);
+  if (R == 0) return 0;  // empty proposal list: nothing to write (out may be a null, zero-size buffer)
+  DRN_CHECK_ARG(feat && out && boxes, "roipool: null pointer");
   DRN_CHECK_ARG(h > 0 && w > 0, "roipool: empty feature map");
-  if (R == 0) return 0;
   dim3 grid(R, 7);
   if (dtype == DRN_BF16) {
     DRN_CHECK_ARG(C % 8 == 0, "roipool: C=%d not a multiple of 8", C);

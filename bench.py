@@ -131,6 +131,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="also print a per-kernel-family time breakdown to stderr")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="after warm-up run ONE step between cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`; prints no bench line)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -245,6 +247,12 @@ def main():
     for _ in range(max(args.warmup, 3)):
         vec, loss_keys = step(batched_dev)
     sync_all()
+    if args.profile_step:
+        torch.cuda.cudart().cudaProfilerStart()
+        step(batched_dev)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()

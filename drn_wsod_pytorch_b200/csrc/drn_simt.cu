@@ -362,6 +362,147 @@ roipool_bf16_kernel(const uint4* __restrict__ f8, int h, int w, int C, const flo
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// ROIPool v2: range-max tables along x + per-bin gather.
+//
+// The direct kernels above re-read every feature cell under every ROI (measured: 19 GB of L2->SM
+// traffic for R=4000 on the 74x124x2048 map, L2-bound at 1.07 ms).  max() is idempotent, so a
+// horizontal window [ws, we) equals max(T_j[ws], T_j[we - 2^j]) with j = floor(log2(we - ws)) and
+// T_j[y][x] = max F[y][x .. x+2^j) -- the classic sparse table, built once per image along x only
+// (levels 1..4: windows 2,4,8,16; wider bins take ceil(width/16) lookups).  Each bin then costs
+// 2 lookups per feature row instead of (we - ws); results are bit-identical (max has no rounding).
+// Kernel 1 builds T_1..T_4 (one CTA per feature row x 64-byte... channel slice, row staged in smem);
+// kernel 2 is one CTA per (ROI, 512-byte channel chunk): 8 warps x 49 bins, 16 B per lane.  CTAs are
+// rasterised chunk-major so the tables of the chunk being gathered stay L2-resident.
+// ------------------------------------------------------------------------------------------
+constexpr int XT_LEVELS = 4;        // T_1..T_4
+constexpr int XT_SLOTS = 8;         // 16-byte channel vectors per build CTA (128 B of channels)
+
+struct VecF32 {
+  typedef float4 T;
+  static __device__ __forceinline__ T vmax(T a, T b) {
+    return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+  }
+  static __device__ __forceinline__ T lowest() { return make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX); }
+  static __device__ __forceinline__ T zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  static __device__ __forceinline__ T scale(T m, float mul) {
+    return make_float4(__fmul_rn(m.x, mul), __fmul_rn(m.y, mul), __fmul_rn(m.z, mul), __fmul_rn(m.w, mul));
+  }
+};
+struct VecBF16 {
+  typedef uint4 T;
+  static __device__ __forceinline__ T vmax(T a, T b) { return max8bf(a, b); }
+  static __device__ __forceinline__ T lowest() { return make_uint4(0xFF7FFF7Fu, 0xFF7FFF7Fu, 0xFF7FFF7Fu, 0xFF7FFF7Fu); }
+  static __device__ __forceinline__ T zero() { return make_uint4(0u, 0u, 0u, 0u); }
+  static __device__ __forceinline__ T scale(T m, float mul) {
+    T o;
+    const __nv_bfloat162* pm = reinterpret_cast<const __nv_bfloat162*>(&m);
+    __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(pm[i]);
+      po[i] = __floats2bfloat162_rn(__fmul_rn(f.x, mul), __fmul_rn(f.y, mul));
+    }
+    return o;
+  }
+};
+
+// tables: [XT_LEVELS][h][w][CV] vectors.  grid = (h, CV / XT_SLOTS), block = 256, smem = 2 * w * XT_SLOTS vectors
+template <typename V>
+__global__ void __launch_bounds__(256)
+xtable_build_kernel(const typename V::T* __restrict__ feat, int h, int w, int CV, typename V::T* __restrict__ tables) {
+  typedef typename V::T T;
+  extern __shared__ __align__(16) unsigned char xt_smem[];
+  T* buf0 = reinterpret_cast<T*>(xt_smem);
+  T* buf1 = buf0 + (size_t)w * XT_SLOTS;
+  const int y = blockIdx.x, cv0 = blockIdx.y * XT_SLOTS;
+  const int n = w * XT_SLOTS;
+  const T* row = feat + (size_t)y * w * CV + cv0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) buf0[i] = __ldg(row + (size_t)(i / XT_SLOTS) * CV + (i % XT_SLOTS));
+  __syncthreads();
+  T* in = buf0;
+  T* out = buf1;
+#pragma unroll 1
+  for (int j = 1; j <= XT_LEVELS; ++j) {
+    const int half = 1 << (j - 1);
+    T* trow = tables + ((size_t)(j - 1) * h + y) * w * CV + cv0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int x = i / XT_SLOTS, sl = i % XT_SLOTS;
+      T v = in[i];
+      if (x + half < w) v = V::vmax(v, in[i + half * XT_SLOTS]);  // truncated at the right edge
+      out[i] = v;
+      trow[(size_t)x * CV + sl] = v;
+    }
+    __syncthreads();
+    T* t = in; in = out; out = t;
+  }
+}
+
+// grid = (R, CV / 32), block = 256 (8 warps); lane = 16-byte vector inside the 512-byte channel chunk
+template <typename V>
+__global__ void __launch_bounds__(256)
+roipool_gather_kernel(const typename V::T* __restrict__ feat, const typename V::T* __restrict__ tables, int h, int w,
+                      int CV, const float* __restrict__ boxes, const float* __restrict__ obj, float scale,
+                      typename V::T* __restrict__ out) {
+  typedef typename V::T T;
+  const int r = blockIdx.x;
+  const int cv = blockIdx.y * 32 + (threadIdx.x & 31);
+  const int warp = threadIdx.x >> 5;
+  const bool cv_ok = cv < CV;
+  const float* box = boxes + 4 * (size_t)r;
+  // torchvision roi_pool geometry (see roi_geometry above), all bins of this ROI
+  const int sw = (int)roundf(__fmul_rn(box[0], scale));
+  const int sh = (int)roundf(__fmul_rn(box[1], scale));
+  const int ew = (int)roundf(__fmul_rn(box[2], scale));
+  const int eh = (int)roundf(__fmul_rn(box[3], scale));
+  const int rw = max(ew - sw + 1, 1), rh = max(eh - sh + 1, 1);
+  const float bh = __fdiv_rn((float)rh, 7.f), bw = __fdiv_rn((float)rw, 7.f);
+  const float mul = obj ? __fadd_rn(__ldg(obj + r), 1.f) : 1.f;
+  const size_t plane = (size_t)h * w * CV;
+  T* orow = out + (size_t)r * 49 * CV + cv;
+#pragma unroll 1
+  for (int b = warp; b < 49; b += 8) {
+    const int ph = b / 7, pw = b - ph * 7;
+    const int hs = min(max((int)floorf(__fmul_rn((float)ph, bh)) + sh, 0), h);
+    const int he = min(max((int)ceilf(__fmul_rn((float)(ph + 1), bh)) + sh, 0), h);
+    const int ws = min(max((int)floorf(__fmul_rn((float)pw, bw)) + sw, 0), w);
+    const int we = min(max((int)ceilf(__fmul_rn((float)(pw + 1), bw)) + sw, 0), w);
+    const int width = we - ws;
+    T m = V::zero();
+    if (he > hs && width > 0 && cv_ok) {
+      m = V::lowest();
+      int j = 31 - __clz(width);               // floor(log2(width))
+      if (j > XT_LEVELS) j = XT_LEVELS;
+      const int win = 1 << j;
+      const T* tab = (j == 0) ? feat : tables + (size_t)(j - 1) * plane;
+      const int x_last = we - win;             // right-aligned final window
+      if (width <= 2 * win) {
+        // common case: one or two lookups per row, two rows in flight
+        int y = hs;
+        for (; y + 1 < he; y += 2) {
+          const T* p0 = tab + ((size_t)y * w) * CV + cv;
+          const T* p1 = p0 + (size_t)w * CV;
+          const T a0 = __ldg(p0 + (size_t)ws * CV), a1 = __ldg(p0 + (size_t)x_last * CV);
+          const T b0 = __ldg(p1 + (size_t)ws * CV), b1 = __ldg(p1 + (size_t)x_last * CV);
+          m = V::vmax(m, V::vmax(V::vmax(a0, a1), V::vmax(b0, b1)));
+        }
+        if (y < he) {
+          const T* p0 = tab + ((size_t)y * w) * CV + cv;
+          m = V::vmax(m, V::vmax(__ldg(p0 + (size_t)ws * CV), __ldg(p0 + (size_t)x_last * CV)));
+        }
+      } else {
+        // very wide bins (> 32 cells): step full windows, finish right-aligned
+        for (int y = hs; y < he; ++y) {
+          const T* p0 = tab + ((size_t)y * w) * CV + cv;
+          for (int x = ws; x < x_last; x += win) m = V::vmax(m, __ldg(p0 + (size_t)x * CV));
+          m = V::vmax(m, __ldg(p0 + (size_t)x_last * CV));
+        }
+      }
+    }
+    if (cv_ok) __stcs(orow + (size_t)b * CV, V::scale(m, mul));
+  }
+}
+
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = __float2bfloat16(in[i]);
@@ -374,6 +515,26 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, float
 }  // namespace drn
 
 using namespace drn;
+
+template <typename V>
+static int roipool_v2(const void* feat, int h, int w, int CV, const float* boxes, const float* objectness, int R,
+                      float spatial_scale, void* out, void* ws, cudaStream_t st) {
+  typedef typename V::T T;
+  const size_t smem = (size_t)2 * w * XT_SLOTS * sizeof(T);
+  DRN_CHECK_ARG(smem <= 200 * 1024, "roipool: feature map too wide for the table builder (w=%d)", w);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(xtable_build_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return set_err("roipool: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  xtable_build_kernel<V><<<dim3(h, CV / XT_SLOTS), 256, smem, st>>>((const T*)feat, h, w, CV, (T*)ws);
+  DRN_CHECK_LAUNCH("roipool xtable build");
+  roipool_gather_kernel<V><<<dim3(R, cdiv(CV, 32)), 256, 0, st>>>((const T*)feat, (const T*)ws, h, w, CV, boxes, objectness,
+                                                                spatial_scale, (T*)out);
+  DRN_CHECK_LAUNCH("roipool gather");
+  return 0;
+}
 
 extern "C" {
 
@@ -437,21 +598,36 @@ int drn_maxpool2x2_nhwc(const void* in, int N, int H, int W, int C, int stride, 
   return 0;
 }
 
+size_t drn_roipool_workspace_bytes(int h, int w, int C, int dtype) {
+  if (h <= 0 || w <= 0 || C <= 0) return 0;
+  return (size_t)XT_LEVELS * h * w * C * (dtype == DRN_BF16 ? 2 : 4);
+}
+
 int drn_roipool_fwd(const void* feat, int h, int w, int C, const float* boxes, const float* objectness,
-                    int R, float spatial_scale, int dtype, void* out, drn_stream_t stream) {
+                    int R, float spatial_scale, int dtype, void* out, void* workspace, size_t workspace_bytes,
+                    drn_stream_t stream) {
   DRN_CHECK_ARG(R >= 0, "roipool: R=%d", R);
   if (R == 0) return 0;  // empty proposal list: nothing to write (out may be a null, zero-size buffer)
   DRN_CHECK_ARG(feat && out && boxes, "roipool: null pointer");
   DRN_CHECK_ARG(h > 0 && w > 0, "roipool: empty feature map");
+  const int vec = dtype == DRN_BF16 ? 8 : 4;
+  DRN_CHECK_ARG(C % vec == 0, "roipool: C=%d not a multiple of %d", C, vec);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int CV = C / vec;
+  if (workspace && CV % XT_SLOTS == 0) {
+    DRN_CHECK_ARG(workspace_bytes >= drn_roipool_workspace_bytes(h, w, C, dtype),
+                  "roipool: workspace of %zu bytes is smaller than drn_roipool_workspace_bytes()", workspace_bytes);
+    DRN_CHECK_ARG((uintptr_t)workspace % 16 == 0, "roipool: workspace must be 16-byte aligned");
+    if (dtype == DRN_BF16)
+      return roipool_v2<VecBF16>(feat, h, w, CV, boxes, objectness, R, spatial_scale, out, workspace, st);
+    return roipool_v2<VecF32>(feat, h, w, CV, boxes, objectness, R, spatial_scale, out, workspace, st);
+  }
+  // no workspace (or odd channel count): direct scan kernels
   dim3 grid(R, 7);
   if (dtype == DRN_BF16) {
-    DRN_CHECK_ARG(C % 8 == 0, "roipool: C=%d not a multiple of 8", C);
-    roipool_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)feat, h, w, C, boxes,
-        objectness, spatial_scale, (uint4*)out);
+    roipool_bf16_kernel<<<grid, 256, 0, st>>>((const uint4*)feat, h, w, C, boxes, objectness, spatial_scale, (uint4*)out);
   } else {
-    DRN_CHECK_ARG(C % 4 == 0, "roipool: C=%d not a multiple of 4", C);
-    roipool_f32_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const float*)feat, h, w, C, boxes,
-        objectness, spatial_scale, (float*)out);
+    roipool_f32_kernel<<<grid, 128, 0, st>>>((const float*)feat, h, w, C, boxes, objectness, spatial_scale, (float*)out);
   }
   DRN_CHECK_LAUNCH("roipool");
   return 0;

@@ -1,16 +1,23 @@
 // tcgen05 / TMEM / TMA implicit-GEMM for sm_100a: the dense contractions of the hot path
 // (ResNet-WS / VGG 3x3 + 1x1 convs, fc6, fc7, concatenated heads) in bf16 with fp32 accumulation.
 //
-//   out[m][n] = act( (sum_k A[m][k] * W[n][k]) * scale[n] + bias[n] + residual[m][n] )
+//   out[m][n] = drop( act( (sum_k A[m][k] * W[n][k]) * scale[n] + bias[n] + residual[m][n] ) )
 //
 // A is either a row-major [M][K] matrix (linear layers, 1x1 convs: 2D TMA) or an NHWC activation
-// tensor read through a 4D TMA box of 8x16 output pixels x 64 channels shifted by the filter tap
-// (3x3 convs: implicit im2col, zero padding comes from TMA out-of-bounds fill).  W is [N][K] K-major.
+// tensor read through a 4D TMA box of TILE_H x TILE_W output pixels x 64 channels shifted by the filter
+// tap (3x3 convs: implicit im2col, zero padding comes from TMA out-of-bounds fill).  W is [N][K] K-major.
 //
 // Persistent warp-specialised CTA (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-
-// thread tcgen05.mma issuer, warps 2..5 = epilogue (tcgen05.ld -> scale/bias/residual/ReLU -> global).
-// smem ring of STAGES x (128x64 A + BNx64 B) bf16 tiles in the 128B-swizzled K-major canonical layout;
-// two TMEM accumulator stages (2 x BN fp32 columns) so the epilogue of tile i overlaps the MMAs of i+1.
+// thread tcgen05.mma issuer, warps 2..5 = epilogue.  smem ring of STAGES x (128x64 A + BNx64 B) bf16
+// tiles in the 128B-swizzled K-major canonical layout; two TMEM accumulator stages (2 x BN fp32 columns)
+// so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Epilogue (bf16 output): every warp owns the 32 accumulator rows of its TMEM lane quadrant and walks
+// the tile in 64-column chunks: tcgen05.ld -> scale/bias (from smem) -> + residual -> ReLU -> dropout ->
+// bf16 -> 128B-swizzled 32x64 staging buffer -> one TMA store per chunk.  The residual chunk is TMA-
+// loaded into the same staging buffer two chunks ahead, so all global traffic of the kernel is
+// TMA (full 128 B lines) and clipping of partial tiles is done by the TMA unit.  fp32 output (head
+// logits, a few hundred KB) keeps a direct register->global path.
 #include "common.cuh"
 #include <cuda.h>
 
@@ -20,8 +27,9 @@ namespace tc {
 constexpr int BM = 128;      // UMMA M (cta_group::1)
 constexpr int BK = 64;       // one 128-byte swizzle atom of bf16 along K
 constexpr int UMMA_K = 16;
-constexpr int TILE_W = 16, TILE_H = 8;  // conv mode: 8 x 16 output pixels = 128 rows
 constexpr int NUM_THREADS = 192;
+constexpr int EPI_CHUNK = 64;                    // columns per staging buffer (128 B of bf16)
+constexpr int EPI_BUF_BYTES = 32 * EPI_CHUNK * 2;  // 32 rows x 128 B
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -56,6 +64,19 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // K-major, 128B-swizzled canonical smem descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
 // start>>4 [0,14) | LBO>>4 [16,30) (ignored for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B between
@@ -87,7 +108,7 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -97,7 +118,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// same counter-based RNG as drn_dropout_inplace (drn_heads.cu): one draw per output element
+__device__ __forceinline__ uint32_t mix32(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return (uint32_t)(x >> 32);
 }
 
 struct Params {
@@ -107,30 +137,40 @@ struct Params {
   int KB;       // number of 64-wide K blocks (= taps * Cin/64)
   int conv;     // 0 = 2D A, 1 = 4D NHWC A with 3x3 taps
   int NB, H, W, Cin, dil;  // conv mode geometry
+  int tile_w, tile_h;      // conv mode: output-pixel tile, tile_w * tile_h == 128, tile_w in {16,32,64,128}
   int tiles_h, tiles_w;
   int num_m_tiles, num_n_tiles;
   // epilogue
   const float* scale;
   const float* bias;
-  const __nv_bfloat16* residual;  // row pitch N
-  void* out;
+  int has_residual;        // residual arrives through map_r (bf16, same geometry as the output)
+  void* out;               // used by the fp32 direct path only
   int out_f32;
   int ldo;
   int relu;
+  // fused dropout (train-mode fc6/fc7): keep iff mix32(seed*P + m*N + n) < keep_thresh
+  uint32_t drop_keep_thresh;  // 0 = no dropout
+  float drop_inv_keep;
+  unsigned long long drop_seed;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NBUF>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_r, const Params p) {
   constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  constexpr uint32_t EPI_BYTES = 4 * NBUF * EPI_BUF_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;                        // 1024-aligned (stage sizes are multiples of 1 KB)
+  float* sb_smem = reinterpret_cast<float*>(epi_smem + EPI_BYTES);        // [2 acc stages][scale BN | bias BN]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sb_smem + 4 * BN);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = tempty_bar + 2;                                     // [4 warps][NBUF]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4 * NBUF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
@@ -138,8 +178,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b) : "memory");
+    if (!p.out_f32) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_o) : "memory");
+    if (p.has_residual) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_r) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    for (int s = 0; s < 4 * NBUF; ++s) mbar_init(&res_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -165,8 +208,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int per_img = p.tiles_h * p.tiles_w;
           img = mt / per_img;
           const int r = mt - img * per_img;
-          h0 = (r / p.tiles_w) * TILE_H;
-          w0 = (r % p.tiles_w) * TILE_W;
+          h0 = (r / p.tiles_w) * p.tile_h;
+          w0 = (r % p.tiles_w) * p.tile_w;
         }
         for (int kb = 0; kb < p.KB; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -218,86 +261,170 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;
+    const int etid = (warp - 2) * 32 + lane;  // 0..127 within the epilogue group
+    uint8_t* my_bufs = epi_smem + quad * (NBUF * EPI_BUF_BYTES);
+    uint64_t* my_res_bar = res_bar + quad * NBUF;
+    const uint32_t sw_xor = (uint32_t)(lane & 7);
+    // warp's 32-row sub-box inside a conv tile
+    const int sub_h = (quad * 32) / (p.conv ? p.tile_w : 32), sub_w = (quad * 32) % (p.conv ? p.tile_w : 32);
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t gchunk = 0;  // running chunk counter of this warp -> staging buffer ring position
+    constexpr int NCHUNK = (BN + EPI_CHUNK - 1) / EPI_CHUNK;
+    // Staging ring discipline (per warp, one bulk group per stored chunk, chunk g lives in slot g % NBUF):
+    // a slot may be overwritten once the store of chunk g - NBUF has drained.  Residual chunks are
+    // TMA-loaded PREFETCH chunks ahead; when chunk g starts, the youngest committed store is g - 1, so
+    // the load for chunk g + PREFETCH may leave NBUF - PREFETCH - 1 stores pending.
+    // NBUF < 3 (deep-K GEMMs that spend the smem on pipeline stages instead): no residual support.
+    constexpr int PREFETCH = NBUF >= 3 ? NBUF - 2 : 0;
+
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile % p.num_m_tiles, nt = tile / p.num_m_tiles;
+      int img = 0, hh0 = 0, ww0 = 0;
       long long m_global;
       bool row_ok;
       if (p.conv) {
         const int per_img = p.tiles_h * p.tiles_w;
-        const int img = mt / per_img;
+        img = mt / per_img;
         const int r = mt - img * per_img;
-        const int hh = (r / p.tiles_w) * TILE_H + row / TILE_W;
-        const int ww = (r % p.tiles_w) * TILE_W + row % TILE_W;
+        hh0 = (r / p.tiles_w) * p.tile_h;
+        ww0 = (r % p.tiles_w) * p.tile_w;
+        const int hh = hh0 + row / p.tile_w, ww = ww0 + row % p.tile_w;
         row_ok = hh < p.H && ww < p.W;
         m_global = ((long long)img * p.H + hh) * p.W + ww;
       } else {
         m_global = (long long)mt * BM + row;
         row_ok = m_global < p.M;
       }
+      const int ncols = min(BN, p.N - nt * BN);            // valid columns of this tile (multiple of 8)
+      const int nchunk = (ncols + EPI_CHUNK - 1) / EPI_CHUNK;
+
+      // per-tile scale / bias into smem (broadcast reads later)
+      float* s_scale = sb_smem + acc * 2 * BN;
+      float* s_bias = s_scale + BN;
+      for (int i = etid; i < BN; i += 128) {
+        const int n = nt * BN + i;
+        s_scale[i] = (p.scale && n < p.N) ? __ldg(p.scale + n) : 1.f;
+        s_bias[i] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+
+      auto issue_residual = [&](int c, uint32_t g) {
+        // lane 0 only: TMA-load residual chunk c of this tile into ring slot g % NBUF (slot already free)
+        const int b = g % NBUF;
+        mbar_arrive_expect_tx(&my_res_bar[b], EPI_BUF_BYTES);
+        if (p.conv)
+          tma_load_4d(&map_r, &my_res_bar[b], my_bufs + b * EPI_BUF_BYTES, nt * BN + c * EPI_CHUNK, ww0 + sub_w, hh0 + sub_h, img);
+        else
+          tma_load_2d(&map_r, &my_res_bar[b], my_bufs + b * EPI_BUF_BYTES, nt * BN + c * EPI_CHUNK, mt * BM + quad * 32);
+      };
+      if (NBUF >= 3 && !p.out_f32 && p.has_residual && lane == 0) {
+        bulk_wait_read<NBUF - PREFETCH>();
+        for (int c = 0; c < PREFETCH && c < nchunk; ++c) issue_residual(c, gchunk + c);
+      }
+
       mbar_wait(&tfull_bar[acc], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+
+      if (!p.out_f32) {
+        // ---------------------------------------------------------- bf16 output through smem + TMA store
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c, v);
-        const int n0 = nt * BN + c;
-        if (row_ok && n0 < p.N) {
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          const int nvalid = min(32, p.N - n0);  // multiple of 8 (host checks N % 8 == 0)
-          if (p.scale) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (j < nvalid) {
-                const float4 s = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + j));
-                f[j] *= s.x; f[j + 1] *= s.y; f[j + 2] *= s.z; f[j + 3] *= s.w;
-              }
+        for (int c = 0; c < NCHUNK; ++c) {
+          if (c >= nchunk) break;
+          const uint32_t g = gchunk + c;
+          const int b = g % NBUF;
+          uint8_t* buf = my_bufs + b * EPI_BUF_BYTES;
+          if (NBUF >= 3 && p.has_residual) {
+            if (lane == 0 && c + PREFETCH < nchunk) {
+              bulk_wait_read<(NBUF >= 3 ? NBUF - PREFETCH - 1 : 0)>();
+              issue_residual(c + PREFETCH, g + PREFETCH);
+            }
+            mbar_wait(&my_res_bar[b], (g / NBUF) & 1);
+          } else {
+            if (lane == 0) bulk_wait_read<NBUF - 1>();
+            __syncwarp();
           }
-          if (p.bias) {
+          uint8_t* my_row = buf + lane * 128;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (j < nvalid) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-              }
-          }
-          if (p.residual) {
-            const __nv_bfloat16* rp = p.residual + m_global * p.N + n0;
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            tmem_ld32_nowait(taddr + c * EPI_CHUNK + half * 32, v);
+            tmem_ld_wait();
+            const int cl = c * EPI_CHUNK + half * 32;  // column inside the tile
 #pragma unroll
-            for (int j = 0; j < 32; j += 8)
-              if (j < nvalid) {
-                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp + j));
+            for (int j = 0; j < 32; j += 8) {
+              float f[8];
+              const float4 s0 = *reinterpret_cast<const float4*>(s_scale + cl + j);
+              const float4 s1 = *reinterpret_cast<const float4*>(s_scale + cl + j + 4);
+              const float4 b0 = *reinterpret_cast<const float4*>(s_bias + cl + j);
+              const float4 b1 = *reinterpret_cast<const float4*>(s_bias + cl + j + 4);
+              f[0] = fmaf(__uint_as_float(v[j + 0]), s0.x, b0.x); f[1] = fmaf(__uint_as_float(v[j + 1]), s0.y, b0.y);
+              f[2] = fmaf(__uint_as_float(v[j + 2]), s0.z, b0.z); f[3] = fmaf(__uint_as_float(v[j + 3]), s0.w, b0.w);
+              f[4] = fmaf(__uint_as_float(v[j + 4]), s1.x, b1.x); f[5] = fmaf(__uint_as_float(v[j + 5]), s1.y, b1.y);
+              f[6] = fmaf(__uint_as_float(v[j + 6]), s1.z, b1.z); f[7] = fmaf(__uint_as_float(v[j + 7]), s1.w, b1.w);
+              const uint32_t q = (uint32_t)(half * 4 + (j >> 3));
+              uint4* slot = reinterpret_cast<uint4*>(my_row + ((q ^ sw_xor) << 4));
+              if (NBUF >= 3 && p.has_residual) {
+                const uint4 rv = *slot;
                 const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float2 rf = __bfloat1622float2(r2[q]);
-                  f[j + 2 * q] += rf.x; f[j + 2 * q + 1] += rf.y;
+                for (int t = 0; t < 4; ++t) {
+                  const float2 rf = __bfloat1622float2(r2[t]);
+                  f[2 * t] += rf.x; f[2 * t + 1] += rf.y;
                 }
               }
-          }
-          if (p.relu) {
+              if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                for (int t = 0; t < 8; ++t) f[t] = fmaxf(f[t], 0.f);
+              }
+              if (p.drop_keep_thresh) {
+                const unsigned long long base = p.drop_seed * 0x100000001B3ull +
+                                                (unsigned long long)m_global * (unsigned long long)p.N +
+                                                (unsigned long long)(nt * BN + cl + j);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) f[t] = (mix32(base + t) < p.drop_keep_thresh) ? f[t] * p.drop_inv_keep : 0.f;
+              }
+              uint4 o;
+              __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) o2[t] = __floats2bfloat162_rn(f[2 * t], f[2 * t + 1]);
+              *slot = o;
+            }
           }
-          if (p.out_f32) {
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.conv)
+              tma_store_4d(&map_o, buf, nt * BN + c * EPI_CHUNK, ww0 + sub_w, hh0 + sub_h, img);
+            else
+              tma_store_2d(&map_o, buf, nt * BN + c * EPI_CHUNK, mt * BM + quad * 32);
+            bulk_commit();
+          }
+          __syncwarp();
+        }
+        gchunk += nchunk;
+      } else {
+        // ---------------------------------------------------------- fp32 output, direct stores (head logits)
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v[32];
+          tmem_ld32_nowait(taddr + c, v);
+          tmem_ld_wait();
+          const int n0 = nt * BN + c;
+          if (row_ok && n0 < p.N) {
+            const int nvalid = min(32, p.N - n0);  // multiple of 8 (host checks N % 8 == 0)
             float* op = reinterpret_cast<float*>(p.out) + m_global * p.ldo + n0;
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
-              if (j < nvalid) *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          } else {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + m_global * p.ldo + n0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8)
               if (j < nvalid) {
-                uint4 o;
-                __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) o2[q] = __floats2bfloat162_rn(f[j + 2 * q], f[j + 2 * q + 1]);
-                *reinterpret_cast<uint4*>(op + j) = o;
+                float4 o;
+                o.x = fmaf(__uint_as_float(v[j + 0]), s_scale[c + j + 0], s_bias[c + j + 0]);
+                o.y = fmaf(__uint_as_float(v[j + 1]), s_scale[c + j + 1], s_bias[c + j + 1]);
+                o.z = fmaf(__uint_as_float(v[j + 2]), s_scale[c + j + 2], s_bias[c + j + 2]);
+                o.w = fmaf(__uint_as_float(v[j + 3]), s_scale[c + j + 3], s_bias[c + j + 3]);
+                if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                *reinterpret_cast<float4*>(op + j) = o;
               }
           }
         }
@@ -307,6 +434,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) bulk_wait_all();  // staging smem must outlive the last TMA store
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -357,25 +485,28 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int STAGES>
-static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 256 + 1024;
+template <int BN, int STAGES, int NBUF>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mr, const Params& p,
+                  cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 4 * NBUF * EPI_BUF_BYTES + 4 * BN * sizeof(float) +
+                          (2 * STAGES + 4 + 4 * NBUF) * sizeof(uint64_t) + 16 + 1024;
+  static_assert(smem <= 232448, "gemm_tc: shared memory budget exceeded");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_err("gemm_tc: cudaFuncSetAttribute(%zu B smem): %s", smem, cudaGetErrorString(e));
     configured = true;
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, st>>>(ma, mb, p);
+  gemm_tc_kernel<BN, STAGES, NBUF><<<grid, NUM_THREADS, smem, st>>>(ma, mb, mo, mr, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_err("gemm_tc launch: %s", cudaGetErrorString(e));
   return 0;
 }
 
-static int pick_bn(int m_tiles, int N) {
-  // minimise (waves x per-tile cost); per-tile cost ~ BN + fixed overhead (pipeline fill + epilogue tail)
+// tile-shape choice: minimise waves x (per-tile MMA time + fixed fill/drain), per-tile time ~ KB * BN (+ epilogue ~ BN)
+static int pick_bn(int m_tiles, int N, int KB) {
   const int sms = num_sms();
   int best = 64;
   double best_cost = 1e30;
@@ -385,10 +516,27 @@ static int pick_bn(int m_tiles, int N) {
     if (bn > 64 && N < bn) continue;
     const int tiles = m_tiles * ((N + bn - 1) / bn);
     const int waves = (tiles + sms - 1) / sms;
-    const double cost = (double)waves * (bn + 24);
+    // mainloop: per k-block max(MMA = bn/2 cycles*4, L2 feed = (16 KB + bn*128 B) / 64 B/cycle); epilogue ~ 6*bn; fill ~ 1500
+    const double mma = 2.0 * bn, feed = (16384.0 + bn * 128.0) / 64.0;
+    const double per_tile = KB * (mma > feed ? mma : feed) + 6.0 * bn;
+    const double cost = waves * per_tile + 1500.0;
     if (cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
+}
+
+// conv-mode spatial tile: tile_w x tile_h = 128 output pixels; fewest tiles wins, squarer wins ties
+static void pick_conv_tile(int H, int W, int* tw_out, int* th_out) {
+  const int cand[4] = {16, 32, 64, 128};
+  int best = 16;
+  long best_tiles = -1;
+  for (int i = 0; i < 4; ++i) {
+    const int tw = cand[i], th = 128 / tw;
+    const long tiles = (long)((W + tw - 1) / tw) * ((H + th - 1) / th);
+    if (best_tiles < 0 || tiles < best_tiles) { best_tiles = tiles; best = tw; }
+  }
+  *tw_out = best;
+  *th_out = 128 / best;
 }
 
 }  // namespace tc
@@ -398,42 +546,77 @@ using namespace drn;
 
 extern "C" int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int Cin, const void* w, int ksize,
                                       int dilation, const float* scale, const float* bias, const void* residual,
-                                      int relu, void* out, int out_dtype, int Cout, int ldo, drn_stream_t stream) {
+                                      int relu, void* out, int out_dtype, int Cout, int ldo, float dropout_p,
+                                      uint64_t dropout_seed, drn_stream_t stream) {
   using namespace drn::tc;
   DRN_CHECK_ARG(in && w && out, "conv_igemm_bf16_tc: null pointer");
   DRN_CHECK_ARG(ksize == 1 || ksize == 3, "conv_igemm_bf16_tc: ksize %d", ksize);
   DRN_CHECK_ARG(Cin % 64 == 0, "conv_igemm_bf16_tc: Cin=%d must be a multiple of 64", Cin);
   DRN_CHECK_ARG(Cout % 8 == 0, "conv_igemm_bf16_tc: Cout=%d must be a multiple of 8", Cout);
   DRN_CHECK_ARG(ldo >= Cout && ldo % 8 == 0, "conv_igemm_bf16_tc: ldo=%d", ldo);
-  DRN_CHECK_ARG(((uintptr_t)in % 16 == 0) && ((uintptr_t)w % 16 == 0) && ((uintptr_t)out % 16 == 0),
+  DRN_CHECK_ARG(((uintptr_t)in % 16 == 0) && ((uintptr_t)w % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
+                    ((uintptr_t)residual % 16 == 0),
                 "conv_igemm_bf16_tc: operands must be 16-byte aligned");
+  DRN_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "conv_igemm_bf16_tc: dropout p=%f", dropout_p);
+  DRN_CHECK_ARG(!(residual && out_dtype == DRN_F32), "conv_igemm_bf16_tc: residual needs bf16 output");
+  DRN_CHECK_ARG(!(dropout_p > 0.f && out_dtype == DRN_F32), "conv_igemm_bf16_tc: fused dropout needs bf16 output");
   const long long Mll = (long long)N * H * W;
   if (Mll == 0) return 0;
   DRN_CHECK_ARG(Mll < (1ll << 31), "conv_igemm_bf16_tc: too many rows");
   Params p{};
   p.N = Cout;
-  p.scale = scale; p.bias = bias; p.residual = (const __nv_bfloat16*)residual;
+  p.scale = scale; p.bias = bias; p.has_residual = residual != nullptr;
   p.out = out; p.out_f32 = (out_dtype == DRN_F32); p.ldo = ldo; p.relu = relu;
+  if (dropout_p > 0.f) {
+    const double keep = 1.0 - (double)dropout_p;
+    p.drop_keep_thresh = (uint32_t)(keep * 4294967295.0);
+    p.drop_inv_keep = (float)(1.0 / keep);
+    p.drop_seed = dropout_seed;
+  }
   const int Ktot = ksize * ksize * Cin;
   p.KB = Ktot / BK;
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mo, mr;
+  memset(&mo, 0, sizeof(mo));
+  memset(&mr, 0, sizeof(mr));
   if (ksize == 3) {
     p.conv = 1; p.NB = N; p.H = H; p.W = W; p.Cin = Cin; p.dil = dilation;
-    p.tiles_h = (H + TILE_H - 1) / TILE_H; p.tiles_w = (W + TILE_W - 1) / TILE_W;
+    pick_conv_tile(H, W, &p.tile_w, &p.tile_h);
+    p.tiles_h = (H + p.tile_h - 1) / p.tile_h; p.tiles_w = (W + p.tile_w - 1) / p.tile_w;
     p.num_m_tiles = N * p.tiles_h * p.tiles_w;
     const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
-    const cuuint32_t box[4] = {BK, TILE_W, TILE_H, 1};
+    const cuuint32_t box[4] = {BK, (cuuint32_t)p.tile_w, (cuuint32_t)p.tile_h, 1};
     if (make_map(&ma, in, 4, dims, strides, box)) return 1;
+    if (!p.out_f32) {
+      const int bw = p.tile_w < 32 ? p.tile_w : 32;
+      const cuuint32_t obox[4] = {EPI_CHUNK, (cuuint32_t)bw, (cuuint32_t)(32 / bw), 1};
+      const cuuint64_t odims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+      const cuuint64_t ostr[3] = {(cuuint64_t)ldo * 2, (cuuint64_t)W * ldo * 2, (cuuint64_t)H * W * ldo * 2};
+      if (make_map(&mo, out, 4, odims, ostr, obox)) return 1;
+      if (residual) {
+        const cuuint64_t rstr[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, (cuuint64_t)H * W * Cout * 2};
+        if (make_map(&mr, residual, 4, odims, rstr, obox)) return 1;
+      }
+    }
   } else {
-    p.conv = 0; p.M = (int)Mll;
+    p.conv = 0; p.M = (int)Mll; p.tile_w = 32; p.tile_h = 4;
     p.num_m_tiles = (int)((Mll + BM - 1) / BM);
     const cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)Mll};
     const cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
     const cuuint32_t box[2] = {BK, BM};
     if (make_map(&ma, in, 2, dims, strides, box)) return 1;
+    if (!p.out_f32) {
+      const cuuint32_t obox[2] = {EPI_CHUNK, 32};
+      const cuuint64_t odims[2] = {(cuuint64_t)Cout, (cuuint64_t)Mll};
+      const cuuint64_t ostr[1] = {(cuuint64_t)ldo * 2};
+      if (make_map(&mo, out, 2, odims, ostr, obox)) return 1;
+      if (residual) {
+        const cuuint64_t rstr[1] = {(cuuint64_t)Cout * 2};
+        if (make_map(&mr, residual, 2, odims, rstr, obox)) return 1;
+      }
+    }
   }
-  const int bn = pick_bn(p.num_m_tiles, Cout);
+  const int bn = pick_bn(p.num_m_tiles, Cout, p.KB);
   p.num_n_tiles = (Cout + bn - 1) / bn;
   {
     const cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
@@ -442,7 +625,8 @@ extern "C" int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int C
     if (make_map(&mb, w, 2, dims, strides, box)) return 1;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (bn == 256) return launch<256, 4>(ma, mb, p, st);
-  if (bn == 128) return launch<128, 6>(ma, mb, p, st);
-  return launch<64, 8>(ma, mb, p, st);
+  if (bn == 256 && !residual && p.KB >= 48) return launch<256, 4, 1>(ma, mb, mo, mr, p, st);  // deep K: stages over staging
+  if (bn == 256) return launch<256, 3, 4>(ma, mb, mo, mr, p, st);
+  if (bn == 128) return launch<128, 4, 4>(ma, mb, mo, mr, p, st);
+  return launch<64, 6, 4>(ma, mb, mo, mr, p, st);
 }

@@ -6,7 +6,7 @@ PyTorch is only used by callers for device memory (`tensor.data_ptr()`) and the 
 import ctypes
 import os
 import re
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_uint64, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdrn_b200.so")
@@ -23,9 +23,10 @@ _PROTOS = {
     "drn_version": [],
     "drn_conv3x3_c3_fwd": [_P, c_int, c_int, c_int, c_int, _FP, _FP, _P, _P, _P, c_int, c_int, c_int, _P, c_int, _P],
     "drn_conv_igemm_f32": [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, _P, _P, c_int, _P, c_int, c_int, _P],
-    "drn_conv_igemm_bf16_tc": [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, _P, _P, c_int, _P, c_int, c_int, c_int, _P],
+    "drn_conv_igemm_bf16_tc": [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, _P, _P, c_int, _P, c_int, c_int, c_int,
+                               c_float, c_uint64, _P],
     "drn_maxpool2x2_nhwc": [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
-    "drn_roipool_fwd": [_P, c_int, c_int, c_int, _P, _P, c_int, c_float, c_int, _P, _P],
+    "drn_roipool_fwd": [_P, c_int, c_int, c_int, _P, _P, c_int, c_float, c_int, _P, _P, c_size_t, _P],
     "drn_wsddn_mil_fwd": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_float, _P, _P, _P, _P, _P],
     "drn_oicr_pgt": [_P, c_int, c_int, _P, _P, c_int, _P, c_int, _P, c_int, c_int, _FP, _P, _P, _P, _P, _P],
     "drn_label_proposals": [_P, c_int, _P, _P, c_int, c_int, _FP, _IP, c_int, _P, _P, _P, _P],
@@ -64,6 +65,8 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = c_int
+    lib.drn_roipool_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
+    lib.drn_roipool_workspace_bytes.restype = c_size_t
     _lib = lib
     return lib
 

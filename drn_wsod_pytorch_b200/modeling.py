@@ -140,15 +140,19 @@ def run_conv(conv: Conv2d, x, precision, relu, residual=None):
     return ops.conv_bf16_tc(x, p, conv.kernel_size, conv.dilation, relu, residual)
 
 
-def run_linear(x2d, packed, precision, relu, out_dtype=None):
+def run_linear(x2d, packed, precision, relu, out_dtype=None, dropout=None):
     """x2d: [M, K] -> [M, Npad] through the same implicit-GEMM kernels (a linear layer is a 1x1 conv
-    over an M x 1 'image')."""
+    over an M x 1 'image').  dropout = (p, seed): train-mode F.dropout, fused into the tensor-core
+    epilogue on the bf16 path, a separate in-place kernel on the exact-fp32 path."""
     M, K = x2d.shape
     x4 = x2d.view(1, M, 1, K)
     if precision == "fp32":
         y = ops.conv_f32(x4, packed, 1, 1, relu)
+        if dropout is not None:
+            ops.dropout_(y, dropout[0], dropout[1])
     else:
-        y = ops.conv_bf16_tc(x4, packed, 1, 1, relu, out_dtype=out_dtype or torch.bfloat16)
+        dp, ds = dropout if dropout is not None else (0.0, 0)
+        y = ops.conv_bf16_tc(x4, packed, 1, 1, relu, out_dtype=out_dtype or torch.bfloat16, dropout_p=dp, dropout_seed=ds)
     return y.view(M, packed["cout"])
 
 
@@ -404,10 +408,11 @@ class DiscriminativeAdaptionNeck(nn.Module):
         x = pooled2d
         for i, fc in enumerate(self.fcs):
             perm = self.in_channels if (i == 0 and bin_major) else None
-            x = run_linear(x, fc.packed(self.precision, permute_c49=perm), self.precision, relu=True)
+            drop = None
             if self.training:  # box_head.py:90
                 self._seed += 1
-                ops.dropout_(x, 0.5, self._seed)
+                drop = (0.5, self._seed)
+            x = run_linear(x, fc.packed(self.precision, permute_c49=perm), self.precision, relu=True, dropout=drop)
         return x
 
     def forward(self, x):

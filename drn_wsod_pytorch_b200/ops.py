@@ -51,14 +51,14 @@ def conv_f32(x, packed, ksize, dilation, relu, residual=None, out=None, ldo=None
     return out
 
 
-def conv_bf16_tc(x, packed, ksize, dilation, relu, residual=None, out_dtype=torch.bfloat16):
-    """tcgen05 implicit-GEMM conv / linear.  x: [N,H,W,Cin] bf16 NHWC."""
+def conv_bf16_tc(x, packed, ksize, dilation, relu, residual=None, out_dtype=torch.bfloat16, dropout_p=0.0, dropout_seed=0):
+    """tcgen05 implicit-GEMM conv / linear (+ fused train-mode dropout).  x: [N,H,W,Cin] bf16 NHWC."""
     _chk(x, "x")
     N, H, W, Cin = x.shape
     Cout = packed["cout"]
     out = torch.empty((N, H, W, Cout), device=x.device, dtype=out_dtype)
     call("drn_conv_igemm_bf16_tc", x, N, H, W, Cin, packed["w"], ksize, dilation, packed["scale"], packed["bias"],
-         residual, int(relu), out, _dt(out), Cout, Cout, current_stream())
+         residual, int(relu), out, _dt(out), Cout, Cout, float(dropout_p), int(dropout_seed), current_stream())
     return out
 
 
@@ -71,15 +71,29 @@ def maxpool2x2(x, stride):
     return out
 
 
-def roipool(feat_hwc, boxes, objectness, spatial_scale):
-    """feat_hwc: [h,w,C]; boxes [R,4] fp32; objectness [R] fp32 or None -> [R, 49*C] (bin-major)."""
+_ROIPOOL_WS = {}
+
+
+def roipool(feat_hwc, boxes, objectness, spatial_scale, use_tables=None):
+    """feat_hwc: [h,w,C]; boxes [R,4] fp32; objectness [R] fp32 or None -> [R, 49*C] (bin-major).
+    use_tables: build the per-image range-max tables (default: when R is large enough to amortise them)."""
     _chk(feat_hwc, "features")
     _chk(boxes, "boxes")
     h, w, C = feat_hwc.shape
     R = boxes.shape[0]
     out = torch.empty((R, 49 * C), device=feat_hwc.device, dtype=feat_hwc.dtype)
+    if use_tables is None:
+        use_tables = R >= 256
+    ws, ws_bytes = None, 0
+    if use_tables:
+        ws_bytes = lib.load().drn_roipool_workspace_bytes(h, w, C, _dt(feat_hwc))
+        key = (feat_hwc.device, torch.cuda.current_stream().cuda_stream)
+        ws = _ROIPOOL_WS.get(key)
+        if ws is None or ws.numel() < ws_bytes:  # grow-only scratch, reused across calls on the same stream
+            ws = torch.empty((ws_bytes,), device=feat_hwc.device, dtype=torch.uint8)
+            _ROIPOOL_WS[key] = ws
     call("drn_roipool_fwd", feat_hwc, h, w, C, boxes, objectness, R, float(spatial_scale), _dt(feat_hwc), out,
-         current_stream())
+         ws, ws_bytes, current_stream())
     return out
 
 

@@ -15,6 +15,7 @@
  */
 #ifndef DRN_B200_H
 #define DRN_B200_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -55,12 +56,16 @@ int drn_conv_igemm_f32(const float* in, int N, int H, int W, int Cin, const floa
                        int relu, float* out, int Cout, int ldo, drn_stream_t stream);
 
 /* Tensor-core (tcgen05/TMEM/TMA) implicit-GEMM convolution / linear layer, bf16 in, fp32 accumulate.
- * Same reference lines as drn_conv_igemm_f32.  in: [N][H][W][Cin] bf16; w: [Cout][ksize*ksize*Cin]
- * bf16 (K-major, K order (kh,kw,cin)); bias/scale fp32 [Cout]; residual bf16 [N][H][W][Cout] or NULL;
- * out dtype DRN_BF16 or DRN_F32, row pitch ldo elements.  Cin % 64 == 0, Cout % 16 == 0. */
+ * Same reference lines as drn_conv_igemm_f32, plus the train-mode F.dropout of
+ * WSL/roi_heads/box_head.py:90 fused into the epilogue (dropout_p > 0: same counter-based mask as
+ * drn_dropout_inplace with the same seed, element index = row * Cout + col).
+ * in: [N][H][W][Cin] bf16; w: [Cout][ksize*ksize*Cin] bf16 (K-major, K order (kh,kw,cin)); bias/scale
+ * fp32 [Cout]; residual bf16 [N][H][W][Cout] (pitch Cout) or NULL; out dtype DRN_BF16 or DRN_F32 (F32:
+ * no residual / dropout), row pitch ldo elements.  Cin % 64 == 0, Cout % 8 == 0, ldo % 8 == 0. */
 int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int Cin, const void* w, int ksize,
                            int dilation, const float* scale, const float* bias, const void* residual,
-                           int relu, void* out, int out_dtype, int Cout, int ldo, drn_stream_t stream);
+                           int relu, void* out, int out_dtype, int Cout, int ldo, float dropout_p,
+                           uint64_t dropout_seed, drn_stream_t stream);
 
 /* MaxPool2d(kernel 2, stride 1|2, padding 0), NHWC.
  * Replaces nn.MaxPool2d in WSL/backbone/resnet_ws.py:93-94,110-111,403,415 and vgg.py:93-94,108-109. */
@@ -71,10 +76,14 @@ int drn_maxpool2x2_nhwc(const void* in, int N, int H, int W, int C, int stride, 
  * Replaces detectron2/modeling/poolers.py:191-226 (ROIPooler.forward -> torchvision.ops.RoIPool)
  * and WSL/roi_heads/roi_heads_oicr.py:342-343 / roi_heads_wsddn.py:285-286.
  * feat: [h][w][C] (one image); boxes: [R][4] fp32 XYXY image px; objectness: [R] fp32 or NULL;
- * out: [R][49][C], bin-major ((ph*7+pw)*C + c) -- fc6's weight is permuted to that K order. */
+ * out: [R][49][C], bin-major ((ph*7+pw)*C + c) -- fc6's weight is permuted to that K order.
+ * workspace: >= drn_roipool_workspace_bytes(h, w, C, dtype) bytes of scratch for the per-image
+ * range-max tables (16-byte aligned), or NULL to use the direct per-cell scan (same results, slower
+ * for large R).  Results are bit-identical either way (max has no rounding). */
+size_t drn_roipool_workspace_bytes(int h, int w, int C, int dtype);
 int drn_roipool_fwd(const void* feat_nhwc, int h, int w, int C, const float* boxes,
                     const float* objectness, int R, float spatial_scale, int dtype, void* out,
-                    drn_stream_t stream);
+                    void* workspace, size_t workspace_bytes, drn_stream_t stream);
 
 /* WSDDN dual-softmax MIL head + image-level BCE.
  * Replaces WSL/roi_heads/fast_rcnn.py:493-527 (softmax(cls,1)*softmax(det,0)), :689-700

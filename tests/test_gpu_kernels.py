@@ -38,8 +38,9 @@ def _edge_boxes():
             [0, 0, 10000, 10000], [4.0, 12.0, 4.0, 100.0], [100, 3.9999, 101, 4.0001], [-30, 10, 40, 60]]
 
 
-@pytest.mark.parametrize("C,h,w,R", [(64, 19, 27, 300), (512, 74, 124, 64), (2048, 18, 18, 32)])
-def test_roipool_fp32_bit_exact(C, h, w, R):
+@pytest.mark.parametrize("tables", [False, True])
+@pytest.mark.parametrize("C,h,w,R", [(64, 19, 27, 300), (512, 74, 124, 64), (2048, 18, 18, 32), (32, 40, 250, 64)])
+def test_roipool_fp32_bit_exact(C, h, w, R, tables):
     rng = np.random.default_rng(C + R)
     feat = rng.standard_normal((C, h, w)).astype(np.float32)
     H, W = h * 8, w * 8
@@ -51,12 +52,13 @@ def test_roipool_fp32_bit_exact(C, h, w, R):
     tv = O.roi_pool(torch.from_numpy(feat)[None], torch.from_numpy(boxes), 0.125).numpy() * (obj + np.float32(1.0))[:, None, None, None]
     assert np.array_equal(ref, tv), "C restatement disagrees with torchvision"
     f_hwc = torch.from_numpy(feat).permute(1, 2, 0).contiguous().to(DEV)
-    out = ops.roipool(f_hwc, torch.from_numpy(boxes).to(DEV), torch.from_numpy(obj).to(DEV), 0.125)
+    out = ops.roipool(f_hwc, torch.from_numpy(boxes).to(DEV), torch.from_numpy(obj).to(DEV), 0.125, use_tables=tables)
     got = out.view(len(boxes), 49, C).permute(0, 2, 1).reshape(len(boxes), C, 7, 7).cpu().numpy()
     assert np.array_equal(got, ref)  # max-pool is exact; one fp32 multiply by (objectness+1)
 
 
-def test_roipool_bf16_bit_exact():
+@pytest.mark.parametrize("tables", [False, True])
+def test_roipool_bf16_bit_exact(tables):
     rng = np.random.default_rng(5)
     C, h, w, R = 256, 37, 50, 200
     feat = torch.from_numpy(rng.standard_normal((C, h, w)).astype(np.float32)).bfloat16()
@@ -66,18 +68,35 @@ def test_roipool_bf16_bit_exact():
     pooled = O.roi_pool(feat.float()[None], torch.from_numpy(boxes), 0.125)
     ref = (pooled * (torch.from_numpy(obj) + 1).view(-1, 1, 1, 1)).bfloat16()
     out = ops.roipool(feat.permute(1, 2, 0).contiguous().to(DEV), torch.from_numpy(boxes).to(DEV),
-                      torch.from_numpy(obj).to(DEV), 0.125)
+                      torch.from_numpy(obj).to(DEV), 0.125, use_tables=tables)
     got = out.view(R, 49, C).permute(0, 2, 1).reshape(R, C, 7, 7).cpu()
     assert torch.equal(got, ref)
 
 
-def test_roipool_empty_and_constant_properties():
+@pytest.mark.parametrize("tables", [False, True])
+def test_roipool_empty_and_constant_properties(tables):
     f = torch.full((10, 12, 64), 3.5, device=DEV)
     boxes = torch.tensor([[0.0, 0, 50, 50], [20, 20, 90, 70]], device=DEV)
-    out = ops.roipool(f, boxes, None, 0.125)
+    out = ops.roipool(f, boxes, None, 0.125, use_tables=tables)
     assert torch.all(out == 3.5)  # max over a constant map is the constant (idempotence)
-    out0 = ops.roipool(f, boxes[:0].contiguous(), None, 0.125)
+    out0 = ops.roipool(f, boxes[:0].contiguous(), None, 0.125, use_tables=tables)
     assert out0.shape == (0, 49 * 64)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_roipool_full_size_tables_equal_direct_scan(dtype):
+    """BASELINE.json full size (74x124 map, C=2048 / 512, R=4000 / 2000): the range-max-table path and
+    the direct per-cell scan agree bit for bit (size-independent property: max is order-free)."""
+    from drn_wsod_pytorch_b200 import synth
+    C, R = (2048, 4000) if dtype == torch.bfloat16 else (512, 2000)
+    g = torch.Generator().manual_seed(1)
+    f = torch.randn(74, 124, C, generator=g).to(dtype).to(DEV)
+    inp = synth.make_inputs(600, 1000, R, seed=3)
+    boxes, obj = inp["boxes"].to(DEV), inp["objectness"].to(DEV)
+    a = ops.roipool(f, boxes, obj, 0.125, use_tables=False)
+    b = ops.roipool(f, boxes, obj, 0.125, use_tables=True)
+    assert torch.equal(a, b)
+    assert torch.isfinite(b.float()).all()
 
 
 @pytest.mark.parametrize("cin,cout,k,dil,res,relu", [(64, 64, 3, 1, False, True), (64, 128, 3, 2, True, True),
@@ -159,7 +178,8 @@ def test_tc_gemm_bf16(M, K, N, relu, res, f32out):
 
 
 @pytest.mark.parametrize("cin,cout,dil,H,W,res", [(64, 64, 1, 16, 32, False), (128, 256, 2, 21, 35, True), (64, 128, 1, 74, 124, False),
-                                                   (256, 64, 2, 9, 17, True)])
+                                                   (256, 64, 2, 9, 17, True), (512, 512, 2, 74, 124, True), (64, 64, 1, 5, 300, True),
+                                                   (64, 64, 1, 150, 40, False)])
 def test_tc_conv3x3_bf16(cin, cout, dil, H, W, res):
     g = torch.Generator().manual_seed(cin + cout + dil + H)
     N = 2
@@ -176,6 +196,36 @@ def test_tc_conv3x3_bf16(cin, cout, dil, H, W, res):
     out = ops.conv_bf16_tc(x.permute(0, 2, 3, 1).contiguous().to(DEV), packed, 3, dil, True,
                            r.permute(0, 2, 3, 1).contiguous().to(DEV) if res else None)
     torch.testing.assert_close(out.permute(0, 3, 1, 2).float().cpu(), ref, rtol=1e-2, atol=1e-2)
+
+
+def test_tc_gemm_fused_dropout_matches_standalone_kernel():
+    """The epilogue-fused dropout draws the same counter-based mask as drn_dropout_inplace."""
+    M, K, N = 520, 192, 320
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(M, K, generator=g).bfloat16().to(DEV)
+    packed = {"w": (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16().to(DEV), "scale": None,
+              "bias": torch.randn(N, generator=g).to(DEV), "cout": N}
+    plain = ops.conv_bf16_tc(a.view(1, M, 1, K), packed, 1, 1, True).view(M, N)
+    fused = ops.conv_bf16_tc(a.view(1, M, 1, K), packed, 1, 1, True, dropout_p=0.5, dropout_seed=77).view(M, N)
+    ref = ops.dropout_(plain.clone(), 0.5, 77)
+    assert torch.equal(fused, ref)
+    frac = (fused == 0).float().mean().item()
+    assert 0.6 < frac < 0.9  # relu zeros (~50%) + dropped half of the rest
+
+
+@pytest.mark.parametrize("M,K,N", [(9176, 512, 2048), (37500, 64, 256), (4000, 4096, 4096)])
+def test_tc_gemm_bf16_large_residual(M, K, N):
+    """Backbone-sized 1x1 convs with residual: exercises multi-tile-per-CTA staging ring + residual prefetch."""
+    g = torch.Generator().manual_seed(M + N)
+    a = torch.randn(M, K, generator=g).bfloat16()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, generator=g)
+    r = torch.randn(M, N, generator=g).bfloat16()
+    ad, wd, rd = a.to(DEV), w.to(DEV), r.to(DEV)
+    ref = F.relu(ad.float() @ wd.float().t() + bias.to(DEV) + rd.float()).cpu()
+    packed = {"w": wd, "scale": None, "bias": bias.to(DEV), "cout": N}
+    out = ops.conv_bf16_tc(ad.view(1, M, 1, K), packed, 1, 1, True, rd.view(1, M, 1, N))
+    torch.testing.assert_close(out.view(M, N).float().cpu(), ref, rtol=1e-2, atol=2e-2)
 
 
 # ------------------------------------------------------------------ heads

@@ -141,6 +141,7 @@ def main():
     config = {"workload": f"{cfg_name} {H}x{W} R={R} {precision} (BASELINE.json configs[{2 if 'r50' in args.workload else 1}])"
               if args.workload in ("r50_bf16", "r18_fp32") else f"{cfg_name} {H}x{W} R={R} {precision}",
               "images_per_gpu": 1, "proposals_per_image": R, "parallelism": f"dp{world}", "dropout": "on (train mode)",
+              "launch": "one CUDA-graph replay per step (captured per input signature by the public forward)",
               "l2": "no flush: per-step working set (fc6 weights 411 MB + ROI features 0.2-0.8 GB) exceeds the 126 MB L2"}
 
     import drn_wsod_pytorch_b200 as drn
@@ -200,37 +201,13 @@ def main():
     host = make_batched(inp, None, drn, pinned=True)[0]
     loss_keys = None
 
-    # count kernel launches through the C ABI
+    # count kernel launches through the C ABI (one eager step; the timed steps replay exactly these)
     counter = {"n": 0}
     orig_call = drn_lib.call
 
     def counting_call(name, *a):
         counter["n"] += LAUNCHES.get(name, 1)
         return orig_call(name, *a)
-
-    drn_lib.call = counting_call
-    ops.call = counting_call
-
-    # time the dominant kernel (fc6 GEMM) live, on the launching stream, inside the timed region
-    fc6_events = []
-    fc6_K = 49 * model.roi_heads.in_channels
-    orig_tc, orig_f32 = ops.conv_bf16_tc, ops.conv_f32
-
-    def wrap(fn):
-        def inner(x, packed, ksize, dilation, relu, *a, **k):
-            if ksize == 1 and x.shape[-1] == fc6_K and record["on"]:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                out = fn(x, packed, ksize, dilation, relu, *a, **k)
-                e1.record()
-                fc6_events.append((e0, e1))
-                return out
-            return fn(x, packed, ksize, dilation, relu, *a, **k)
-        return inner
-
-    record = {"on": False}
-    ops.conv_bf16_tc, ops.conv_f32 = wrap(orig_tc), wrap(orig_f32)
-    import drn_wsod_pytorch_b200.modeling as M  # noqa: F401  (uses ops.* attributes at call time)
 
     def step(batched):
         losses = model(batched)
@@ -244,40 +221,81 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    # ---- eager pass (CUDA graph off): launch count + per-launch duration of the dominant kernel (fc6 GEMM)
+    # measured with CUDA events on the launching stream inside real steps of the same path
+    graph_default = model.use_cuda_graph
+    model.use_cuda_graph = False
+    fc6_events = []
+    fc6_K = 49 * model.roi_heads.in_channels
+    orig_tc, orig_f32 = ops.conv_bf16_tc, ops.conv_f32
+    record = {"on": False}
+
+    def wrap(fn):
+        def inner(x, packed, ksize, dilation, relu, *a, **k):
+            if ksize == 1 and x.shape[-1] == fc6_K and record["on"]:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = fn(x, packed, ksize, dilation, relu, *a, **k)
+                e1.record()
+                fc6_events.append((e0, e1))
+                return out
+            return fn(x, packed, ksize, dilation, relu, *a, **k)
+        return inner
+
+    ops.conv_bf16_tc, ops.conv_f32 = wrap(orig_tc), wrap(orig_f32)
+    for _ in range(3):
+        step(batched_dev)
+    sync_all()
+    drn_lib.call = counting_call
+    ops.call = counting_call
+    record["on"] = True
+    eager_steps = max(3, min(args.steps, 10))
+    for _ in range(eager_steps):
         vec, loss_keys = step(batched_dev)
     sync_all()
+    record["on"] = False
+    drn_lib.call = orig_call
+    ops.call = orig_call
+    ops.conv_bf16_tc, ops.conv_f32 = orig_tc, orig_f32
+    launches_per_step = counter["n"] // eager_steps
+    fc6_ms = sum(a.elapsed_time(b) for a, b in fc6_events) / max(1, len(fc6_events))
+    model.use_cuda_graph = graph_default
+
     if args.profile_step:
+        for _ in range(3):
+            step(batched_dev)
+        sync_all()
         torch.cuda.cudart().cudaProfilerStart()
         step(batched_dev)
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
         return
+
+    # ---- timed region: the public forward (CUDA-graph plan per input signature), inputs resident in HBM
+    for _ in range(max(args.warmup, 3)):
+        vec, loss_keys = step(batched_dev)
+    sync_all()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    counter["n"] = 0
-    record["on"] = True
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         vec, _ = step(batched_dev)
     e1.record()
     sync_all()
-    record["on"] = False
-    launches = counter["n"]
+    launches = launches_per_step * args.steps
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = t.item()
-    fc6_ms = sum(a.elapsed_time(b) for a, b in fc6_events) / max(1, len(fc6_events))
 
     # end-to-end: pinned host inputs -> H2D -> forward+loss -> D2H loss read, every step
     def e2e_step():
-        d = {"image": host["image"].to(dev, non_blocking=True), "height": H, "width": W,
-             "proposals": host["proposals"].to(dev, non_blocking=True), "instances": host["instances"].to(dev, non_blocking=True)}
-        v, _ = step([d])
+        # the user-facing call: pinned HOST tensors in (the model's plan copies them H2D into its static
+        # buffers inside this call), loss vector read back to the host
+        v, _ = step([host])
         return v.cpu()
 
     for _ in range(3):
@@ -309,8 +327,10 @@ def main():
                                                "oicr_pgt", "label_proposals", "oicr_stage", "dropout_")}
         for n, f in saved.items():
             setattr(ops, n, fam_wrap(n, f))
+        model.use_cuda_graph = False
         step(batched_dev)
         torch.cuda.synchronize()
+        model.use_cuda_graph = graph_default
         for n, f in saved.items():
             setattr(ops, n, f)
         print("breakdown (ms, 1 step):", {n: round(sum(a.elapsed_time(b) for a, b in ev), 3) for n, ev in fams.items()},

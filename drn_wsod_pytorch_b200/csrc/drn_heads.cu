@@ -386,9 +386,11 @@ __device__ __forceinline__ uint32_t mix32(uint64_t x) {
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-dropout_kernel(T* __restrict__ x, long long n, uint32_t keep_thresh, float inv_keep, uint64_t seed) {
+dropout_kernel(T* __restrict__ x, long long n, uint32_t keep_thresh, float inv_keep, uint64_t seed,
+               const uint64_t* __restrict__ seed_dev) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (seed_dev) seed += __ldg(seed_dev);
   const bool keep = mix32(seed * 0x100000001B3ull + (uint64_t)i) < keep_thresh;
   float v;
   if constexpr (sizeof(T) == 4) v = x[i]; else v = __bfloat162float(x[i]);
@@ -485,7 +487,8 @@ int drn_oicr_boxreg_loss(const float* deltas, int ld, int col_off, int R, int K,
   return 0;
 }
 
-int drn_dropout_inplace(void* x, int64_t n, int dtype, float p, uint64_t seed, drn_stream_t stream) {
+int drn_dropout_inplace(void* x, int64_t n, int dtype, float p, uint64_t seed, const uint64_t* seed_dev,
+                        drn_stream_t stream) {
   DRN_CHECK_ARG(x || n == 0, "dropout: null pointer");
   DRN_CHECK_ARG(p >= 0.f && p < 1.f, "dropout: p=%f", p);
   if (n == 0 || p == 0.f) return 0;
@@ -493,9 +496,9 @@ int drn_dropout_inplace(void* x, int64_t n, int dtype, float p, uint64_t seed, d
   const uint32_t thr = (uint32_t)(keep * 4294967295.0);
   const unsigned grid = (unsigned)((n + 255) / 256);
   if (dtype == DRN_BF16)
-    dropout_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)x, n, thr, (float)(1.0 / keep), seed);
+    dropout_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)x, n, thr, (float)(1.0 / keep), seed, seed_dev);
   else
-    dropout_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)x, n, thr, (float)(1.0 / keep), seed);
+    dropout_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)x, n, thr, (float)(1.0 / keep), seed, seed_dev);
   DRN_CHECK_LAUNCH("dropout");
   return 0;
 }

@@ -12,11 +12,17 @@
 // tiles in the 128B-swizzled K-major canonical layout; two TMEM accumulator stages (2 x BN fp32 columns)
 // so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
+// Residual add (ResNet shortcuts) rides the tensor core: after the K loop the producer streams the
+// residual tile through the same smem ring as 64-column "k-blocks" and the MMA thread multiplies them
+// with a 64x64 identity that lives in smem (D[:, 64c:64c+64] += R_c * I, exact in fp32), so the
+// shortcut is prefetched STAGES deep like any operand and the epilogue never waits on a load
+// (a TMA-loaded residual in the epilogue was latency-bound: 33 us -> see profiles/).  FrozenBN scale
+// is folded into the weights by the host when a residual is present (the kernel rejects scale+residual).
+//
 // Epilogue (bf16 output): every warp owns the 32 accumulator rows of its TMEM lane quadrant and walks
-// the tile in 64-column chunks: tcgen05.ld -> scale/bias (from smem) -> + residual -> ReLU -> dropout ->
-// bf16 -> 128B-swizzled 32x64 staging buffer -> one TMA store per chunk.  The residual chunk is TMA-
-// loaded into the same staging buffer two chunks ahead, so all global traffic of the kernel is
-// TMA (full 128 B lines) and clipping of partial tiles is done by the TMA unit.  fp32 output (head
+// the tile in 64-column chunks: tcgen05.ld -> scale/bias (from smem) -> ReLU -> dropout -> bf16 ->
+// 128B-swizzled 32x64 staging buffer -> one TMA store per chunk, so all global traffic of the kernel
+// is TMA (full 128 B lines) and clipping of partial tiles is done by the TMA unit.  fp32 output (head
 // logits, a few hundred KB) keeps a direct register->global path.
 #include "common.cuh"
 #include <cuda.h>
@@ -30,6 +36,7 @@ constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;
 constexpr int EPI_CHUNK = 64;                    // columns per staging buffer (128 B of bf16)
 constexpr int EPI_BUF_BYTES = 32 * EPI_CHUNK * 2;  // 32 rows x 128 B
+constexpr int IDENT_BYTES = 64 * 64 * 2;           // 64x64 bf16 identity (B operand of the residual MMAs)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -152,6 +159,7 @@ struct Params {
   uint32_t drop_keep_thresh;  // 0 = no dropout
   float drop_inv_keep;
   unsigned long long drop_seed;
+  const unsigned long long* drop_seed_dev;  // optional device-resident addend (fresh masks under graph replay)
 };
 
 template <int BN, int STAGES, int NBUF>
@@ -164,13 +172,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;                        // 1024-aligned (stage sizes are multiples of 1 KB)
-  float* sb_smem = reinterpret_cast<float*>(epi_smem + EPI_BYTES);        // [2 acc stages][scale BN | bias BN]
+  uint8_t* ident = epi_smem + EPI_BYTES;                                  // 8 KB, 1024-aligned
+  float* sb_smem = reinterpret_cast<float*>(ident + IDENT_BYTES);         // [2 acc stages][scale BN | bias BN]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sb_smem + 4 * BN);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* res_bar = tempty_bar + 2;                                     // [4 warps][NBUF]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4 * NBUF);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
@@ -182,13 +190,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (p.has_residual) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_r) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
-    for (int s = 0; s < 4 * NBUF; ++s) mbar_init(&res_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (p.has_residual && threadIdx.x >= 64 && threadIdx.x < 128) {
+    // identity in the canonical K-major SWIZZLE_128B layout: row n at n*128, 16-byte chunk q at (q ^ (n & 7))
+    const int n = threadIdx.x - 64;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (q == (n >> 3)) {
+        const uint32_t one = 0x3F80u << (16 * (n & 1));  // bf16 1.0 at element n & 7 of the chunk
+        const int wsel = (n & 7) >> 1;
+        v.x = wsel == 0 ? one : 0u; v.y = wsel == 1 ? one : 0u; v.z = wsel == 2 ? one : 0u; v.w = wsel == 3 ? one : 0u;
+      }
+      *reinterpret_cast<uint4*>(ident + n * 128 + ((q ^ (n & 7)) << 4)) = v;
+    }
+    fence_async_smem();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -226,6 +248,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tma_load_2d(&map_b, &full_bar[stage], sb, kb * BK, nt * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if (p.has_residual) {
+          const int nchunk = (min(BN, p.N - nt * BN) + EPI_CHUNK - 1) / EPI_CHUNK;
+          for (int c = 0; c < nchunk; ++c) {  // shortcut tile as extra "k-blocks": 128 rows x 64 output columns each
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], A_BYTES);
+            uint8_t* sa = smem + stage * STAGE_BYTES;
+            if (p.conv)
+              tma_load_4d(&map_r, &full_bar[stage], sa, nt * BN + c * EPI_CHUNK, w0, h0, img);
+            else
+              tma_load_2d(&map_r, &full_bar[stage], sa, nt * BN + c * EPI_CHUNK, mt * BM);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -251,8 +286,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-          if (kb == p.KB - 1) umma_commit(&tfull_bar[acc]);
+          if (kb == p.KB - 1 && !p.has_residual) umma_commit(&tfull_bar[acc]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (p.has_residual) {
+          const int nt = tile / p.num_m_tiles;
+          const int nchunk = (min(BN, p.N - nt * BN) + EPI_CHUNK - 1) / EPI_CHUNK;
+          constexpr uint32_t idesc64 = make_idesc(64);
+          const uint64_t idesc_b = make_smem_desc(smem_u32(ident));
+          for (int c = 0; c < nchunk; ++c) {
+            mbar_wait(&full_bar[stage], phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t adesc = make_smem_desc(smem_u32(smem + stage * STAGE_BYTES));
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_bf16(tmem_d + c * EPI_CHUNK, adesc + 2 * k, idesc_b + 2 * k, idesc64, 1u);
+            umma_commit(&empty_bar[stage]);
+            if (c == nchunk - 1) umma_commit(&tfull_bar[acc]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
@@ -263,20 +315,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int row = quad * 32 + lane;
     const int etid = (warp - 2) * 32 + lane;  // 0..127 within the epilogue group
     uint8_t* my_bufs = epi_smem + quad * (NBUF * EPI_BUF_BYTES);
-    uint64_t* my_res_bar = res_bar + quad * NBUF;
     const uint32_t sw_xor = (uint32_t)(lane & 7);
     // warp's 32-row sub-box inside a conv tile
     const int sub_h = (quad * 32) / (p.conv ? p.tile_w : 32), sub_w = (quad * 32) % (p.conv ? p.tile_w : 32);
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t gchunk = 0;  // running chunk counter of this warp -> staging buffer ring position
+    uint32_t gchunk = 0;  // running chunk counter of this warp -> staging ring slot (one bulk group per chunk)
+    const unsigned long long drop_seed = p.drop_seed + ((p.drop_keep_thresh && p.drop_seed_dev) ? __ldg(p.drop_seed_dev) : 0ull);
     constexpr int NCHUNK = (BN + EPI_CHUNK - 1) / EPI_CHUNK;
-    // Staging ring discipline (per warp, one bulk group per stored chunk, chunk g lives in slot g % NBUF):
-    // a slot may be overwritten once the store of chunk g - NBUF has drained.  Residual chunks are
-    // TMA-loaded PREFETCH chunks ahead; when chunk g starts, the youngest committed store is g - 1, so
-    // the load for chunk g + PREFETCH may leave NBUF - PREFETCH - 1 stores pending.
-    // NBUF < 3 (deep-K GEMMs that spend the smem on pipeline stages instead): no residual support.
-    constexpr int PREFETCH = NBUF >= 3 ? NBUF - 2 : 0;
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile % p.num_m_tiles, nt = tile / p.num_m_tiles;
@@ -309,20 +355,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
 
-      auto issue_residual = [&](int c, uint32_t g) {
-        // lane 0 only: TMA-load residual chunk c of this tile into ring slot g % NBUF (slot already free)
-        const int b = g % NBUF;
-        mbar_arrive_expect_tx(&my_res_bar[b], EPI_BUF_BYTES);
-        if (p.conv)
-          tma_load_4d(&map_r, &my_res_bar[b], my_bufs + b * EPI_BUF_BYTES, nt * BN + c * EPI_CHUNK, ww0 + sub_w, hh0 + sub_h, img);
-        else
-          tma_load_2d(&map_r, &my_res_bar[b], my_bufs + b * EPI_BUF_BYTES, nt * BN + c * EPI_CHUNK, mt * BM + quad * 32);
-      };
-      if (NBUF >= 3 && !p.out_f32 && p.has_residual && lane == 0) {
-        bulk_wait_read<NBUF - PREFETCH>();
-        for (int c = 0; c < PREFETCH && c < nchunk; ++c) issue_residual(c, gchunk + c);
-      }
-
       mbar_wait(&tfull_bar[acc], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
@@ -335,16 +367,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t g = gchunk + c;
           const int b = g % NBUF;
           uint8_t* buf = my_bufs + b * EPI_BUF_BYTES;
-          if (NBUF >= 3 && p.has_residual) {
-            if (lane == 0 && c + PREFETCH < nchunk) {
-              bulk_wait_read<(NBUF >= 3 ? NBUF - PREFETCH - 1 : 0)>();
-              issue_residual(c + PREFETCH, g + PREFETCH);
-            }
-            mbar_wait(&my_res_bar[b], (g / NBUF) & 1);
-          } else {
-            if (lane == 0) bulk_wait_read<NBUF - 1>();
-            __syncwarp();
-          }
+          if (lane == 0) bulk_wait_read<NBUF - 1>();  // the store that last used this slot has drained
+          __syncwarp();
           uint8_t* my_row = buf + lane * 128;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
@@ -365,21 +389,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               f[6] = fmaf(__uint_as_float(v[j + 6]), s1.z, b1.z); f[7] = fmaf(__uint_as_float(v[j + 7]), s1.w, b1.w);
               const uint32_t q = (uint32_t)(half * 4 + (j >> 3));
               uint4* slot = reinterpret_cast<uint4*>(my_row + ((q ^ sw_xor) << 4));
-              if (NBUF >= 3 && p.has_residual) {
-                const uint4 rv = *slot;
-                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                  const float2 rf = __bfloat1622float2(r2[t]);
-                  f[2 * t] += rf.x; f[2 * t + 1] += rf.y;
-                }
-              }
               if (p.relu) {
 #pragma unroll
                 for (int t = 0; t < 8; ++t) f[t] = fmaxf(f[t], 0.f);
               }
               if (p.drop_keep_thresh) {
-                const unsigned long long base = p.drop_seed * 0x100000001B3ull +
+                const unsigned long long base = drop_seed * 0x100000001B3ull +
                                                 (unsigned long long)m_global * (unsigned long long)p.N +
                                                 (unsigned long long)(nt * BN + cl + j);
 #pragma unroll
@@ -488,8 +503,8 @@ static int num_sms() {
 template <int BN, int STAGES, int NBUF>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mr, const Params& p,
                   cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 4 * NBUF * EPI_BUF_BYTES + 4 * BN * sizeof(float) +
-                          (2 * STAGES + 4 + 4 * NBUF) * sizeof(uint64_t) + 16 + 1024;
+  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 4 * NBUF * EPI_BUF_BYTES + IDENT_BYTES +
+                          4 * BN * sizeof(float) + (2 * STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
   static_assert(smem <= 232448, "gemm_tc: shared memory budget exceeded");
   static bool configured = false;
   if (!configured) {
@@ -547,7 +562,7 @@ using namespace drn;
 extern "C" int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int Cin, const void* w, int ksize,
                                       int dilation, const float* scale, const float* bias, const void* residual,
                                       int relu, void* out, int out_dtype, int Cout, int ldo, float dropout_p,
-                                      uint64_t dropout_seed, drn_stream_t stream) {
+                                      uint64_t dropout_seed, const uint64_t* dropout_seed_dev, drn_stream_t stream) {
   using namespace drn::tc;
   DRN_CHECK_ARG(in && w && out, "conv_igemm_bf16_tc: null pointer");
   DRN_CHECK_ARG(ksize == 1 || ksize == 3, "conv_igemm_bf16_tc: ksize %d", ksize);
@@ -558,7 +573,7 @@ extern "C" int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int C
                     ((uintptr_t)residual % 16 == 0),
                 "conv_igemm_bf16_tc: operands must be 16-byte aligned");
   DRN_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "conv_igemm_bf16_tc: dropout p=%f", dropout_p);
-  DRN_CHECK_ARG(!(residual && out_dtype == DRN_F32), "conv_igemm_bf16_tc: residual needs bf16 output");
+  DRN_CHECK_ARG(!(residual && scale), "conv_igemm_bf16_tc: fold the per-channel scale into the weights when a residual is given");
   DRN_CHECK_ARG(!(dropout_p > 0.f && out_dtype == DRN_F32), "conv_igemm_bf16_tc: fused dropout needs bf16 output");
   const long long Mll = (long long)N * H * W;
   if (Mll == 0) return 0;
@@ -572,6 +587,7 @@ extern "C" int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int C
     p.drop_keep_thresh = (uint32_t)(keep * 4294967295.0);
     p.drop_inv_keep = (float)(1.0 / keep);
     p.drop_seed = dropout_seed;
+    p.drop_seed_dev = (const unsigned long long*)dropout_seed_dev;
   }
   const int Ktot = ksize * ksize * Cin;
   p.KB = Ktot / BK;
@@ -593,10 +609,12 @@ extern "C" int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int C
       const cuuint64_t odims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
       const cuuint64_t ostr[3] = {(cuuint64_t)ldo * 2, (cuuint64_t)W * ldo * 2, (cuuint64_t)H * W * ldo * 2};
       if (make_map(&mo, out, 4, odims, ostr, obox)) return 1;
-      if (residual) {
-        const cuuint64_t rstr[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, (cuuint64_t)H * W * Cout * 2};
-        if (make_map(&mr, residual, 4, odims, rstr, obox)) return 1;
-      }
+    }
+    if (residual) {
+      const cuuint64_t rdims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+      const cuuint64_t rstr[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, (cuuint64_t)H * W * Cout * 2};
+      const cuuint32_t rbox[4] = {EPI_CHUNK, (cuuint32_t)p.tile_w, (cuuint32_t)p.tile_h, 1};
+      if (make_map(&mr, residual, 4, rdims, rstr, rbox)) return 1;
     }
   } else {
     p.conv = 0; p.M = (int)Mll; p.tile_w = 32; p.tile_h = 4;
@@ -610,10 +628,12 @@ extern "C" int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int C
       const cuuint64_t odims[2] = {(cuuint64_t)Cout, (cuuint64_t)Mll};
       const cuuint64_t ostr[1] = {(cuuint64_t)ldo * 2};
       if (make_map(&mo, out, 2, odims, ostr, obox)) return 1;
-      if (residual) {
-        const cuuint64_t rstr[1] = {(cuuint64_t)Cout * 2};
-        if (make_map(&mr, residual, 2, odims, rstr, obox)) return 1;
-      }
+    }
+    if (residual) {
+      const cuuint64_t rdims[2] = {(cuuint64_t)Cout, (cuuint64_t)Mll};
+      const cuuint64_t rstr[1] = {(cuuint64_t)Cout * 2};
+      const cuuint32_t rbox[2] = {EPI_CHUNK, BM};
+      if (make_map(&mr, residual, 2, rdims, rstr, rbox)) return 1;
     }
   }
   const int bn = pick_bn(p.num_m_tiles, Cout, p.KB);
@@ -625,8 +645,8 @@ extern "C" int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int C
     if (make_map(&mb, w, 2, dims, strides, box)) return 1;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (bn == 256 && !residual && p.KB >= 48) return launch<256, 4, 1>(ma, mb, mo, mr, p, st);  // deep K: stages over staging
+  if (bn == 256 && p.KB >= 48) return launch<256, 4, 1>(ma, mb, mo, mr, p, st);  // deep K: smem goes to pipeline stages
   if (bn == 256) return launch<256, 3, 4>(ma, mb, mo, mr, p, st);
-  if (bn == 128) return launch<128, 4, 4>(ma, mb, mo, mr, p, st);
-  return launch<64, 6, 4>(ma, mb, mo, mr, p, st);
+  if (bn == 128) return launch<128, 5, 2>(ma, mb, mo, mr, p, st);
+  return launch<64, 7, 2>(ma, mb, mo, mr, p, st);
 }

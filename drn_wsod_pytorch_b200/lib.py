@@ -24,7 +24,7 @@ _PROTOS = {
     "drn_conv3x3_c3_fwd": [_P, c_int, c_int, c_int, c_int, _FP, _FP, _P, _P, _P, c_int, c_int, c_int, _P, c_int, _P],
     "drn_conv_igemm_f32": [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, _P, _P, c_int, _P, c_int, c_int, _P],
     "drn_conv_igemm_bf16_tc": [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, _P, _P, c_int, _P, c_int, c_int, c_int,
-                               c_float, c_uint64, _P],
+                               c_float, c_uint64, _P, _P],
     "drn_maxpool2x2_nhwc": [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "drn_roipool_fwd": [_P, c_int, c_int, c_int, _P, _P, c_int, c_float, c_int, _P, _P, c_size_t, _P],
     "drn_wsddn_mil_fwd": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_float, _P, _P, _P, _P, _P],
@@ -33,7 +33,7 @@ _PROTOS = {
     "drn_oicr_stage_fwd": [_P, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, c_float, _P, _P, _P, _P, _P, _P, _P],
     "drn_oicr_boxreg_loss": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _FP, c_float, c_float, _P, _P, _P, _P],
     "drn_oicr_infer": [_P, c_int, c_int, c_int, c_int, c_int, _IP, _IP, _P, _FP, _P, _P, _P],
-    "drn_dropout_inplace": [_P, c_int64, c_int, c_float, c_uint64, _P],
+    "drn_dropout_inplace": [_P, c_int64, c_int, c_float, c_uint64, _P, _P],
     "drn_cast_f32_to_bf16": [_P, _P, c_int64, _P],
     "drn_cast_bf16_to_f32": [_P, _P, c_int64, _P],
 }

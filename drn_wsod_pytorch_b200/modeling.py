@@ -92,6 +92,11 @@ class Conv2d(nn.Module):
             if self.in_channels == 3 or precision == "fp32":
                 wp = w.permute(2, 3, 1, 0).reshape(-1, cout).contiguous()  # [(kh,kw,cin)][cout]
             else:
+                # tensor-core path: FrozenBN scale folded into the bf16 filter (the epilogue is bias-only and
+                # the shortcut can be accumulated by the MMA itself, see csrc/drn_tc.cu)
+                if scale is not None:
+                    w = w * scale.view(-1, 1, 1, 1)
+                    scale = None
                 wp = w.permute(0, 2, 3, 1).reshape(cout, -1).contiguous().to(torch.bfloat16)  # [cout][(kh,kw,cin)]
         hit = {"key": key, "w": wp, "scale": scale, "bias": bias, "cout": cout}
         self._cache[precision] = hit
@@ -142,17 +147,19 @@ def run_conv(conv: Conv2d, x, precision, relu, residual=None):
 
 def run_linear(x2d, packed, precision, relu, out_dtype=None, dropout=None):
     """x2d: [M, K] -> [M, Npad] through the same implicit-GEMM kernels (a linear layer is a 1x1 conv
-    over an M x 1 'image').  dropout = (p, seed): train-mode F.dropout, fused into the tensor-core
-    epilogue on the bf16 path, a separate in-place kernel on the exact-fp32 path."""
+    over an M x 1 'image').  dropout = (p, seed, seed_dev): train-mode F.dropout (effective seed =
+    seed + *seed_dev), fused into the tensor-core epilogue on the bf16 path, a separate in-place kernel
+    on the exact-fp32 path."""
     M, K = x2d.shape
     x4 = x2d.view(1, M, 1, K)
     if precision == "fp32":
         y = ops.conv_f32(x4, packed, 1, 1, relu)
         if dropout is not None:
-            ops.dropout_(y, dropout[0], dropout[1])
+            ops.dropout_(y, dropout[0], dropout[1], dropout[2])
     else:
-        dp, ds = dropout if dropout is not None else (0.0, 0)
-        y = ops.conv_bf16_tc(x4, packed, 1, 1, relu, out_dtype=out_dtype or torch.bfloat16, dropout_p=dp, dropout_seed=ds)
+        dp, ds, dd = dropout if dropout is not None else (0.0, 0, None)
+        y = ops.conv_bf16_tc(x4, packed, 1, 1, relu, out_dtype=out_dtype or torch.bfloat16, dropout_p=dp, dropout_seed=ds,
+                             dropout_seed_dev=dd)
     return y.view(M, packed["cout"])
 
 
@@ -397,7 +404,7 @@ class DiscriminativeAdaptionNeck(nn.Module):
             size = dim
         self._output_size = size
         self.precision = precision_of(cfg)
-        self._seed = 0
+        self._seed_dev = None  # device-resident dropout counter: advances inside captured CUDA graphs too
 
     @property
     def output_shape(self):
@@ -406,13 +413,14 @@ class DiscriminativeAdaptionNeck(nn.Module):
     def run(self, pooled2d, bin_major):
         """pooled2d: [R, 49*C] (bin-major from the fused ROIPool) or [R, C*49] (reference order)."""
         x = pooled2d
+        if self.training and (self._seed_dev is None or self._seed_dev.device != x.device):
+            self._seed_dev = torch.zeros((1,), dtype=torch.int64, device=x.device)
         for i, fc in enumerate(self.fcs):
             perm = self.in_channels if (i == 0 and bin_major) else None
-            drop = None
-            if self.training:  # box_head.py:90
-                self._seed += 1
-                drop = (0.5, self._seed)
+            drop = (0.5, i + 1, self._seed_dev) if self.training else None  # box_head.py:90
             x = run_linear(x, fc.packed(self.precision, permute_c49=perm), self.precision, relu=True, dropout=drop)
+        if self.training:
+            self._seed_dev.add_(len(self.fcs))  # next call draws a fresh mask (captured as a graph node)
         return x
 
     def forward(self, x):
@@ -540,6 +548,8 @@ class _WSLROIHeads(nn.Module):
         self.output_dir, self.vis_test, self.vis_period = cfg.OUTPUT_DIR, cfg.WSL.VIS_TEST, cfg.VIS_PERIOD
         self._heads_cache = None
         self._counter = None
+        self._gt_cache = {}
+        self._device = torch.device(cfg.MODEL.DEVICE)
         self.last_trace = None
         self.keep_trace = False
 
@@ -574,26 +584,37 @@ class _WSLROIHeads(nn.Module):
             x = ops.to_bf16(x.contiguous()) if want == torch.bfloat16 else ops.to_f32(x.contiguous())
         return x.contiguous()
 
-    def _roi_logits(self, features, proposals, i):
+    def _roi_logits(self, features, boxes, obj, i):
         """ROIPool x (objectness+1) -> fc6 -> fc7 -> all head logits for image i: [R, ld] fp32."""
-        p = proposals[i]
-        boxes = p.proposal_boxes.tensor.float().contiguous()
-        obj = p.objectness_logits.float().contiguous()
         pooled = ops.roipool(self._features_hwc(features, i), boxes, obj, self.pooler_scale)
         feat = self.box_head.run(pooled, bin_major=True)
         heads = self._heads_packed()
         logits = run_linear(feat, heads, self.precision, relu=False, out_dtype=torch.float32)
-        return boxes, obj, feat, logits, heads
+        return feat, logits, heads
 
     def _image_level_gt(self, targets):
-        """roi_heads.py:137-153 (device-side unique; G is read back once per image because it sizes launches)."""
+        """roi_heads.py:137-153: sorted distinct GT classes per image + one-hot.  G (their number) sizes
+        kernel launches, so it has to be known on the host: computed with numpy when the GT arrives on
+        the CPU (the dataloader case, no device sync); for device-resident GT the result is cached on
+        the tensor's (data_ptr, version) so a repeated batch does not sync either."""
         K = self.num_classes
         out = []
         for t in targets:
-            gt = torch.unique(t.gt_classes, sorted=True).to(torch.int64)
-            oh = torch.zeros((K,), dtype=torch.float32, device=gt.device)
-            oh[gt] = 1.0
-            out.append((gt, oh))
+            gc = t.gt_classes
+            dev = self._device if gc.device.type == "cpu" else gc.device
+            key = (gc.data_ptr(), gc._version, gc.numel(), str(gc.device))
+            hit = self._gt_cache.get(key) if gc.is_cuda else None
+            if hit is None:
+                classes = sorted(set(int(c) for c in gc.tolist()))  # one D2H sync if gc lives on the device
+                gt = torch.tensor(classes, dtype=torch.int64).to(dev)
+                oh_host = torch.zeros((K,), dtype=torch.float32)
+                oh_host[classes] = 1.0
+                hit = (gt, oh_host.to(dev))
+                if gc.is_cuda:
+                    if len(self._gt_cache) > 64:
+                        self._gt_cache.clear()
+                    self._gt_cache[key] = hit
+            out.append(hit)
         self.gt_classes_img = [g for g, _ in out]
         self.gt_classes_img_int = self.gt_classes_img
         self.gt_classes_img_oh = torch.stack([o for _, o in out], dim=0) if out else None
@@ -608,14 +629,20 @@ class _WSLROIHeads(nn.Module):
     def forward(self, images, features, proposals, targets=None):
         if self.training:
             assert targets, "'targets' argument is required during training"
-            losses = self._forward_train(features, proposals, targets)
-            self.iter += 1
-            if self.iter_test > 0:
-                self.epoch_test += 1
-            self.iter_test = 0
-            return proposals, losses
-        pred_instances, all_scores, all_boxes = self._forward_eval(features, proposals)
-        self.iter_test += 1
+            self._device = proposals[0].proposal_boxes.tensor.device
+            img_gt = self._image_level_gt(targets)
+            dev_out = self._train_device(
+                features,
+                [p.proposal_boxes.tensor.float().contiguous() for p in proposals],
+                [p.objectness_logits.float().contiguous() for p in proposals],
+                [t.gt_boxes.tensor.float().contiguous() for t in targets],
+                [t.gt_classes.to(torch.int64).contiguous() for t in targets],
+                [g for g, _ in img_gt], [o for _, o in img_gt])
+            return proposals, self._train_post(dev_out, proposals, targets)
+        dev_out = self._eval_device(features,
+                                    [p.proposal_boxes.tensor.float().contiguous() for p in proposals],
+                                    [p.objectness_logits.float().contiguous() for p in proposals])
+        pred_instances, all_scores, all_boxes = self._eval_post(dev_out, proposals)
         return pred_instances, {}, all_scores, all_boxes
 
     def forward_with_given_boxes(self, features, instances):
@@ -624,11 +651,12 @@ class _WSLROIHeads(nn.Module):
         return instances, [], []
 
     # -- train ---------------------------------------------------------------------------------------
-    def _forward_train(self, features, proposals, targets):
-        K, N, S = self.num_classes, len(proposals), self.refine_K
-        dev = proposals[0].proposal_boxes.tensor.device
-        storage = _event_storage()
-        img_gt = self._image_level_gt(targets)
+    def _train_device(self, features, boxes_l, obj_l, gtb_l, gtc_l, gt_int_l, gt_oh_l):
+        """Device pipeline of roi_heads_oicr.py:320-421 for N images: launches only -- no host sync, no
+        data-dependent shapes -- so the meta-arch can capture it (together with the backbone) in a CUDA
+        graph.  Returns a dict of device tensors."""
+        K, N, S = self.num_classes, len(boxes_l), self.refine_K
+        dev = boxes_l[0].device
         if self._counter is None or self._counter.device != dev:
             self._counter = torch.zeros((1,), dtype=torch.int32, device=dev)
         nloss = 1 + S + sum(self.refine_reg)
@@ -636,21 +664,17 @@ class _WSLROIHeads(nn.Module):
         stage_stats = [[None] * N for _ in range(S)]
         label_counts = [[None] * N for _ in range(S + 1)]
         mil_scale = (1.0 / (N * N)) if self.box_predictor.mean_loss else (1.0 / N)
-        traces = []
-        img_scores = []
+        traces, img_scores, lab0_l, midx0_l = [], [], [], []
         for i in range(N):
-            boxes, obj, feat, logits, heads = self._roi_logits(features, proposals, i)
+            boxes, obj = boxes_l[i], obj_l[i]
+            feat, logits, heads = self._roi_logits(features, boxes, obj, i)
             offs = heads["offs"]
-            gt_int, gt_oh = img_gt[i]
-            tg = targets[i]
+            gt_int, gt_oh = gt_int_l[i], gt_oh_l[i]
             # labelling against the real GT (roi_heads_oicr.py:266): feeds logging + proposals' gt fields
-            lab0, midx0, cnt0 = ops.label_proposals(boxes, tg.gt_boxes.tensor.float().contiguous(),
-                                                    tg.gt_classes.to(torch.int64).contiguous(), K,
-                                                    self.iou_thresholds, self.iou_labels)
+            lab0, midx0, cnt0 = ops.label_proposals(boxes, gtb_l[i], gtc_l[i], K, self.iou_thresholds, self.iou_labels)
             label_counts[0][i] = cnt0
-            proposals[i].gt_classes = lab0
-            if len(tg) > 0:
-                proposals[i].gt_boxes = type(tg.gt_boxes)(tg.gt_boxes.tensor[midx0])
+            lab0_l.append(lab0)
+            midx0_l.append(midx0)
             scores, img_score = ops.wsddn_mil(logits, K, offs["cls"], offs["det"], gt_oh, self.box_predictor.mean_loss,
                                               mil_scale, loss_buf[i, 0:1])
             img_scores.append(img_score)
@@ -679,13 +703,30 @@ class _WSLROIHeads(nn.Module):
                 tr["stages"].append(dict(pgt_idx=pgt_idx, pgt_scores=pgt_score, pgt_boxes=pgt_box, pgt_weights=pgt_w,
                                          labels=labels, matched=midx, probs=probs, weights=weights))
             traces.append(tr)
-        self.pred_class_img_logits = torch.stack(img_scores, dim=0)
-        self.last_trace = traces if self.keep_trace else None
+        return {"loss_buf": loss_buf, "img_scores": torch.stack(img_scores, dim=0), "label_counts": label_counts,
+                "stage_stats": stage_stats, "lab0": lab0_l, "midx0": midx0_l, "traces": traces}
 
-        # assemble the loss dict (keys/normalisation of fast_rcnn.py:317-329, :1128-1144, :1146-1211)
+    def _train_post(self, d, proposals, targets):
+        """Host side of the train forward: loss dict (keys/normalisation of fast_rcnn.py:317-329,
+        :1128-1144, :1146-1211), the attributes/fields the reference sets, EventStorage scalars."""
+        K, N, S = self.num_classes, len(proposals), self.refine_K
+        loss_buf, stage_stats, label_counts = d["loss_buf"], d["stage_stats"], d["label_counts"]
+        dev = loss_buf.device
+        for i in range(N):  # roi_heads.py:314-336
+            proposals[i].gt_classes = d["lab0"][i]
+            if len(targets[i]) > 0:
+                tb = targets[i].gt_boxes
+                proposals[i].gt_boxes = type(tb)(tb.tensor.to(dev)[d["midx0"][i]])
+        self.pred_class_img_logits = d["img_scores"]
+        self.last_trace = d["traces"] if self.keep_trace else None
+        self.iter += 1
+        if self.iter_test > 0:
+            self.epoch_test += 1
+        self.iter_test = 0
+
         losses = {}
         if N == 1:
-            row = loss_buf[0]
+            row = loss_buf[0].clone()  # fresh storage: the plan's buffers are overwritten by the next replay
             losses["loss_cls"] = row[0]
             col = 1
             for k in range(S):
@@ -703,6 +744,7 @@ class _WSLROIHeads(nn.Module):
                     rs = torch.tensor([len(p) for p in proposals], dtype=torch.float32, device=dev)
                     losses[f"loss_box_reg_r{k}"] = (loss_buf[:, col] * rs).sum() / Rtot; col += 1
 
+        storage = _event_storage()
         if storage is not None:  # the reference's scalars (roi_heads.py:346-349, roi_heads_oicr.py:345-348, fast_rcnn.py:1098-1126)
             pend = []
             for s, suffix in enumerate([""] + [f"_r{k}" for k in range(S)]):
@@ -722,34 +764,44 @@ class _WSLROIHeads(nn.Module):
         return losses
 
     # -- eval ----------------------------------------------------------------------------------------
-    def _forward_eval(self, features, proposals):
+    def _eval_device(self, features, boxes_l, obj_l):
+        """Device pipeline of the eval forward up to (all_scores, all_boxes): capturable like _train_device."""
         K, S = self.num_classes, self.refine_K
-        results, all_scores, all_boxes = [], [], []
-        for i in range(len(proposals)):
-            boxes, obj, feat, logits, heads = self._roi_logits(features, proposals, i)
+        scores_l, boxes_out = [], []
+        for i in range(len(boxes_l)):
+            boxes, obj = boxes_l[i], obj_l[i]
+            feat, logits, heads = self._roi_logits(features, boxes, obj, i)
             offs = heads["offs"]
-            p = proposals[i]
             if S > 0:
                 bw = self.box_refinery[-1].bbox_w
                 ks = [S - 1] if self.refine_reg[-1] else list(range(S))
                 nreg = 1 if self.cls_agnostic_bbox_reg else K
                 sc, bx = ops.oicr_infer(logits, K, [offs[f"cls_score_{k}"] for k in ks],
                                         [offs[f"bbox_pred_{k}"] for k in ks], boxes, bw, nreg)
-                layer = self.box_refinery[-1]
             else:
-                layer = self.box_predictor
                 gt_oh = torch.zeros((K,), dtype=torch.float32, device=boxes.device)
                 dummy = torch.empty((1,), dtype=torch.float32, device=boxes.device)
                 scores, _ = ops.wsddn_mil(logits, K, offs["cls"], offs["det"], gt_oh, True, 1.0, dummy)
                 # fast_rcnn.py:668-687: zero background column; :645-666 boxes = apply_deltas(0, proposals)
                 sc = torch.cat((scores, scores.new_zeros(scores.shape[0], 1)), dim=1)
-                bx = ops.oicr_infer(logits, K, [offs["cls"]], [-1], boxes, layer.bbox_w, K)[1]
+                bx = ops.oicr_infer(logits, K, [offs["cls"]], [-1], boxes, self.box_predictor.bbox_w, K)[1]
+            scores_l.append(sc)
+            boxes_out.append(bx)
+        return {"scores": scores_l, "boxes": boxes_out}
+
+    def _eval_post(self, d, proposals):
+        """Tail of the eval forward (threshold + NMS: data-dependent shapes, stays outside the graph)."""
+        layer = self.box_refinery[-1] if self.refine_K > 0 else self.box_predictor
+        results, all_scores, all_boxes = [], [], []
+        for i, p in enumerate(proposals):
+            sc, bx = d["scores"][i].clone(), d["boxes"][i].clone()  # returned to the caller (TTA): fresh storage
             inst_cls, box_cls = type(p), type(p.proposal_boxes)
             res, _ = fast_rcnn_inference_single_image(bx, sc, p.image_size, layer.test_score_thresh, layer.test_nms_thresh,
                                                       layer.test_topk_per_image, inst_cls, box_cls)
             results.append(res)
             all_scores.append(sc.unsqueeze(0))
             all_boxes.append(bx.unsqueeze(0))
+        self.iter_test += 1
         return results, all_scores, all_boxes
 
 
@@ -772,9 +824,45 @@ class OICRROIHeads(_WSLROIHeads):
 # ------------------------------------------------------------------------------------------------
 # meta architecture
 # ------------------------------------------------------------------------------------------------
+class _GraphPlan:
+    """One captured CUDA graph of a device pipeline `fn(list_of_tensors) -> pytree of tensors` for one
+    input signature.  Inputs are copied into static buffers (directly from pinned host memory when the
+    caller hands CPU tensors), the graph is replayed, outputs are the plan's static tensors.
+
+    The hot path is ~85 small-to-large kernels; launched one by one from Python each costs ~15 us of
+    host time, which is more than most backbone layers take on the GPU -- a graph replay costs one
+    launch."""
+
+    def __init__(self, fn, inputs):
+        dev = next(t.device for t in inputs if t.is_cuda)
+        self.static_in = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in inputs]
+        for st, t in zip(self.static_in, inputs):
+            st.copy_(t, non_blocking=True)
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):  # eager warm-up: one-time lazy init (smem attributes, weight packing, scratch)
+            fn(self.static_in)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        ops.drop_scratch(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = fn(self.static_in)
+
+    def run(self, inputs):
+        for st, t in zip(self.static_in, inputs):
+            if st.data_ptr() != t.data_ptr():
+                st.copy_(t, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
 @META_ARCH_REGISTRY.register()
 class GeneralizedRCNNWSL(nn.Module):
     """projects/WSL/wsl/modeling/meta_arch/rcnn.py:23-265 with precomputed proposals."""
+
+    MAX_PLANS = 8  # captured graphs kept alive (each owns its activation pool)
 
     def __init__(self, cfg):
         super().__init__()
@@ -790,6 +878,11 @@ class GeneralizedRCNNWSL(nn.Module):
         assert self.pixel_mean.shape == self.pixel_std.shape
         self.cpg = False
         self._mean_std_host = None
+        b = cfg.get("B200") if hasattr(cfg, "get") else None
+        self.use_cuda_graph = bool(b.get("CUDA_GRAPH", True)) if b is not None else True
+        if os.environ.get("DRN_B200_CUDA_GRAPH") is not None:
+            self.use_cuda_graph = os.environ["DRN_B200_CUDA_GRAPH"] not in ("0", "false", "False")
+        self._plans = {}
 
     @property
     def device(self):
@@ -801,10 +894,27 @@ class GeneralizedRCNNWSL(nn.Module):
             self._mean_std_host = (key, self.pixel_mean.flatten().tolist(), self.pixel_std.flatten().tolist())
         return self._mean_std_host[1], self._mean_std_host[2]
 
+    def invalidate_plans(self):
+        """Drop every captured graph (they hold pointers to derived weight layouts)."""
+        self._plans.clear()
+
+    def _apply(self, fn, *a, **k):
+        self._plans = {}
+        self._sig_tensors = None
+        return super()._apply(fn, *a, **k)
+
+    def _weights_signature(self):
+        """Cheap staleness check for the captured plans: in-place updates (load_state_dict, an optimizer
+        step) bump the version counters; module-level moves go through _apply and drop the plans."""
+        if getattr(self, "_sig_tensors", None) is None:
+            self._sig_tensors = list(self.state_dict(keep_vars=True).values())
+        return tuple(t._version for t in self._sig_tensors)
+
     def preprocess_image(self, batched_inputs):
-        """rcnn.py:242-249.  Normalisation is fused into the first conv, so this only moves the raw
-        images to the device and records the zero-padded canvas ImageList.from_tensors would build."""
-        images = [x["image"].to(self.device, non_blocking=True).float().contiguous() for x in batched_inputs]
+        """rcnn.py:242-249.  Normalisation is fused into the first conv, so this only records the images
+        (moved to the device as fp32, or left on the host for the graph plan to copy into its static
+        buffers) and the zero-padded canvas ImageList.from_tensors would build."""
+        images = [x["image"] for x in batched_inputs]
         sizes = [(im.shape[-2], im.shape[-1]) for im in images]
         canvas = (max(s[0] for s in sizes), max(s[1] for s in sizes))
         return images, sizes, canvas
@@ -815,28 +925,77 @@ class GeneralizedRCNNWSL(nn.Module):
         f = feats[0] if len(feats) == 1 else torch.cat(feats, dim=0)
         return {self.backbone._out_features[0]: f.permute(0, 3, 1, 2)}
 
+    def _run_device(self, kind, canvas, groups, fn):
+        """Run `fn(flat tensor list)` eagerly or through the captured plan for this input signature.
+        groups: list of equally long tensor lists (one entry per image)."""
+        flat = [t for g in groups for t in g]
+        if not self.use_cuda_graph:
+            dev = self.device
+            flat = [t.to(dev, non_blocking=True) for t in flat]
+            flat[: len(groups[0])] = [t.float().contiguous() for t in flat[: len(groups[0])]]
+            return fn(flat)
+        key = (kind, canvas, self.roi_heads.keep_trace, tuple((tuple(t.shape), t.dtype) for t in flat), self._weights_signature())
+        plan = self._plans.get(key)
+        if plan is None:
+            if len(self._plans) >= self.MAX_PLANS:
+                self._plans.pop(next(iter(self._plans)))
+            img_n = len(groups[0])
+            proto = [t.to(torch.float32) if i < img_n else t for i, t in enumerate(flat)]
+            dev = self.device
+            proto = [t if t.is_cuda else t.to(dev) for t in proto]
+            plan = _GraphPlan(fn, proto)
+            self._plans[key] = plan
+        return plan.run(flat)
+
     def forward(self, batched_inputs):
         if not self.training:
             return self.inference(batched_inputs)
         images, sizes, canvas = self.preprocess_image(batched_inputs)
-        gt_instances = [x["instances"].to(self.device) for x in batched_inputs] if "instances" in batched_inputs[0] else None
-        features = self._features(images, canvas)
         assert self.load_proposals and "proposals" in batched_inputs[0]
-        proposals = [x["proposals"].to(self.device) for x in batched_inputs]
-        _, detector_losses = self.roi_heads(ImageList(None, sizes), features, proposals, gt_instances)
+        assert "instances" in batched_inputs[0], "'targets' argument is required during training"
+        n = len(images)
+        rh = self.roi_heads
+        rh._device = self.device
+        targets = [x["instances"] for x in batched_inputs]
+        proposals = [x["proposals"] for x in batched_inputs]
+        img_gt = rh._image_level_gt(targets)  # host-known G (no sync for CPU-resident / repeated GT)
+
+        def fn(flat):
+            g = [flat[i * n:(i + 1) * n] for i in range(7)]
+            features = self._features(g[0], canvas)
+            return rh._train_device(features, g[1], g[2], g[3], g[4], g[5], g[6])
+
+        groups = [images,
+                  [p.proposal_boxes.tensor for p in proposals], [p.objectness_logits for p in proposals],
+                  [t.gt_boxes.tensor for t in targets], [t.gt_classes for t in targets],
+                  [g for g, _ in img_gt], [o for _, o in img_gt]]
+        groups = [[t if t.dtype in (torch.int64, torch.uint8) or i == 0 else t.float() for t in g] for i, g in enumerate(groups)]
+        dev_out = self._run_device("train", canvas, groups, fn)
+        proposals = [p.to(self.device) for p in proposals]
         losses = {}
-        losses.update(detector_losses)
+        losses.update(rh._train_post(dev_out, proposals, targets))
         return losses
 
     def inference(self, batched_inputs, detected_instances=None, do_postprocess=True):
         assert not self.training
         images, sizes, canvas = self.preprocess_image(batched_inputs)
-        features = self._features(images, canvas)
         if detected_instances is None:
             assert self.load_proposals and "proposals" in batched_inputs[0]
-            proposals = [x["proposals"].to(self.device) for x in batched_inputs]
-            results, _, all_scores, all_boxes = self.roi_heads(ImageList(None, sizes), features, proposals, None)
+            n = len(images)
+            rh = self.roi_heads
+            proposals = [x["proposals"] for x in batched_inputs]
+
+            def fn(flat):
+                g = [flat[i * n:(i + 1) * n] for i in range(3)]
+                return rh._eval_device(self._features(g[0], canvas), g[1], g[2])
+
+            groups = [images, [p.proposal_boxes.tensor.float() for p in proposals],
+                      [p.objectness_logits.float() for p in proposals]]
+            dev_out = self._run_device("eval", canvas, groups, fn)
+            proposals = [p.to(self.device) for p in proposals]
+            results, all_scores, all_boxes = rh._eval_post(dev_out, proposals)
         else:
+            features = self._features([im.to(self.device).float().contiguous() for im in images], canvas)
             detected_instances = [x.to(self.device) for x in detected_instances]
             results, all_scores, all_boxes = self.roi_heads.forward_with_given_boxes(features, detected_instances)
         if do_postprocess:

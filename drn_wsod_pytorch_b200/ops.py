@@ -51,14 +51,16 @@ def conv_f32(x, packed, ksize, dilation, relu, residual=None, out=None, ldo=None
     return out
 
 
-def conv_bf16_tc(x, packed, ksize, dilation, relu, residual=None, out_dtype=torch.bfloat16, dropout_p=0.0, dropout_seed=0):
+def conv_bf16_tc(x, packed, ksize, dilation, relu, residual=None, out_dtype=torch.bfloat16, dropout_p=0.0, dropout_seed=0,
+                 dropout_seed_dev=None):
     """tcgen05 implicit-GEMM conv / linear (+ fused train-mode dropout).  x: [N,H,W,Cin] bf16 NHWC."""
     _chk(x, "x")
     N, H, W, Cin = x.shape
     Cout = packed["cout"]
     out = torch.empty((N, H, W, Cout), device=x.device, dtype=out_dtype)
     call("drn_conv_igemm_bf16_tc", x, N, H, W, Cin, packed["w"], ksize, dilation, packed["scale"], packed["bias"],
-         residual, int(relu), out, _dt(out), Cout, Cout, float(dropout_p), int(dropout_seed), current_stream())
+         residual, int(relu), out, _dt(out), Cout, Cout, float(dropout_p), int(dropout_seed), dropout_seed_dev,
+         current_stream())
     return out
 
 
@@ -97,8 +99,15 @@ def roipool(feat_hwc, boxes, objectness, spatial_scale, use_tables=None):
     return out
 
 
-def dropout_(x, p, seed):
-    call("drn_dropout_inplace", x, x.numel(), _dt(x), float(p), int(seed), current_stream())
+def drop_scratch(stream):
+    """Free the grow-only scratch buffers that were created for `stream` (a warm-up side stream)."""
+    for key in [k for k in _ROIPOOL_WS if k[1] == stream.cuda_stream]:
+        del _ROIPOOL_WS[key]
+
+
+def dropout_(x, p, seed, seed_dev=None):
+    """In place.  Effective seed = seed + *seed_dev (seed_dev: 1-element int64 device tensor or None)."""
+    call("drn_dropout_inplace", x, x.numel(), _dt(x), float(p), int(seed), seed_dev, current_stream())
     return x
 
 

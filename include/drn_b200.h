@@ -58,14 +58,16 @@ int drn_conv_igemm_f32(const float* in, int N, int H, int W, int Cin, const floa
 /* Tensor-core (tcgen05/TMEM/TMA) implicit-GEMM convolution / linear layer, bf16 in, fp32 accumulate.
  * Same reference lines as drn_conv_igemm_f32, plus the train-mode F.dropout of
  * WSL/roi_heads/box_head.py:90 fused into the epilogue (dropout_p > 0: same counter-based mask as
- * drn_dropout_inplace with the same seed, element index = row * Cout + col).
+ * drn_dropout_inplace with the same seed, element index = row * Cout + col; effective seed =
+ * dropout_seed + *dropout_seed_dev when the device pointer is non-NULL, so a captured CUDA graph
+ * draws a fresh mask on every replay).
  * in: [N][H][W][Cin] bf16; w: [Cout][ksize*ksize*Cin] bf16 (K-major, K order (kh,kw,cin)); bias/scale
  * fp32 [Cout]; residual bf16 [N][H][W][Cout] (pitch Cout) or NULL; out dtype DRN_BF16 or DRN_F32 (F32:
  * no residual / dropout), row pitch ldo elements.  Cin % 64 == 0, Cout % 8 == 0, ldo % 8 == 0. */
 int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int Cin, const void* w, int ksize,
                            int dilation, const float* scale, const float* bias, const void* residual,
                            int relu, void* out, int out_dtype, int Cout, int ldo, float dropout_p,
-                           uint64_t dropout_seed, drn_stream_t stream);
+                           uint64_t dropout_seed, const uint64_t* dropout_seed_dev, drn_stream_t stream);
 
 /* MaxPool2d(kernel 2, stride 1|2, padding 0), NHWC.
  * Replaces nn.MaxPool2d in WSL/backbone/resnet_ws.py:93-94,110-111,403,415 and vgg.py:93-94,108-109. */
@@ -154,10 +156,11 @@ int drn_oicr_infer(const float* logits, int ld, int R, int K, int nreg, int S, c
                    float* all_scores, float* all_boxes, drn_stream_t stream);
 
 /* Train-mode dropout of the fc6/fc7 activations, in place: x = keep ? x/(1-p) : 0 with a
- * counter-based RNG keyed by (seed, element index).
+ * counter-based RNG keyed by (seed + *seed_dev (if non-NULL), element index).
  * Replaces F.dropout(p=0.5) in WSL/roi_heads/box_head.py:90 (mask not comparable to torch's RNG;
  * parity runs keep the box head in eval mode exactly like the survey's oracle). */
-int drn_dropout_inplace(void* x, int64_t n, int dtype, float p, uint64_t seed, drn_stream_t stream);
+int drn_dropout_inplace(void* x, int64_t n, int dtype, float p, uint64_t seed, const uint64_t* seed_dev,
+                        drn_stream_t stream);
 
 /* dtype / layout helpers used by the weight cache (not on the per-image path). */
 int drn_cast_f32_to_bf16(const float* in, void* out, int64_t n, drn_stream_t stream);

@@ -168,8 +168,10 @@ def test_tc_gemm_bf16(M, K, N, relu, res, f32out):
     scale = torch.rand(N, generator=g) + 0.5
     bias = torch.randn(N, generator=g)
     r = torch.randn(M, N, generator=g).bfloat16() if res else None
+    if res:  # the shortcut is accumulated by the MMA: per-channel scale must be folded into the weights
+        w, scale = (w.float() * scale[:, None]).bfloat16(), None
     ref = _bf16_ref_gemm(a, w, scale, bias, r, relu)
-    packed = {"w": w.to(DEV), "scale": scale.to(DEV), "bias": bias.to(DEV), "cout": N}
+    packed = {"w": w.to(DEV), "scale": scale.to(DEV) if scale is not None else None, "bias": bias.to(DEV), "cout": N}
     out = ops.conv_bf16_tc(a.view(1, M, 1, K).to(DEV), packed, 1, 1, relu, r.view(1, M, 1, N).to(DEV) if res else None,
                            out_dtype=torch.float32 if f32out else torch.bfloat16)
     got = out.view(M, N).float().cpu()
@@ -188,11 +190,17 @@ def test_tc_conv3x3_bf16(cin, cout, dil, H, W, res):
     scale = torch.rand(cout, generator=g) + 0.5
     bias = torch.randn(cout, generator=g)
     r = torch.randn(N, cout, H, W, generator=g).bfloat16() if res else None
-    ref = F.conv2d(x.float(), w.float(), None, padding=dil, dilation=dil) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+    if res:  # shortcut accumulated by the MMA: scale folded into the filter
+        w, scale = (w.float() * scale.view(-1, 1, 1, 1)).bfloat16(), None
+    ref = F.conv2d(x.float(), w.float(), None, padding=dil, dilation=dil)
+    if scale is not None:
+        ref = ref * scale.view(1, -1, 1, 1)
+    ref = ref + bias.view(1, -1, 1, 1)
     if res:
         ref = ref + r.float()
     ref = F.relu(ref)
-    packed = {"w": w.permute(0, 2, 3, 1).reshape(cout, -1).contiguous().to(DEV), "scale": scale.to(DEV), "bias": bias.to(DEV), "cout": cout}
+    packed = {"w": w.permute(0, 2, 3, 1).reshape(cout, -1).contiguous().to(DEV),
+              "scale": scale.to(DEV) if scale is not None else None, "bias": bias.to(DEV), "cout": cout}
     out = ops.conv_bf16_tc(x.permute(0, 2, 3, 1).contiguous().to(DEV), packed, 3, dil, True,
                            r.permute(0, 2, 3, 1).contiguous().to(DEV) if res else None)
     torch.testing.assert_close(out.permute(0, 3, 1, 2).float().cpu(), ref, rtol=1e-2, atol=1e-2)

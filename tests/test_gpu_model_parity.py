@@ -127,3 +127,66 @@ def test_bf16_tensor_core_path_close_to_fp32_oracle(case):
     s, gs = tr["scores"].cpu().numpy(), g["img0/scores"]
     big = gs > 0.05 * gs.max()
     assert np.max(np.abs(s[big] - gs[big]) / gs[big]) < 0.25
+
+
+# ------------------------------------------------------------------ CUDA-graph plans (the default launch path)
+def test_graph_plan_replay_tracks_new_inputs_and_matches_eager():
+    """A captured plan must (a) give the eager result, (b) follow NEW input values of the same shape on
+    replay (static buffers are refilled), (c) accept host tensors, (d) re-capture on a new shape."""
+    case = "oicr_r18_small"
+    cfg, model, _ = _build(case)
+    model.train()
+    model.roi_heads.box_head.eval()
+    inp_a = helpers.case_inputs(case)
+    (H, W, R, G, seed) = helpers.CASES[case][3][0]
+    from drn_wsod_pytorch_b200 import synth
+    inp_b = [synth.make_inputs(H, W, R, seed=seed + 100, num_gt=G)]
+    inp_c = [synth.make_inputs(H + 16, W, R + 5, seed=seed + 200, num_gt=G)]
+
+    def run(inputs, graph, device=DEV):
+        model.use_cuda_graph = graph
+        out = model(helpers.to_batched(inputs, drn.Instances, drn.Boxes, device=device))
+        idx = [st["pgt_idx"].clone() for st in model.roi_heads.last_trace[0]["stages"]]
+        return {k: v.item() for k, v in out.items()}, idx
+
+    eager = {n: run(i, False) for n, i in (("a", inp_a), ("b", inp_b), ("c", inp_c))}
+    assert not model._plans
+    for name, inputs in (("a", inp_a), ("b", inp_b), ("a", inp_a), ("c", inp_c), ("b", inp_b)):
+        got, idx = run(inputs, True)
+        for k, v in eager[name][0].items():
+            assert got[k] == v, (name, k, got[k], v)  # same kernels, same order: bit-identical
+        for x, y in zip(idx, eager[name][1]):
+            assert torch.equal(x, y)
+    assert len(model._plans) == 2  # (a, b) share one plan, c has its own
+    got, _ = run(inp_b, True, device="cpu")  # host tensors: copied H2D into the plan's static buffers
+    assert got == eager["b"][0]
+    # stale-weight protection: an in-place parameter update must not replay the old packed weights
+    with torch.no_grad():
+        model.roi_heads.box_predictor.cls.bias[3] += 2.0  # (a uniform shift would cancel in the softmax)
+    changed, _ = run(inp_a, True)
+    model.use_cuda_graph = False
+    ref, _ = run(inp_a, False)
+    assert changed == ref and changed["loss_cls"] != eager["a"][0]["loss_cls"]
+
+
+def test_graph_plan_eval_matches_eager_and_dropout_mask_advances():
+    case = "oicr_r18_small"
+    cfg, model, _ = _build(case)
+    inputs = helpers.case_inputs(case)
+    model.eval()
+    outs = []
+    for graph in (False, True, True):
+        model.use_cuda_graph = graph
+        res, sc, bx = model.inference(helpers.to_batched(inputs, drn.Instances, drn.Boxes, device=DEV, train=False),
+                                      do_postprocess=False)
+        outs.append((sc[0].clone(), bx[0].clone(), res[0].scores.clone()))
+    for o in outs[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(o, outs[0]))
+    # train mode with dropout ON: consecutive replays of one plan must draw different masks
+    model.train()
+    model.use_cuda_graph = True
+    batched = helpers.to_batched(inputs, drn.Instances, drn.Boxes, device=DEV)
+    l1 = model(batched)["loss_cls_r0"].item()
+    l2 = model(batched)["loss_cls_r0"].item()
+    l3 = model(batched)["loss_cls_r0"].item()
+    assert len({l1, l2, l3}) == 3

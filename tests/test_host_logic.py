@@ -27,14 +27,14 @@ def test_cabi_library_exports_every_header_symbol():
     assert len(syms) >= 15
     for s in syms:
         assert hasattr(handle, s), f"{s} declared in include/drn_b200.h but not exported"
-    assert set(lib._PROTOS) | {"drn_last_error"} == set(syms), "lib.py prototypes out of sync with the header"
+    assert set(lib._PROTOS) | {"drn_last_error", "drn_roipool_workspace_bytes"} == set(syms), "lib.py prototypes out of sync with the header"
     handle.drn_version.restype = ctypes.c_int
     assert handle.drn_version() >= 100
 
 
 def test_cabi_argument_errors_are_reported_not_crashed():
     handle = lib.load()
-    rc = handle.drn_roipool_fwd(None, 4, 4, 64, None, None, 3, ctypes.c_float(0.125), 0, None, None)
+    rc = handle.drn_roipool_fwd(None, 4, 4, 64, None, None, 3, ctypes.c_float(0.125), 0, None, None, 0, None)
     assert rc != 0 and b"null pointer" in handle.drn_last_error()
     with pytest.raises(RuntimeError, match="Cin"):
         lib.call("drn_conv_igemm_f32", 1, 1, 4, 4, 3, 1, 3, 1, None, None, None, 0, 1, 64, 64, None)

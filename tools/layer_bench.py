@@ -61,10 +61,16 @@ def main():
     for key, (cnt, (x, packed, ksize, dil, relu, res, kw)) in agg.items():
         for _ in range(3):
             orig(x, packed, ksize, dil, relu, res, **kw)
+        # capture REPS back-to-back launches in a CUDA graph so the number is GPU time, not Python launch time
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            for _ in range(args.reps):
+                orig(x, packed, ksize, dil, relu, res, **kw)
+        gr.replay()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(args.reps):
-            orig(x, packed, ksize, dil, relu, res, **kw)
+        gr.replay()
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / args.reps

@@ -26,6 +26,8 @@
 // logits, a few hundred KB) keeps a direct register->global path.
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace drn {
 namespace tc {
@@ -85,6 +87,33 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- CTA-pair (cta_group::2) variants.  In a 2-CTA cluster the even CTA (rank 0) is the MMA leader; the
+// shared::cluster address of "the same variable in the leader" is the local address with the peer bit
+// cleared (cute/arch/copy_sm100_tma.hpp Sm100MmaPeerBitMask).
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // arrive on the leader CTA's copy of `bar`
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
 // K-major, 128B-swizzled canonical smem descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
 // start>>4 [0,14) | LBO>>4 [16,30) (ignored for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B between
 // 8-row groups | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64).
@@ -100,8 +129,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 
 // kind::f16 instruction descriptor: D=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16 [10,13)=1, K-major A/B,
 // N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int n, int m = BM) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -114,6 +143,18 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {  // arrive on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -160,17 +201,79 @@ struct Params {
   float drop_inv_keep;
   unsigned long long drop_seed;
   const unsigned long long* drop_seed_dev;  // optional device-resident addend (fresh masks under graph replay)
+  int debug;  // DRN_TC_DEBUG (profiling experiments only): 1 = skip TMA stores, 2 = skip epilogue math, 4 = skip tcgen05.ld
 };
 
-template <int BN, int STAGES, int NBUF>
+__device__ __forceinline__ float4 lds128f(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// One 32-row x 64-column epilogue chunk of one warp: TMEM -> (scale) + bias -> max(., floor) -> (dropout) ->
+// bf16 -> this lane's 128-byte row of the swizzled staging slot.  All smem traffic uses explicit
+// shared-space instructions (LDS/STS): generic LD.E/ST.E here cost ~4x (measured, profiles/).
+template <bool SCALE, bool DROP>
+__device__ __forceinline__ void epi_chunk(uint32_t taddr, uint32_t scale_s, uint32_t bias_s, uint32_t row_s, uint32_t sw_xor,
+                                          float floor_v, unsigned long long drop_base, uint32_t keep_thresh, float inv_keep) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t v[32];
+    tmem_ld32_nowait(taddr + half * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      const int cl = half * 32 + j;
+      float f[8];
+      const float4 b0 = lds128f(bias_s + cl * 4), b1 = lds128f(bias_s + cl * 4 + 16);
+      if constexpr (SCALE) {
+        const float4 s0 = lds128f(scale_s + cl * 4), s1 = lds128f(scale_s + cl * 4 + 16);
+        f[0] = fmaf(__uint_as_float(v[j + 0]), s0.x, b0.x); f[1] = fmaf(__uint_as_float(v[j + 1]), s0.y, b0.y);
+        f[2] = fmaf(__uint_as_float(v[j + 2]), s0.z, b0.z); f[3] = fmaf(__uint_as_float(v[j + 3]), s0.w, b0.w);
+        f[4] = fmaf(__uint_as_float(v[j + 4]), s1.x, b1.x); f[5] = fmaf(__uint_as_float(v[j + 5]), s1.y, b1.y);
+        f[6] = fmaf(__uint_as_float(v[j + 6]), s1.z, b1.z); f[7] = fmaf(__uint_as_float(v[j + 7]), s1.w, b1.w);
+      } else {
+        f[0] = __uint_as_float(v[j + 0]) + b0.x; f[1] = __uint_as_float(v[j + 1]) + b0.y;
+        f[2] = __uint_as_float(v[j + 2]) + b0.z; f[3] = __uint_as_float(v[j + 3]) + b0.w;
+        f[4] = __uint_as_float(v[j + 4]) + b1.x; f[5] = __uint_as_float(v[j + 5]) + b1.y;
+        f[6] = __uint_as_float(v[j + 6]) + b1.z; f[7] = __uint_as_float(v[j + 7]) + b1.w;
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) f[t] = fmaxf(f[t], floor_v);  // ReLU: floor 0; no activation: floor -inf
+      if constexpr (DROP) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) f[t] = (mix32(drop_base + cl + t) < keep_thresh) ? f[t] * inv_keep : 0.f;
+      }
+      const uint32_t q = (uint32_t)(cl >> 3);
+      sts128(row_s + ((q ^ sw_xor) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+             pack_bf16x2(f[6], f[7]));
+    }
+  }
+}
+
+// CG = 1: one CTA computes a 128 x BN tile.  CG = 2: a CTA pair (2-CTA cluster, tcgen05 cta_group::2)
+// computes a 256 x BN tile: each CTA stages its own 128 A rows and HALF of the B rows, the leader's MMA
+// reads both halves (the peer's through the pair's shared-memory path), so the per-SM operand feed drops
+// from 16 KB + BN*128 B to 16 KB + BN*64 B per k-block -- the SM<-L2 ingest limit (~64 B/clk/SM) is what
+// bounds every GEMM here whose K loop is fed from L2.
+template <int BN, int STAGES, int NBUF, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_r, const Params p) {
-  constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t BROWS = BN / CG;                       // B rows staged by this CTA
+  constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BROWS * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   constexpr uint32_t EPI_BYTES = 4 * NBUF * EPI_BUF_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset arithmetic keeps the shared address space
   uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;                        // 1024-aligned (stage sizes are multiples of 1 KB)
   uint8_t* ident = epi_smem + EPI_BYTES;                                  // 8 KB, 1024-aligned
   float* sb_smem = reinterpret_cast<float*>(ident + IDENT_BYTES);         // [2 acc stages][scale BN | bias BN]
@@ -181,7 +284,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int cta_rank = (CG == 2) ? (int)cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
+  const int unit = blockIdx.x / CG, num_units = gridDim.x / CG;   // a unit = one CTA (CG=1) or one CTA pair
+  const int num_mp = (p.num_m_tiles + CG - 1) / CG;               // M tiles per unit step (pairs for CG=2)
+  const int num_tiles = num_mp * p.num_n_tiles;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
@@ -189,17 +296,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (!p.out_f32) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_o) : "memory");
     if (p.has_residual) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_r) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4 * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
-  if (p.has_residual && threadIdx.x >= 64 && threadIdx.x < 128) {
-    // identity in the canonical K-major SWIZZLE_128B layout: row n at n*128, 16-byte chunk q at (q ^ (n & 7))
-    const int n = threadIdx.x - 64;
+  if (p.has_residual && threadIdx.x >= 64 && threadIdx.x < 64 + 64 / CG) {
+    // (this CTA's rows of) the 64x64 identity in the canonical K-major SWIZZLE_128B layout: local row j at
+    // j*128, 16-byte chunk q at (q ^ (j & 7)); row j is output column n = rank*32 + j (CG=2) or j (CG=1)
+    const int j = threadIdx.x - 64;
+    const int n = cta_rank * (64 / CG) + j;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -208,70 +322,94 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int wsel = (n & 7) >> 1;
         v.x = wsel == 0 ? one : 0u; v.y = wsel == 1 ? one : 0u; v.z = wsel == 2 ? one : 0u; v.w = wsel == 3 ? one : 0u;
       }
-      *reinterpret_cast<uint4*>(ident + n * 128 + ((q ^ (n & 7)) << 4)) = v;
+      *reinterpret_cast<uint4*>(ident + j * 128 + ((q ^ (j & 7)) << 4)) = v;
     }
     fence_async_smem();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // peer barriers initialised before any remote arrive / 2-SM TMA
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (every CTA)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       const int cblocks = p.conv ? (p.Cin / BK) : 1;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile % p.num_m_tiles, nt = tile / p.num_m_tiles;
+      for (int tile = unit; tile < num_tiles; tile += num_units) {
+        const int mt = (tile % num_mp) * CG + cta_rank, nt = tile / num_mp;
         int img = 0, h0 = 0, w0 = 0;
         if (p.conv) {
           const int per_img = p.tiles_h * p.tiles_w;
-          img = mt / per_img;
+          img = mt / per_img;  // a padding tile of an odd pair lands at img == NB: all loads zero-fill, all stores clip
           const int r = mt - img * per_img;
           h0 = (r / p.tiles_w) * p.tile_h;
           w0 = (r % p.tiles_w) * p.tile_w;
         }
         for (int kb = 0; kb < p.KB; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], CG * STAGE_BYTES);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          if (p.conv) {
-            const int tap = kb / cblocks, cb = kb - tap * cblocks;
-            const int dh = (tap / 3 - 1) * p.dil, dw = (tap % 3 - 1) * p.dil;
-            tma_load_4d(&map_a, &full_bar[stage], sa, cb * BK, w0 + dw, h0 + dh, img);
+          const int brow = nt * BN + cta_rank * (int)BROWS;
+          if constexpr (CG == 2) {
+            if (p.conv) {
+              const int tap = kb / cblocks, cb = kb - tap * cblocks;
+              const int dh = (tap / 3 - 1) * p.dil, dw = (tap % 3 - 1) * p.dil;
+              tma2_load_4d(&map_a, &full_bar[stage], sa, cb * BK, w0 + dw, h0 + dh, img);
+            } else {
+              tma2_load_2d(&map_a, &full_bar[stage], sa, kb * BK, mt * BM);
+            }
+            tma2_load_2d(&map_b, &full_bar[stage], sb, kb * BK, brow);
           } else {
-            tma_load_2d(&map_a, &full_bar[stage], sa, kb * BK, mt * BM);
+            if (p.conv) {
+              const int tap = kb / cblocks, cb = kb - tap * cblocks;
+              const int dh = (tap / 3 - 1) * p.dil, dw = (tap % 3 - 1) * p.dil;
+              tma_load_4d(&map_a, &full_bar[stage], sa, cb * BK, w0 + dw, h0 + dh, img);
+            } else {
+              tma_load_2d(&map_a, &full_bar[stage], sa, kb * BK, mt * BM);
+            }
+            tma_load_2d(&map_b, &full_bar[stage], sb, kb * BK, brow);
           }
-          tma_load_2d(&map_b, &full_bar[stage], sb, kb * BK, nt * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (p.has_residual) {
           const int nchunk = (min(BN, p.N - nt * BN) + EPI_CHUNK - 1) / EPI_CHUNK;
           for (int c = 0; c < nchunk; ++c) {  // shortcut tile as extra "k-blocks": 128 rows x 64 output columns each
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], A_BYTES);
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], CG * A_BYTES);
             uint8_t* sa = smem + stage * STAGE_BYTES;
-            if (p.conv)
-              tma_load_4d(&map_r, &full_bar[stage], sa, nt * BN + c * EPI_CHUNK, w0, h0, img);
-            else
-              tma_load_2d(&map_r, &full_bar[stage], sa, nt * BN + c * EPI_CHUNK, mt * BM);
+            if constexpr (CG == 2) {
+              if (p.conv) tma2_load_4d(&map_r, &full_bar[stage], sa, nt * BN + c * EPI_CHUNK, w0, h0, img);
+              else tma2_load_2d(&map_r, &full_bar[stage], sa, nt * BN + c * EPI_CHUNK, mt * BM);
+            } else {
+              if (p.conv) tma_load_4d(&map_r, &full_bar[stage], sa, nt * BN + c * EPI_CHUNK, w0, h0, img);
+              else tma_load_2d(&map_r, &full_bar[stage], sa, nt * BN + c * EPI_CHUNK, mt * BM);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN);
+    // ------------------------------------------------------------------ MMA issuer (one thread of the leader CTA)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc(BN, BM * CG);
+      constexpr uint32_t idesc64 = make_idesc(64, BM * CG);
+      const uint64_t ident_desc = make_smem_desc(smem_u32(ident));
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t id, uint32_t accum) {
+        if constexpr (CG == 2) umma2_bf16(d, ad, bd, id, accum); else umma_bf16(d, ad, bd, id, accum);
+      };
+      auto commit = [&](uint64_t* bar) {
+        if constexpr (CG == 2) umma2_commit_both(bar); else umma_commit(bar);
+      };
+      for (int tile = unit; tile < num_tiles; tile += num_units) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -283,26 +421,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the >>4 encoded address
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            mma(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-          if (kb == p.KB - 1 && !p.has_residual) umma_commit(&tfull_bar[acc]);
+          commit(&empty_bar[stage]);  // frees the smem slot (in both CTAs) once these MMAs retire
+          if (kb == p.KB - 1 && !p.has_residual) commit(&tfull_bar[acc]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (p.has_residual) {
-          const int nt = tile / p.num_m_tiles;
+          const int nt = tile / num_mp;
           const int nchunk = (min(BN, p.N - nt * BN) + EPI_CHUNK - 1) / EPI_CHUNK;
-          constexpr uint32_t idesc64 = make_idesc(64);
-          const uint64_t idesc_b = make_smem_desc(smem_u32(ident));
           for (int c = 0; c < nchunk; ++c) {
             mbar_wait(&full_bar[stage], phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t adesc = make_smem_desc(smem_u32(smem + stage * STAGE_BYTES));
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_bf16(tmem_d + c * EPI_CHUNK, adesc + 2 * k, idesc_b + 2 * k, idesc64, 1u);
-            umma_commit(&empty_bar[stage]);
-            if (c == nchunk - 1) umma_commit(&tfull_bar[acc]);
+              mma(tmem_d + c * EPI_CHUNK, adesc + 2 * k, ident_desc + 2 * k, idesc64, 1u);
+            commit(&empty_bar[stage]);
+            if (c == nchunk - 1) commit(&tfull_bar[acc]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -310,7 +446,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..5, every CTA: its own 128 rows)
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;
     const int etid = (warp - 2) * 32 + lane;  // 0..127 within the epilogue group
@@ -323,9 +459,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint32_t gchunk = 0;  // running chunk counter of this warp -> staging ring slot (one bulk group per chunk)
     const unsigned long long drop_seed = p.drop_seed + ((p.drop_keep_thresh && p.drop_seed_dev) ? __ldg(p.drop_seed_dev) : 0ull);
     constexpr int NCHUNK = (BN + EPI_CHUNK - 1) / EPI_CHUNK;
+    const float relu_floor = p.relu ? 0.f : -INFINITY;
+    float pre_sc[2] = {1.f, 1.f}, pre_bi[2] = {0.f, 0.f};
+    auto fetch_sb = [&](int nt_) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int idx = etid + 128 * i, n = nt_ * BN + idx;
+        const bool ok = idx < BN && n < p.N;
+        pre_sc[i] = (ok && p.scale) ? __ldg(p.scale + n) : 1.f;
+        pre_bi[i] = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
+      }
+    };
+    if (unit < num_tiles) fetch_sb(unit / num_mp);
 
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int mt = tile % p.num_m_tiles, nt = tile / p.num_m_tiles;
+    for (int tile = unit; tile < num_tiles; tile += num_units) {
+      const int mt = (tile % num_mp) * CG + cta_rank, nt = tile / num_mp;
       int img = 0, hh0 = 0, ww0 = 0;
       long long m_global;
       bool row_ok;
@@ -336,7 +484,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         hh0 = (r / p.tiles_w) * p.tile_h;
         ww0 = (r % p.tiles_w) * p.tile_w;
         const int hh = hh0 + row / p.tile_w, ww = ww0 + row % p.tile_w;
-        row_ok = hh < p.H && ww < p.W;
+        row_ok = img < p.NB && hh < p.H && ww < p.W;
         m_global = ((long long)img * p.H + hh) * p.W + ww;
       } else {
         m_global = (long long)mt * BM + row;
@@ -345,15 +493,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int ncols = min(BN, p.N - nt * BN);            // valid columns of this tile (multiple of 8)
       const int nchunk = (ncols + EPI_CHUNK - 1) / EPI_CHUNK;
 
-      // per-tile scale / bias into smem (broadcast reads later)
+      // per-tile scale / bias into smem (broadcast reads later); the values were fetched one tile ahead
       float* s_scale = sb_smem + acc * 2 * BN;
       float* s_bias = s_scale + BN;
-      for (int i = etid; i < BN; i += 128) {
-        const int n = nt * BN + i;
-        s_scale[i] = (p.scale && n < p.N) ? __ldg(p.scale + n) : 1.f;
-        s_bias[i] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int idx = etid + 128 * i;
+        if (idx < BN) { s_scale[idx] = pre_sc[i]; s_bias[idx] = pre_bi[i]; }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tile + num_units < num_tiles) fetch_sb((tile + num_units) / num_mp);  // in flight while this tile is drained
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -369,47 +518,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           uint8_t* buf = my_bufs + b * EPI_BUF_BYTES;
           if (lane == 0) bulk_wait_read<NBUF - 1>();  // the store that last used this slot has drained
           __syncwarp();
-          uint8_t* my_row = buf + lane * 128;
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t v[32];
-            tmem_ld32_nowait(taddr + c * EPI_CHUNK + half * 32, v);
-            tmem_ld_wait();
-            const int cl = c * EPI_CHUNK + half * 32;  // column inside the tile
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float f[8];
-              const float4 s0 = *reinterpret_cast<const float4*>(s_scale + cl + j);
-              const float4 s1 = *reinterpret_cast<const float4*>(s_scale + cl + j + 4);
-              const float4 b0 = *reinterpret_cast<const float4*>(s_bias + cl + j);
-              const float4 b1 = *reinterpret_cast<const float4*>(s_bias + cl + j + 4);
-              f[0] = fmaf(__uint_as_float(v[j + 0]), s0.x, b0.x); f[1] = fmaf(__uint_as_float(v[j + 1]), s0.y, b0.y);
-              f[2] = fmaf(__uint_as_float(v[j + 2]), s0.z, b0.z); f[3] = fmaf(__uint_as_float(v[j + 3]), s0.w, b0.w);
-              f[4] = fmaf(__uint_as_float(v[j + 4]), s1.x, b1.x); f[5] = fmaf(__uint_as_float(v[j + 5]), s1.y, b1.y);
-              f[6] = fmaf(__uint_as_float(v[j + 6]), s1.z, b1.z); f[7] = fmaf(__uint_as_float(v[j + 7]), s1.w, b1.w);
-              const uint32_t q = (uint32_t)(half * 4 + (j >> 3));
-              uint4* slot = reinterpret_cast<uint4*>(my_row + ((q ^ sw_xor) << 4));
-              if (p.relu) {
-#pragma unroll
-                for (int t = 0; t < 8; ++t) f[t] = fmaxf(f[t], 0.f);
-              }
-              if (p.drop_keep_thresh) {
-                const unsigned long long base = drop_seed * 0x100000001B3ull +
-                                                (unsigned long long)m_global * (unsigned long long)p.N +
-                                                (unsigned long long)(nt * BN + cl + j);
-#pragma unroll
-                for (int t = 0; t < 8; ++t) f[t] = (mix32(base + t) < p.drop_keep_thresh) ? f[t] * p.drop_inv_keep : 0.f;
-              }
-              uint4 o;
-              __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) o2[t] = __floats2bfloat162_rn(f[2 * t], f[2 * t + 1]);
-              *slot = o;
+          if (!(p.debug & 2)) {
+            const uint32_t row_s = smem_u32(buf) + lane * 128;
+            const uint32_t ta = taddr + c * EPI_CHUNK;
+            const uint32_t sc_s = smem_u32(s_scale) + c * EPI_CHUNK * 4, bi_s = smem_u32(s_bias) + c * EPI_CHUNK * 4;
+            const unsigned long long dbase = drop_seed * 0x100000001B3ull + (unsigned long long)m_global * (unsigned long long)p.N +
+                                             (unsigned long long)(nt * BN + c * EPI_CHUNK);
+            if (p.drop_keep_thresh) {
+              if (p.scale) epi_chunk<true, true>(ta, sc_s, bi_s, row_s, sw_xor, relu_floor, dbase, p.drop_keep_thresh, p.drop_inv_keep);
+              else epi_chunk<false, true>(ta, sc_s, bi_s, row_s, sw_xor, relu_floor, dbase, p.drop_keep_thresh, p.drop_inv_keep);
+            } else {
+              if (p.scale) epi_chunk<true, false>(ta, sc_s, bi_s, row_s, sw_xor, relu_floor, 0ull, 0u, 1.f);
+              else epi_chunk<false, false>(ta, sc_s, bi_s, row_s, sw_xor, relu_floor, 0ull, 0u, 1.f);
             }
           }
           fence_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && !(p.debug & 1)) {
             if (p.conv)
               tma_store_4d(&map_o, buf, nt * BN + c * EPI_CHUNK, ww0 + sub_w, hh0 + sub_h, img);
             else
@@ -446,7 +571,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (CG == 2 && !leader) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) bulk_wait_all();  // staging smem must outlive the last TMA store
@@ -454,9 +581,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the leader's MMAs read the peer's smem: nobody leaves early
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if constexpr (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -500,39 +631,47 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int STAGES, int NBUF>
+template <int BN, int STAGES, int NBUF, int CG>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mr, const Params& p,
                   cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 4 * NBUF * EPI_BUF_BYTES + IDENT_BYTES +
+  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + (BN / CG) * BK * 2) + 4 * NBUF * EPI_BUF_BYTES + IDENT_BYTES +
                           4 * BN * sizeof(float) + (2 * STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
   static_assert(smem <= 232448, "gemm_tc: shared memory budget exceeded");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, NBUF, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_err("gemm_tc: cudaFuncSetAttribute(%zu B smem): %s", smem, cudaGetErrorString(e));
     configured = true;
   }
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc_kernel<BN, STAGES, NBUF><<<grid, NUM_THREADS, smem, st>>>(ma, mb, mo, mr, p);
-  cudaError_t e = cudaGetLastError();
+  const int units = ((p.num_m_tiles + CG - 1) / CG) * p.num_n_tiles;
+  const int max_units = num_sms() / CG;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(CG * (units < max_units ? units : max_units)));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, NBUF, CG>, ma, mb, mo, mr, p);
   if (e != cudaSuccess) return set_err("gemm_tc launch: %s", cudaGetErrorString(e));
   return 0;
 }
 
-// tile-shape choice: minimise waves x (per-tile MMA time + fixed fill/drain), per-tile time ~ KB * BN (+ epilogue ~ BN)
-static int pick_bn(int m_tiles, int N, int KB) {
-  const int sms = num_sms();
+// tile-shape choice: minimise waves x per-tile time, per k-block max(MMA cycles, operand bytes / 64 B/clk SM<-L2 ingest)
+static int pick_bn(int m_tiles, int N, int KB, int cg) {
+  const int units_max = num_sms() / cg;
   int best = 64;
   double best_cost = 1e30;
   const int cands[3] = {256, 128, 64};
   for (int i = 0; i < 3; ++i) {
     const int bn = cands[i];
     if (bn > 64 && N < bn) continue;
-    const int tiles = m_tiles * ((N + bn - 1) / bn);
-    const int waves = (tiles + sms - 1) / sms;
-    // mainloop: per k-block max(MMA = bn/2 cycles*4, L2 feed = (16 KB + bn*128 B) / 64 B/cycle); epilogue ~ 6*bn; fill ~ 1500
-    const double mma = 2.0 * bn, feed = (16384.0 + bn * 128.0) / 64.0;
+    const int units = ((m_tiles + cg - 1) / cg) * ((N + bn - 1) / bn);
+    const int waves = (units + units_max - 1) / units_max;
+    const double mma = 2.0 * bn, feed = (16384.0 + bn * 128.0 / cg) / 64.0;
     const double per_tile = KB * (mma > feed ? mma : feed) + 6.0 * bn;
     const double cost = waves * per_tile + 1500.0;
     if (cost < best_cost) { best_cost = cost; best = bn; }
@@ -589,6 +728,10 @@ extern "C" int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int C
     p.drop_seed = dropout_seed;
     p.drop_seed_dev = (const unsigned long long*)dropout_seed_dev;
   }
+  {
+    const char* e = getenv("DRN_TC_DEBUG");
+    p.debug = e ? atoi(e) : 0;
+  }
   const int Ktot = ksize * ksize * Cin;
   p.KB = Ktot / BK;
   CUtensorMap ma, mb, mo, mr;
@@ -636,17 +779,29 @@ extern "C" int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int C
       if (make_map(&mr, residual, 2, rdims, rstr, rbox)) return 1;
     }
   }
-  const int bn = pick_bn(p.num_m_tiles, Cout, p.KB);
+  // CTA pairs (cta_group::2) whenever there are at least two M tiles to pair; DRN_TC_CTA_GROUP=1 forces single CTAs
+  static int cg_env = -1;
+  if (cg_env < 0) {
+    const char* e = getenv("DRN_TC_CTA_GROUP");
+    cg_env = (e && e[0] == '1') ? 1 : 2;
+  }
+  const int cg = (cg_env == 2 && p.num_m_tiles >= 2) ? 2 : 1;
+  const int bn = pick_bn(p.num_m_tiles, Cout, p.KB, cg);
   p.num_n_tiles = (Cout + bn - 1) / bn;
   {
     const cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
     const cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
-    const cuuint32_t box[2] = {BK, (cuuint32_t)bn};
+    const cuuint32_t box[2] = {BK, (cuuint32_t)(bn / cg)};
     if (make_map(&mb, w, 2, dims, strides, box)) return 1;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (bn == 256 && p.KB >= 48) return launch<256, 4, 1>(ma, mb, mo, mr, p, st);  // deep K: smem goes to pipeline stages
-  if (bn == 256) return launch<256, 3, 4>(ma, mb, mo, mr, p, st);
-  if (bn == 128) return launch<128, 5, 2>(ma, mb, mo, mr, p, st);
-  return launch<64, 7, 2>(ma, mb, mo, mr, p, st);
+  if (cg == 2) {
+    if (bn == 256 && p.KB >= 48) return launch<256, 6, 1, 2>(ma, mb, mo, mr, p, st);  // deep K: smem goes to pipeline stages
+    if (bn == 256) return launch<256, 5, 2, 2>(ma, mb, mo, mr, p, st);
+    if (bn == 128) return launch<128, 7, 2, 2>(ma, mb, mo, mr, p, st);
+    return launch<64, 8, 2, 2>(ma, mb, mo, mr, p, st);
+  }
+  if (bn == 256) return launch<256, 4, 1, 1>(ma, mb, mo, mr, p, st);
+  if (bn == 128) return launch<128, 5, 2, 1>(ma, mb, mo, mr, p, st);
+  return launch<64, 7, 2, 1>(ma, mb, mo, mr, p, st);
 }

@@ -35,6 +35,7 @@ def main():
     weights = helpers.case_weights(cfg, model)
     model.load_state_dict({**weights, "pixel_mean": model.pixel_mean, "pixel_std": model.pixel_std}, strict=True)
     model.train()
+    model.use_cuda_graph = False  # record the individual C-ABI calls
     batched = bench.make_batched(synth.make_inputs(H, W, R, seed=0), torch.device("cuda:0"), drn)
     calls = []
     orig = ops.conv_bf16_tc

@@ -18,66 +18,98 @@ int set_err(const char* fmt, ...) {
 
 // ------------------------------------------------------------------------------------------
 // a1+a2: (img - mean)/std fused into the 3x3, Cin=3 first convolution (stride 1 or 2, pad 1).
-// One thread = one output pixel x 16 output channels; 4 adjacent threads cover the 64-channel row
-// of a pixel so the NHWC store is a contiguous 256 B (fp32) / 128 B (bf16) per pixel.
+// One thread = NPX adjacent output pixels x 16 output channels: every filter value fetched from smem
+// (one LDS.128 per 4 channels) feeds NPX FMAs, so the inner loop is FMA-bound instead of LDS-bound
+// (the first version, 1 pixel per thread, spent 4 LDS cycles per FMA cycle: 117 us at 600x1000).
+// Adjacent threads cover the 64-channel row of a pixel group so NHWC stores are contiguous.
 // ------------------------------------------------------------------------------------------
-template <typename OutT>
-__global__ void __launch_bounds__(256)
-conv3x3_c3_kernel(const float* __restrict__ img, int H, int W, int Hp, int Wp, float m0, float m1, float m2, float s0,
-                  float s1, float s2, const float* __restrict__ wp, const float* __restrict__ scale,
-                  const float* __restrict__ bias, int Cout, int stride, int relu, int Ho, int Wo,
-                  OutT* __restrict__ out) {
+constexpr int C3_NPX = 4;
+
+template <typename OutT, int STRIDE>
+__global__ void __launch_bounds__(128)
+conv3x3_c3_kernel(const float* __restrict__ img, int H, int W, float m0, float m1, float m2, float s0, float s1, float s2,
+                  const float* __restrict__ wp, const float* __restrict__ scale, const float* __restrict__ bias,
+                  int Cout, int relu, int Ho, int Wo, OutT* __restrict__ out) {
   extern __shared__ float sw[];  // [27][Cout]
   for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) sw[i] = wp[i];
   __syncthreads();
+  constexpr int NCOL = (C3_NPX - 1) * STRIDE + 3;  // input columns under NPX adjacent outputs
   const int groups = Cout >> 4;
+  const int wq = (Wo + C3_NPX - 1) / C3_NPX;       // pixel groups per output row
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long pix = gid / groups;
+  const long long pg = gid / groups;
   const int cg = (int)(gid % groups);
-  if (pix >= (long long)Ho * Wo) return;
-  const int oh = (int)(pix / Wo), ow = (int)(pix % Wo);
+  if (pg >= (long long)Ho * wq) return;
+  const int oh = (int)(pg / wq), ow0 = (int)(pg % wq) * C3_NPX;
   const float mean[3] = {m0, m1, m2};
   const float stdv[3] = {s0, s1, s2};
-  float x[27];
+  float acc[C3_NPX][16];
 #pragma unroll
-  for (int kh = 0; kh < 3; ++kh)
+  for (int p = 0; p < C3_NPX; ++p)
 #pragma unroll
-    for (int kw = 0; kw < 3; ++kw) {
-      const int ih = oh * stride - 1 + kh, iw = ow * stride - 1 + kw;
-      // (ih, iw) outside the valid H x W image but inside the Hp x Wp canvas is ImageList zero padding
-      const bool inb = (ih >= 0) && (ih < H) && (iw >= 0) && (iw < W);
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float v = 0.f;
-        if (inb) v = __fdiv_rn(__fsub_rn(__ldg(img + ((long long)c * H + ih) * W + iw), mean[c]), stdv[c]);
-        x[(kh * 3 + kw) * 3 + c] = v;
-      }
-    }
-  float acc[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int j = 0; j < 16; ++j) acc[p][j] = 0.f;
   const float* wrow = sw + cg * 16;
 #pragma unroll
-  for (int k = 0; k < 27; ++k) {
-    const float4* w4 = reinterpret_cast<const float4*>(wrow + k * Cout);
+  for (int kh = 0; kh < 3; ++kh) {
+    const int ih = oh * STRIDE - 1 + kh;
+    const bool rowok = ih >= 0 && ih < H;  // rows/cols outside the valid H x W image are ImageList zero padding
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 wv = w4[q];
-      acc[q * 4 + 0] = fmaf(x[k], wv.x, acc[q * 4 + 0]);
-      acc[q * 4 + 1] = fmaf(x[k], wv.y, acc[q * 4 + 1]);
-      acc[q * 4 + 2] = fmaf(x[k], wv.z, acc[q * 4 + 2]);
-      acc[q * 4 + 3] = fmaf(x[k], wv.w, acc[q * 4 + 3]);
+    for (int c = 0; c < 3; ++c) {
+      float x[NCOL];
+#pragma unroll
+      for (int i = 0; i < NCOL; ++i) {
+        const int iw = ow0 * STRIDE - 1 + i;
+        float v = 0.f;
+        if (rowok && iw >= 0 && iw < W) v = __fdiv_rn(__fsub_rn(__ldg(img + ((long long)c * H + ih) * W + iw), mean[c]), stdv[c]);
+        x[i] = v;
+      }
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const float4* w4 = reinterpret_cast<const float4*>(wrow + ((kh * 3 + kw) * 3 + c) * Cout);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 wv = w4[q];
+#pragma unroll
+          for (int p = 0; p < C3_NPX; ++p) {
+            const float xv = x[p * STRIDE + kw];
+            acc[p][q * 4 + 0] = fmaf(xv, wv.x, acc[p][q * 4 + 0]);
+            acc[p][q * 4 + 1] = fmaf(xv, wv.y, acc[p][q * 4 + 1]);
+            acc[p][q * 4 + 2] = fmaf(xv, wv.z, acc[p][q * 4 + 2]);
+            acc[p][q * 4 + 3] = fmaf(xv, wv.w, acc[p][q * 4 + 3]);
+          }
+        }
+      }
     }
   }
-  OutT* o = out + pix * Cout + cg * 16;
+  float sc[16], bi[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    const int c = cg * 16 + j;
-    float v = acc[j];
-    if (scale) v = v * __ldg(scale + c);
-    v += __ldg(bias + c);
-    if (relu) v = fmaxf(v, 0.f);
-    if constexpr (sizeof(OutT) == 4) o[j] = v; else o[j] = __float2bfloat16(v);
+    sc[j] = scale ? __ldg(scale + cg * 16 + j) : 1.f;
+    bi[j] = __ldg(bias + cg * 16 + j);
+  }
+#pragma unroll
+  for (int p = 0; p < C3_NPX; ++p) {
+    const int ow = ow0 + p;
+    if (ow >= Wo) break;
+    OutT* o = out + ((long long)oh * Wo + ow) * Cout + cg * 16;
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float t = scale ? acc[p][j] * sc[j] : acc[p][j];  // same rounding sequence as the reference: conv, *scale, +bias
+      t += bi[j];
+      v[j] = relu ? fmaxf(t, 0.f) : t;
+    }
+    if constexpr (sizeof(OutT) == 4) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+      uint4 pk[2];
+      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(pk);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h2[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      *reinterpret_cast<uint4*>(o) = pk[0];
+      *reinterpret_cast<uint4*>(o + 8) = pk[1];
+    }
   }
 }
 
@@ -549,16 +581,19 @@ int drn_conv3x3_c3_fwd(const float* img, int H, int W, int Hp, int Wp, const flo
   DRN_CHECK_ARG(stride == 1 || stride == 2, "conv3x3_c3: stride %d", stride);
   DRN_CHECK_ARG(H > 0 && W > 0 && Hp >= H && Wp >= W, "conv3x3_c3: bad image/canvas size %dx%d in %dx%d", H, W, Hp, Wp);
   const int Ho = (Hp + 2 - 3) / stride + 1, Wo = (Wp + 2 - 3) / stride + 1;
-  const long long threads = (long long)Ho * Wo * (Cout / 16);
-  const int grid = (int)((threads + 255) / 256);
+  const long long threads = (long long)Ho * ((Wo + C3_NPX - 1) / C3_NPX) * (Cout / 16);
+  const int grid = (int)((threads + 127) / 128);
   const size_t smem = 27 * Cout * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
-  if (out_dtype == DRN_F32)
-    conv3x3_c3_kernel<float><<<grid, 256, smem, st>>>(img, H, W, Hp, Wp, mean3[0], mean3[1], mean3[2], std3[0],
-        std3[1], std3[2], w_packed, scale, bias, Cout, stride, relu, Ho, Wo, (float*)out);
-  else
-    conv3x3_c3_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(img, H, W, Hp, Wp, mean3[0], mean3[1], mean3[2],
-        std3[0], std3[1], std3[2], w_packed, scale, bias, Cout, stride, relu, Ho, Wo, (__nv_bfloat16*)out);
+#define DRN_C3_LAUNCH(T, S)                                                                                          \
+  conv3x3_c3_kernel<T, S><<<grid, 128, smem, st>>>(img, H, W, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], \
+                                                   w_packed, scale, bias, Cout, relu, Ho, Wo, (T*)out)
+  if (out_dtype == DRN_F32) {
+    if (stride == 1) DRN_C3_LAUNCH(float, 1); else DRN_C3_LAUNCH(float, 2);
+  } else {
+    if (stride == 1) DRN_C3_LAUNCH(__nv_bfloat16, 1); else DRN_C3_LAUNCH(__nv_bfloat16, 2);
+  }
+#undef DRN_C3_LAUNCH
   DRN_CHECK_LAUNCH("conv3x3_c3");
   return 0;
 }

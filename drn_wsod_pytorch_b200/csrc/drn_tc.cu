@@ -331,6 +331,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if constexpr (CG == 2) cluster_sync_all();  // peer barriers initialised before any remote arrive / 2-SM TMA
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM alloc, descriptor prefetch) may run
+  // while the previous kernel of the stream is still draining; global memory is only touched after this point.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (every CTA)
@@ -650,11 +654,18 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  static int pdl_env = -1;
+  if (pdl_env < 0) {
+    const char* e = getenv("DRN_TC_PDL");
+    pdl_env = (e && e[0] == '0') ? 0 : 1;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_env ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, NBUF, CG>, ma, mb, mo, mr, p);
   if (e != cudaSuccess) return set_err("gemm_tc launch: %s", cudaGetErrorString(e));
   return 0;

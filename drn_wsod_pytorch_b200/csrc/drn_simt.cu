@@ -395,20 +395,23 @@ roipool_bf16_kernel(const uint4* __restrict__ f8, int h, int w, int C, const flo
 }
 
 // ------------------------------------------------------------------------------------------
-// ROIPool v2: range-max tables along x + per-bin gather.
+// ROIPool v2: range-max (sparse) tables + per-bin gather.
 //
 // The direct kernels above re-read every feature cell under every ROI (measured: 19 GB of L2->SM
-// traffic for R=4000 on the 74x124x2048 map, L2-bound at 1.07 ms).  max() is idempotent, so a
-// horizontal window [ws, we) equals max(T_j[ws], T_j[we - 2^j]) with j = floor(log2(we - ws)) and
-// T_j[y][x] = max F[y][x .. x+2^j) -- the classic sparse table, built once per image along x only
-// (levels 1..4: windows 2,4,8,16; wider bins take ceil(width/16) lookups).  Each bin then costs
-// 2 lookups per feature row instead of (we - ws); results are bit-identical (max has no rounding).
-// Kernel 1 builds T_1..T_4 (one CTA per feature row x 64-byte... channel slice, row staged in smem);
-// kernel 2 is one CTA per (ROI, 512-byte channel chunk): 8 warps x 49 bins, 16 B per lane.  CTAs are
-// rasterised chunk-major so the tables of the chunk being gathered stay L2-resident.
+// traffic for R=4000 on the 74x124x2048 map, L2-bound at 1.07 ms).  max() is idempotent, so a window
+// [ws, we) equals max(T_j[ws], T_j[we - 2^j]) with j = floor(log2(we - ws)) and T_j[x] = max F[x .. x+2^j)
+// -- the classic sparse table, built once per image: x windows 2,4,8,16 (wider bins take
+// ceil(width/16) lookups) crossed with y windows 1,2.  A bin of hh x width cells then costs
+// ceil(hh/2) x 2 lookups instead of hh x width loads; results are bit-identical (max has no rounding).
+// Kernel 1 builds the 9 tables (one CTA per feature row x 128-byte channel slice, rows y and y+1 staged
+// in smem); kernel 2 is one CTA per (ROI, 512-byte channel chunk): 8 warps x 49 bins, 16 B per lane.
+// CTAs are rasterised chunk-major so the tables of the chunk being gathered stay L2-resident.
 // ------------------------------------------------------------------------------------------
-constexpr int XT_LEVELS = 4;        // T_1..T_4
+constexpr int XT_LEVELS = 4;        // x windows 2,4,8,16 (level j = 1..4; j = 0 is the map itself)
+constexpr int YT_LEVELS = 1;        // y windows 2 (level i = 1; i = 0 is a single row)
+constexpr int XT_TABLES = (YT_LEVELS + 1) * (XT_LEVELS + 1) - 1;  // every (i, j) except (0, 0)
 constexpr int XT_SLOTS = 8;         // 16-byte channel vectors per build CTA (128 B of channels)
+__host__ __device__ constexpr int xt_index(int i, int j) { return i * (XT_LEVELS + 1) + j - 1; }
 
 struct VecF32 {
   typedef float4 T;
@@ -439,99 +442,141 @@ struct VecBF16 {
   }
 };
 
-// tables: [XT_LEVELS][h][w][CV] vectors.  grid = (h, CV / XT_SLOTS), block = 256, smem = 2 * w * XT_SLOTS vectors
+// tables: [XT_TABLES][h][w][CV] vectors, table (i, j) at xt_index(i, j):
+//   T_ij[y][x] = max F[y .. min(y+2^i, h)) [x .. min(x+2^j, w))     (windows truncated at the map edge)
+// grid = (h, CV / XT_SLOTS), block = 256, smem = 4 * w * XT_SLOTS vectors (rows y and y+1, ping-pong)
 template <typename V>
 __global__ void __launch_bounds__(256)
 xtable_build_kernel(const typename V::T* __restrict__ feat, int h, int w, int CV, typename V::T* __restrict__ tables) {
   typedef typename V::T T;
   extern __shared__ __align__(16) unsigned char xt_smem[];
-  T* buf0 = reinterpret_cast<T*>(xt_smem);
-  T* buf1 = buf0 + (size_t)w * XT_SLOTS;
-  const int y = blockIdx.x, cv0 = blockIdx.y * XT_SLOTS;
   const int n = w * XT_SLOTS;
-  const T* row = feat + (size_t)y * w * CV + cv0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) buf0[i] = __ldg(row + (size_t)(i / XT_SLOTS) * CV + (i % XT_SLOTS));
+  T* a0 = reinterpret_cast<T*>(xt_smem);  // row y, level j-1
+  T* a1 = a0 + n;                         // row y, level j
+  T* b0 = a1 + n;                         // row y+1 (or a copy of row y on the last row), level j-1
+  T* b1 = b0 + n;
+  const int y = blockIdx.x, cv0 = blockIdx.y * XT_SLOTS;
+  const int y1 = min(y + 1, h - 1);
+  const size_t plane = (size_t)h * w * CV;
+  const T* row0 = feat + (size_t)y * w * CV + cv0;
+  const T* row1 = feat + (size_t)y1 * w * CV + cv0;
+  T* out0 = tables + (size_t)y * w * CV + cv0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const size_t off = (size_t)(i / XT_SLOTS) * CV + (i % XT_SLOTS);
+    const T u = __ldg(row0 + off), v = __ldg(row1 + off);
+    a0[i] = u;
+    b0[i] = v;
+    out0[(size_t)xt_index(1, 0) * plane + off] = V::vmax(u, v);
+  }
   __syncthreads();
-  T* in = buf0;
-  T* out = buf1;
 #pragma unroll 1
   for (int j = 1; j <= XT_LEVELS; ++j) {
     const int half = 1 << (j - 1);
-    T* trow = tables + ((size_t)(j - 1) * h + y) * w * CV + cv0;
+    T* t0 = out0 + (size_t)xt_index(0, j) * plane;
+    T* t1 = out0 + (size_t)xt_index(1, j) * plane;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       const int x = i / XT_SLOTS, sl = i % XT_SLOTS;
-      T v = in[i];
-      if (x + half < w) v = V::vmax(v, in[i + half * XT_SLOTS]);  // truncated at the right edge
-      out[i] = v;
-      trow[(size_t)x * CV + sl] = v;
+      T u = a0[i], v = b0[i];
+      if (x + half < w) {  // truncated at the right edge
+        u = V::vmax(u, a0[i + half * XT_SLOTS]);
+        v = V::vmax(v, b0[i + half * XT_SLOTS]);
+      }
+      a1[i] = u;
+      b1[i] = v;
+      const size_t off = (size_t)x * CV + sl;
+      t0[off] = u;
+      t1[off] = V::vmax(u, v);
     }
     __syncthreads();
-    T* t = in; in = out; out = t;
+    T* t = a0; a0 = a1; a1 = t;
+    t = b0; b0 = b1; b1 = t;
   }
 }
 
-// grid = (R, CV / 32), block = 256 (8 warps); lane = 16-byte vector inside the 512-byte channel chunk
+// grid = (R, CV / 32), block = 224: warp ph (0..6) owns bin row ph, lane = 16-byte vector inside the
+// 512-byte channel chunk.  Bin geometry (torchvision roi_pool, see roi_geometry above) is computed once per
+// CTA by 14 threads; the per-lookup work is one 32-bit multiply-add + one 16-byte load (the first version
+// recomputed geometry and 64-bit addresses per lookup and was instruction-issue bound: 45 instr/load).
 template <typename V>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(224)
 roipool_gather_kernel(const typename V::T* __restrict__ feat, const typename V::T* __restrict__ tables, int h, int w,
                       int CV, const float* __restrict__ boxes, const float* __restrict__ obj, float scale,
                       typename V::T* __restrict__ out) {
   typedef typename V::T T;
+  __shared__ int s_y0[7], s_ylast[7], s_nrow[7], s_i[7];      // per bin row: first window row, last window row, #windows, y level
+  __shared__ int s_x0[7], s_x1[7], s_j[7], s_wd[7];           // per bin col: first / right-aligned window col, x level, width
   const int r = blockIdx.x;
-  const int cv = blockIdx.y * 32 + (threadIdx.x & 31);
-  const int warp = threadIdx.x >> 5;
-  const bool cv_ok = cv < CV;
-  const float* box = boxes + 4 * (size_t)r;
-  // torchvision roi_pool geometry (see roi_geometry above), all bins of this ROI
-  const int sw = (int)roundf(__fmul_rn(box[0], scale));
-  const int sh = (int)roundf(__fmul_rn(box[1], scale));
-  const int ew = (int)roundf(__fmul_rn(box[2], scale));
-  const int eh = (int)roundf(__fmul_rn(box[3], scale));
-  const int rw = max(ew - sw + 1, 1), rh = max(eh - sh + 1, 1);
-  const float bh = __fdiv_rn((float)rh, 7.f), bw = __fdiv_rn((float)rw, 7.f);
-  const float mul = obj ? __fadd_rn(__ldg(obj + r), 1.f) : 1.f;
-  const size_t plane = (size_t)h * w * CV;
-  T* orow = out + (size_t)r * 49 * CV + cv;
-#pragma unroll 1
-  for (int b = warp; b < 49; b += 8) {
-    const int ph = b / 7, pw = b - ph * 7;
-    const int hs = min(max((int)floorf(__fmul_rn((float)ph, bh)) + sh, 0), h);
-    const int he = min(max((int)ceilf(__fmul_rn((float)(ph + 1), bh)) + sh, 0), h);
-    const int ws = min(max((int)floorf(__fmul_rn((float)pw, bw)) + sw, 0), w);
-    const int we = min(max((int)ceilf(__fmul_rn((float)(pw + 1), bw)) + sw, 0), w);
-    const int width = we - ws;
-    T m = V::zero();
-    if (he > hs && width > 0 && cv_ok) {
-      m = V::lowest();
-      int j = 31 - __clz(width);               // floor(log2(width))
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cv = blockIdx.y * 32 + lane;
+  if (threadIdx.x < 14) {
+    const float* box = boxes + 4 * (size_t)r;
+    const bool is_y = threadIdx.x < 7;
+    const int p = is_y ? threadIdx.x : threadIdx.x - 7;
+    const int lim = is_y ? h : w;
+    const int s0 = (int)roundf(__fmul_rn(box[is_y ? 1 : 0], scale));
+    const int e0 = (int)roundf(__fmul_rn(box[is_y ? 3 : 2], scale));
+    const int rl = max(e0 - s0 + 1, 1);
+    const float bs = __fdiv_rn((float)rl, 7.f);
+    const int lo = min(max((int)floorf(__fmul_rn((float)p, bs)) + s0, 0), lim);
+    const int hi = min(max((int)ceilf(__fmul_rn((float)(p + 1), bs)) + s0, 0), lim);
+    const int len = hi - lo;  // <= 0: empty bin
+    if (is_y) {
+      const int i = len >= 2 ? 1 : 0;
+      s_i[p] = i;
+      s_y0[p] = lo;
+      s_ylast[p] = hi - (1 << i);
+      s_nrow[p] = len > 0 ? (len + (1 << i) - 1) >> i : 0;
+    } else {
+      int j = len > 0 ? 31 - __clz(len) : 0;
       if (j > XT_LEVELS) j = XT_LEVELS;
+      s_j[p] = j;
+      s_x0[p] = lo;
+      s_x1[p] = hi - (1 << j);
+      s_wd[p] = len;
+    }
+  }
+  __syncthreads();
+  if (cv >= CV) return;
+  const int ph = warp;
+  const float mul = obj ? __fadd_rn(__ldg(obj + r), 1.f) : 1.f;
+  const int i = s_i[ph], y0 = s_y0[ph], ylast = s_ylast[ph], nrow = s_nrow[ph];
+  const int ystep = 1 << i;
+  const unsigned plane = (unsigned)h * w * CV;       // vectors per table (< 2^27 for any map that fits the builder)
+  const unsigned rowpitch = (unsigned)w * CV;
+  T* orow = out + ((size_t)r * 49 + ph * 7) * CV + cv;
+#pragma unroll 1
+  for (int pw = 0; pw < 7; ++pw) {
+    const int j = s_j[pw], wd = s_wd[pw];
+    T m = V::zero();
+    if (nrow > 0 && wd > 0) {
+      m = V::lowest();
+      const T* tab = ((i | j) == 0 ? feat : tables + (size_t)xt_index(i, j) * plane) + cv;
+      const unsigned xo0 = (unsigned)s_x0[pw] * CV, xo1 = (unsigned)s_x1[pw] * CV;
       const int win = 1 << j;
-      const T* tab = (j == 0) ? feat : tables + (size_t)(j - 1) * plane;
-      const int x_last = we - win;             // right-aligned final window
-      if (width <= 2 * win) {
-        // common case: one or two lookups per row, two rows in flight
-        int y = hs;
-        for (; y + 1 < he; y += 2) {
-          const T* p0 = tab + ((size_t)y * w) * CV + cv;
-          const T* p1 = p0 + (size_t)w * CV;
-          const T a0 = __ldg(p0 + (size_t)ws * CV), a1 = __ldg(p0 + (size_t)x_last * CV);
-          const T b0 = __ldg(p1 + (size_t)ws * CV), b1 = __ldg(p1 + (size_t)x_last * CV);
+      if (wd <= 2 * win) {
+        // common case: two lookups per window row (they coincide when wd == win), two rows in flight
+        int k = 0;
+        for (; k + 1 < nrow; k += 2) {
+          const unsigned ra = (unsigned)(y0 + k * ystep) * rowpitch;
+          const unsigned rb = (unsigned)min(y0 + (k + 1) * ystep, ylast) * rowpitch;
+          const T a0 = __ldg(tab + ra + xo0), a1 = __ldg(tab + ra + xo1);
+          const T b0 = __ldg(tab + rb + xo0), b1 = __ldg(tab + rb + xo1);
           m = V::vmax(m, V::vmax(V::vmax(a0, a1), V::vmax(b0, b1)));
         }
-        if (y < he) {
-          const T* p0 = tab + ((size_t)y * w) * CV + cv;
-          m = V::vmax(m, V::vmax(__ldg(p0 + (size_t)ws * CV), __ldg(p0 + (size_t)x_last * CV)));
+        if (k < nrow) {
+          const unsigned ra = (unsigned)min(y0 + k * ystep, ylast) * rowpitch;
+          m = V::vmax(m, V::vmax(__ldg(tab + ra + xo0), __ldg(tab + ra + xo1)));
         }
       } else {
         // very wide bins (> 32 cells): step full windows, finish right-aligned
-        for (int y = hs; y < he; ++y) {
-          const T* p0 = tab + ((size_t)y * w) * CV + cv;
-          for (int x = ws; x < x_last; x += win) m = V::vmax(m, __ldg(p0 + (size_t)x * CV));
-          m = V::vmax(m, __ldg(p0 + (size_t)x_last * CV));
+        for (int k = 0; k < nrow; ++k) {
+          const unsigned ra = (unsigned)min(y0 + k * ystep, ylast) * rowpitch;
+          for (unsigned xo = xo0; xo < xo1; xo += (unsigned)win * CV) m = V::vmax(m, __ldg(tab + ra + xo));
+          m = V::vmax(m, __ldg(tab + ra + xo1));
         }
       }
     }
-    if (cv_ok) __stcs(orow + (size_t)b * CV, V::scale(m, mul));
+    __stcs(orow + (size_t)pw * CV, V::scale(m, mul));
   }
 }
 
@@ -552,8 +597,9 @@ template <typename V>
 static int roipool_v2(const void* feat, int h, int w, int CV, const float* boxes, const float* objectness, int R,
                       float spatial_scale, void* out, void* ws, cudaStream_t st) {
   typedef typename V::T T;
-  const size_t smem = (size_t)2 * w * XT_SLOTS * sizeof(T);
+  const size_t smem = (size_t)4 * w * XT_SLOTS * sizeof(T);
   DRN_CHECK_ARG(smem <= 200 * 1024, "roipool: feature map too wide for the table builder (w=%d)", w);
+  DRN_CHECK_ARG((unsigned long long)XT_TABLES * h * w * CV < (1ull << 31), "roipool: feature map too large for 32-bit table offsets");
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(xtable_build_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -562,7 +608,7 @@ static int roipool_v2(const void* feat, int h, int w, int CV, const float* boxes
   }
   xtable_build_kernel<V><<<dim3(h, CV / XT_SLOTS), 256, smem, st>>>((const T*)feat, h, w, CV, (T*)ws);
   DRN_CHECK_LAUNCH("roipool xtable build");
-  roipool_gather_kernel<V><<<dim3(R, cdiv(CV, 32)), 256, 0, st>>>((const T*)feat, (const T*)ws, h, w, CV, boxes, objectness,
+  roipool_gather_kernel<V><<<dim3(R, cdiv(CV, 32)), 224, 0, st>>>((const T*)feat, (const T*)ws, h, w, CV, boxes, objectness,
                                                                 spatial_scale, (T*)out);
   DRN_CHECK_LAUNCH("roipool gather");
   return 0;
@@ -635,7 +681,7 @@ int drn_maxpool2x2_nhwc(const void* in, int N, int H, int W, int C, int stride, 
 
 size_t drn_roipool_workspace_bytes(int h, int w, int C, int dtype) {
   if (h <= 0 || w <= 0 || C <= 0) return 0;
-  return (size_t)XT_LEVELS * h * w * C * (dtype == DRN_BF16 ? 2 : 4);
+  return (size_t)XT_TABLES * h * w * C * (dtype == DRN_BF16 ? 2 : 4);
 }
 
 int drn_roipool_fwd(const void* feat, int h, int w, int C, const float* boxes, const float* objectness,

@@ -209,12 +209,12 @@ def main():
         counter["n"] += LAUNCHES.get(name, 1)
         return orig_call(name, *a)
 
+    from drn_wsod_pytorch_b200 import distributed as D
+
     def step(batched):
-        losses = model(batched)
-        vec = torch.stack([losses[k] for k in sorted(losses)])
-        if dist is not None:
-            dist.all_reduce(vec, op=dist.ReduceOp.AVG)  # comm.reduce_dict equivalent (detectron2/utils/comm.py:234-263)
-        return vec, sorted(losses)
+        losses = D.reduce_dict(model(batched))  # one packed all-reduce (detectron2/utils/comm.py:234-263 equivalent); identity at N=1
+        keys = sorted(losses)
+        return torch.stack([losses[k] for k in keys]), keys
 
     def sync_all():
         if dist is not None:

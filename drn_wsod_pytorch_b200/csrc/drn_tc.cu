@@ -168,6 +168,18 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[3
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+        "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+        "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 
 // same counter-based RNG as drn_dropout_inplace (drn_heads.cu): one draw per output element
 __device__ __forceinline__ uint32_t mix32(uint64_t x) {
@@ -202,6 +214,41 @@ struct Params {
   unsigned long long drop_seed;
   const unsigned long long* drop_seed_dev;  // optional device-resident addend (fresh masks under graph replay)
   int debug;  // DRN_TC_DEBUG (profiling experiments only): 1 = skip TMA stores, 2 = skip epilogue math, 4 = skip tcgen05.ld
+  // stream-K (deep-K GEMMs whose tile count does not fill whole waves): every unit gets an equal share of the
+  // tiles x K-blocks iteration space; a unit that starts inside a tile dumps that partial accumulator to sk_ws
+  // and raises sk_flags[unit], the unit that began the tile (and reaches it last in time) adds it and runs the epilogue
+  int stream_k;
+  float* sk_ws;
+  unsigned int* sk_flags;
+};
+
+struct Piece { int tile, kb0, kb1, kind; };  // kind: 0 = whole tile, 1 = tail part (dump partial), 2 = head part (owner)
+
+struct Sched {
+  int KB, num_tiles, num_units, sk, cur;
+  long long g, g1;
+  __device__ Sched(int unit, int num_units_, int num_tiles_, int KB_, int sk_) : KB(KB_), num_tiles(num_tiles_), num_units(num_units_), sk(sk_), cur(unit) {
+    const long long total = (long long)num_tiles_ * KB_;
+    const long long W = (total + num_units_ - 1) / num_units_;
+    g = (long long)unit * W;
+    g1 = g + W < total ? g + W : total;
+  }
+  __device__ bool next(Piece& pc) {
+    if (!sk) {
+      if (cur >= num_tiles) return false;
+      pc.tile = cur; pc.kb0 = 0; pc.kb1 = KB; pc.kind = 0;
+      cur += num_units;
+      return true;
+    }
+    if (g >= g1) return false;
+    pc.tile = (int)(g / KB);
+    pc.kb0 = (int)(g - (long long)pc.tile * KB);
+    const long long left = g1 - g;
+    pc.kb1 = (KB - pc.kb0 <= left) ? KB : pc.kb0 + (int)left;
+    pc.kind = pc.kb0 > 0 ? 1 : (pc.kb1 < KB ? 2 : 0);
+    g += pc.kb1 - pc.kb0;
+    return true;
+  }
 };
 
 __device__ __forceinline__ float4 lds128f(uint32_t saddr) {
@@ -342,7 +389,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       const int cblocks = p.conv ? (p.Cin / BK) : 1;
-      for (int tile = unit; tile < num_tiles; tile += num_units) {
+      Sched sched(unit, num_units, num_tiles, p.KB, p.stream_k);
+      Piece pc;
+      while (sched.next(pc)) {
+        const int tile = pc.tile;
         const int mt = (tile % num_mp) * CG + cta_rank, nt = tile / num_mp;
         int img = 0, h0 = 0, w0 = 0;
         if (p.conv) {
@@ -352,7 +402,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           h0 = (r / p.tiles_w) * p.tile_h;
           w0 = (r % p.tiles_w) * p.tile_w;
         }
-        for (int kb = 0; kb < p.KB; ++kb) {
+        for (int kb = pc.kb0; kb < pc.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], CG * STAGE_BYTES);
           uint8_t* sa = smem + stage * STAGE_BYTES;
@@ -379,7 +429,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (p.has_residual) {
+        if (p.has_residual && pc.kind != 1) {
           const int nchunk = (min(BN, p.N - nt * BN) + EPI_CHUNK - 1) / EPI_CHUNK;
           for (int c = 0; c < nchunk; ++c) {  // shortcut tile as extra "k-blocks": 128 rows x 64 output columns each
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -413,11 +463,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       auto commit = [&](uint64_t* bar) {
         if constexpr (CG == 2) umma2_commit_both(bar); else umma_commit(bar);
       };
-      for (int tile = unit; tile < num_tiles; tile += num_units) {
+      Sched sched(unit, num_units, num_tiles, p.KB, p.stream_k);
+      Piece pc;
+      while (sched.next(pc)) {
+        const int tile = pc.tile;
+        const bool with_res = p.has_residual && pc.kind != 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.KB; ++kb) {
+        for (int kb = pc.kb0; kb < pc.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
@@ -425,13 +479,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the >>4 encoded address
-            mma(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            mma(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > pc.kb0 || k > 0) ? 1u : 0u);
           }
           commit(&empty_bar[stage]);  // frees the smem slot (in both CTAs) once these MMAs retire
-          if (kb == p.KB - 1 && !p.has_residual) commit(&tfull_bar[acc]);
+          if (kb == pc.kb1 - 1 && !with_res) commit(&tfull_bar[acc]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (p.has_residual) {
+        if (with_res) {
           const int nt = tile / num_mp;
           const int nchunk = (min(BN, p.N - nt * BN) + EPI_CHUNK - 1) / EPI_CHUNK;
           for (int c = 0; c < nchunk; ++c) {
@@ -474,9 +528,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         pre_bi[i] = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
       }
     };
-    if (unit < num_tiles) fetch_sb(unit / num_mp);
+    Sched sched(unit, num_units, num_tiles, p.KB, p.stream_k);
+    Piece pc, pc_next;
+    bool have = sched.next(pc);
+    if (have) fetch_sb(pc.tile / num_mp);
 
-    for (int tile = unit; tile < num_tiles; tile += num_units) {
+    while (have) {
+      const bool have_next = sched.next(pc_next);
+      const int tile = pc.tile;
       const int mt = (tile % num_mp) * CG + cta_rank, nt = tile / num_mp;
       int img = 0, hh0 = 0, ww0 = 0;
       long long m_global;
@@ -506,13 +565,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (idx < BN) { s_scale[idx] = pre_sc[i]; s_bias[idx] = pre_bi[i]; }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (tile + num_units < num_tiles) fetch_sb((tile + num_units) / num_mp);  // in flight while this tile is drained
+      if (have_next) fetch_sb(pc_next.tile / num_mp);  // in flight while this tile is drained
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
 
-      if (!p.out_f32) {
+      if (pc.kind == 1) {
+        // ---------------------------------------------------------- stream-K tail part: dump the raw fp32 partial
+        // layout [column][128 rows] so that a warp's 32 lanes (rows) write / read 128 contiguous bytes
+        float* wsp = p.sk_ws + (size_t)(unit * CG + cta_rank) * (BN * 128) + row;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v[32];
+          tmem_ld32_nowait(taddr + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) __stcg(wsp + (size_t)(c + j) * 128, __uint_as_float(v[j]));
+        }
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (etid == 0) {
+          unsigned int* flag = p.sk_flags + unit * CG + cta_rank;
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(1u) : "memory");
+        }
+      } else if (pc.kind == 2) {
+        // ---------------------------------------------------------- stream-K head part (owner): fold in the partner's
+        // partial (written by unit + 1 at the very start of the kernel), then fall through to the normal epilogue
+        unsigned int* flag = p.sk_flags + (unit + 1) * CG + cta_rank;
+        if (etid == 0) {
+          unsigned int f;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(flag) : "memory");
+          } while (f == 0u);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const float* wsp = p.sk_ws + (size_t)((unit + 1) * CG + cta_rank) * (BN * 128) + row;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v[32];
+          tmem_ld32_nowait(taddr + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldcg(wsp + (size_t)(c + j) * 128));
+          tmem_st32(taddr + c, v);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (etid == 0) *flag = 0u;  // self-resetting: ready for the next launch
+      }
+
+      if (pc.kind == 1) {
+        // nothing to store
+      } else if (!p.out_f32) {
         // ---------------------------------------------------------- bf16 output through smem + TMA store
 #pragma unroll 1
         for (int c = 0; c < NCHUNK; ++c) {
@@ -579,6 +683,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (CG == 2 && !leader) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      pc = pc_next;
+      have = have_next;
     }
     if (lane == 0) bulk_wait_all();  // staging smem must outlive the last TMA store
   }
@@ -635,9 +741,12 @@ static int num_sms() {
   return n;
 }
 
+constexpr size_t SK_FLAG_BYTES = 4096;
+constexpr size_t SK_WS_BYTES = SK_FLAG_BYTES + (size_t)148 * 128 * 256 * sizeof(float);  // one 128 x 256 fp32 partial per SM
+
 template <int BN, int STAGES, int NBUF, int CG>
-static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mr, const Params& p,
-                  cudaStream_t st) {
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mr, Params p,
+                  cudaStream_t st, void* workspace, size_t workspace_bytes) {
   constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + (BN / CG) * BK * 2) + 4 * NBUF * EPI_BUF_BYTES + IDENT_BYTES +
                           4 * BN * sizeof(float) + (2 * STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
   static_assert(smem <= 232448, "gemm_tc: shared memory budget exceeded");
@@ -649,6 +758,27 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
   }
   const int units = ((p.num_m_tiles + CG - 1) / CG) * p.num_n_tiles;
   const int max_units = num_sms() / CG;
+  // stream-K (opt-in, DRN_TC_STREAMK=1) when whole-tile scheduling would leave > 6 % of the machine idle in the last
+  // wave and K is deep enough that every unit's share spans at least one whole tile (see Sched).  Measured on
+  // fc6 (M=4000, N=2048, K=100352: 1.73 waves): 1836 us vs 1212 us for whole-tile waves -- units then sit at
+  // different K offsets, so the A/B tiles shared by co-scheduled CTAs no longer meet in L2 and every CTA streams
+  // its operands from HBM (12.8 GB instead of ~2 GB).  Kept for shapes whose operands fit in L2; off by default.
+  p.stream_k = 0;
+  if (workspace && workspace_bytes >= SK_WS_BYTES && !p.out_f32 && units > max_units && max_units <= 148 && p.KB >= 8) {
+    const int waves = (units + max_units - 1) / max_units;
+    const double ideal = (double)units / max_units;
+    const long long share = ((long long)units * p.KB + max_units - 1) / max_units;
+    static int sk_env = -1;
+    if (sk_env < 0) {
+      const char* e = getenv("DRN_TC_STREAMK");
+      sk_env = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (sk_env && waves / ideal > 1.06 && share >= p.KB) {
+      p.stream_k = 1;
+      p.sk_flags = (unsigned int*)workspace;
+      p.sk_ws = (float*)((char*)workspace + SK_FLAG_BYTES);
+    }
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(CG * (units < max_units ? units : max_units)));
   cfg.blockDim = dim3(NUM_THREADS);
@@ -709,10 +839,13 @@ static void pick_conv_tile(int H, int W, int* tw_out, int* th_out) {
 
 using namespace drn;
 
+extern "C" size_t drn_gemm_workspace_bytes(void) { return drn::tc::SK_WS_BYTES; }
+
 extern "C" int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int Cin, const void* w, int ksize,
                                       int dilation, const float* scale, const float* bias, const void* residual,
                                       int relu, void* out, int out_dtype, int Cout, int ldo, float dropout_p,
-                                      uint64_t dropout_seed, const uint64_t* dropout_seed_dev, drn_stream_t stream) {
+                                      uint64_t dropout_seed, const uint64_t* dropout_seed_dev, void* workspace,
+                                      size_t workspace_bytes, drn_stream_t stream) {
   using namespace drn::tc;
   DRN_CHECK_ARG(in && w && out, "conv_igemm_bf16_tc: null pointer");
   DRN_CHECK_ARG(ksize == 1 || ksize == 3, "conv_igemm_bf16_tc: ksize %d", ksize);
@@ -807,12 +940,12 @@ extern "C" int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int C
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (cg == 2) {
-    if (bn == 256 && p.KB >= 48) return launch<256, 6, 1, 2>(ma, mb, mo, mr, p, st);  // deep K: smem goes to pipeline stages
-    if (bn == 256) return launch<256, 5, 2, 2>(ma, mb, mo, mr, p, st);
-    if (bn == 128) return launch<128, 7, 2, 2>(ma, mb, mo, mr, p, st);
-    return launch<64, 8, 2, 2>(ma, mb, mo, mr, p, st);
+    if (bn == 256 && p.KB >= 48) return launch<256, 6, 1, 2>(ma, mb, mo, mr, p, st, workspace, workspace_bytes);  // deep K: smem goes to pipeline stages
+    if (bn == 256) return launch<256, 5, 2, 2>(ma, mb, mo, mr, p, st, workspace, workspace_bytes);
+    if (bn == 128) return launch<128, 7, 2, 2>(ma, mb, mo, mr, p, st, workspace, workspace_bytes);
+    return launch<64, 8, 2, 2>(ma, mb, mo, mr, p, st, workspace, workspace_bytes);
   }
-  if (bn == 256) return launch<256, 4, 1, 1>(ma, mb, mo, mr, p, st);
-  if (bn == 128) return launch<128, 5, 2, 1>(ma, mb, mo, mr, p, st);
-  return launch<64, 7, 2, 1>(ma, mb, mo, mr, p, st);
+  if (bn == 256) return launch<256, 4, 1, 1>(ma, mb, mo, mr, p, st, workspace, workspace_bytes);
+  if (bn == 128) return launch<128, 5, 2, 1>(ma, mb, mo, mr, p, st, workspace, workspace_bytes);
+  return launch<64, 7, 2, 1>(ma, mb, mo, mr, p, st, workspace, workspace_bytes);
 }

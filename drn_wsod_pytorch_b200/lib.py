@@ -24,7 +24,7 @@ _PROTOS = {
     "drn_conv3x3_c3_fwd": [_P, c_int, c_int, c_int, c_int, _FP, _FP, _P, _P, _P, c_int, c_int, c_int, _P, c_int, _P],
     "drn_conv_igemm_f32": [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, _P, _P, c_int, _P, c_int, c_int, _P],
     "drn_conv_igemm_bf16_tc": [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, _P, _P, c_int, _P, c_int, c_int, c_int,
-                               c_float, c_uint64, _P, _P],
+                               c_float, c_uint64, _P, _P, c_size_t, _P],
     "drn_maxpool2x2_nhwc": [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "drn_roipool_fwd": [_P, c_int, c_int, c_int, _P, _P, c_int, c_float, c_int, _P, _P, c_size_t, _P],
     "drn_wsddn_mil_fwd": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_float, _P, _P, _P, _P, _P],
@@ -67,6 +67,8 @@ def load():
         fn.restype = c_int
     lib.drn_roipool_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
     lib.drn_roipool_workspace_bytes.restype = c_size_t
+    lib.drn_gemm_workspace_bytes.argtypes = []
+    lib.drn_gemm_workspace_bytes.restype = c_size_t
     _lib = lib
     return lib
 

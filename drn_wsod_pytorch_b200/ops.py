@@ -51,6 +51,20 @@ def conv_f32(x, packed, ksize, dilation, relu, residual=None, out=None, ldo=None
     return out
 
 
+_GEMM_WS = {}
+
+
+def _gemm_workspace(device):
+    """Zero-initialised stream-K scratch, one per (device, stream): kernels on one stream are ordered, so
+    they can share it; the kernel resets the flags it raises."""
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    ws = _GEMM_WS.get(key)
+    if ws is None:
+        ws = torch.zeros((lib.load().drn_gemm_workspace_bytes(),), device=device, dtype=torch.uint8)
+        _GEMM_WS[key] = ws
+    return ws
+
+
 def conv_bf16_tc(x, packed, ksize, dilation, relu, residual=None, out_dtype=torch.bfloat16, dropout_p=0.0, dropout_seed=0,
                  dropout_seed_dev=None):
     """tcgen05 implicit-GEMM conv / linear (+ fused train-mode dropout).  x: [N,H,W,Cin] bf16 NHWC."""
@@ -58,9 +72,10 @@ def conv_bf16_tc(x, packed, ksize, dilation, relu, residual=None, out_dtype=torc
     N, H, W, Cin = x.shape
     Cout = packed["cout"]
     out = torch.empty((N, H, W, Cout), device=x.device, dtype=out_dtype)
+    ws = _gemm_workspace(x.device) if (ksize == 1 and Cin >= 1024) else None  # deep-K GEMMs only
     call("drn_conv_igemm_bf16_tc", x, N, H, W, Cin, packed["w"], ksize, dilation, packed["scale"], packed["bias"],
          residual, int(relu), out, _dt(out), Cout, Cout, float(dropout_p), int(dropout_seed), dropout_seed_dev,
-         current_stream())
+         ws, 0 if ws is None else ws.numel(), current_stream())
     return out
 
 
@@ -101,8 +116,9 @@ def roipool(feat_hwc, boxes, objectness, spatial_scale, use_tables=None):
 
 def drop_scratch(stream):
     """Free the grow-only scratch buffers that were created for `stream` (a warm-up side stream)."""
-    for key in [k for k in _ROIPOOL_WS if k[1] == stream.cuda_stream]:
-        del _ROIPOOL_WS[key]
+    for d in (_ROIPOOL_WS, _GEMM_WS):
+        for key in [k for k in d if k[1] == stream.cuda_stream]:
+            del d[key]
 
 
 def dropout_(x, p, seed, seed_dev=None):

@@ -67,7 +67,12 @@ int drn_conv_igemm_f32(const float* in, int N, int H, int W, int Cin, const floa
 int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int Cin, const void* w, int ksize,
                            int dilation, const float* scale, const float* bias, const void* residual,
                            int relu, void* out, int out_dtype, int Cout, int ldo, float dropout_p,
-                           uint64_t dropout_seed, const uint64_t* dropout_seed_dev, drn_stream_t stream);
+                           uint64_t dropout_seed, const uint64_t* dropout_seed_dev, void* workspace,
+                           size_t workspace_bytes, drn_stream_t stream);
+/* Scratch for the stream-K schedule of deep-K GEMMs (fc6/fc7): drn_gemm_workspace_bytes() bytes, 16-byte
+ * aligned, ZERO-INITIALISED once by the caller (the kernel resets the flags it uses), not shared by
+ * kernels that may run concurrently.  NULL disables stream-K (whole-tile waves). */
+size_t drn_gemm_workspace_bytes(void);
 
 /* MaxPool2d(kernel 2, stride 1|2, padding 0), NHWC.
  * Replaces nn.MaxPool2d in WSL/backbone/resnet_ws.py:93-94,110-111,403,415 and vgg.py:93-94,108-109. */

@@ -298,12 +298,18 @@ def main():
         v, _ = step([host])
         return v.cpu()
 
+    # input prefetch (model.prefetch): the H2D copy of step i+1's inputs is started right after step i is
+    # launched, so it overlaps step i's kernels -- still one full H2D of every input per step, inside the timed region
     for _ in range(3):
         e2e_step()
     sync_all()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        loss_host = e2e_step()
+    batches = [[host], [host]]  # two batch objects over the same pinned tensors (prefetch is keyed on the batch object)
+    model.prefetch(batches[0])
+    for i in range(args.steps):
+        v, _ = step(batches[i & 1])
+        model.prefetch(batches[(i + 1) & 1])
+        loss_host = v.cpu()
     sync_all()
     t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
     if dist is not None:

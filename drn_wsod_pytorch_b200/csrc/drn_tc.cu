@@ -686,7 +686,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       pc = pc_next;
       have = have_next;
     }
-    if (lane == 0) bulk_wait_all();  // staging smem must outlive the last TMA store
+    if (lane == 0) bulk_wait_read<0>();  // staging smem must outlive the last TMA store's read (global visibility comes with grid completion)
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

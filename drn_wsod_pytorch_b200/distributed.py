@@ -34,9 +34,12 @@ def reduce_dict(losses: Dict[str, torch.Tensor], average: bool = True) -> Dict[s
     if ws == 1:
         return dict(losses)
     keys, vec = pack_losses(losses)
-    dist.all_reduce(vec, op=dist.ReduceOp.SUM)
-    if average:
-        vec = vec / ws
+    if average and dist.get_backend() == "nccl":
+        dist.all_reduce(vec, op=dist.ReduceOp.AVG)  # averaged inside the collective
+    else:
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM)
+        if average:
+            vec = vec / ws
     return {k: vec[i] for i, k in enumerate(keys)}
 
 

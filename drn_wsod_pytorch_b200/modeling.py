@@ -602,18 +602,22 @@ class _WSLROIHeads(nn.Module):
         for t in targets:
             gc = t.gt_classes
             dev = self._device if gc.device.type == "cpu" else gc.device
-            key = (gc.data_ptr(), gc._version, gc.numel(), str(gc.device))
-            hit = self._gt_cache.get(key) if gc.is_cuda else None
+            if gc.is_cuda:
+                key = ("dev", gc.data_ptr(), gc._version, gc.numel(), str(gc.device))
+                hit = self._gt_cache.get(key)
+                classes = None if hit is not None else sorted(set(int(c) for c in gc.tolist()))  # one D2H sync
+            else:
+                classes = sorted(set(int(c) for c in gc.tolist()))
+                key = ("set", tuple(classes), str(dev))  # device copies are cached per class set: no H2D per step
+                hit = self._gt_cache.get(key)
             if hit is None:
-                classes = sorted(set(int(c) for c in gc.tolist()))  # one D2H sync if gc lives on the device
                 gt = torch.tensor(classes, dtype=torch.int64).to(dev)
                 oh_host = torch.zeros((K,), dtype=torch.float32)
                 oh_host[classes] = 1.0
                 hit = (gt, oh_host.to(dev))
-                if gc.is_cuda:
-                    if len(self._gt_cache) > 64:
-                        self._gt_cache.clear()
-                    self._gt_cache[key] = hit
+                if len(self._gt_cache) > 4096:
+                    self._gt_cache.clear()
+                self._gt_cache[key] = hit
             out.append(hit)
         self.gt_classes_img = [g for g, _ in out]
         self.gt_classes_img_int = self.gt_classes_img
@@ -706,13 +710,13 @@ class _WSLROIHeads(nn.Module):
         return {"loss_buf": loss_buf, "img_scores": torch.stack(img_scores, dim=0), "label_counts": label_counts,
                 "stage_stats": stage_stats, "lab0": lab0_l, "midx0": midx0_l, "traces": traces}
 
-    def _train_post(self, d, proposals, targets):
+    def _train_post(self, d, proposals, targets, attach=True):
         """Host side of the train forward: loss dict (keys/normalisation of fast_rcnn.py:317-329,
         :1128-1144, :1146-1211), the attributes/fields the reference sets, EventStorage scalars."""
         K, N, S = self.num_classes, len(proposals), self.refine_K
         loss_buf, stage_stats, label_counts = d["loss_buf"], d["stage_stats"], d["label_counts"]
         dev = loss_buf.device
-        for i in range(N):  # roi_heads.py:314-336
+        for i in range(N if attach else 0):  # roi_heads.py:314-336 (only the ROI-heads API returns the proposals)
             proposals[i].gt_classes = d["lab0"][i]
             if len(targets[i]) > 0:
                 tb = targets[i].gt_boxes
@@ -850,10 +854,48 @@ class _GraphPlan:
         with torch.cuda.graph(self.graph):
             self.out = fn(self.static_in)
 
+        self.staging = None
+        self.copy_stream = None
+        self.staged_event = None
+        self.staged_key = None
+        self.refill_done = None
+
+    @staticmethod
+    def _ident(inputs):
+        return tuple((t.data_ptr(), t._version) for t in inputs)
+
+    def stage(self, inputs):
+        """Prefetch: start the H2D copy of the NEXT call's inputs into staging buffers on a side stream, so
+        it overlaps the step that is currently running (what a dataloader prefetcher does).  `run` picks the
+        staged copy up (one D2D refill of the static buffers) when it is handed the same tensors."""
+        dev = self.static_in[0].device
+        if self.staging is None:
+            self.staging = [torch.empty_like(t) for t in self.static_in]
+            self.copy_stream = torch.cuda.Stream(dev)
+            self.staged_event = torch.cuda.Event()
+        if self.refill_done is not None:
+            self.copy_stream.wait_event(self.refill_done)  # the previous staging -> static refill has drained the buffers
+        with torch.cuda.stream(self.copy_stream):
+            for sg, t in zip(self.staging, inputs):
+                sg.copy_(t, non_blocking=True)
+            self.staged_event.record(self.copy_stream)
+        self.staged_key = self._ident(inputs)
+
     def run(self, inputs):
-        for st, t in zip(self.static_in, inputs):
+        staged = self.staged_key is not None and self.staged_key == self._ident(inputs)
+        if staged:
+            torch.cuda.current_stream().wait_event(self.staged_event)
+            src = self.staging
+            self.staged_key = None
+        else:
+            src = inputs
+        for st, t in zip(self.static_in, src):
             if st.data_ptr() != t.data_ptr():
                 st.copy_(t, non_blocking=True)
+        if staged:
+            if self.refill_done is None:
+                self.refill_done = torch.cuda.Event()
+            self.refill_done.record()
         self.graph.replay()
         return self.out
 
@@ -863,6 +905,8 @@ class GeneralizedRCNNWSL(nn.Module):
     """projects/WSL/wsl/modeling/meta_arch/rcnn.py:23-265 with precomputed proposals."""
 
     MAX_PLANS = 8  # captured graphs kept alive (each owns its activation pool)
+    CAPTURE_AFTER = 2  # an input signature is captured the 2nd time it is seen: multi-scale training, where
+    #                    (H, W, R) change every iteration, stays on the eager launch path instead of re-capturing
 
     def __init__(self, cfg):
         super().__init__()
@@ -883,6 +927,7 @@ class GeneralizedRCNNWSL(nn.Module):
         if os.environ.get("DRN_B200_CUDA_GRAPH") is not None:
             self.use_cuda_graph = os.environ["DRN_B200_CUDA_GRAPH"] not in ("0", "false", "False")
         self._plans = {}
+        self._seen = {}
 
     @property
     def device(self):
@@ -897,6 +942,7 @@ class GeneralizedRCNNWSL(nn.Module):
     def invalidate_plans(self):
         """Drop every captured graph (they hold pointers to derived weight layouts)."""
         self._plans.clear()
+        self._seen.clear()
 
     def _apply(self, fn, *a, **k):
         self._plans = {}
@@ -925,18 +971,17 @@ class GeneralizedRCNNWSL(nn.Module):
         f = feats[0] if len(feats) == 1 else torch.cat(feats, dim=0)
         return {self.backbone._out_features[0]: f.permute(0, 3, 1, 2)}
 
-    def _run_device(self, kind, canvas, groups, fn):
-        """Run `fn(flat tensor list)` eagerly or through the captured plan for this input signature.
-        groups: list of equally long tensor lists (one entry per image)."""
+    def _plan_for(self, kind, canvas, groups, fn, force=False):
         flat = [t for g in groups for t in g]
-        if not self.use_cuda_graph:
-            dev = self.device
-            flat = [t.to(dev, non_blocking=True) for t in flat]
-            flat[: len(groups[0])] = [t.float().contiguous() for t in flat[: len(groups[0])]]
-            return fn(flat)
         key = (kind, canvas, self.roi_heads.keep_trace, tuple((tuple(t.shape), t.dtype) for t in flat), self._weights_signature())
         plan = self._plans.get(key)
         if plan is None:
+            seen = self._seen.get(key, 0) + 1
+            if len(self._seen) > 4096:
+                self._seen.clear()
+            self._seen[key] = seen
+            if seen < self.CAPTURE_AFTER and not force:
+                return None, flat
             if len(self._plans) >= self.MAX_PLANS:
                 self._plans.pop(next(iter(self._plans)))
             img_n = len(groups[0])
@@ -945,11 +990,23 @@ class GeneralizedRCNNWSL(nn.Module):
             proto = [t if t.is_cuda else t.to(dev) for t in proto]
             plan = _GraphPlan(fn, proto)
             self._plans[key] = plan
-        return plan.run(flat)
+        return plan, flat
 
-    def forward(self, batched_inputs):
-        if not self.training:
-            return self.inference(batched_inputs)
+    def _run_device(self, kind, canvas, groups, fn):
+        """Run `fn(flat tensor list)` eagerly or through the captured plan for this input signature.
+        groups: list of equally long tensor lists (one entry per image).  Returns (outputs, device inputs)."""
+        plan = None
+        if self.use_cuda_graph:
+            plan, flat = self._plan_for(kind, canvas, groups, fn)
+        if plan is None:  # graphs disabled, or a signature seen for the first time: eager launches
+            flat = [t for g in groups for t in g]
+            dev = self.device
+            flat = [t.to(dev, non_blocking=True).contiguous() for t in flat]
+            flat[: len(groups[0])] = [t.float().contiguous() for t in flat[: len(groups[0])]]
+            return fn(flat), flat
+        return plan.run(flat), plan.static_in
+
+    def _train_groups(self, batched_inputs):
         images, sizes, canvas = self.preprocess_image(batched_inputs)
         assert self.load_proposals and "proposals" in batched_inputs[0]
         assert "instances" in batched_inputs[0], "'targets' argument is required during training"
@@ -970,10 +1027,29 @@ class GeneralizedRCNNWSL(nn.Module):
                   [t.gt_boxes.tensor for t in targets], [t.gt_classes for t in targets],
                   [g for g, _ in img_gt], [o for _, o in img_gt]]
         groups = [[t if t.dtype in (torch.int64, torch.uint8) or i == 0 else t.float() for t in g] for i, g in enumerate(groups)]
-        dev_out = self._run_device("train", canvas, groups, fn)
-        proposals = [p.to(self.device) for p in proposals]
+        return canvas, groups, fn, proposals, targets
+
+    def prefetch(self, batched_inputs):
+        """Optional: start moving the NEXT batch to the device while the current step runs (train mode,
+        CUDA-graph path).  Call it with the same `batched_inputs` object you will pass to forward next."""
+        if not (self.training and self.use_cuda_graph):
+            return
+        prep = self._train_groups(batched_inputs)
+        canvas, groups, fn, _, _ = prep
+        plan, flat = self._plan_for("train", canvas, groups, fn, force=True)
+        plan.stage(flat)
+        self._prefetched = (batched_inputs, prep)  # forward() with the same object reuses the host-side preparation
+
+    def forward(self, batched_inputs):
+        if not self.training:
+            return self.inference(batched_inputs)
+        pre = getattr(self, "_prefetched", None)
+        self._prefetched = None
+        canvas, groups, fn, proposals, targets = pre[1] if (pre is not None and pre[0] is batched_inputs) else self._train_groups(batched_inputs)
+        dev_out, _ = self._run_device("train", canvas, groups, fn)
+        # rcnn.py:184 discards the proposals the ROI heads return, so their gt_* fields are not materialised here
         losses = {}
-        losses.update(rh._train_post(dev_out, proposals, targets))
+        losses.update(self.roi_heads._train_post(dev_out, proposals, targets, attach=False))
         return losses
 
     def inference(self, batched_inputs, detected_instances=None, do_postprocess=True):
@@ -991,7 +1067,7 @@ class GeneralizedRCNNWSL(nn.Module):
 
             groups = [images, [p.proposal_boxes.tensor.float() for p in proposals],
                       [p.objectness_logits.float() for p in proposals]]
-            dev_out = self._run_device("eval", canvas, groups, fn)
+            dev_out, _ = self._run_device("eval", canvas, groups, fn)
             proposals = [p.to(self.device) for p in proposals]
             results, all_scores, all_boxes = rh._eval_post(dev_out, proposals)
         else:

@@ -151,6 +151,9 @@ def test_graph_plan_replay_tracks_new_inputs_and_matches_eager():
 
     eager = {n: run(i, False) for n, i in (("a", inp_a), ("b", inp_b), ("c", inp_c))}
     assert not model._plans
+    run(inp_a, True)
+    run(inp_c, True)
+    assert not model._plans  # a signature is captured the second time it is seen (first sighting runs eagerly)
     for name, inputs in (("a", inp_a), ("b", inp_b), ("a", inp_a), ("c", inp_c), ("b", inp_b)):
         got, idx = run(inputs, True)
         for k, v in eager[name][0].items():
@@ -160,6 +163,15 @@ def test_graph_plan_replay_tracks_new_inputs_and_matches_eager():
     assert len(model._plans) == 2  # (a, b) share one plan, c has its own
     got, _ = run(inp_b, True, device="cpu")  # host tensors: copied H2D into the plan's static buffers
     assert got == eager["b"][0]
+    # prefetch: inputs staged on a side stream ahead of the call, picked up by identity; unrelated inputs ignore the stage
+    model.use_cuda_graph = True
+    host_a = helpers.to_batched(inp_a, drn.Instances, drn.Boxes, device="cpu")
+    host_b = helpers.to_batched(inp_b, drn.Instances, drn.Boxes, device="cpu")
+    model.prefetch(host_a)
+    assert {k: v.item() for k, v in model(host_a).items()} == eager["a"][0]
+    model.prefetch(host_a)
+    assert {k: v.item() for k, v in model(host_b).items()} == eager["b"][0]
+    assert {k: v.item() for k, v in model(host_a).items()} == eager["a"][0]
     # stale-weight protection: an in-place parameter update must not replay the old packed weights
     with torch.no_grad():
         model.roi_heads.box_predictor.cls.bias[3] += 2.0  # (a uniform shift would cancel in the softmax)

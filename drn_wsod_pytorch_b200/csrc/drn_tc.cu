@@ -923,13 +923,16 @@ extern "C" int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int C
       if (make_map(&mr, residual, 2, rdims, rstr, rbox)) return 1;
     }
   }
-  // CTA pairs (cta_group::2) whenever there are at least two M tiles to pair; DRN_TC_CTA_GROUP=1 forces single CTAs
+  // CTA pairs (cta_group::2) pay ~1 us of cluster launch + two cluster barriers and win once the operand feed matters:
+  // measured cross-over (profiles/r1_gemm_sweep_cg2_vs_cg1.txt) at ~9000 blocks of 128x256x64 MACs.
+  // DRN_TC_CTA_GROUP=1 / 2 forces single CTAs / pairs.
   static int cg_env = -1;
   if (cg_env < 0) {
     const char* e = getenv("DRN_TC_CTA_GROUP");
-    cg_env = (e && e[0] == '1') ? 1 : 2;
+    cg_env = (e && e[0] == '1') ? 1 : (e && e[0] == '2') ? 2 : 0;
   }
-  const int cg = (cg_env == 2 && p.num_m_tiles >= 2) ? 2 : 1;
+  const long long work = (long long)p.num_m_tiles * ((Cout + 255) / 256) * p.KB;
+  const int cg = (p.num_m_tiles >= 2 && (cg_env == 2 || (cg_env == 0 && work >= 9000))) ? 2 : 1;
   const int bn = pick_bn(p.num_m_tiles, Cout, p.KB, cg);
   p.num_n_tiles = (Cout + bn - 1) / bn;
   {

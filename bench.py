@@ -32,7 +32,7 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = os.environ.get("DRN_BENCH_WORKLOAD", "r50_bf16")  # BASELINE.json configs[2]: the 4k-proposal metric
 METRIC = "images/sec (4k proposals/img) WSOD forward+loss"
 # kernels launched per C-ABI call (for the gpu_launches claim)
-LAUNCHES = {"drn_wsddn_mil_fwd": 3, "drn_label_proposals": 2}
+LAUNCHES = {"drn_wsddn_mil_fwd": 3, "drn_wsddn_mil_pgt_fwd": 2, "drn_label_proposals": 2, "drn_roipool_fwd": 2}  # (memset counted as a launch)
 
 
 def _peaks():

@@ -18,9 +18,11 @@ mil_rowstats_kernel(const float* __restrict__ logits, int ld, int R, int K, int 
   if (r >= R) return;
   const float* x = logits + (long long)r * ld + cls_off;
   float m = -INFINITY;
-  for (int k = 0; k < K; ++k) m = fmaxf(m, x[k]);
+#pragma unroll 8
+  for (int k = 0; k < K; ++k) m = fmaxf(m, __ldg(x + k));  // unrolled: 8 independent loads in flight per thread
   float s = 0.f;
-  for (int k = 0; k < K; ++k) s += expf(x[k] - m);
+#pragma unroll 8
+  for (int k = 0; k < K; ++k) s += expf(__ldg(x + k) - m);
   rowmax[r] = m;
   rowsum[r] = s;
 }
@@ -234,14 +236,17 @@ oicr_stage_kernel(const float* __restrict__ logits, int ld, int col_off, int R, 
     const float* x = logits + (long long)r * ld + col_off;
     float m = -INFINITY;
     int am = 0;
+#pragma unroll 8
     for (int k = 0; k < C1; ++k) {
-      const float v = x[k];
+      const float v = __ldg(x + k);
       if (v > m) { m = v; am = k; }  // argmax: first maximum
     }
     float s = 0.f;
-    for (int k = 0; k < C1; ++k) s += expf(x[k] - m);
+#pragma unroll 8
+    for (int k = 0; k < C1; ++k) s += expf(__ldg(x + k) - m);
     float* p = probs + (long long)r * C1;
-    for (int k = 0; k < C1; ++k) p[k] = expf(x[k] - m) / s;
+#pragma unroll 8
+    for (int k = 0; k < C1; ++k) p[k] = expf(__ldg(x + k) - m) / s;
     const int lab = (int)labels[r];
     float w = pgt_weight[matched[r]];
     if (lab == -1) w = 0.f;                 // fast_rcnn.py:1090
@@ -283,6 +288,293 @@ oicr_stage_kernel(const float* __restrict__ logits, int ld, int col_off, int R, 
     stats[0] = sh[2]; stats[1] = sh[3]; stats[2] = sh[4]; stats[3] = sh[5];
     stats[4] = sh[0]; stats[5] = sh[1];  // numerator / #valid, for multi-image batches
     *counter = 0u;
+  }
+}
+
+// ---------------------------------------------------------------- fused tail (4 kernels instead of 13)
+// The separate kernels above are one launch per reference function; at R = 4000 each is a few microseconds
+// of work behind ~5-10 us of launch + cold-start latency (measured: 122 us per image for the whole tail).
+// The fused variants keep the same device functions and reduction orders (results are bit-identical) and
+// hand the serial dependencies -- image score -> pseudo GT -> labels -> loss -> next pseudo GT -- from one
+// kernel to the next through "last block" epilogues instead of extra launches.
+
+// WSDDN MIL + BCE + stage-0 pseudo-GT mining (after mil_rowstats_kernel).  grid = K CTAs (one per class), 512 threads.
+__global__ void __launch_bounds__(512)
+mil_pgt_fused_kernel(const float* __restrict__ logits, int ld, int R, int K, int cls_off, int det_off,
+                     const float* __restrict__ rowmax, const float* __restrict__ rowsum,
+                     const float* __restrict__ gt_onehot, int mean_loss, float loss_scale,
+                     const float* __restrict__ boxes, const int64_t* __restrict__ gt_classes, int G,
+                     float* __restrict__ scores, float* __restrict__ img_score, float* __restrict__ loss,
+                     int64_t* __restrict__ pgt_idx, float* __restrict__ pgt_score, float* __restrict__ pgt_box,
+                     float* __restrict__ pgt_weight, float* __restrict__ bce_terms, uint32_t* __restrict__ counter) {
+  __shared__ float sh[32];
+  __shared__ float sv[16];
+  __shared__ int si[16];
+  __shared__ bool is_last;
+  const int c = blockIdx.x;
+  const float* det = logits + det_off + c;
+  float m = -INFINITY;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) m = fmaxf(m, det[(long long)r * ld]);
+  m = block_max(m, sh);
+  float s = 0.f;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) s += expf(det[(long long)r * ld] - m);
+  s = block_sum(s, sh);
+  float tot = 0.f, bv = -INFINITY;
+  int bi = 0x7fffffff;
+  const float* cls = logits + cls_off + c;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    const float pc = expf(cls[(long long)r * ld] - rowmax[r]) / rowsum[r];
+    const float pd = expf(det[(long long)r * ld] - m) / s;
+    const float sc = pc * pd;
+    scores[(long long)r * K + c] = sc;
+    tot += sc;
+    if (better(sc, r, bv, bi)) { bv = sc; bi = r; }
+  }
+  tot = block_sum(tot, sh);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { sv[wid] = bv; si[wid] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i)
+      if (better(sv[i], si[i], bv, bi)) { bv = sv[i]; bi = si[i]; }
+    if (bi == 0x7fffffff) bi = 0;
+    const float p = fminf(fmaxf(tot, 1e-6f), 1.0f - 1e-6f);
+    img_score[c] = p;
+    const float y = gt_onehot[c];
+    const float lp = fmaxf(logf(p), -100.f), l1p = fmaxf(logf(1.f - p), -100.f);
+    bce_terms[c] = -(y * lp + (1.f - y) * l1p);
+    for (int g = 0; g < G; ++g)
+      if ((int)gt_classes[g] == c) {  // roi_heads_oicr.py:491-567, stage 0: the proposal itself is the pseudo-GT box
+        pgt_idx[g] = bi;
+        pgt_score[g] = bv;
+        pgt_weight[g] = p;
+        pgt_box[4 * g + 0] = boxes[4 * bi + 0]; pgt_box[4 * g + 1] = boxes[4 * bi + 1];
+        pgt_box[4 * g + 2] = boxes[4 * bi + 2]; pgt_box[4 * g + 3] = boxes[4 * bi + 3];
+      }
+    __threadfence();
+    is_last = (atomicAdd(counter, 1u) == (unsigned)(gridDim.x - 1));
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    const volatile float* bt = bce_terms;
+    float t = 0.f;
+    for (int k = 0; k < K; ++k) t += bt[k];  // fixed order, as mil_finalize_kernel
+    if (mean_loss) t = t / (float)K;
+    loss[0] = t * loss_scale;
+    *counter = 0u;
+  }
+}
+
+// One refinement stage: [first labelling vs the real GT] + labelling vs this stage's pseudo GT + weighted CE +
+// softmax + accuracy counters + block partial argmax of the new probabilities; the last block reduces everything
+// and mines the NEXT stage's pseudo GT.  grid = ceil(R / 256), 256 threads.
+struct StageFusedArgs {
+  const float* logits; int ld, col_off, R, K;
+  const float* boxes;
+  const int64_t* gt_img; int G;            // image-level classes (sorted), G <= MAX_G
+  const float* pgt_box; const float* pgt_weight;
+  MatcherCfg mc;
+  float loss_scale;
+  const float* gt_boxes; const int64_t* gt_classes; int Gb;   // real GT (first labelling), Gb == -1: skip
+  int64_t* labels0; int64_t* matched0; int32_t* counts0;
+  int64_t* labels; int64_t* matched; int32_t* counts;
+  float* probs; float* loss; float* stats; float* weights;
+  int has_next;
+  const float* img_score; const float* deltas; int ld_deltas, agnostic; float wx, wy, ww, wh;
+  int64_t* next_idx; float* next_score; float* next_box; float* next_weight;
+  float* part;       // [9][nb] sums + [G][nb] (value) ; indices in part_idx
+  int* part_idx;     // [G][nb]
+  uint32_t* counter;
+};
+
+__device__ __forceinline__ void match_row(const Box4& p, float ap, const float (*sg)[5], const int* sc, int G, int K,
+                                          const MatcherCfg& mc, int& lab_out, int& mi) {
+  mi = 0;
+  if (G == 0) { lab_out = K; return; }
+  float best = -INFINITY;
+  bool best_nan = false;
+  for (int g = 0; g < G; ++g) {
+    const Box4 gb = {sg[g][0], sg[g][1], sg[g][2], sg[g][3]};
+    const float v = iou_rn(gb, sg[g][4], p, ap);
+    if (!best_nan && (v > best || v != v)) { best = v; mi = g; best_nan = (v != v); }
+  }
+  int ml = 1;
+  for (int i = 0; i <= mc.nthr; ++i) {
+    const float lo = (i == 0) ? -INFINITY : mc.thr[i - 1];
+    const float hi = (i == mc.nthr) ? INFINITY : mc.thr[i];
+    if (best >= lo && best < hi) ml = mc.lab[i];
+  }
+  lab_out = sc[mi];
+  if (ml == 0) lab_out = K;
+  if (ml == -1) lab_out = -1;
+}
+
+__global__ void __launch_bounds__(STAGE_THREADS)
+oicr_stage_fused_kernel(const StageFusedArgs a) {
+  __shared__ float sg[MAX_G][5];
+  __shared__ int scl[MAX_G];
+  __shared__ float sg0[MAX_G][5];
+  __shared__ int scl0[MAX_G];
+  __shared__ float sh[32];
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  __shared__ bool is_last;
+  const int C1 = a.K + 1, K = a.K, G = a.G, nb = gridDim.x;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    const float x1 = a.pgt_box[4 * g], y1 = a.pgt_box[4 * g + 1], x2 = a.pgt_box[4 * g + 2], y2 = a.pgt_box[4 * g + 3];
+    sg[g][0] = x1; sg[g][1] = y1; sg[g][2] = x2; sg[g][3] = y2;
+    sg[g][4] = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
+    scl[g] = (int)a.gt_img[g];
+  }
+  const int Gb = a.Gb;
+  for (int g = threadIdx.x; g < Gb; g += blockDim.x) {
+    const float x1 = a.gt_boxes[4 * g], y1 = a.gt_boxes[4 * g + 1], x2 = a.gt_boxes[4 * g + 2], y2 = a.gt_boxes[4 * g + 3];
+    sg0[g][0] = x1; sg0[g][1] = y1; sg0[g][2] = x2; sg0[g][3] = y2;
+    sg0[g][4] = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
+    scl0[g] = (int)a.gt_classes[g];
+  }
+  __syncthreads();
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  float lw = 0.f, valid = 0.f, acc = 0.f, nfg = 0.f, fgacc = 0.f, fneg = 0.f;
+  float c_fg = 0.f, c_bg = 0.f, c_ig = 0.f, c0_fg = 0.f, c0_bg = 0.f, c0_ig = 0.f;
+  float myprob[1];
+  (void)myprob;
+  float pbuf_m = 0.f, pbuf_s = 1.f;
+  const float* x = nullptr;
+  if (r < a.R) {
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(a.boxes) + r);
+    const Box4 p = {bb.x, bb.y, bb.z, bb.w};
+    const float ap = __fmul_rn(__fsub_rn(p.x2, p.x1), __fsub_rn(p.y2, p.y1));
+    if (Gb >= 0) {  // roi_heads_oicr.py:266: labelling against the real GT (logging + proposals' gt fields)
+      int l0, m0;
+      match_row(p, ap, sg0, scl0, Gb, K, a.mc, l0, m0);
+      a.labels0[r] = l0;
+      a.matched0[r] = m0;
+      if (l0 == -1) c0_ig = 1.f; else if (l0 == K) c0_bg = 1.f; else c0_fg = 1.f;
+    }
+    int lab, mi;
+    match_row(p, ap, sg, scl, G, K, a.mc, lab, mi);
+    a.labels[r] = lab;
+    a.matched[r] = mi;
+    if (lab == -1) c_ig = 1.f; else if (lab == K) c_bg = 1.f; else c_fg = 1.f;
+    x = a.logits + (long long)r * a.ld + a.col_off;
+    float m = -INFINITY;
+    int am = 0;
+#pragma unroll 8
+    for (int k = 0; k < C1; ++k) {
+      const float v = __ldg(x + k);
+      if (v > m) { m = v; am = k; }
+    }
+    float s = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < C1; ++k) s += expf(__ldg(x + k) - m);
+    float* pr = a.probs + (long long)r * C1;
+#pragma unroll 8
+    for (int k = 0; k < C1; ++k) pr[k] = expf(__ldg(x + k) - m) / s;
+    pbuf_m = m; pbuf_s = s;
+    float w = a.pgt_weight[mi];
+    if (lab == -1) w = 0.f;
+    if (a.weights) a.weights[r] = w;
+    if (w > 1e-12f) valid = 1.f;
+    if (lab >= 0) lw = (-((x[lab] - m) - logf(s))) * w;
+    const bool fg = lab >= 0 && lab < K;
+    if (am == lab) acc = 1.f;
+    if (fg) {
+      nfg = 1.f;
+      if (am == lab) fgacc = 1.f;
+      if (am == K) fneg = 1.f;
+    }
+  }
+  float v;
+  v = block_sum(lw, sh);    if (threadIdx.x == 0) a.part[0 * nb + blockIdx.x] = v;
+  v = block_sum(valid, sh); if (threadIdx.x == 0) a.part[1 * nb + blockIdx.x] = v;
+  v = block_sum(acc, sh);   if (threadIdx.x == 0) a.part[2 * nb + blockIdx.x] = v;
+  v = block_sum(nfg, sh);   if (threadIdx.x == 0) a.part[3 * nb + blockIdx.x] = v;
+  v = block_sum(fgacc, sh); if (threadIdx.x == 0) a.part[4 * nb + blockIdx.x] = v;
+  v = block_sum(fneg, sh);  if (threadIdx.x == 0) a.part[5 * nb + blockIdx.x] = v;
+  v = block_sum(c_fg, sh);  if (threadIdx.x == 0) a.part[6 * nb + blockIdx.x] = v;
+  v = block_sum(c_bg, sh);  if (threadIdx.x == 0) a.part[7 * nb + blockIdx.x] = v;
+  v = block_sum(c_ig, sh);  if (threadIdx.x == 0) a.part[8 * nb + blockIdx.x] = v;
+  if (Gb >= 0) {
+    v = block_sum(c0_fg, sh); if (threadIdx.x == 0) a.part[9 * nb + blockIdx.x] = v;
+    v = block_sum(c0_bg, sh); if (threadIdx.x == 0) a.part[10 * nb + blockIdx.x] = v;
+    v = block_sum(c0_ig, sh); if (threadIdx.x == 0) a.part[11 * nb + blockIdx.x] = v;
+  }
+  if (a.has_next) {
+    // block-partial argmax of the new probabilities for every image-level class (input of the next get_pgt)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int g = 0; g < G; ++g) {
+      float bv = -INFINITY;
+      int bi = 0x7fffffff;
+      if (r < a.R) { bv = expf(x[scl[g]] - pbuf_m) / pbuf_s; bi = r; }  // == probs[r][class g], same expression
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+      }
+      __syncthreads();
+      if (lane == 0) { sv[wid] = bv; si[wid] = bi; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i)
+          if (better(sv[i], si[i], bv, bi)) { bv = sv[i]; bi = si[i]; }
+        a.part[(12 + g) * nb + blockIdx.x] = bv;
+        a.part_idx[g * nb + blockIdx.x] = bi;
+      }
+    }
+  }
+  __threadfence();
+  if (threadIdx.x == 0) is_last = (atomicAdd(a.counter, 1u) == (unsigned)(nb - 1));
+  __syncthreads();
+  if (!is_last) return;
+  const int nsum = Gb >= 0 ? 12 : 9;
+  if (threadIdx.x < nsum) {
+    float s = 0.f;
+    const volatile float* pp = a.part + threadIdx.x * nb;
+    for (int b = 0; b < nb; ++b) s += pp[b];  // fixed order
+    sh[threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a.loss[0] = (sh[0] / sh[1]) * a.loss_scale;
+    a.stats[0] = sh[2]; a.stats[1] = sh[3]; a.stats[2] = sh[4]; a.stats[3] = sh[5];
+    a.stats[4] = sh[0]; a.stats[5] = sh[1];
+    a.counts[0] = (int)sh[6]; a.counts[1] = (int)sh[7]; a.counts[2] = (int)sh[8];
+    if (Gb >= 0) { a.counts0[0] = (int)sh[9]; a.counts0[1] = (int)sh[10]; a.counts0[2] = (int)sh[11]; }
+    *a.counter = 0u;
+  }
+  if (a.has_next && threadIdx.x < G) {
+    const int g = threadIdx.x;
+    const volatile float* pv = a.part + (12 + g) * nb;
+    const volatile int* pi = a.part_idx + g * nb;
+    float bv = pv[0];
+    int bi = pi[0];
+    for (int b = 1; b < nb; ++b) {
+      const float ov = pv[b];
+      const int oi = pi[b];
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (bi == 0x7fffffff) bi = 0;
+    const int c = scl[g];
+    a.next_idx[g] = bi;
+    a.next_score[g] = bv;
+    a.next_weight[g] = a.img_score[c];
+    Box4 b = {a.boxes[4 * bi + 0], a.boxes[4 * bi + 1], a.boxes[4 * bi + 2], a.boxes[4 * bi + 3]};
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+    if (a.deltas) {
+      const float* d = a.deltas + (long long)bi * a.ld_deltas + (a.agnostic ? 0 : 4 * c);
+      d0 = d[0]; d1 = d[1]; d2 = d[2]; d3 = d[3];
+    }
+    b = apply_deltas_rn(b, d0, d1, d2, d3, a.wx, a.wy, a.ww, a.wh);  // fast_rcnn.py:1511-1532 re-derived boxes
+    a.next_box[4 * g + 0] = b.x1; a.next_box[4 * g + 1] = b.y1;
+    a.next_box[4 * g + 2] = b.x2; a.next_box[4 * g + 3] = b.y2;
   }
 }
 
@@ -500,6 +792,70 @@ int drn_dropout_inplace(void* x, int64_t n, int dtype, float p, uint64_t seed, c
   else
     dropout_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)x, n, thr, (float)(1.0 / keep), seed, seed_dev);
   DRN_CHECK_LAUNCH("dropout");
+  return 0;
+}
+
+int drn_wsddn_mil_pgt_fwd(const float* logits, int ld, int R, int K, int cls_off, int det_off,
+                          const float* gt_onehot, int mean_loss, float loss_scale, const float* boxes,
+                          const int64_t* gt_classes, int G, float* scores, float* img_score, float* loss,
+                          int64_t* pgt_idx, float* pgt_score, float* pgt_box, float* pgt_weight, float* ws,
+                          uint32_t* counter, drn_stream_t stream) {
+  DRN_CHECK_ARG(logits && gt_onehot && boxes && scores && img_score && loss && ws && counter, "wsddn_mil_pgt: null pointer");
+  DRN_CHECK_ARG(G == 0 || (gt_classes && pgt_idx && pgt_score && pgt_box && pgt_weight), "wsddn_mil_pgt: null pseudo-GT outputs");
+  DRN_CHECK_ARG(R > 0 && K > 0, "wsddn_mil_pgt: R=%d K=%d", R, K);
+  DRN_CHECK_ARG(cls_off + K <= ld && det_off + K <= ld, "wsddn_mil_pgt: column ranges exceed ld=%d", ld);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* rowmax = ws;
+  float* rowsum = ws + R;
+  float* bce = ws + 2 * (long long)R;  // [K]
+  mil_rowstats_kernel<<<cdiv(R, 256), 256, 0, st>>>(logits, ld, R, K, cls_off, rowmax, rowsum);
+  mil_pgt_fused_kernel<<<K, 512, 0, st>>>(logits, ld, R, K, cls_off, det_off, rowmax, rowsum, gt_onehot, mean_loss,
+      loss_scale, boxes, gt_classes, G, scores, img_score, loss, pgt_idx, pgt_score, pgt_box, pgt_weight, bce, counter);
+  DRN_CHECK_LAUNCH("wsddn_mil_pgt");
+  return 0;
+}
+
+int drn_oicr_stage_fused_fwd(const float* logits, int ld, int col_off, int R, int K, const float* boxes,
+                             const int64_t* gt_classes_img, int G, const float* pgt_box, const float* pgt_weight,
+                             const float* thresholds, const int* labels_cfg, int nthr, float loss_scale,
+                             const float* gt_boxes, const int64_t* gt_classes, int Gb, int64_t* labels0,
+                             int64_t* matched0, int32_t* counts0, int64_t* labels, int64_t* matched_idx,
+                             int32_t* counts, float* probs, float* loss, float* stats, float* weights,
+                             const float* img_score, const float* deltas, int ld_deltas, int cls_agnostic,
+                             const float* bbox_w, int64_t* next_pgt_idx, float* next_pgt_score,
+                             float* next_pgt_box, float* next_pgt_weight, float* part_ws, uint32_t* counter,
+                             drn_stream_t stream) {
+  DRN_CHECK_ARG(logits && boxes && gt_classes_img && pgt_box && pgt_weight && labels && matched_idx && counts && probs &&
+                    loss && stats && part_ws && counter, "oicr_stage_fused: null pointer");
+  DRN_CHECK_ARG(R > 0 && G > 0 && G <= MAX_G, "oicr_stage_fused: R=%d G=%d (max %d)", R, G, MAX_G);
+  DRN_CHECK_ARG(col_off + K + 1 <= ld, "oicr_stage_fused: columns exceed ld=%d", ld);
+  DRN_CHECK_ARG(nthr >= 0 && nthr <= 4, "oicr_stage_fused: %d thresholds (max 4)", nthr);
+  DRN_CHECK_ARG(Gb <= MAX_G, "oicr_stage_fused: Gb=%d exceeds %d", Gb, MAX_G);
+  DRN_CHECK_ARG(Gb < 0 || (labels0 && matched0 && counts0 && (Gb == 0 || (gt_boxes && gt_classes))),
+                "oicr_stage_fused: first-labelling buffers missing");
+  const int has_next = next_pgt_idx != nullptr;
+  DRN_CHECK_ARG(!has_next || (img_score && bbox_w && next_pgt_score && next_pgt_box && next_pgt_weight),
+                "oicr_stage_fused: next pseudo-GT buffers missing");
+  StageFusedArgs a;
+  a.logits = logits; a.ld = ld; a.col_off = col_off; a.R = R; a.K = K; a.boxes = boxes;
+  a.gt_img = gt_classes_img; a.G = G; a.pgt_box = pgt_box; a.pgt_weight = pgt_weight;
+  a.mc.nthr = nthr;
+  for (int i = 0; i < nthr; ++i) a.mc.thr[i] = thresholds[i];
+  for (int i = 0; i <= nthr; ++i) a.mc.lab[i] = labels_cfg[i];
+  a.loss_scale = loss_scale;
+  a.gt_boxes = gt_boxes; a.gt_classes = gt_classes; a.Gb = Gb;
+  a.labels0 = labels0; a.matched0 = matched0; a.counts0 = counts0;
+  a.labels = labels; a.matched = matched_idx; a.counts = counts;
+  a.probs = probs; a.loss = loss; a.stats = stats; a.weights = weights;
+  a.has_next = has_next; a.img_score = img_score; a.deltas = deltas; a.ld_deltas = ld_deltas; a.agnostic = cls_agnostic;
+  a.wx = bbox_w ? bbox_w[0] : 1.f; a.wy = bbox_w ? bbox_w[1] : 1.f; a.ww = bbox_w ? bbox_w[2] : 1.f; a.wh = bbox_w ? bbox_w[3] : 1.f;
+  a.next_idx = next_pgt_idx; a.next_score = next_pgt_score; a.next_box = next_pgt_box; a.next_weight = next_pgt_weight;
+  const int nb = cdiv(R, STAGE_THREADS);
+  a.part = part_ws;                                        // [(12 + G) * nb] floats ...
+  a.part_idx = reinterpret_cast<int*>(part_ws + (size_t)(12 + G) * nb);  // ... followed by [G * nb] ints
+  a.counter = counter;
+  oicr_stage_fused_kernel<<<nb, STAGE_THREADS, 0, (cudaStream_t)stream>>>(a);
+  DRN_CHECK_LAUNCH("oicr_stage_fused");
   return 0;
 }
 

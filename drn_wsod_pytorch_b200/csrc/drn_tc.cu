@@ -404,11 +404,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         for (int kb = pc.kb0; kb < pc.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], CG * STAGE_BYTES);
+          const bool skip_a = (p.debug & 32) != 0;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], CG * (skip_a ? B_BYTES : STAGE_BYTES));
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           const int brow = nt * BN + cta_rank * (int)BROWS;
-          if constexpr (CG == 2) {
+          if (skip_a) {
+            if constexpr (CG == 2) tma2_load_2d(&map_b, &full_bar[stage], sb, kb * BK, brow);
+            else tma_load_2d(&map_b, &full_bar[stage], sb, kb * BK, brow);
+          } else if constexpr (CG == 2) {
             if (p.conv) {
               const int tap = kb / cblocks, cb = kb - tap * cblocks;
               const int dh = (tap / 3 - 1) * p.dil, dw = (tap % 3 - 1) * p.dil;
@@ -423,7 +427,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               const int dh = (tap / 3 - 1) * p.dil, dw = (tap % 3 - 1) * p.dil;
               tma_load_4d(&map_a, &full_bar[stage], sa, cb * BK, w0 + dw, h0 + dh, img);
             } else {
-              tma_load_2d(&map_a, &full_bar[stage], sa, kb * BK, mt * BM);
+              tma_load_2d(&map_a, &full_bar[stage], sa, kb * BK, mt * BM - ((p.debug & 8) ? ((p.debug >> 8) & 15) : 0));
             }
             tma_load_2d(&map_b, &full_bar[stage], sb, kb * BK, brow);
           }
@@ -475,11 +479,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(&full_bar[stage], phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + A_BYTES);
+          uint64_t adesc = make_smem_desc(sa);
+          const uint64_t bdesc = make_smem_desc(sa + A_BYTES);
+          if (p.debug & 8) {  // hardware probe: shifted (non-1024-aligned) descriptor start, optional base_offset field [49,52)
+            const uint32_t shift = (p.debug >> 8) & 15;
+            adesc = make_smem_desc(sa + shift * 128);
+            if (p.debug & 16) adesc |= (uint64_t)(shift & 7) << 49;
+          }
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the >>4 encoded address
-            mma(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > pc.kb0 || k > 0) ? 1u : 0u);
+            if (!(p.debug & 64) || k == 0) mma(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > pc.kb0 || k > 0) ? 1u : 0u);
           }
           commit(&empty_bar[stage]);  // frees the smem slot (in both CTAs) once these MMAs retire
           if (kb == pc.kb1 - 1 && !with_res) commit(&tfull_bar[acc]);

@@ -31,6 +31,10 @@ _PROTOS = {
     "drn_oicr_pgt": [_P, c_int, c_int, _P, _P, c_int, _P, c_int, _P, c_int, c_int, _FP, _P, _P, _P, _P, _P],
     "drn_label_proposals": [_P, c_int, _P, _P, c_int, c_int, _FP, _IP, c_int, _P, _P, _P, _P],
     "drn_oicr_stage_fwd": [_P, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, c_float, _P, _P, _P, _P, _P, _P, _P],
+    "drn_wsddn_mil_pgt_fwd": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_float, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P,
+                              _P, _P, _P],
+    "drn_oicr_stage_fused_fwd": [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _FP, _IP, c_int, c_float, _P, _P, c_int,
+                                 _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _FP, _P, _P, _P, _P, _P, _P, _P],
     "drn_oicr_boxreg_loss": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _FP, c_float, c_float, _P, _P, _P, _P],
     "drn_oicr_infer": [_P, c_int, c_int, c_int, c_int, c_int, _IP, _IP, _P, _FP, _P, _P, _P],
     "drn_dropout_inplace": [_P, c_int64, c_int, c_float, c_uint64, _P, _P],

@@ -548,6 +548,7 @@ class _WSLROIHeads(nn.Module):
         self.output_dir, self.vis_test, self.vis_period = cfg.OUTPUT_DIR, cfg.WSL.VIS_TEST, cfg.VIS_PERIOD
         self._heads_cache = None
         self._counter = None
+        self.fused_tail = os.environ.get("DRN_B200_FUSED_TAIL", "1") != "0"
         self._gt_cache = {}
         self._device = torch.device(cfg.MODEL.DEVICE)
         self.last_trace = None
@@ -674,28 +675,47 @@ class _WSLROIHeads(nn.Module):
             feat, logits, heads = self._roi_logits(features, boxes, obj, i)
             offs = heads["offs"]
             gt_int, gt_oh = gt_int_l[i], gt_oh_l[i]
-            # labelling against the real GT (roi_heads_oicr.py:266): feeds logging + proposals' gt fields
-            lab0, midx0, cnt0 = ops.label_proposals(boxes, gtb_l[i], gtc_l[i], K, self.iou_thresholds, self.iou_labels)
-            label_counts[0][i] = cnt0
-            lab0_l.append(lab0)
-            midx0_l.append(midx0)
-            scores, img_score = ops.wsddn_mil(logits, K, offs["cls"], offs["det"], gt_oh, self.box_predictor.mean_loss,
-                                              mil_scale, loss_buf[i, 0:1])
+            if S == 0 or not self.fused_tail:
+                # one kernel per reference function (WSDDN heads, or DRN_B200_FUSED_TAIL=0)
+                # labelling against the real GT (roi_heads_oicr.py:266): feeds logging + proposals' gt fields
+                lab0, midx0, cnt0 = ops.label_proposals(boxes, gtb_l[i], gtc_l[i], K, self.iou_thresholds, self.iou_labels)
+                scores, img_score = ops.wsddn_mil(logits, K, offs["cls"], offs["det"], gt_oh, self.box_predictor.mean_loss,
+                                                  mil_scale, loss_buf[i, 0:1])
+                pgt = None
+            else:
+                scores, img_score, pgt = ops.wsddn_mil_pgt(logits, K, offs["cls"], offs["det"], gt_oh, self.box_predictor.mean_loss,
+                                                           mil_scale, loss_buf[i, 0:1], boxes, gt_int, self._counter)
+                lab0 = midx0 = cnt0 = None
             img_scores.append(img_score)
-            tr = {"scores": scores, "img_score": img_score, "logits": logits, "feat": feat, "labels_gt": lab0, "stages": []}
+            tr = {"scores": scores, "img_score": img_score, "logits": logits, "feat": feat, "stages": []}
             prev, prev_ld_deltas, prev_deltas, col = scores, 0, None, 1
             for k in range(S):
                 bw = self.box_refinery[k].bbox_w
-                pgt_idx, pgt_score, pgt_box, pgt_w = ops.oicr_pgt(prev, boxes, gt_int, img_score, k > 0, prev_deltas,
-                                                                  prev_ld_deltas, self.cls_agnostic_bbox_reg, bw)
-                labels, midx, cnt = ops.label_proposals(boxes, pgt_box, gt_int, K, self.iou_thresholds, self.iou_labels)
+                doff = offs[f"bbox_pred_{k}"] if self.refine_reg[k] else -1
+                if pgt is None:
+                    pgt_idx, pgt_score, pgt_box, pgt_w = ops.oicr_pgt(prev, boxes, gt_int, img_score, k > 0, prev_deltas,
+                                                                      prev_ld_deltas, self.cls_agnostic_bbox_reg, bw)
+                    labels, midx, cnt = ops.label_proposals(boxes, pgt_box, gt_int, K, self.iou_thresholds, self.iou_labels)
+                    probs, stats, weights = ops.oicr_stage(logits, offs[f"cls_score_{k}"], K, labels, midx, pgt_w, 1.0,
+                                                           loss_buf[i, col:col + 1], self._counter)
+                else:
+                    pgt_idx, pgt_score, pgt_box, pgt_w = pgt
+                    nxt = None
+                    if k + 1 < S:
+                        nxt = dict(img_score=img_score, deltas=logits[:, doff:] if doff >= 0 else None,
+                                   ld_deltas=logits.shape[1] if doff >= 0 else 0, cls_agnostic=self.cls_agnostic_bbox_reg,
+                                   bbox_w=self.box_refinery[k + 1].bbox_w)
+                    o = ops.oicr_stage_fused(logits, offs[f"cls_score_{k}"], K, boxes, gt_int, pgt_box, pgt_w, self.iou_thresholds,
+                                             self.iou_labels, 1.0, loss_buf[i, col:col + 1], self._counter,
+                                             first_gt=(gtb_l[i], gtc_l[i]) if k == 0 else None, nxt=nxt)
+                    labels, midx, cnt, probs, stats, weights = o["labels"], o["matched"], o["counts"], o["probs"], o["stats"], o["weights"]
+                    if k == 0:
+                        lab0, midx0, cnt0 = o["first"]
+                    pgt = o["next"]
                 label_counts[k + 1][i] = cnt
-                probs, stats, weights = ops.oicr_stage(logits, offs[f"cls_score_{k}"], K, labels, midx, pgt_w, 1.0,
-                                                       loss_buf[i, col:col + 1], self._counter)
                 stage_stats[k][i] = stats
                 col += 1
-                if self.refine_reg[k]:
-                    doff = offs[f"bbox_pred_{k}"]
+                if doff >= 0:
                     lw = self.box_refinery[k].loss_weight.get("loss_box_reg", 1.0)
                     ops.oicr_boxreg_loss(logits, doff, K, self.cls_agnostic_bbox_reg, boxes, pgt_box, labels, midx, bw,
                                          self.box_refinery[k].smooth_l1_beta, lw, loss_buf[i, col:col + 1], self._counter)
@@ -706,6 +726,10 @@ class _WSLROIHeads(nn.Module):
                 prev = probs
                 tr["stages"].append(dict(pgt_idx=pgt_idx, pgt_scores=pgt_score, pgt_boxes=pgt_box, pgt_weights=pgt_w,
                                          labels=labels, matched=midx, probs=probs, weights=weights))
+            label_counts[0][i] = cnt0
+            lab0_l.append(lab0)
+            midx0_l.append(midx0)
+            tr["labels_gt"] = lab0
             traces.append(tr)
         return {"loss_buf": loss_buf, "img_scores": torch.stack(img_scores, dim=0), "label_counts": label_counts,
                 "stage_stats": stage_stats, "lab0": lab0_l, "midx0": midx0_l, "traces": traces}

@@ -176,6 +176,53 @@ def oicr_stage(logits, col_off, K, labels, matched, pgt_weight, loss_scale, loss
     return probs, stats, weights
 
 
+def wsddn_mil_pgt(logits, K, cls_off, det_off, gt_onehot, mean_loss, loss_scale, loss_out, boxes, gt_int, counter):
+    """Fused WSDDN MIL + stage-0 pseudo-GT mining -> scores, img_score, (pgt_idx, pgt_score, pgt_box, pgt_weight)."""
+    R, ld = logits.shape
+    dev = logits.device
+    G = gt_int.numel()
+    scores = torch.empty((R, K), device=dev, dtype=torch.float32)
+    img_score = torch.empty((K,), device=dev, dtype=torch.float32)
+    ws = torch.empty((2 * R + K,), device=dev, dtype=torch.float32)
+    pgt = (torch.empty((G,), device=dev, dtype=torch.int64), torch.empty((G,), device=dev, dtype=torch.float32),
+           torch.empty((G, 4), device=dev, dtype=torch.float32), torch.empty((G,), device=dev, dtype=torch.float32))
+    call("drn_wsddn_mil_pgt_fwd", logits, ld, R, K, cls_off, det_off, gt_onehot, int(mean_loss), float(loss_scale), boxes,
+         gt_int, G, scores, img_score, loss_out, pgt[0], pgt[1], pgt[2], pgt[3], ws, counter, current_stream())
+    return scores, img_score, pgt
+
+
+def oicr_stage_fused(logits, col_off, K, boxes, gt_int, pgt_box, pgt_weight, thresholds, labels_cfg, loss_scale, loss_out,
+                     counter, first_gt=None, nxt=None):
+    """One fused refinement stage (labelling + weighted CE + softmax [+ first labelling vs the real GT]
+    [+ next stage's pseudo GT]).  first_gt = (gt_boxes, gt_classes); nxt = dict(img_score, deltas, ld_deltas,
+    cls_agnostic, bbox_w).  Returns dict(labels, matched, counts, probs, stats, weights, first=(...)|None, next=(...)|None)."""
+    R, ld = logits.shape
+    dev = logits.device
+    G = gt_int.numel()
+    nb = (R + 255) // 256
+    i64 = lambda *s: torch.empty(s, device=dev, dtype=torch.int64)
+    f32 = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
+    out = dict(labels=i64(R), matched=i64(R), counts=torch.empty((3,), device=dev, dtype=torch.int32), probs=f32(R, K + 1),
+               stats=f32(6), weights=f32(R), first=None, next=None)
+    part = f32((12 + 2 * G) * nb)
+    if first_gt is not None:
+        gtb, gtc = first_gt
+        Gb = gtc.numel()
+        out["first"] = (i64(R), i64(R), torch.empty((3,), device=dev, dtype=torch.int32))
+        f_args = (gtb if Gb else None, gtc if Gb else None, Gb) + out["first"]
+    else:
+        f_args = (None, None, -1, None, None, None)
+    if nxt is not None:
+        out["next"] = (i64(G), f32(G), f32(G, 4), f32(G))
+        n_args = (nxt["img_score"], nxt["deltas"], int(nxt["ld_deltas"]), int(nxt["cls_agnostic"]), fvec(nxt["bbox_w"])) + out["next"]
+    else:
+        n_args = (None, None, 0, 0, None, None, None, None, None)
+    call("drn_oicr_stage_fused_fwd", logits, ld, col_off, R, K, boxes, gt_int, G, pgt_box, pgt_weight, fvec(thresholds),
+         ivec(labels_cfg), len(thresholds), float(loss_scale), *f_args, out["labels"], out["matched"], out["counts"],
+         out["probs"], loss_out, out["stats"], out["weights"], *n_args, part, counter, current_stream())
+    return out
+
+
 def oicr_boxreg_loss(logits, col_off, K, cls_agnostic, boxes, pgt_box, labels, matched, bbox_w, beta, loss_scale,
                      loss_out, counter):
     R, ld = logits.shape

@@ -140,6 +140,32 @@ int drn_oicr_stage_fwd(const float* logits, int ld, int col_off, int R, int K, c
                        float* probs, float* loss, float* stats, float* weights, float* part_ws,
                        uint32_t* counter, drn_stream_t stream);
 
+/* Fused tail, part 1: drn_wsddn_mil_fwd + the stage-0 call of drn_oicr_pgt in ONE kernel (one CTA per class;
+ * the class CTA that owns an image-level GT class also mines its pseudo GT: argmax over proposals of the
+ * WSDDN score, box = that proposal, weight = image score).  Same arithmetic and reduction order as the
+ * separate kernels (bit-identical outputs).  ws: [2*R + K] fp32; counter: [1] uint32 zero-initialised, self-resetting. */
+int drn_wsddn_mil_pgt_fwd(const float* logits, int ld, int R, int K, int cls_off, int det_off,
+                          const float* gt_onehot, int mean_loss, float loss_scale, const float* boxes,
+                          const int64_t* gt_classes_img, int G, float* scores, float* img_score, float* loss,
+                          int64_t* pgt_idx, float* pgt_score, float* pgt_box, float* pgt_weight, float* ws,
+                          uint32_t* counter, drn_stream_t stream);
+
+/* Fused tail, part 2: one refinement stage = drn_label_proposals (vs this stage's pseudo GT; optionally also the
+ * first labelling vs the real GT, Gb >= 0) + drn_oicr_stage_fwd + the NEXT stage's drn_oicr_pgt (next_pgt_idx !=
+ * NULL: argmax of this stage's probabilities, boxes re-derived through apply_deltas with `deltas` or zeros) in ONE
+ * kernel; replaces the same reference lines.  counts / counts0: [3] int32 (#fg, #bg, #ignore).
+ * part_ws: [(12 + 2 * G) * ceil(R/256)] 4-byte words of scratch. */
+int drn_oicr_stage_fused_fwd(const float* logits, int ld, int col_off, int R, int K, const float* boxes,
+                             const int64_t* gt_classes_img, int G, const float* pgt_box, const float* pgt_weight,
+                             const float* thresholds_host, const int* labels_host, int nthr, float loss_scale,
+                             const float* gt_boxes, const int64_t* gt_classes, int Gb, int64_t* labels0,
+                             int64_t* matched0, int32_t* counts0, int64_t* labels, int64_t* matched_idx,
+                             int32_t* counts, float* probs, float* loss, float* stats, float* weights,
+                             const float* img_score, const float* deltas, int ld_deltas, int cls_agnostic,
+                             const float* bbox_w_host, int64_t* next_pgt_idx, float* next_pgt_score,
+                             float* next_pgt_box, float* next_pgt_weight, float* part_ws, uint32_t* counter,
+                             drn_stream_t stream);
+
 /* Box regression loss of a refinement stage with REFINE_REG[k] (reg/ configs).
  * Replaces WSL/roi_heads/fast_rcnn.py:1146-1211 with smooth_l1(beta) and
  * detectron2/modeling/box_regression.py:38-71 (get_deltas).  deltas: [R][ld] at col_off, 4K wide

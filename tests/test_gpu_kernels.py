@@ -319,6 +319,49 @@ def test_oicr_stage_chain_exact_indices():
         prev = probs
 
 
+@pytest.mark.parametrize("R,K,G", [(4000, 20, 2), (1500, 80, 5), (300, 20, 1)])
+def test_fused_tail_is_bit_identical_to_the_per_function_kernels(R, K, G):
+    """drn_wsddn_mil_pgt_fwd + drn_oicr_stage_fused_fwd (4 launches) against the one-kernel-per-reference-function
+    chain (13 launches): every output must be bit-identical (same device functions, same reduction order)."""
+    S = 3
+    inp = helpers.synth.make_inputs(600, 1000, R, seed=R + K, num_gt=G, num_classes=K)
+    logits, ld = _rand_logits(R, K, S, R)
+    d_logits, boxes = logits.to(DEV), inp["boxes"].to(DEV)
+    gtb, gtc = inp["gt_boxes"].to(DEV), inp["gt_classes"].to(DEV)
+    gt_int = torch.unique(inp["gt_classes"]).to(DEV)
+    oh = torch.zeros(K, device=DEV); oh[gt_int] = 1
+    counter = torch.zeros(1, dtype=torch.int32, device=DEV)
+    thr, labs, bw = [0.5], [0, 1], (10.0, 10.0, 5.0, 5.0)
+    # --- per-function chain
+    la = torch.zeros(1 + S, device=DEV)
+    lab0, midx0, cnt0 = ops.label_proposals(boxes, gtb, gtc, K, thr, labs)
+    scores_a, img_a = ops.wsddn_mil(d_logits, K, 0, K, oh, True, 1.0, la[0:1])
+    ref_stages, prev = [], scores_a
+    for k in range(S):
+        pgt = ops.oicr_pgt(prev, boxes, gt_int, img_a, k > 0, None, 0, False, bw)
+        lab, mi, cnt = ops.label_proposals(boxes, pgt[2], gt_int, K, thr, labs)
+        probs, stats, wts = ops.oicr_stage(d_logits, 2 * K + k * (K + 1), K, lab, mi, pgt[3], 1.0, la[k + 1:k + 2], counter)
+        ref_stages.append((pgt, lab, mi, cnt, probs, stats, wts))
+        prev = probs
+    # --- fused chain
+    lb = torch.zeros(1 + S, device=DEV)
+    scores_b, img_b, pgt = ops.wsddn_mil_pgt(d_logits, K, 0, K, oh, True, 1.0, lb[0:1], boxes, gt_int, counter)
+    assert torch.equal(scores_a, scores_b) and torch.equal(img_a, img_b)
+    for k in range(S):
+        nxt = None if k == S - 1 else dict(img_score=img_b, deltas=None, ld_deltas=0, cls_agnostic=False, bbox_w=bw)
+        o = ops.oicr_stage_fused(d_logits, 2 * K + k * (K + 1), K, boxes, gt_int, pgt[2], pgt[3], thr, labs, 1.0, lb[k + 1:k + 2],
+                                 counter, first_gt=(gtb, gtc) if k == 0 else None, nxt=nxt)
+        rp, lab, mi, cnt, probs, stats, wts = ref_stages[k]
+        for a, b in zip(pgt, rp):
+            assert torch.equal(a, b), f"stage {k} pseudo GT differs"
+        assert torch.equal(o["labels"], lab) and torch.equal(o["matched"], mi) and torch.equal(o["counts"], cnt)
+        assert torch.equal(o["probs"], probs) and torch.equal(o["stats"], stats) and torch.equal(o["weights"], wts)
+        if k == 0:
+            assert torch.equal(o["first"][0], lab0) and torch.equal(o["first"][1], midx0) and torch.equal(o["first"][2], cnt0)
+        pgt = o["next"]
+    assert torch.equal(la, lb) and counter.item() == 0
+
+
 def test_label_proposals_no_gt_and_ignore_band():
     boxes = helpers.synth.make_inputs(300, 400, 500, seed=1)["boxes"]
     lab, mi, cnt = ops.label_proposals(boxes.to(DEV), None, None, 20, [0.5], [0, 1])

@@ -493,21 +493,26 @@ xtable_build_kernel(const typename V::T* __restrict__ feat, int h, int w, int CV
   }
 }
 
-// grid = (R, CV / 32), block = 224: warp ph (0..6) owns bin row ph, lane = 16-byte vector inside the
-// 512-byte channel chunk.  Bin geometry (torchvision roi_pool, see roi_geometry above) is computed once per
+// One work item = (ROI r, 512-byte channel chunk): item = chunk * R + r (chunk-major, so the tables being
+// gathered stay in L2).  grid = #items (one item per CTA) or a small persistent grid that strides over the
+// items (used while a GEMM shares the SMs).  block = 224: warp ph (0..6) owns bin row ph, lane = 16-byte vector
+// inside the chunk.  Bin geometry (torchvision roi_pool, see roi_geometry above) is computed once per
 // CTA by 14 threads; the per-lookup work is one 32-bit multiply-add + one 16-byte load (the first version
 // recomputed geometry and 64-bit addresses per lookup and was instruction-issue bound: 45 instr/load).
-template <typename V>
-__global__ void __launch_bounds__(224)
-roipool_gather_kernel(const typename V::T* __restrict__ feat, const typename V::T* __restrict__ tables, int h, int w,
+template <typename V, bool PERSIST>
+__device__ __forceinline__ void
+roipool_gather_body(const typename V::T* __restrict__ feat, const typename V::T* __restrict__ tables, int h, int w,
                       int CV, const float* __restrict__ boxes, const float* __restrict__ obj, float scale,
-                      typename V::T* __restrict__ out) {
+                      typename V::T* __restrict__ out, int R, int nitems) {
   typedef typename V::T T;
   __shared__ int s_y0[7], s_ylast[7], s_nrow[7], s_i[7];      // per bin row: first window row, last window row, #windows, y level
   __shared__ int s_x0[7], s_x1[7], s_j[7], s_wd[7];           // per bin col: first / right-aligned window col, x level, width
-  const int r = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int cv = blockIdx.y * 32 + lane;
+#pragma unroll 1
+  for (int item = PERSIST ? (int)blockIdx.x : 0; item < (PERSIST ? nitems : 1); item += (int)gridDim.x) {
+  const int r = PERSIST ? item % R : (int)blockIdx.x;
+  const int cv = (PERSIST ? item / R : (int)blockIdx.y) * 32 + lane;
+  if (PERSIST && item != (int)blockIdx.x) __syncthreads();  // the previous item's geometry has been consumed
   if (threadIdx.x < 14) {
     const float* box = boxes + 4 * (size_t)r;
     const bool is_y = threadIdx.x < 7;
@@ -536,7 +541,7 @@ roipool_gather_kernel(const typename V::T* __restrict__ feat, const typename V::
     }
   }
   __syncthreads();
-  if (cv >= CV) return;
+  if (cv >= CV) continue;
   const int ph = warp;
   const float mul = obj ? __fadd_rn(__ldg(obj + r), 1.f) : 1.f;
   const int i = s_i[ph], y0 = s_y0[ph], ylast = s_ylast[ph], nrow = s_nrow[ph];
@@ -578,6 +583,23 @@ roipool_gather_kernel(const typename V::T* __restrict__ feat, const typename V::
     }
     __stcs(orow + (size_t)pw * CV, V::scale(m, mul));
   }
+  }  // items
+}
+
+template <typename V>
+__global__ void __launch_bounds__(224)
+roipool_gather_kernel(const typename V::T* __restrict__ feat, const typename V::T* __restrict__ tables, int h, int w,
+                      int CV, const float* __restrict__ boxes, const float* __restrict__ obj, float scale,
+                      typename V::T* __restrict__ out, int R, int nitems) {
+  roipool_gather_body<V, false>(feat, tables, h, w, CV, boxes, obj, scale, out, R, nitems);
+}
+// persistent variant: capped at 40 registers so that one or two of its CTAs fit next to a resident GEMM CTA
+template <typename V>
+__global__ void __maxnreg__(40)
+roipool_gather_persistent_kernel(const typename V::T* __restrict__ feat, const typename V::T* __restrict__ tables, int h,
+                                 int w, int CV, const float* __restrict__ boxes, const float* __restrict__ obj,
+                                 float scale, typename V::T* __restrict__ out, int R, int nitems) {
+  roipool_gather_body<V, true>(feat, tables, h, w, CV, boxes, obj, scale, out, R, nitems);
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
@@ -595,23 +617,58 @@ using namespace drn;
 
 template <typename V>
 static int roipool_v2(const void* feat, int h, int w, int CV, const float* boxes, const float* objectness, int R,
-                      float spatial_scale, void* out, void* ws, cudaStream_t st) {
+                      float spatial_scale, void* out, void* ws, bool build, bool gather, int max_ctas, cudaStream_t st) {
   typedef typename V::T T;
   const size_t smem = (size_t)4 * w * XT_SLOTS * sizeof(T);
   DRN_CHECK_ARG(smem <= 200 * 1024, "roipool: feature map too wide for the table builder (w=%d)", w);
   DRN_CHECK_ARG((unsigned long long)XT_TABLES * h * w * CV < (1ull << 31), "roipool: feature map too large for 32-bit table offsets");
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(xtable_build_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return set_err("roipool: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = true;
+  if (build) {
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(xtable_build_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return set_err("roipool: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      configured = true;
+    }
+    xtable_build_kernel<V><<<dim3(h, CV / XT_SLOTS), 256, smem, st>>>((const T*)feat, h, w, CV, (T*)ws);
+    DRN_CHECK_LAUNCH("roipool xtable build");
   }
-  xtable_build_kernel<V><<<dim3(h, CV / XT_SLOTS), 256, smem, st>>>((const T*)feat, h, w, CV, (T*)ws);
-  DRN_CHECK_LAUNCH("roipool xtable build");
-  roipool_gather_kernel<V><<<dim3(R, cdiv(CV, 32)), 224, 0, st>>>((const T*)feat, (const T*)ws, h, w, CV, boxes, objectness,
-                                                                spatial_scale, (T*)out);
-  DRN_CHECK_LAUNCH("roipool gather");
+  if (gather && R > 0) {
+    const long long nitems = (long long)R * cdiv(CV, 32);
+    DRN_CHECK_ARG(nitems < (1ll << 31), "roipool: too many (ROI, chunk) items");
+    const int grid = (max_ctas > 0 && max_ctas < nitems) ? max_ctas : (int)nitems;
+    if (grid < nitems) {
+      // a GEMM CTA with ~210 KB of shared memory has to fit on the same SM: both kernels must run under the
+      // same (maximum) shared-memory carve-out, or the SM drains before it switches configuration
+      static bool carveout_set = false;
+      if (!carveout_set) {
+        cudaError_t e = cudaFuncSetAttribute(roipool_gather_persistent_kernel<V>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                             (int)cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return set_err("roipool: cudaFuncSetAttribute(carveout): %s", cudaGetErrorString(e));
+        carveout_set = true;
+      }
+      roipool_gather_persistent_kernel<V><<<grid, 224, 0, st>>>((const T*)feat, (const T*)ws, h, w, CV, boxes, objectness,
+                                                           spatial_scale, (T*)out, R, (int)nitems);
+    } else
+      roipool_gather_kernel<V><<<dim3(R, cdiv(CV, 32)), 224, 0, st>>>((const T*)feat, (const T*)ws, h, w, CV, boxes, objectness,
+                                                            spatial_scale, (T*)out, R, (int)nitems);
+    DRN_CHECK_LAUNCH("roipool gather");
+  }
   return 0;
+}
+
+static int roipool_tables_dispatch(const void* feat, int h, int w, int C, const float* boxes, const float* objectness,
+                                   int R, float spatial_scale, int dtype, void* out, void* workspace,
+                                   size_t workspace_bytes, bool build, bool gather, int max_ctas, cudaStream_t st) {
+  const int vec = dtype == DRN_BF16 ? 8 : 4;
+  DRN_CHECK_ARG(feat && workspace, "roipool: null pointer");
+  DRN_CHECK_ARG(h > 0 && w > 0, "roipool: empty feature map");
+  DRN_CHECK_ARG(C % vec == 0 && (C / vec) % XT_SLOTS == 0, "roipool: C=%d does not fit the table layout", C);
+  DRN_CHECK_ARG(workspace_bytes >= drn_roipool_workspace_bytes(h, w, C, dtype),
+                "roipool: workspace of %zu bytes is smaller than drn_roipool_workspace_bytes()", workspace_bytes);
+  DRN_CHECK_ARG((uintptr_t)workspace % 16 == 0, "roipool: workspace must be 16-byte aligned");
+  if (dtype == DRN_BF16)
+    return roipool_v2<VecBF16>(feat, h, w, C / vec, boxes, objectness, R, spatial_scale, out, workspace, build, gather, max_ctas, st);
+  return roipool_v2<VecF32>(feat, h, w, C / vec, boxes, objectness, R, spatial_scale, out, workspace, build, gather, max_ctas, st);
 }
 
 extern "C" {
@@ -695,14 +752,9 @@ int drn_roipool_fwd(const void* feat, int h, int w, int C, const float* boxes, c
   DRN_CHECK_ARG(C % vec == 0, "roipool: C=%d not a multiple of %d", C, vec);
   cudaStream_t st = (cudaStream_t)stream;
   const int CV = C / vec;
-  if (workspace && CV % XT_SLOTS == 0) {
-    DRN_CHECK_ARG(workspace_bytes >= drn_roipool_workspace_bytes(h, w, C, dtype),
-                  "roipool: workspace of %zu bytes is smaller than drn_roipool_workspace_bytes()", workspace_bytes);
-    DRN_CHECK_ARG((uintptr_t)workspace % 16 == 0, "roipool: workspace must be 16-byte aligned");
-    if (dtype == DRN_BF16)
-      return roipool_v2<VecBF16>(feat, h, w, CV, boxes, objectness, R, spatial_scale, out, workspace, st);
-    return roipool_v2<VecF32>(feat, h, w, CV, boxes, objectness, R, spatial_scale, out, workspace, st);
-  }
+  if (workspace && CV % XT_SLOTS == 0)
+    return roipool_tables_dispatch(feat, h, w, C, boxes, objectness, R, spatial_scale, dtype, out, workspace, workspace_bytes,
+                                   true, true, 0, st);
   // no workspace (or odd channel count): direct scan kernels
   dim3 grid(R, 7);
   if (dtype == DRN_BF16) {
@@ -712,6 +764,27 @@ int drn_roipool_fwd(const void* feat, int h, int w, int C, const float* boxes, c
   }
   DRN_CHECK_LAUNCH("roipool");
   return 0;
+}
+
+int drn_roipool_tables_supported(int C, int dtype) {
+  const int vec = dtype == DRN_BF16 ? 8 : 4;
+  return (C > 0 && C % vec == 0 && (C / vec) % XT_SLOTS == 0) ? 1 : 0;
+}
+
+int drn_roipool_build_tables(const void* feat, int h, int w, int C, int dtype, void* workspace, size_t workspace_bytes,
+                             drn_stream_t stream) {
+  return roipool_tables_dispatch(feat, h, w, C, nullptr, nullptr, 0, 0.f, dtype, nullptr, workspace, workspace_bytes, true,
+                                 false, 0, (cudaStream_t)stream);
+}
+
+int drn_roipool_rows_fwd(const void* feat, int h, int w, int C, const float* boxes, const float* objectness, int R,
+                         float spatial_scale, int dtype, void* out, const void* tables, size_t tables_bytes,
+                         int max_ctas, drn_stream_t stream) {
+  DRN_CHECK_ARG(R >= 0, "roipool: R=%d", R);
+  if (R == 0) return 0;
+  DRN_CHECK_ARG(out && boxes, "roipool: null pointer");
+  return roipool_tables_dispatch(feat, h, w, C, boxes, objectness, R, spatial_scale, dtype, out, const_cast<void*>(tables),
+                                 tables_bytes, false, true, max_ctas, (cudaStream_t)stream);
 }
 
 int drn_cast_f32_to_bf16(const float* in, void* out, int64_t n, drn_stream_t stream) {

@@ -217,27 +217,54 @@ struct Params {
   // stream-K (deep-K GEMMs whose tile count does not fill whole waves): every unit gets an equal share of the
   // tiles x K-blocks iteration space; a unit that starts inside a tile dumps that partial accumulator to sk_ws
   // and raises sk_flags[unit], the unit that began the tile (and reaches it last in time) adds it and runs the epilogue
+  // stream_k == 2, "tail split-K": the whole waves of tiles run data-parallel; the tiles of the last, partial wave
+  // are cut into sk_parts K-ranges that are scheduled K-range-major (so concurrently running units still sit at the
+  // same K offset and share their operand tiles in L2 -- what plain stream-K loses); parts 0..sk_parts-2 dump their
+  // fp32 partial, the last part (scheduled last) folds them in, in part order, and runs the epilogue.
   int stream_k;
+  int sk_tail0, sk_tail, sk_parts;  // first tail tile, number of tail tiles, K-ranges per tail tile
   float* sk_ws;
   unsigned int* sk_flags;
 };
 
-struct Piece { int tile, kb0, kb1, kind; };  // kind: 0 = whole tile, 1 = tail part (dump partial), 2 = head part (owner)
+// kind: 0 = whole tile, 1 = dumps its partial accumulator to workspace slot `slot`, 2 = owner: folds in the partials
+// of slots [slot, slot + nslots) and runs the epilogue
+struct Piece { int tile, kb0, kb1, kind, slot, nslots; };
 
 struct Sched {
-  int KB, num_tiles, num_units, sk, cur;
+  int KB, num_tiles, num_units, sk, cur, unit;
+  int tail0, tail, parts, v;
   long long g, g1;
-  __device__ Sched(int unit, int num_units_, int num_tiles_, int KB_, int sk_) : KB(KB_), num_tiles(num_tiles_), num_units(num_units_), sk(sk_), cur(unit) {
-    const long long total = (long long)num_tiles_ * KB_;
+  __device__ Sched(int unit_, int num_units_, int num_tiles_, const Params& p)
+      : KB(p.KB), num_tiles(num_tiles_), num_units(num_units_), sk(p.stream_k), cur(unit_), unit(unit_),
+        tail0(p.sk_tail0), tail(p.sk_tail), parts(p.sk_parts), v(unit_) {
+    const long long total = (long long)num_tiles_ * KB;
     const long long W = (total + num_units_ - 1) / num_units_;
-    g = (long long)unit * W;
+    g = (long long)unit_ * W;
     g1 = g + W < total ? g + W : total;
   }
   __device__ bool next(Piece& pc) {
-    if (!sk) {
+    pc.slot = 0; pc.nslots = 0;
+    if (sk == 0) {
       if (cur >= num_tiles) return false;
       pc.tile = cur; pc.kb0 = 0; pc.kb1 = KB; pc.kind = 0;
       cur += num_units;
+      return true;
+    }
+    if (sk == 2) {
+      if (cur < tail0) {  // whole waves, data-parallel
+        pc.tile = cur; pc.kb0 = 0; pc.kb1 = KB; pc.kind = 0;
+        cur += num_units;
+        return true;
+      }
+      if (v >= tail * parts) return false;
+      const int q = v / tail, t = v - q * tail;  // K-range-major order
+      pc.tile = tail0 + t;
+      pc.kb0 = (int)((long long)q * KB / parts);
+      pc.kb1 = (int)((long long)(q + 1) * KB / parts);
+      if (q == parts - 1) { pc.kind = 2; pc.slot = t * (parts - 1); pc.nslots = parts - 1; }
+      else { pc.kind = 1; pc.slot = t * (parts - 1) + q; }
+      v += num_units;
       return true;
     }
     if (g >= g1) return false;
@@ -246,6 +273,8 @@ struct Sched {
     const long long left = g1 - g;
     pc.kb1 = (KB - pc.kb0 <= left) ? KB : pc.kb0 + (int)left;
     pc.kind = pc.kb0 > 0 ? 1 : (pc.kb1 < KB ? 2 : 0);
+    if (pc.kind == 1) pc.slot = unit;
+    if (pc.kind == 2) { pc.slot = unit + 1; pc.nslots = 1; }
     g += pc.kb1 - pc.kb0;
     return true;
   }
@@ -389,7 +418,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       const int cblocks = p.conv ? (p.Cin / BK) : 1;
-      Sched sched(unit, num_units, num_tiles, p.KB, p.stream_k);
+      Sched sched(unit, num_units, num_tiles, p);
       Piece pc;
       while (sched.next(pc)) {
         const int tile = pc.tile;
@@ -467,7 +496,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       auto commit = [&](uint64_t* bar) {
         if constexpr (CG == 2) umma2_commit_both(bar); else umma_commit(bar);
       };
-      Sched sched(unit, num_units, num_tiles, p.KB, p.stream_k);
+      Sched sched(unit, num_units, num_tiles, p);
       Piece pc;
       while (sched.next(pc)) {
         const int tile = pc.tile;
@@ -538,7 +567,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         pre_bi[i] = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
       }
     };
-    Sched sched(unit, num_units, num_tiles, p.KB, p.stream_k);
+    Sched sched(unit, num_units, num_tiles, p);
     Piece pc, pc_next;
     bool have = sched.next(pc);
     if (have) fetch_sb(pc.tile / num_mp);
@@ -584,7 +613,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (pc.kind == 1) {
         // ---------------------------------------------------------- stream-K tail part: dump the raw fp32 partial
         // layout [column][128 rows] so that a warp's 32 lanes (rows) write / read 128 contiguous bytes
-        float* wsp = p.sk_ws + (size_t)(unit * CG + cta_rank) * (BN * 128) + row;
+        float* wsp = p.sk_ws + (size_t)(pc.slot * CG + cta_rank) * (BN * 128) + row;
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
           uint32_t v[32];
@@ -596,32 +625,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (etid == 0) {
-          unsigned int* flag = p.sk_flags + unit * CG + cta_rank;
+          unsigned int* flag = p.sk_flags + pc.slot * CG + cta_rank;
           asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(1u) : "memory");
         }
       } else if (pc.kind == 2) {
-        // ---------------------------------------------------------- stream-K head part (owner): fold in the partner's
-        // partial (written by unit + 1 at the very start of the kernel), then fall through to the normal epilogue
-        unsigned int* flag = p.sk_flags + (unit + 1) * CG + cta_rank;
-        if (etid == 0) {
-          unsigned int f;
-          do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(flag) : "memory");
-          } while (f == 0u);
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const float* wsp = p.sk_ws + (size_t)((unit + 1) * CG + cta_rank) * (BN * 128) + row;
+        // ---------------------------------------------------------- owner: fold in the other parts' partials (they
+        // were scheduled earlier, or run right now on another, resident CTA), in slot order, then fall through to the
+        // normal epilogue
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          uint32_t v[32];
-          tmem_ld32_nowait(taddr + c, v);
-          tmem_ld_wait();
+        for (int s = 0; s < pc.nslots; ++s) {
+          unsigned int* flag = p.sk_flags + (pc.slot + s) * CG + cta_rank;
+          if (etid == 0) {
+            unsigned int f;
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(flag) : "memory");
+            } while (f == 0u);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const float* wsp = p.sk_ws + (size_t)((pc.slot + s) * CG + cta_rank) * (BN * 128) + row;
+#pragma unroll 1
+          for (int c = 0; c < BN; c += 32) {
+            uint32_t v[32];
+            tmem_ld32_nowait(taddr + c, v);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldcg(wsp + (size_t)(c + j) * 128));
-          tmem_st32(taddr + c, v);
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldcg(wsp + (size_t)(c + j) * 128));
+            tmem_st32(taddr + c, v);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (etid == 0) *flag = 0u;  // self-resetting: ready for the next launch
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (etid == 0) *flag = 0u;  // self-resetting: ready for the next launch
       }
 
       if (pc.kind == 1) {
@@ -752,7 +785,9 @@ static int num_sms() {
 }
 
 constexpr size_t SK_FLAG_BYTES = 4096;
-constexpr size_t SK_WS_BYTES = SK_FLAG_BYTES + (size_t)148 * 128 * 256 * sizeof(float);  // one 128 x 256 fp32 partial per SM
+constexpr size_t SK_WS_BYTES = SK_FLAG_BYTES + (size_t)148 * 128 * 256 * sizeof(float);  // stream-K: one 128 x 256 fp32 partial per SM
+constexpr size_t SK_WS_BYTES_MAX = SK_FLAG_BYTES + (size_t)4 * 148 * 128 * 256 * sizeof(float);  // tail split-K: up to 4 per SM
+static int g_tail_split = 0;  // opt-in (drn_gemm_set_tail_split / DRN_TC_TAILSPLIT=1): measured neutral-to-negative, see launch()
 
 template <int BN, int STAGES, int NBUF, int CG>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mr, Params p,
@@ -774,6 +809,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
   // different K offsets, so the A/B tiles shared by co-scheduled CTAs no longer meet in L2 and every CTA streams
   // its operands from HBM (12.8 GB instead of ~2 GB).  Kept for shapes whose operands fit in L2; off by default.
   p.stream_k = 0;
+  p.sk_tail0 = p.sk_tail = p.sk_parts = 0;
   if (workspace && workspace_bytes >= SK_WS_BYTES && !p.out_f32 && units > max_units && max_units <= 148 && p.KB >= 8) {
     const int waves = (units + max_units - 1) / max_units;
     const double ideal = (double)units / max_units;
@@ -787,6 +823,41 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
       p.stream_k = 1;
       p.sk_flags = (unsigned int*)workspace;
       p.sk_ws = (float*)((char*)workspace + SK_FLAG_BYTES);
+    }
+  }
+  // tail split-K (opt-in): cut the tiles of the partial last wave into `parts` K-ranges when that shortens the wave
+  // by >= 15 % -- fc6 (M=4000, N=2048, K=100352) is 128 pair-tiles on 74 pair slots: 1 whole wave + 54 tiles x 4
+  // quarters = 216 quarter-units = 3 rounds of 1/4 wave, 1.75 waves instead of 2.  Measured: 1164 us vs 1153-1193 us
+  // alone, +0.14 ms inside the step (partials add 85 MB of traffic).  The kernel is POWER bound, not wave bound: it
+  // already averages 1430 TFLOP/s over both waves (cuBLAS sustained: 1362), the 40 SMs idle in wave 2 hand their
+  // power budget to the busy ones (SM clock rises), so evening out the waves buys nothing
+  // (profiles/r1_tailsplit_negative_result.txt).
+  static int ts_env = -1;
+  if (ts_env < 0) {
+    const char* e = getenv("DRN_TC_TAILSPLIT");
+    ts_env = (e && e[0] == '1') ? 1 : 0;
+    if (ts_env) g_tail_split = 1;
+  }
+  if (!p.stream_k && g_tail_split && workspace && !p.out_f32 && p.KB >= 256) {
+    const int full = (units / max_units) * max_units, tail = units - full;
+    if (tail > 0 && full > 0) {
+      int best_parts = 1;
+      double best = 1.0;
+      for (int parts = 2; parts <= 8; ++parts) {
+        if (p.KB / parts < 64) break;
+        const double t = (double)((tail * parts + max_units - 1) / max_units) / parts + 0.02 * parts;  // + fixup cost
+        if (t < best - 1e-9) { best = t; best_parts = parts; }
+      }
+      const size_t need = SK_FLAG_BYTES + (size_t)tail * (best_parts - 1) * CG * BN * 128 * sizeof(float);
+      if (best_parts > 1 && best <= 0.85 && (size_t)tail * (best_parts - 1) * CG * sizeof(unsigned int) <= SK_FLAG_BYTES &&
+          need <= workspace_bytes) {
+        p.stream_k = 2;
+        p.sk_tail0 = full;
+        p.sk_tail = tail;
+        p.sk_parts = best_parts;
+        p.sk_flags = (unsigned int*)workspace;
+        p.sk_ws = (float*)((char*)workspace + SK_FLAG_BYTES);
+      }
     }
   }
   cudaLaunchConfig_t cfg{};
@@ -849,7 +920,12 @@ static void pick_conv_tile(int H, int W, int* tw_out, int* th_out) {
 
 using namespace drn;
 
-extern "C" size_t drn_gemm_workspace_bytes(void) { return drn::tc::SK_WS_BYTES; }
+extern "C" size_t drn_gemm_workspace_bytes(void) { return drn::tc::SK_WS_BYTES_MAX; }
+extern "C" int drn_gemm_set_tail_split(int enabled) {
+  const int prev = drn::tc::g_tail_split;
+  drn::tc::g_tail_split = enabled ? 1 : 0;
+  return prev;
+}
 
 extern "C" int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int Cin, const void* w, int ksize,
                                       int dilation, const float* scale, const float* bias, const void* residual,

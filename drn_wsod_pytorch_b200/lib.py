@@ -27,6 +27,9 @@ _PROTOS = {
                                c_float, c_uint64, _P, _P, c_size_t, _P],
     "drn_maxpool2x2_nhwc": [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "drn_roipool_fwd": [_P, c_int, c_int, c_int, _P, _P, c_int, c_float, c_int, _P, _P, c_size_t, _P],
+    "drn_roipool_tables_supported": [c_int, c_int],
+    "drn_roipool_build_tables": [_P, c_int, c_int, c_int, c_int, _P, c_size_t, _P],
+    "drn_roipool_rows_fwd": [_P, c_int, c_int, c_int, _P, _P, c_int, c_float, c_int, _P, _P, c_size_t, c_int, _P],
     "drn_wsddn_mil_fwd": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_float, _P, _P, _P, _P, _P],
     "drn_oicr_pgt": [_P, c_int, c_int, _P, _P, c_int, _P, c_int, _P, c_int, c_int, _FP, _P, _P, _P, _P, _P],
     "drn_label_proposals": [_P, c_int, _P, _P, c_int, c_int, _FP, _IP, c_int, _P, _P, _P, _P],
@@ -71,6 +74,8 @@ def load():
         fn.restype = c_int
     lib.drn_roipool_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
     lib.drn_roipool_workspace_bytes.restype = c_size_t
+    lib.drn_gemm_set_tail_split.argtypes = [c_int]
+    lib.drn_gemm_set_tail_split.restype = c_int
     lib.drn_gemm_workspace_bytes.argtypes = []
     lib.drn_gemm_workspace_bytes.restype = c_size_t
     _lib = lib

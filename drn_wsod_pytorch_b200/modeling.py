@@ -145,7 +145,7 @@ def run_conv(conv: Conv2d, x, precision, relu, residual=None):
     return ops.conv_bf16_tc(x, p, conv.kernel_size, conv.dilation, relu, residual)
 
 
-def run_linear(x2d, packed, precision, relu, out_dtype=None, dropout=None):
+def run_linear(x2d, packed, precision, relu, out_dtype=None, dropout=None, out=None):
     """x2d: [M, K] -> [M, Npad] through the same implicit-GEMM kernels (a linear layer is a 1x1 conv
     over an M x 1 'image').  dropout = (p, seed, seed_dev): train-mode F.dropout (effective seed =
     seed + *seed_dev), fused into the tensor-core epilogue on the bf16 path, a separate in-place kernel
@@ -159,7 +159,7 @@ def run_linear(x2d, packed, precision, relu, out_dtype=None, dropout=None):
     else:
         dp, ds, dd = dropout if dropout is not None else (0.0, 0, None)
         y = ops.conv_bf16_tc(x4, packed, 1, 1, relu, out_dtype=out_dtype or torch.bfloat16, dropout_p=dp, dropout_seed=ds,
-                             dropout_seed_dev=dd)
+                             dropout_seed_dev=dd, out=None if out is None else out.view(1, M, 1, packed["cout"]))
     return y.view(M, packed["cout"])
 
 
@@ -405,22 +405,59 @@ class DiscriminativeAdaptionNeck(nn.Module):
         self._output_size = size
         self.precision = precision_of(cfg)
         self._seed_dev = None  # device-resident dropout counter: advances inside captured CUDA graphs too
+        self._fc_stream = None
 
     @property
     def output_shape(self):
         return ShapeSpec(channels=self._output_size)
 
-    def run(self, pooled2d, bin_major):
-        """pooled2d: [R, 49*C] (bin-major from the fused ROIPool) or [R, C*49] (reference order)."""
+    SEEDS_PER_CALL = 16  # dropout counters consumed per forward: one per (fc layer, row block)
+
+    def prepare(self, device, bin_major=True):
+        """Everything `run` needs besides its input, made on the current stream: packed weights, dropout counter."""
+        if self.training and (self._seed_dev is None or self._seed_dev.device != device):
+            self._seed_dev = torch.zeros((1,), dtype=torch.int64, device=device)
+        for i, fc in enumerate(self.fcs):
+            fc.packed(self.precision, permute_c49=self.in_channels if (i == 0 and bin_major) else None)
+
+    def run(self, pooled2d, bin_major, pool_blocks=None, pool_start=None):
+        """pooled2d: [R, 49*C] (bin-major from the fused ROIPool) or [R, C*49] (reference order).
+        pool_blocks: optional [(r0, r1, event)] -- the rows [r0, r1) of pooled2d are complete once `event`
+        fires (the gathers are queued on the current stream after the event `pool_start`); fc1 then runs block
+        by block on a second stream so that the GEMM of block b overlaps the pooling of block b+1."""
         x = pooled2d
         if self.training and (self._seed_dev is None or self._seed_dev.device != x.device):
             self._seed_dev = torch.zeros((1,), dtype=torch.int64, device=x.device)
+        seed = 0
         for i, fc in enumerate(self.fcs):
             perm = self.in_channels if (i == 0 and bin_major) else None
-            drop = (0.5, i + 1, self._seed_dev) if self.training else None  # box_head.py:90
-            x = run_linear(x, fc.packed(self.precision, permute_c49=perm), self.precision, relu=True, dropout=drop)
+            packed = fc.packed(self.precision, permute_c49=perm)
+            if i == 0 and pool_blocks:
+                assert len(pool_blocks) < self.SEEDS_PER_CALL - len(self.fcs)
+                y = torch.empty((x.shape[0], packed["cout"]), device=x.device, dtype=x.dtype)
+                cur = torch.cuda.current_stream(x.device)
+                if self._fc_stream is None or self._fc_stream.device != x.device:
+                    # high priority: when block b's rows are ready, the GEMM's CTAs are placed ahead of the
+                    # already queued gather CTAs of block b+1, which then fill the SMs' spare warps
+                    self._fc_stream = torch.cuda.Stream(x.device, priority=-1)
+                hp = self._fc_stream
+                # `hp` forks from the point BEFORE the gathers were queued (packed weights and the dropout counter
+                # are older than that: prepare()); inside a graph capture this also joins `hp` to the capture
+                hp.wait_event(pool_start)
+                with torch.cuda.stream(hp):
+                    for r0, r1, ev in pool_blocks:
+                        seed += 1
+                        drop = (0.5, seed, self._seed_dev) if self.training else None
+                        hp.wait_event(ev)
+                        run_linear(x[r0:r1], packed, self.precision, relu=True, dropout=drop, out=y[r0:r1])
+                cur.wait_stream(hp)
+                x = y
+                continue
+            seed += 1
+            drop = (0.5, seed, self._seed_dev) if self.training else None  # box_head.py:90
+            x = run_linear(x, packed, self.precision, relu=True, dropout=drop)
         if self.training:
-            self._seed_dev.add_(len(self.fcs))  # next call draws a fresh mask (captured as a graph node)
+            self._seed_dev.add_(self.SEEDS_PER_CALL)  # next call draws fresh masks (captured as a graph node)
         return x
 
     def forward(self, x):
@@ -549,6 +586,10 @@ class _WSLROIHeads(nn.Module):
         self._heads_cache = None
         self._counter = None
         self.fused_tail = os.environ.get("DRN_B200_FUSED_TAIL", "1") != "0"
+        # opt-in: measured gain 0.02-0.05 ms of 2.7 (the GEMM is SM<-L2 feed bound, a co-resident gather starves:
+        # profiles/r1_overlap_negative_result.txt), less than the tail split-K schedule of the one-piece fc6 saves
+        self.overlap_pool = os.environ.get("DRN_B200_OVERLAP_POOL", "0") != "0"
+        self.pool_ctas_per_sm = int(os.environ.get("DRN_B200_POOL_CTAS_PER_SM", "0"))
         self._gt_cache = {}
         self._device = torch.device(cfg.MODEL.DEVICE)
         self.last_trace = None
@@ -585,10 +626,60 @@ class _WSLROIHeads(nn.Module):
             x = ops.to_bf16(x.contiguous()) if want == torch.bfloat16 else ops.to_f32(x.contiguous())
         return x.contiguous()
 
+    @staticmethod
+    def _row_blocks(R, n_out, sms=148):
+        """Row blocks for the pooling/fc6 overlap: split R into 256-row-aligned blocks only if the fc6
+        GEMM (128x256 tiles on `sms` SMs) needs no more waves block by block than in one piece."""
+        nt = -(-n_out // 256)
+        waves = lambda rows: -(-(-(-rows // 128) * nt) // sms)
+        whole = waves(R)
+        for nb in range(min(whole, 8), 1, -1):
+            step = -(-(-(-R // nb)) // 256) * 256
+            blocks = [(r0, min(r0 + step, R)) for r0 in range(0, R, step)]
+            if len(blocks) == nb and sum(waves(b - a) for a, b in blocks) <= whole:
+                return blocks
+        return [(0, R)]
+
+    def _pool(self, fh, boxes, obj):
+        """ROIPool x (objectness+1) of one image -> (pooled [R, 49C], pool_blocks or None).  With enough rows
+        the proposals are pooled in row blocks, each followed by an event, so that fc6 of block b (tensor
+        pipe, launched on a high-priority stream by the box head) runs while block b+1 is being gathered
+        (L2/LSU): the two kernels share the SMs."""
+        R = boxes.shape[0]
+        fc1 = self.box_head.fcs[0] if hasattr(self.box_head, "fcs") else None
+        blocks = [(0, R)]
+        if self.overlap_pool and self.precision != "fp32" and fc1 is not None and R >= 512:
+            blocks = self._row_blocks(R, fc1.out_features)
+        tables = ops.roipool_tables(fh) if len(blocks) > 1 else None
+        if tables is None:
+            return ops.roipool(fh, boxes, obj, self.pooler_scale), None
+        dev = fh.device
+        pooled = torch.empty((R, 49 * fh.shape[2]), device=dev, dtype=fh.dtype)
+        cur = torch.cuda.current_stream(dev)
+        start = torch.cuda.Event()
+        start.record(cur)
+        out = [start]
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        for b, (r0, r1) in enumerate(blocks):
+            # blocks after the first share the SMs with the previous block's GEMM: a persistent grid of a few
+            # CTAs per SM leaves the GEMM's CTA (one per SM, most of the registers and shared memory) its place
+            ops.roipool_rows(fh, boxes[r0:r1], None if obj is None else obj[r0:r1], self.pooler_scale, tables, pooled[r0:r1],
+                             max_ctas=self.pool_ctas_per_sm * sms if b > 0 else 0)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            out.append((r0, r1, ev))
+        return pooled, out
+
     def _roi_logits(self, features, boxes, obj, i):
         """ROIPool x (objectness+1) -> fc6 -> fc7 -> all head logits for image i: [R, ld] fp32."""
-        pooled = ops.roipool(self._features_hwc(features, i), boxes, obj, self.pooler_scale)
-        feat = self.box_head.run(pooled, bin_major=True)
+        dan = isinstance(self.box_head, DiscriminativeAdaptionNeck)
+        if dan:
+            self.box_head.prepare(boxes.device)
+        pooled, pool_blocks = self._pool(self._features_hwc(features, i), boxes, obj)
+        if pool_blocks is not None and dan:
+            feat = self.box_head.run(pooled, bin_major=True, pool_blocks=pool_blocks[1:], pool_start=pool_blocks[0])
+        else:
+            feat = self.box_head.run(pooled, bin_major=True)
         heads = self._heads_packed()
         logits = run_linear(feat, heads, self.precision, relu=False, out_dtype=torch.float32)
         return feat, logits, heads

@@ -66,12 +66,17 @@ def _gemm_workspace(device):
 
 
 def conv_bf16_tc(x, packed, ksize, dilation, relu, residual=None, out_dtype=torch.bfloat16, dropout_p=0.0, dropout_seed=0,
-                 dropout_seed_dev=None):
-    """tcgen05 implicit-GEMM conv / linear (+ fused train-mode dropout).  x: [N,H,W,Cin] bf16 NHWC."""
+                 dropout_seed_dev=None, out=None):
+    """tcgen05 implicit-GEMM conv / linear (+ fused train-mode dropout).  x: [N,H,W,Cin] bf16 NHWC.
+    out: optional preallocated [N,H,W,Cout] destination (e.g. a row block of a larger matrix)."""
     _chk(x, "x")
     N, H, W, Cin = x.shape
     Cout = packed["cout"]
-    out = torch.empty((N, H, W, Cout), device=x.device, dtype=out_dtype)
+    if out is None:
+        out = torch.empty((N, H, W, Cout), device=x.device, dtype=out_dtype)
+    else:
+        _chk(out, "out")
+        assert out.numel() == N * H * W * Cout
     ws = _gemm_workspace(x.device) if (ksize == 1 and Cin >= 1024) else None  # deep-K GEMMs only
     call("drn_conv_igemm_bf16_tc", x, N, H, W, Cin, packed["w"], ksize, dilation, packed["scale"], packed["bias"],
          residual, int(relu), out, _dt(out), Cout, Cout, float(dropout_p), int(dropout_seed), dropout_seed_dev,
@@ -111,6 +116,34 @@ def roipool(feat_hwc, boxes, objectness, spatial_scale, use_tables=None):
             _ROIPOOL_WS[key] = ws
     call("drn_roipool_fwd", feat_hwc, h, w, C, boxes, objectness, R, float(spatial_scale), _dt(feat_hwc), out,
          ws, ws_bytes, current_stream())
+    return out
+
+
+def roipool_tables(feat_hwc):
+    """Build the per-image range-max tables of `feat_hwc` on the current stream; returns the scratch tensor
+    (reused per stream) for roipool_rows, or None when the channel count does not fit the table layout."""
+    _chk(feat_hwc, "features")
+    h, w, C = feat_hwc.shape
+    if not lib.load().drn_roipool_tables_supported(C, _dt(feat_hwc)):
+        return None
+    ws_bytes = lib.load().drn_roipool_workspace_bytes(h, w, C, _dt(feat_hwc))
+    key = (feat_hwc.device, torch.cuda.current_stream().cuda_stream)
+    ws = _ROIPOOL_WS.get(key)
+    if ws is None or ws.numel() < ws_bytes:
+        ws = torch.empty((ws_bytes,), device=feat_hwc.device, dtype=torch.uint8)
+        _ROIPOOL_WS[key] = ws
+    call("drn_roipool_build_tables", feat_hwc, h, w, C, _dt(feat_hwc), ws, ws.numel(), current_stream())
+    return ws
+
+
+def roipool_rows(feat_hwc, boxes, objectness, spatial_scale, tables, out, max_ctas=0):
+    """Pool the given rows (boxes [r,4], objectness [r] or None) into out [r, 49*C] from prebuilt tables,
+    on the current stream (the caller orders it after roipool_tables).  max_ctas > 0: persistent grid."""
+    _chk(boxes, "boxes")
+    _chk(out, "out")
+    h, w, C = feat_hwc.shape
+    call("drn_roipool_rows_fwd", feat_hwc, h, w, C, boxes, objectness, boxes.shape[0], float(spatial_scale), _dt(feat_hwc),
+         out, tables, tables.numel(), int(max_ctas), current_stream())
     return out
 
 

@@ -69,10 +69,14 @@ int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int Cin, const v
                            int relu, void* out, int out_dtype, int Cout, int ldo, float dropout_p,
                            uint64_t dropout_seed, const uint64_t* dropout_seed_dev, void* workspace,
                            size_t workspace_bytes, drn_stream_t stream);
-/* Scratch for the stream-K schedule of deep-K GEMMs (fc6/fc7): drn_gemm_workspace_bytes() bytes, 16-byte
- * aligned, ZERO-INITIALISED once by the caller (the kernel resets the flags it uses), not shared by
- * kernels that may run concurrently.  NULL disables stream-K (whole-tile waves). */
+/* Scratch for the split-K schedules of deep-K GEMMs (fc6): drn_gemm_workspace_bytes() bytes, 16-byte aligned,
+ * ZERO-INITIALISED once by the caller (the kernel resets the flags it uses), not shared by kernels that may run
+ * concurrently.  NULL = whole tiles only.  drn_gemm_set_tail_split(1) (default 0; returns the previous
+ * setting) lets a GEMM with K >= 16384 whose tiles end in a partial wave cut that wave's tiles into K-ranges
+ * ("tail split-K": fp32 partials summed in a fixed order -- deterministic, but not bit-identical to the
+ * one-piece accumulation).  Both schedules are measured negative results on fc6, kept for other shapes. */
 size_t drn_gemm_workspace_bytes(void);
+int drn_gemm_set_tail_split(int enabled);
 
 /* MaxPool2d(kernel 2, stride 1|2, padding 0), NHWC.
  * Replaces nn.MaxPool2d in WSL/backbone/resnet_ws.py:93-94,110-111,403,415 and vgg.py:93-94,108-109. */
@@ -91,6 +95,20 @@ size_t drn_roipool_workspace_bytes(int h, int w, int C, int dtype);
 int drn_roipool_fwd(const void* feat_nhwc, int h, int w, int C, const float* boxes,
                     const float* objectness, int R, float spatial_scale, int dtype, void* out,
                     void* workspace, size_t workspace_bytes, drn_stream_t stream);
+
+/* The two halves of drn_roipool_fwd, for callers that pool the proposals of one image in several row
+ * blocks (so that the fc6 GEMM of block b overlaps the pooling of block b+1 on another stream):
+ * drn_roipool_build_tables fills the per-image range-max tables once, drn_roipool_rows_fwd pools R rows
+ * (boxes/objectness/out already offset to the block) from tables built earlier on an ordered stream;
+ * max_ctas > 0 runs the gather as a persistent grid of that many CTAs (a small footprint per SM, so that
+ * a concurrently running GEMM keeps its place), 0 = one CTA per (row, channel chunk).
+ * drn_roipool_tables_supported(C, dtype) != 0 iff the channel count fits the table layout. */
+int drn_roipool_tables_supported(int C, int dtype);
+int drn_roipool_build_tables(const void* feat_nhwc, int h, int w, int C, int dtype, void* workspace,
+                             size_t workspace_bytes, drn_stream_t stream);
+int drn_roipool_rows_fwd(const void* feat_nhwc, int h, int w, int C, const float* boxes,
+                         const float* objectness, int R, float spatial_scale, int dtype, void* out,
+                         const void* tables, size_t tables_bytes, int max_ctas, drn_stream_t stream);
 
 /* WSDDN dual-softmax MIL head + image-level BCE.
  * Replaces WSL/roi_heads/fast_rcnn.py:493-527 (softmax(cls,1)*softmax(det,0)), :689-700

@@ -242,6 +242,35 @@ def test_tc_gemm_stream_k_matches_reference_and_is_deterministic(monkeypatch):
     assert torch.equal(fused, ops.dropout_(outs[0].clone(), 0.5, 11))
 
 
+@pytest.mark.parametrize("M,K,N", [(4000, 16384, 2048), (2000, 25088, 4096), (4000, 16448, 2048)])
+def test_tc_gemm_tail_split_k(M, K, N):
+    """fc6-shaped GEMMs (128 pair-tiles on 74 CTA pairs = 1.73 waves) take the tail split-K schedule: the 54 tiles
+    of the partial wave are cut into 4 K-ranges whose fp32 partials meet in the workspace.  Checks values against a
+    torch matmul of the same bf16 operands, agreement with the whole-tile schedule (summation order only), run-to-run
+    bit-identity (fixed fold order, self-resetting flags) and the fused dropout mask."""
+    from drn_wsod_pytorch_b200 import lib
+    g = torch.Generator().manual_seed(K)
+    a = torch.randn(M, K, generator=g).bfloat16().to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16().to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    packed = {"w": w, "scale": None, "bias": bias, "cout": N}
+    ref = F.relu(a.float() @ w.float().t() + bias)
+    L = lib.load()
+    prev = L.drn_gemm_set_tail_split(1)
+    try:
+        outs = [ops.conv_bf16_tc(a.view(1, M, 1, K), packed, 1, 1, True).view(M, N) for _ in range(3)]
+        fused = ops.conv_bf16_tc(a.view(1, M, 1, K), packed, 1, 1, True, dropout_p=0.5, dropout_seed=11).view(M, N)
+        L.drn_gemm_set_tail_split(0)
+        whole = ops.conv_bf16_tc(a.view(1, M, 1, K), packed, 1, 1, True).view(M, N)
+    finally:
+        L.drn_gemm_set_tail_split(prev)
+    torch.testing.assert_close(outs[0].float(), ref, rtol=1e-2, atol=2e-2)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    torch.testing.assert_close(outs[0].float(), whole.float(), rtol=1e-2, atol=1e-2)
+    assert not torch.equal(outs[0], whole) or M * N < 148 * 128 * 256  # the split really happened (different rounding somewhere)
+    assert torch.equal(fused, ops.dropout_(outs[0].clone(), 0.5, 11))
+
+
 @pytest.mark.parametrize("M,K,N", [(9176, 512, 2048), (37500, 64, 256), (4000, 4096, 4096)])
 def test_tc_gemm_bf16_large_residual(M, K, N):
     """Backbone-sized 1x1 convs with residual: exercises multi-tile-per-CTA staging ring + residual prefetch."""

@@ -257,3 +257,51 @@ def test_graph_plan_eval_matches_eager_and_dropout_mask_advances():
     l2 = model(batched)["loss_cls_r0"].item()
     l3 = model(batched)["loss_cls_r0"].item()
     assert len({l1, l2, l3}) == 3
+
+
+def test_pool_fc6_row_block_overlap_is_bit_identical_to_one_piece():
+    """The ROIPool -> fc6 pipeline in row blocks on two streams (opt-in, DRN_B200_OVERLAP_POOL=1) must give
+    exactly the tensors of the single-launch path, eagerly and under graph capture, and the dropout masks of
+    the row blocks must not repeat."""
+    cfg = drn.builtin_config("oicr_WSR_18_DC5_1x", ["MODEL.DEVICE", DEV, "B200.PRECISION", "bf16"])
+    model = drn.build_model(cfg)
+    weights = helpers.case_weights(cfg, model)
+    model.load_state_dict({**weights, "pixel_mean": model.pixel_mean, "pixel_std": model.pixel_std}, strict=True)
+    rh = model.roi_heads
+    rh.keep_trace = True
+    R = 2048
+    assert len(rh._row_blocks(R, rh.box_head.fcs[0].out_features)) > 1
+    assert rh._row_blocks(300, 4096) == [(0, 300)] and rh._row_blocks(2048, 2048) == [(0, 2048)]
+    for blocks in (rh._row_blocks(4000, 2048), rh._row_blocks(R, 4096), rh._row_blocks(8000, 2048)):
+        assert blocks[0][0] == 0 and all(a[1] == b[0] for a, b in zip(blocks, blocks[1:])) and all(b[0] % 256 == 0 for b in blocks)
+    inp = [helpers.synth.make_inputs(192, 256, R, seed=3, num_gt=2)]
+    batched = helpers.to_batched(inp, drn.Instances, drn.Boxes, device=DEV)
+    model.train()
+    rh.box_head.eval()
+    from drn_wsod_pytorch_b200 import lib
+    prev = lib.load().drn_gemm_set_tail_split(0)  # the one-piece fc6 would otherwise take the tail split-K schedule (other rounding)
+    try:
+        out = {}
+        for overlap in (False, True):
+            for graph in (False, True):
+                rh.overlap_pool = overlap
+                model.use_cuda_graph = graph
+                model.invalidate_plans()
+                for _ in range(3 if graph else 1):
+                    losses = model(batched)
+                tr = rh.last_trace[0]
+                out[(overlap, graph)] = ({k: v.item() for k, v in losses.items()}, tr["feat"].clone(), tr["logits"].clone())
+                assert bool(model._plans) == graph
+    finally:
+        lib.load().drn_gemm_set_tail_split(prev)
+    ref = out[(False, False)]
+    for key, got in out.items():
+        assert got[0] == ref[0], key
+        assert torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2]), key
+    # dropout on: the two row blocks of fc6 draw different masks, and the keep rate is 1/2
+    rh.overlap_pool = True
+    model.use_cuda_graph = False
+    rh.box_head.train()
+    model(batched)
+    feat = rh.last_trace[0]["feat"]
+    assert 0.45 < (feat == 0).float().mean().item() < 0.75  # relu zeros + dropped half

@@ -3,6 +3,8 @@
 Tensors are torch CUDA tensors used purely as device buffers; all arithmetic happens inside
 libdrn_b200.so.  Activations are NHWC.  Nothing here falls back to torch ops.
 """
+import os
+
 import torch
 
 from . import lib
@@ -52,10 +54,13 @@ def conv_f32(x, packed, ksize, dilation, relu, residual=None, out=None, ldo=None
 
 
 _GEMM_WS = {}
+# the split-K schedules of the deep-K GEMMs are opt-in (both measured slower on fc6: profiles/r1_*_negative_result.txt);
+# only then is their zero-initialised scratch allocated (inside a graph capture the zero-fill is replayed every step)
+SPLIT_K_WORKSPACE = os.environ.get("DRN_TC_STREAMK") == "1" or os.environ.get("DRN_TC_TAILSPLIT") == "1"
 
 
 def _gemm_workspace(device):
-    """Zero-initialised stream-K scratch, one per (device, stream): kernels on one stream are ordered, so
+    """Zero-initialised split-K scratch, one per (device, stream): kernels on one stream are ordered, so
     they can share it; the kernel resets the flags it raises."""
     key = (device, torch.cuda.current_stream().cuda_stream)
     ws = _GEMM_WS.get(key)
@@ -77,7 +82,7 @@ def conv_bf16_tc(x, packed, ksize, dilation, relu, residual=None, out_dtype=torc
     else:
         _chk(out, "out")
         assert out.numel() == N * H * W * Cout
-    ws = _gemm_workspace(x.device) if (ksize == 1 and Cin >= 1024) else None  # deep-K GEMMs only
+    ws = _gemm_workspace(x.device) if (SPLIT_K_WORKSPACE and ksize == 1 and Cin >= 1024) else None  # deep-K GEMMs only
     call("drn_conv_igemm_bf16_tc", x, N, H, W, Cin, packed["w"], ksize, dilation, packed["scale"], packed["bias"],
          residual, int(relu), out, _dt(out), Cout, Cout, float(dropout_p), int(dropout_seed), dropout_seed_dev,
          ws, 0 if ws is None else ws.numel(), current_stream())

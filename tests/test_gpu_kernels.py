@@ -257,6 +257,7 @@ def test_tc_gemm_tail_split_k(M, K, N):
     ref = F.relu(a.float() @ w.float().t() + bias)
     L = lib.load()
     prev = L.drn_gemm_set_tail_split(1)
+    prev_ws, ops.SPLIT_K_WORKSPACE = ops.SPLIT_K_WORKSPACE, True
     try:
         outs = [ops.conv_bf16_tc(a.view(1, M, 1, K), packed, 1, 1, True).view(M, N) for _ in range(3)]
         fused = ops.conv_bf16_tc(a.view(1, M, 1, K), packed, 1, 1, True, dropout_p=0.5, dropout_seed=11).view(M, N)
@@ -264,6 +265,7 @@ def test_tc_gemm_tail_split_k(M, K, N):
         whole = ops.conv_bf16_tc(a.view(1, M, 1, K), packed, 1, 1, True).view(M, N)
     finally:
         L.drn_gemm_set_tail_split(prev)
+        ops.SPLIT_K_WORKSPACE = prev_ws
     torch.testing.assert_close(outs[0].float(), ref, rtol=1e-2, atol=2e-2)
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
     torch.testing.assert_close(outs[0].float(), whole.float(), rtol=1e-2, atol=1e-2)

@@ -6,7 +6,7 @@ PyTorch is only used by callers for device memory (`tensor.data_ptr()`) and the 
 import ctypes
 import os
 import re
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdrn_b200.so")
@@ -40,6 +40,8 @@ _PROTOS = {
                                  _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _FP, _P, _P, _P, _P, _P, _P, _P],
     "drn_oicr_boxreg_loss": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _FP, c_float, c_float, _P, _P, _P, _P],
     "drn_oicr_infer": [_P, c_int, c_int, c_int, c_int, c_int, _IP, _IP, _P, _FP, _P, _P, _P],
+    "drn_detections_fwd": [_P, _P, c_int, c_int, c_int, c_float, c_float, c_float, c_double, c_int, _P, _P, _P, _P, _P, _P, c_size_t,
+                           _P],
     "drn_dropout_inplace": [_P, c_int64, c_int, c_float, c_uint64, _P, _P],
     "drn_cast_f32_to_bf16": [_P, _P, c_int64, _P],
     "drn_cast_bf16_to_f32": [_P, _P, c_int64, _P],
@@ -74,6 +76,8 @@ def load():
         fn.restype = c_int
     lib.drn_roipool_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
     lib.drn_roipool_workspace_bytes.restype = c_size_t
+    lib.drn_detections_workspace_bytes.argtypes = [c_int, c_int]
+    lib.drn_detections_workspace_bytes.restype = c_size_t
     lib.drn_gemm_set_tail_split.argtypes = [c_int]
     lib.drn_gemm_set_tail_split.restype = c_int
     lib.drn_gemm_workspace_bytes.argtypes = []

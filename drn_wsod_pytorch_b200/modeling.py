@@ -515,32 +515,21 @@ class OICROutputLayers(_OutputLayers):
             nn.init.constant_(l.bias, 0)
 
 
-def fast_rcnn_inference_single_image(all_boxes, all_scores, image_shape, score_thresh, nms_thresh, topk, inst_cls, box_cls):
-    """Tail of fast_rcnn.py:88-141: finite filter, drop bg column, clip, threshold, per-class NMS, top-k.
-    (Kept on torch/torchvision ops: SURVEY.md §8f row 2 'next'.)"""
-    import torchvision
-
-    boxes, scores = all_boxes, all_scores
-    valid = torch.isfinite(boxes).all(dim=1) & torch.isfinite(scores).all(dim=1)
-    if not valid.all():
-        boxes, scores = boxes[valid], scores[valid]
-    scores = scores[:, :-1]
-    nreg = boxes.shape[1] // 4
-    b = box_cls(boxes.reshape(-1, 4).clone())
-    b.clip(image_shape)
-    boxes = b.tensor.view(-1, nreg, 4)
-    mask = scores > score_thresh
-    inds = mask.nonzero()
-    boxes = boxes[inds[:, 0], 0] if nreg == 1 else boxes[mask]
-    scores = scores[mask]
-    keep = torchvision.ops.batched_nms(boxes.float(), scores, inds[:, 1], nms_thresh)
-    if topk >= 0:
-        keep = keep[:topk]
+def fast_rcnn_inference_single_image(all_boxes, all_scores, image_shape, score_thresh, nms_thresh, topk, inst_cls, box_cls,
+                                     dets=None):
+    """fast_rcnn.py:88-141: finite filter, drop bg column, clip, threshold, per-class NMS, top-k -- one C-ABI call
+    (drn_detections_fwd) with fixed-size outputs; `dets` = its outputs when the call was already made inside the
+    captured device pipeline.  The only host work is reading the detection count and slicing."""
+    if dets is None:
+        cap = topk if topk >= 0 else all_scores.shape[0] * (all_scores.shape[1] - 1)
+        dets = ops.detections(all_scores, all_boxes, image_shape, score_thresh, nms_thresh, cap)
+    boxes, scores, classes, rows, count = dets
+    n = int(count.item())
     res = inst_cls(image_shape)
-    res.pred_boxes = box_cls(boxes[keep])
-    res.scores = scores[keep]
-    res.pred_classes = inds[keep, 1]
-    return res, inds[keep, 0]
+    res.pred_boxes = box_cls(boxes[:n].clone())
+    res.scores = scores[:n].clone()
+    res.pred_classes = classes[:n].clone()
+    return res, rows[:n].clone()
 
 
 class _WSLROIHeads(nn.Module):
@@ -737,7 +726,8 @@ class _WSLROIHeads(nn.Module):
             return proposals, self._train_post(dev_out, proposals, targets)
         dev_out = self._eval_device(features,
                                     [p.proposal_boxes.tensor.float().contiguous() for p in proposals],
-                                    [p.objectness_logits.float().contiguous() for p in proposals])
+                                    [p.objectness_logits.float().contiguous() for p in proposals],
+                                    [tuple(p.image_size) for p in proposals])
         pred_instances, all_scores, all_boxes = self._eval_post(dev_out, proposals)
         return pred_instances, {}, all_scores, all_boxes
 
@@ -883,10 +873,12 @@ class _WSLROIHeads(nn.Module):
         return losses
 
     # -- eval ----------------------------------------------------------------------------------------
-    def _eval_device(self, features, boxes_l, obj_l):
-        """Device pipeline of the eval forward up to (all_scores, all_boxes): capturable like _train_device."""
+    def _eval_device(self, features, boxes_l, obj_l, image_sizes):
+        """Device pipeline of the eval forward: (all_scores, all_boxes) and the thresholded / NMS-ed / top-k
+        detections in fixed-size buffers -- capturable like _train_device."""
         K, S = self.num_classes, self.refine_K
-        scores_l, boxes_out = [], []
+        layer = self.box_refinery[-1] if S > 0 else self.box_predictor
+        scores_l, boxes_out, dets = [], [], []
         for i in range(len(boxes_l)):
             boxes, obj = boxes_l[i], obj_l[i]
             feat, logits, heads = self._roi_logits(features, boxes, obj, i)
@@ -906,17 +898,20 @@ class _WSLROIHeads(nn.Module):
                 bx = ops.oicr_infer(logits, K, [offs["cls"]], [-1], boxes, self.box_predictor.bbox_w, K)[1]
             scores_l.append(sc)
             boxes_out.append(bx)
-        return {"scores": scores_l, "boxes": boxes_out}
+            topk = layer.test_topk_per_image
+            dets.append(ops.detections(sc, bx, image_sizes[i], layer.test_score_thresh, layer.test_nms_thresh,
+                                       topk if topk >= 0 else sc.shape[0] * K))
+        return {"scores": scores_l, "boxes": boxes_out, "dets": dets}
 
     def _eval_post(self, d, proposals):
-        """Tail of the eval forward (threshold + NMS: data-dependent shapes, stays outside the graph)."""
+        """Host tail of the eval forward: read the detection counts, slice the fixed-size device outputs."""
         layer = self.box_refinery[-1] if self.refine_K > 0 else self.box_predictor
         results, all_scores, all_boxes = [], [], []
         for i, p in enumerate(proposals):
             sc, bx = d["scores"][i].clone(), d["boxes"][i].clone()  # returned to the caller (TTA): fresh storage
             inst_cls, box_cls = type(p), type(p.proposal_boxes)
             res, _ = fast_rcnn_inference_single_image(bx, sc, p.image_size, layer.test_score_thresh, layer.test_nms_thresh,
-                                                      layer.test_topk_per_image, inst_cls, box_cls)
+                                                      layer.test_topk_per_image, inst_cls, box_cls, dets=d["dets"][i])
             results.append(res)
             all_scores.append(sc.unsqueeze(0))
             all_boxes.append(bx.unsqueeze(0))
@@ -1175,14 +1170,15 @@ class GeneralizedRCNNWSL(nn.Module):
             n = len(images)
             rh = self.roi_heads
             proposals = [x["proposals"] for x in batched_inputs]
+            img_sizes = [tuple(p.image_size) for p in proposals]  # Boxes.clip bounds of the detections (fast_rcnn.py:112-114)
 
             def fn(flat):
                 g = [flat[i * n:(i + 1) * n] for i in range(3)]
-                return rh._eval_device(self._features(g[0], canvas), g[1], g[2])
+                return rh._eval_device(self._features(g[0], canvas), g[1], g[2], img_sizes)
 
             groups = [images, [p.proposal_boxes.tensor.float() for p in proposals],
                       [p.objectness_logits.float() for p in proposals]]
-            dev_out, _ = self._run_device("eval", canvas, groups, fn)
+            dev_out, _ = self._run_device(("eval", tuple(img_sizes)), canvas, groups, fn)
             proposals = [p.to(self.device) for p in proposals]
             results, all_scores, all_boxes = rh._eval_post(dev_out, proposals)
         else:

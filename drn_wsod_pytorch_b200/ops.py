@@ -280,6 +280,28 @@ def oicr_infer(logits, K, col_offs, delta_offs, boxes, bbox_w, nreg):
     return all_scores, all_boxes
 
 
+def detections(all_scores, all_boxes, image_hw, score_thresh, nms_thresh, cap):
+    """Device-side fast_rcnn_inference_single_image: returns fixed-size (boxes [cap,4], scores [cap], classes [cap]
+    int64, rows [cap] int64, count int32[1]); the first `count` entries are the detections, best first."""
+    _chk(all_scores, "all_scores")
+    _chk(all_boxes, "all_boxes")
+    R, K1 = all_scores.shape
+    K = K1 - 1
+    nreg = all_boxes.shape[1] // 4
+    dev = all_scores.device
+    cap = int(cap)
+    out_boxes = torch.empty((cap, 4), device=dev, dtype=torch.float32)
+    out_scores = torch.empty((cap,), device=dev, dtype=torch.float32)
+    out_classes = torch.empty((cap,), device=dev, dtype=torch.int64)
+    out_rows = torch.empty((cap,), device=dev, dtype=torch.int64)
+    count = torch.empty((1,), device=dev, dtype=torch.int32)
+    nbytes = lib.load().drn_detections_workspace_bytes(R, K)
+    ws = torch.empty((max(nbytes, 16),), device=dev, dtype=torch.uint8)
+    call("drn_detections_fwd", all_scores, all_boxes, R, K, nreg, float(image_hw[0]), float(image_hw[1]), float(score_thresh),
+         float(nms_thresh), cap, out_boxes, out_scores, out_classes, out_rows, count, ws, ws.numel(), current_stream())
+    return out_boxes, out_scores, out_classes, out_rows, count
+
+
 def to_bf16(x):
     out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
     call("drn_cast_f32_to_bf16", x.contiguous(), out, x.numel(), current_stream())

@@ -204,6 +204,22 @@ int drn_oicr_infer(const float* logits, int ld, int R, int K, int nreg, int S, c
                    const int* delta_offs_host, const float* boxes, const float* bbox_w_host,
                    float* all_scores, float* all_boxes, drn_stream_t stream);
 
+/* Detections of one image from (all_scores, all_boxes): finite filter, drop the background column, clip
+ * to the image, score threshold, per-class NMS, top-k -- all on the device with fixed-size outputs.
+ * Replaces WSL/roi_heads/fast_rcnn.py:88-141 (fast_rcnn_inference_single_image),
+ * detectron2/layers/nms.py:10-29 (batched_nms -> torchvision nms; the exact per-class form, see
+ * csrc/drn_nms.cu for the restated arithmetic) and detectron2/structures/boxes.py (Boxes.clip).
+ * all_scores: [R][K+1]; all_boxes: [R][4*nreg], nreg = K or 1 (class-agnostic); cap = number of output
+ * slots (TEST.DETECTIONS_PER_IMAGE, or R*K for "all").  Outputs (first *num_out entries valid, sorted by
+ * score descending, ties in (row, class) order): out_boxes [cap][4], out_scores [cap], out_classes [cap]
+ * int64, out_rows [cap] int64 (index of the proposal row, the reference's filter_inds[:, 0]).
+ * workspace: drn_detections_workspace_bytes(R, K) bytes, 16-byte aligned.  R <= 8192. */
+size_t drn_detections_workspace_bytes(int R, int K);
+int drn_detections_fwd(const float* all_scores, const float* all_boxes, int R, int K, int nreg, float img_h,
+                       float img_w, float score_thresh, double nms_thresh, int cap, float* out_boxes,
+                       float* out_scores, int64_t* out_classes, int64_t* out_rows, int32_t* num_out,
+                       void* workspace, size_t workspace_bytes, drn_stream_t stream);
+
 /* Train-mode dropout of the fc6/fc7 activations, in place: x = keep ? x/(1-p) : 0 with a
  * counter-based RNG keyed by (seed + *seed_dev (if non-NULL), element index).
  * Replaces F.dropout(p=0.5) in WSL/roi_heads/box_head.py:90 (mask not comparable to torch's RNG;

@@ -86,3 +86,20 @@ def rel_err(a, b, floor=1e-6):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b) / (np.abs(b) + floor))) if a.size else 0.0
+
+
+def rand_dets(R, K, seed, nreg_k=True, cluster=True):
+    g = torch.Generator().manual_seed(seed)
+    if cluster:  # heavily overlapping boxes around a few centres, like proposals around objects
+        ctr = torch.rand(8, 2, generator=g) * torch.tensor([900.0, 500.0]) + 50
+        which = torch.randint(0, 8, (R,), generator=g)
+        c = ctr[which] + torch.randn(R, 2, generator=g) * 25
+        wh = torch.rand(R, 2, generator=g) * 150 + 30
+        boxes = torch.cat([c - wh / 2, c + wh / 2], dim=1)
+    else:
+        xy = torch.rand(R, 2, generator=g) * torch.tensor([900.0, 500.0])
+        boxes = torch.cat([xy, xy + torch.rand(R, 2, generator=g) * 200 + 5], dim=1)
+    scores = torch.softmax(torch.randn(R, K + 1, generator=g) * 3, dim=1)
+    nreg = K if nreg_k else 1
+    all_boxes = (boxes[:, None, :] + torch.randn(R, nreg, 4, generator=g) * (2.0 if nreg_k else 0.0)).reshape(R, 4 * nreg)
+    return all_boxes.contiguous(), scores.contiguous()

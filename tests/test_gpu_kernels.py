@@ -423,3 +423,56 @@ def test_dropout_statistics():
     ops.dropout_(x, 0.5, 123)
     kept = (x != 0).float().mean().item()
     assert abs(kept - 0.5) < 5e-3 and torch.all((x == 0) | (x == 2.0))
+
+
+# ------------------------------------------------------------------ inference tail (threshold + per-class NMS + top-k)
+def _check_detections(all_boxes, scores, hw, spec, cap=None):
+    K = scores.shape[1] - 1
+    topk = spec.detections_per_image
+    cap = cap if cap is not None else (topk if topk >= 0 else scores.shape[0] * K)
+    b, s, c, r, n = ops.detections(scores.to(DEV), all_boxes.to(DEV), hw, spec.score_thresh_test, spec.nms_thresh_test, cap)
+    n = int(n.item())
+    rb, rs, rc, rr = O.inference_single_image_exact(all_boxes, scores, hw, spec)
+    assert n == len(rs)
+    assert torch.equal(c[:n].cpu(), rc) and torch.equal(r[:n].cpu(), rr)       # bit-exact kept (row, class) pairs, in order
+    assert torch.equal(s[:n].cpu(), rs) and torch.equal(b[:n].cpu(), rb)       # scores / clipped boxes are copies
+    return n
+
+
+@pytest.mark.parametrize("R,K,nreg_k,cluster", [(1500, 20, True, True), (300, 5, False, True), (4000, 20, False, True),
+                                                 (4000, 80, True, False), (1, 3, True, True), (33, 1, False, True)])
+def test_detections_tail_bit_exact_vs_oracle(R, K, nreg_k, cluster):
+    spec = O.Spec(num_classes=K)
+    for seed in range(2):
+        all_boxes, scores = helpers.rand_dets(R, K, 7 * R + seed, nreg_k, cluster)
+        if seed == 1 and R > 10:  # non-finite rows are dropped, ties keep candidate order, degenerate boxes never suppress
+            scores[5, 1 % (K + 1)] = float("nan")
+            all_boxes[9, 0] = float("inf")
+            scores[20:40] = scores[20]
+            all_boxes[50:60, 2] = all_boxes[50:60, 0]
+        _check_detections(all_boxes, scores, (600, 1000), spec)
+
+
+def test_detections_tail_edge_cases():
+    spec = O.Spec(num_classes=4)
+    all_boxes, scores = helpers.rand_dets(200, 4, 3, True, True)
+    # nothing above the threshold -> zero detections
+    spec_hi = O.Spec(num_classes=4, score_thresh_test=2.0)
+    assert _check_detections(all_boxes, scores, (600, 1000), spec_hi) == 0
+    # top-k disabled: every kept candidate comes back (capacity R*K)
+    spec_all = O.Spec(num_classes=4, detections_per_image=-1)
+    n = _check_detections(all_boxes, scores, (600, 1000), spec_all)
+    assert n > 100
+    # nms threshold 1.0 keeps everything above the score threshold; 0.0 keeps one box per overlapping cluster
+    for thr in (1.0, 0.0, 0.5):
+        _check_detections(all_boxes, scores, (600, 1000), O.Spec(num_classes=4, nms_thresh_test=thr, detections_per_image=-1))
+    # boxes far outside the image clip to zero area and are never suppressed (0/0 -> NaN -> not greater)
+    far = all_boxes.clone() + 5000.0
+    _check_detections(far, scores, (600, 1000), spec_all)
+    # identical boxes and identical scores: first candidate wins
+    same_b = all_boxes[:1].repeat(200, 1)
+    same_s = scores[:1].repeat(200, 1)
+    assert _check_detections(same_b, same_s, (600, 1000), spec_all) == 4
+    # empty proposal list
+    b, s, c, r, cnt = ops.detections(torch.zeros(0, 5, device=DEV), torch.zeros(0, 16, device=DEV), (600, 1000), 1e-5, 0.3, 100)
+    assert int(cnt.item()) == 0

@@ -103,3 +103,44 @@ def test_roipool_restatement_bit_exact_vs_torchvision():
     ours = O.roi_pool_numpy(feat, boxes, 1.0 / 8)
     ref = O.roi_pool(torch.from_numpy(feat)[None], torch.from_numpy(boxes), 1.0 / 8).numpy()
     assert np.array_equal(ours, ref)
+
+
+_rand_dets = helpers.rand_dets
+
+
+def test_nms_restatement_bit_exact_vs_torchvision():
+    """oracle.nms_numpy restates torchvision.ops.nms (un-vendored): identical keep lists, incl. ties, zero-area
+    boxes and thresholds that sit exactly on an fp32 IoU value."""
+    import torchvision
+
+    for seed in range(6):
+        all_boxes, scores = _rand_dets(700, 1, seed, nreg_k=False, cluster=seed % 2 == 0)
+        s = scores[:, 0].clone()
+        if seed >= 4:  # ties and degenerate boxes
+            s[::7] = s[3]
+            all_boxes[::11, 2] = all_boxes[::11, 0]
+        for thr in (0.3, 0.5, 0.7):
+            ref = torchvision.ops.nms(all_boxes, s, thr).numpy()
+            np.testing.assert_array_equal(O.nms_numpy(all_boxes.numpy(), s.numpy(), thr), ref)
+    # threshold exactly equal to an attained fp32 IoU: the double comparison keeps/suppresses like torchvision
+    b = torch.tensor([[0.0, 0.0, 10.0, 10.0], [0.0, 0.0, 10.0, 3.0]])
+    s = torch.tensor([0.9, 0.8])
+    for thr in (0.3, float(np.float32(0.3)), 0.30000001):
+        np.testing.assert_array_equal(O.nms_numpy(b.numpy(), s.numpy(), thr), torchvision.ops.nms(b, s, thr).numpy())
+
+
+@pytest.mark.parametrize("R,K,nreg_k", [(1500, 20, True), (300, 5, False), (1200, 20, False)])
+def test_exact_per_class_inference_tail_matches_reference_function(R, K, nreg_k):
+    """oracle.inference_single_image_exact (per-class NMS, what the CUDA tail implements) against the restatement
+    that calls torchvision.ops.batched_nms like the reference does (fast_rcnn.py:126 -> layers/nms.py:20)."""
+    spec = O.Spec(num_classes=K)
+    for seed in range(3):
+        all_boxes, scores = _rand_dets(R, K, 100 + seed, nreg_k)
+        if seed == 2:
+            scores[5, 1] = float("nan")
+            all_boxes[9, 0] = float("inf")
+        a = O.inference_single_image(all_boxes, scores, (600, 1000), spec)
+        b = O.inference_single_image_exact(all_boxes, scores, (600, 1000), spec)
+        assert len(a[1]) == spec.detections_per_image or len(a[1]) == len(b[1])
+        for x, y in zip(a[:3], b[:3]):
+            assert torch.equal(x, y)

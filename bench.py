@@ -213,7 +213,9 @@ def main():
     from drn_wsod_pytorch_b200 import distributed as D
 
     def step(batched):
-        losses = D.reduce_dict(model(batched))  # one packed all-reduce (detectron2/utils/comm.py:234-263 equivalent); identity at N=1
+        with torch.no_grad():  # the metric is forward + loss; the backward has its own line (--mode train)
+            losses = model(batched)
+        losses = D.reduce_dict(losses)  # one packed all-reduce (detectron2/utils/comm.py:234-263 equivalent); identity at N=1
         keys = sorted(losses)
         return torch.stack([losses[k] for k in keys]), keys
 

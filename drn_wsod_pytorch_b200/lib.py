@@ -42,6 +42,12 @@ _PROTOS = {
     "drn_oicr_infer": [_P, c_int, c_int, c_int, c_int, c_int, _IP, _IP, _P, _FP, _P, _P, _P],
     "drn_detections_fwd": [_P, _P, c_int, c_int, c_int, c_float, c_float, c_float, c_double, c_int, _P, _P, _P, _P, _P, _P, c_size_t,
                            _P],
+    "drn_wsddn_mil_bwd": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, c_float, _P, _P, _P, _P],
+    "drn_oicr_stage_bwd": [_P, _P, _P, _P, c_float, _P, c_int, c_int, c_int, c_int, _P, _P],
+    "drn_oicr_boxreg_bwd": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _FP, c_float, c_float, c_float, _P, _P, _P],
+    "drn_masked_transpose": [_P, c_int, c_int, _P, c_int, c_int, c_float, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int, _P],
+    "drn_rowsum": [_P, c_int, c_int, c_int, c_int, _P, _P],
+    "drn_permute_cols49": [_P, _P, c_int64, c_int, _P],
     "drn_dropout_inplace": [_P, c_int64, c_int, c_float, c_uint64, _P, _P],
     "drn_cast_f32_to_bf16": [_P, _P, c_int64, _P],
     "drn_cast_bf16_to_f32": [_P, _P, c_int64, _P],

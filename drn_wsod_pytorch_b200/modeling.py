@@ -41,6 +41,24 @@ def _versions(tensors):
     return tuple((t.data_ptr(), t._version, t.device) for t in tensors if t is not None)
 
 
+def _refresh_in_place(old, new):
+    """Derived weight layouts keep their storage when the parameters change in place (an optimizer step,
+    load_state_dict): captured CUDA graphs hold pointers to these buffers, so they are overwritten, not replaced.
+    Returns `old` updated, or `new` when there is nothing compatible to overwrite."""
+    if old is None:
+        return new
+    for k, v in new.items():
+        o = old.get(k)
+        if torch.is_tensor(v) != torch.is_tensor(o) or (torch.is_tensor(v) and (o.shape != v.shape or o.dtype != v.dtype or o.device != v.device)):
+            return new
+    for k, v in new.items():
+        if torch.is_tensor(v):
+            old[k].copy_(v)
+        else:
+            old[k] = v
+    return old
+
+
 # ------------------------------------------------------------------------------------------------
 # layers (parameter holders with the reference's names)
 # ------------------------------------------------------------------------------------------------
@@ -98,7 +116,7 @@ class Conv2d(nn.Module):
                     w = w * scale.view(-1, 1, 1, 1)
                     scale = None
                 wp = w.permute(0, 2, 3, 1).reshape(cout, -1).contiguous().to(torch.bfloat16)  # [cout][(kh,kw,cin)]
-        hit = {"key": key, "w": wp, "scale": scale, "bias": bias, "cout": cout}
+        hit = _refresh_in_place(hit, {"key": key, "w": wp, "scale": scale, "bias": bias, "cout": cout})
         self._cache[precision] = hit
         return hit
 
@@ -111,7 +129,7 @@ class Linear(nn.Linear):
         hit = getattr(self, "_cache", {}).get((precision, permute_c49))
         if hit is not None and hit["key"] == key:
             return hit
-        hit = dict(pack_linear([self.weight], [self.bias], precision, permute_c49, pad_to), key=key)
+        hit = _refresh_in_place(hit, dict(pack_linear([self.weight], [self.bias], precision, permute_c49, pad_to), key=key))
         if not hasattr(self, "_cache"):
             self._cache = {}
         self._cache[(precision, permute_c49)] = hit
@@ -429,6 +447,7 @@ class DiscriminativeAdaptionNeck(nn.Module):
         if self.training and (self._seed_dev is None or self._seed_dev.device != x.device):
             self._seed_dev = torch.zeros((1,), dtype=torch.int64, device=x.device)
         seed = 0
+        self.acts = [x]  # layer inputs/outputs of this call (the backward's masks and GEMM operands)
         for i, fc in enumerate(self.fcs):
             perm = self.in_channels if (i == 0 and bin_major) else None
             packed = fc.packed(self.precision, permute_c49=perm)
@@ -452,10 +471,12 @@ class DiscriminativeAdaptionNeck(nn.Module):
                         run_linear(x[r0:r1], packed, self.precision, relu=True, dropout=drop, out=y[r0:r1])
                 cur.wait_stream(hp)
                 x = y
+                self.acts.append(x)
                 continue
             seed += 1
             drop = (0.5, seed, self._seed_dev) if self.training else None  # box_head.py:90
             x = run_linear(x, packed, self.precision, relu=True, dropout=drop)
+            self.acts.append(x)
         if self.training:
             self._seed_dev.add_(self.SEEDS_PER_CALL)  # next call draws fresh masks (captured as a graph node)
         return x
@@ -604,8 +625,8 @@ class _WSLROIHeads(nn.Module):
             else:
                 offs[f"bbox_pred_{k}"] = -1
         packed.update(key=key, offs=offs)
-        self._heads_cache = packed
-        return packed
+        self._heads_cache = _refresh_in_place(self._heads_cache, packed)
+        return self._heads_cache
 
     def _features_hwc(self, features, i):
         f = features[self.box_in_features[0]]
@@ -671,6 +692,7 @@ class _WSLROIHeads(nn.Module):
             feat = self.box_head.run(pooled, bin_major=True)
         heads = self._heads_packed()
         logits = run_linear(feat, heads, self.precision, relu=False, out_dtype=torch.float32)
+        self._acts = list(getattr(self.box_head, "acts", []))
         return feat, logits, heads
 
     def _image_level_gt(self, targets):
@@ -768,7 +790,8 @@ class _WSLROIHeads(nn.Module):
                                                            mil_scale, loss_buf[i, 0:1], boxes, gt_int, self._counter)
                 lab0 = midx0 = cnt0 = None
             img_scores.append(img_score)
-            tr = {"scores": scores, "img_score": img_score, "logits": logits, "feat": feat, "stages": []}
+            tr = {"scores": scores, "img_score": img_score, "logits": logits, "feat": feat, "stages": [], "acts": self._acts,
+                  "boxes": boxes, "gt_onehot": gt_oh, "dropout_mul": 2.0 if self.box_head.training else 1.0}
             prev, prev_ld_deltas, prev_deltas, col = scores, 0, None, 1
             for k in range(S):
                 bw = self.box_refinery[k].bbox_w
@@ -806,7 +829,7 @@ class _WSLROIHeads(nn.Module):
                     prev_deltas, prev_ld_deltas = None, 0
                 prev = probs
                 tr["stages"].append(dict(pgt_idx=pgt_idx, pgt_scores=pgt_score, pgt_boxes=pgt_box, pgt_weights=pgt_w,
-                                         labels=labels, matched=midx, probs=probs, weights=weights))
+                                         labels=labels, matched=midx, probs=probs, weights=weights, stats=stats))
             label_counts[0][i] = cnt0
             lab0_l.append(lab0)
             midx0_l.append(midx0)
@@ -871,6 +894,107 @@ class _WSLROIHeads(nn.Module):
                     pend += [(f"fast_rcnn/fg_cls_accuracy_r{k}", st[2] / st[1]), (f"fast_rcnn/false_negative_r{k}", st[3] / st[1])]
             self._put_scalars(storage, pend)
         return losses
+
+    # -- backward of the trainable tail ------------------------------------------
+    def trainable_layers(self):
+        """Linear layers whose parameters receive gradients, in the order of the autograd bridge's inputs."""
+        layers = list(self.box_head.fcs) + [self.box_predictor.cls, self.box_predictor.det]
+        layers += [r.cls_score for r in self.box_refinery]
+        layers += [self.box_refinery[k].bbox_pred for k in range(self.refine_K) if self.refine_reg[k]]
+        return layers
+
+    def _dgrad(self, dy, w_op, out_dtype):
+        """dX [R, in] = dY [R, out] W.  w_op: bf16 mode [in][out] (rows = input features, K-major for the tensor-core
+        kernel); fp32 mode [out][in] (the SIMT kernel's [K][N])."""
+        R, Kd = dy.shape
+        if self.precision == "fp32":
+            n = w_op.shape[1]
+            packed = {"w": w_op, "scale": None, "bias": torch.zeros((n,), device=dy.device, dtype=torch.float32), "cout": n}
+            return ops.conv_f32(dy.view(1, R, 1, Kd), packed, 1, 1, False).view(R, n)
+        n = w_op.shape[0]
+        packed = {"w": w_op, "scale": None, "bias": torch.zeros((n,), device=dy.device, dtype=torch.float32), "cout": n}
+        return ops.conv_bf16_tc(dy.view(1, R, 1, Kd), packed, 1, 1, False, out_dtype=out_dtype).view(R, n)
+
+    def _wgrad(self, dy_t, x, R, c49=0):
+        """dW [out, in] (fp32) = dY^T X with dy_t = dY^T [out][Rp] (zero beyond R).  c49 > 0: X's columns are bin-major
+        pooled features and the result's columns are in the parameter's (c, ph, pw) order."""
+        out_f, Rp = dy_t.shape
+        n = x.shape[1]
+        bias0 = torch.zeros((n,), device=x.device, dtype=torch.float32)
+        if self.precision == "fp32":
+            xp = x if Rp == R else torch.cat([x, x.new_zeros(Rp - R, n)], 0)  # [K = Rp][N = in]
+            dW = ops.conv_f32(dy_t.view(1, out_f, 1, Rp), {"w": xp, "scale": None, "bias": bias0, "cout": n}, 1, 1, False).view(out_f, n)
+            return ops.permute_cols49(dW, c49) if c49 else dW
+        x_t, _ = ops.masked_transpose(x, c49=c49, ld_out=Rp)                    # [in][Rp], K-major
+        return ops.conv_bf16_tc(dy_t.view(1, out_f, 1, Rp), {"w": x_t, "scale": None, "bias": bias0, "cout": n}, 1, 1, False,
+                                out_dtype=torch.float32).view(out_f, n)
+
+    def _backward_device(self, d, grad_vec):
+        """Gradients of sum_i grad_vec[i] * loss_i with respect to every trainable parameter: loss -> head
+        logits (drn_wsddn_mil_bwd / drn_oicr_stage_bwd / drn_oicr_boxreg_bwd), then the linear layers backwards
+        as GEMMs on the forward's kernels -- dX = dY W, dW = dY^T X -- with drn_masked_transpose applying the
+        ReLU/dropout mask and producing the K-major operands.  The backbone is frozen (FREEZE_AT 5), so the chain
+        stops at the pooled features.  Returns {parameter: gradient (fp32, parameter layout)}."""
+        K, S = self.num_classes, self.refine_K
+        traces = d["traces"]
+        N = len(traces)
+        heads = self._heads_packed()
+        offs, ld = heads["offs"], heads["cout"]
+        f32 = self.precision == "fp32"
+        wdt = torch.float32 if f32 else torch.bfloat16
+        pad = 16 if f32 else 64
+        mil_scale = (1.0 / (N * N)) if self.box_predictor.mean_loss else (1.0 / N)
+        Rtot = sum(tr["logits"].shape[0] for tr in traces)
+        nvalid = [torch.stack([tr["stages"][k]["stats"] for tr in traces], 0)[:, 5].sum().reshape(1) for k in range(S)]
+        fcs = self.box_head.fcs
+        grads = {}
+
+        def acc(p, g):
+            grads[p] = g if p not in grads else grads[p] + g
+
+        # input-gradient operands: heads W_h transposed (either mode), fc weights ([in][out] bf16 / the parameter itself fp32)
+        wh_op, _ = ops.masked_transpose(heads["w"])
+        w_op = [None] + [fc.weight.detach() if f32 else ops.masked_transpose(fc.packed(self.precision)["w"])[0] for fc in fcs[1:]]
+        head_layers = [("cls", self.box_predictor.cls), ("det", self.box_predictor.det)]
+        head_layers += [(f"cls_score_{k}", self.box_refinery[k].cls_score) for k in range(S)]
+        head_layers += [(f"bbox_pred_{k}", self.box_refinery[k].bbox_pred) for k in range(S) if self.refine_reg[k]]
+        for tr in traces:
+            logits, acts = tr["logits"], tr["acts"]
+            R = logits.shape[0]
+            Rp = -(-R // pad) * pad
+            dlog = torch.zeros((R, ld), device=logits.device, dtype=torch.float32)
+            ops.wsddn_mil_bwd(logits, K, offs["cls"], offs["det"], tr["scores"], tr["gt_onehot"], self.box_predictor.mean_loss,
+                              mil_scale, grad_vec[0:1], dlog)
+            col = 1
+            for k in range(S):
+                st = tr["stages"][k]
+                ops.oicr_stage_bwd(st["probs"], st["labels"], st["weights"], nvalid[k], 1.0, grad_vec[col:col + 1], K,
+                                   offs[f"cls_score_{k}"], dlog)
+                col += 1
+                if self.refine_reg[k]:
+                    layer = self.box_refinery[k]
+                    ops.oicr_boxreg_bwd(logits, offs[f"bbox_pred_{k}"], K, self.cls_agnostic_bbox_reg, tr["boxes"], st["pgt_boxes"],
+                                        st["labels"], st["matched"], layer.bbox_w, layer.smooth_l1_beta,
+                                        layer.loss_weight.get("loss_box_reg", 1.0), Rtot, grad_vec[col:col + 1], dlog)
+                    col += 1
+            # ---- heads: dW_h = dlog^T feat7, db_h = column sums, dfeat7 = dlog W_h
+            dy_t, dy = ops.masked_transpose(dlog, ld_out=Rp, out_dtype=wdt, want_masked=True)
+            dW = self._wgrad(dy_t, acts[-1], R)
+            db = ops.rowsum(dy_t, cols=R)
+            for name, layer in head_layers:
+                o, n = offs[name], layer.out_features
+                acc(layer.weight, dW[o:o + n])
+                acc(layer.bias, db[o:o + n])
+            dx = self._dgrad(dy, wh_op, wdt)
+            # ---- fc layers, last to first (ReLU + dropout mask = the layer's own output)
+            for li in range(len(fcs) - 1, -1, -1):
+                fc, y, x = fcs[li], acts[li + 1], acts[li]
+                dy_t, dy = ops.masked_transpose(dx, mask=y, mul=tr["dropout_mul"], ld_out=Rp, out_dtype=wdt, want_masked=li > 0)
+                acc(fc.weight, self._wgrad(dy_t, x, R, c49=self.in_channels if li == 0 else 0))
+                acc(fc.bias, ops.rowsum(dy_t, cols=R))
+                if li > 0:
+                    dx = self._dgrad(dy, w_op[li], wdt)
+        return grads
 
     # -- eval ----------------------------------------------------------------------------------------
     def _eval_device(self, features, boxes_l, obj_l, image_sizes):
@@ -1010,6 +1134,23 @@ class _GraphPlan:
         return self.out
 
 
+class _WSLLossBridge(torch.autograd.Function):
+    """Connects the loss values computed by the device pipeline to torch autograd: forward hands the loss
+    vector through, backward runs the B200 backward of the trainable tail (`_WSLROIHeads._backward_device`)
+    and returns the parameter gradients, so `sum(losses.values()).backward(); optimizer.step()` works exactly
+    as with the reference model (tools/train_net.py / detectron2/engine/train_loop.py:215-240)."""
+
+    @staticmethod
+    def forward(ctx, roi_heads, dev_out, loss_vec, *params):
+        ctx.roi_heads, ctx.dev_out, ctx.params = roi_heads, dev_out, params
+        return loss_vec.clone()
+
+    @staticmethod
+    def backward(ctx, grad_vec):
+        grads = ctx.roi_heads._backward_device(ctx.dev_out, grad_vec.contiguous().float())
+        return (None, None, None) + tuple(grads.get(p) if p.requires_grad else None for p in ctx.params)
+
+
 @META_ARCH_REGISTRY.register()
 class GeneralizedRCNNWSL(nn.Module):
     """projects/WSL/wsl/modeling/meta_arch/rcnn.py:23-265 with precomputed proposals."""
@@ -1060,11 +1201,40 @@ class GeneralizedRCNNWSL(nn.Module):
         return super()._apply(fn, *a, **k)
 
     def _weights_signature(self):
-        """Cheap staleness check for the captured plans: in-place updates (load_state_dict, an optimizer
-        step) bump the version counters; module-level moves go through _apply and drop the plans."""
+        """Cheap staleness check: in-place updates (load_state_dict, an optimizer step) bump the version
+        counters; module-level moves go through _apply and drop the plans."""
         if getattr(self, "_sig_tensors", None) is None:
             self._sig_tensors = list(self.state_dict(keep_vars=True).values())
         return tuple(t._version for t in self._sig_tensors)
+
+    def _refresh_derived(self):
+        """Bring every derived weight layout (NHWC filters with FrozenBN folded, fc6 K-permutation, concatenated
+        heads, bf16 copies) up to date IN PLACE after a parameter update, on the current stream, so that captured
+        plans -- which hold pointers to those buffers -- stay valid across optimizer steps.  A layout that had to be
+        re-allocated (shape / dtype change) drops the plans."""
+        sig = self._weights_signature()
+        if sig == getattr(self, "_last_sig", None):
+            return
+        self._last_sig = sig
+        rh = self.roi_heads
+        before, after = [], []
+        for m in self.modules():
+            cache = getattr(m, "_cache", None)
+            if not cache:
+                continue
+            for k in list(cache):
+                before.append(id(cache[k]))
+                if isinstance(m, Conv2d):
+                    m.packed(k)
+                else:
+                    m.packed(k[0], permute_c49=k[1])
+                after.append(id(cache[k]))
+        if rh._heads_cache is not None:
+            before.append(id(rh._heads_cache))
+            rh._heads_packed()
+            after.append(id(rh._heads_cache))
+        if before != after:
+            self._plans.clear()
 
     def preprocess_image(self, batched_inputs):
         """rcnn.py:242-249.  Normalisation is fused into the first conv, so this only records the images
@@ -1083,7 +1253,8 @@ class GeneralizedRCNNWSL(nn.Module):
 
     def _plan_for(self, kind, canvas, groups, fn, force=False):
         flat = [t for g in groups for t in g]
-        key = (kind, canvas, self.roi_heads.keep_trace, tuple((tuple(t.shape), t.dtype) for t in flat), self._weights_signature())
+        self._refresh_derived()
+        key = (kind, canvas, self.roi_heads.keep_trace, self.roi_heads.box_head.training, tuple((tuple(t.shape), t.dtype) for t in flat))
         plan = self._plans.get(key)
         if plan is None:
             seen = self._seen.get(key, 0) + 1
@@ -1160,6 +1331,15 @@ class GeneralizedRCNNWSL(nn.Module):
         # rcnn.py:184 discards the proposals the ROI heads return, so their gt_* fields are not materialised here
         losses = {}
         losses.update(self.roi_heads._train_post(dev_out, proposals, targets, attach=False))
+        if torch.is_grad_enabled():
+            params = [p for l in self.roi_heads.trainable_layers() for p in (l.weight, l.bias)]
+            if any(p.requires_grad for p in params):
+                if any(p.requires_grad for p in self.backbone.parameters()):
+                    raise NotImplementedError("the B200 backward covers the ROI heads; the WSL configs freeze the whole backbone "
+                                              "(MODEL.BACKBONE.FREEZE_AT: 5) -- freeze it or run under torch.no_grad()")
+                keys = list(losses)
+                vec = _WSLLossBridge.apply(self.roi_heads, dev_out, torch.stack([losses[k] for k in keys]), *params)
+                losses = {k: vec[i] for i, k in enumerate(keys)}
         return losses
 
     def inference(self, batched_inputs, detected_instances=None, do_postprocess=True):

@@ -302,6 +302,60 @@ def detections(all_scores, all_boxes, image_hw, score_thresh, nms_thresh, cap):
     return out_boxes, out_scores, out_classes, out_rows, count
 
 
+# ---------------------------------------------------------------- backward of the trainable tail
+def wsddn_mil_bwd(logits, K, cls_off, det_off, scores, gt_onehot, mean_loss, loss_scale, grad_loss, dlogits):
+    R, ld = logits.shape
+    ws = torch.empty((K,), device=logits.device, dtype=torch.float32)
+    call("drn_wsddn_mil_bwd", logits, ld, R, K, cls_off, det_off, scores, gt_onehot, int(mean_loss), float(loss_scale), grad_loss,
+         dlogits, ws, current_stream())
+
+
+def oicr_stage_bwd(probs, labels, weights, nvalid, loss_scale, grad_loss, K, col_off, dlogits):
+    R, ld = dlogits.shape
+    call("drn_oicr_stage_bwd", probs, labels, weights, nvalid, float(loss_scale), grad_loss, R, K, ld, col_off, dlogits,
+         current_stream())
+
+
+def oicr_boxreg_bwd(logits, col_off, K, cls_agnostic, boxes, pgt_box, labels, matched, bbox_w, beta, loss_scale, denom, grad_loss,
+                    dlogits):
+    R, ld = logits.shape
+    call("drn_oicr_boxreg_bwd", logits, ld, col_off, R, K, int(cls_agnostic), boxes, pgt_box, labels, matched, fvec(bbox_w),
+         float(beta), float(loss_scale), float(denom), grad_loss, dlogits, current_stream())
+
+
+def masked_transpose(grad, mask=None, mul=1.0, c49=0, ld_out=None, out_dtype=None, want_masked=False):
+    """grad [R, C] (* mask != 0) * mul -> (transposed [C, ld_out] zero-padded beyond R, masked [R, C] or None)."""
+    _chk(grad, "grad")
+    R, C = grad.shape
+    ld_out = R if ld_out is None else ld_out
+    out_dtype = out_dtype or grad.dtype
+    out_t = torch.empty((C, ld_out), device=grad.device, dtype=out_dtype)
+    masked = torch.empty((R, C), device=grad.device, dtype=out_dtype) if want_masked else None
+    if mask is not None:
+        _chk(mask, "mask")
+        assert mask.shape == grad.shape
+    if mask is not None:
+        mask_dt = _dt(mask)
+    else:  # no mask: pick the code of a supported (grad, mask, out) combination
+        mask_dt = DRN_F32 if (grad.dtype == torch.float32 and out_dtype == torch.float32) else DRN_BF16
+    call("drn_masked_transpose", grad, C, _dt(grad), mask, C, mask_dt, float(mul), R, C, int(c49), out_t, ld_out, masked, C,
+         _dt(out_t), current_stream())
+    return out_t, masked
+
+
+def rowsum(x, cols=None):
+    rows, ld = x.shape
+    out = torch.empty((rows,), device=x.device, dtype=torch.float32)
+    call("drn_rowsum", x, ld, rows, ld if cols is None else cols, _dt(x), out, current_stream())
+    return out
+
+
+def permute_cols49(x, c49):
+    out = torch.empty_like(x)
+    call("drn_permute_cols49", x, out, x.shape[0], int(c49), current_stream())
+    return out
+
+
 def to_bf16(x):
     out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
     call("drn_cast_f32_to_bf16", x.contiguous(), out, x.numel(), current_stream())

@@ -227,6 +227,48 @@ int drn_detections_fwd(const float* all_scores, const float* all_boxes, int R, i
 int drn_dropout_inplace(void* x, int64_t n, int dtype, float p, uint64_t seed, const uint64_t* seed_dev,
                         drn_stream_t stream);
 
+/* ---- backward of the trainable tail ------------------------------------------------
+ * The reference gets these from torch autograd; image scores, pseudo GT, proposal weights and next-stage
+ * inputs are detached there (WSL/roi_heads/roi_heads_oicr.py:359-394), so every loss reaches only the logits
+ * of its own head.  dlogits: [R][ld] fp32, same column layout as the forward's concatenated head logits;
+ * grad_loss: device pointer to the upstream gradient of that loss (1 float) or NULL (= 1). */
+
+/* d(loss_cls)/d(cls, det logits): backward of drn_wsddn_mil_fwd (fast_rcnn.py:493-527, :689-700, :317-329).
+ * scores: [R][K] from the forward; g_ws: [K] fp32 scratch. */
+int drn_wsddn_mil_bwd(const float* logits, int ld, int R, int K, int cls_off, int det_off, const float* scores,
+                      const float* gt_onehot, int mean_loss, float loss_scale, const float* grad_loss,
+                      float* dlogits, float* g_ws, drn_stream_t stream);
+
+/* d(loss_cls_r{k})/d(cls_score_k logits): backward of drn_oicr_stage_fwd (fast_rcnn.py:1128-1144):
+ * loss_scale * w_r (softmax - onehot) / *nvalid, zero for label -1.  probs [R][K+1], weights [R] and
+ * nvalid (device, 1 float: stats[5] of the stage, summed over the images of the batch) come from the forward. */
+int drn_oicr_stage_bwd(const float* probs, const int64_t* labels, const float* weights, const float* nvalid,
+                       float loss_scale, const float* grad_loss, int R, int K, int ld, int col_off,
+                       float* dlogits, drn_stream_t stream);
+
+/* d(loss_box_reg_r{k})/d(bbox_pred_k deltas): backward of drn_oicr_boxreg_loss (fast_rcnn.py:1146-1211);
+ * denom = total number of proposals in the batch.  Writes all 4K (or 4) delta columns (zeros off the fg class). */
+int drn_oicr_boxreg_bwd(const float* deltas, int ld, int col_off, int R, int K, int cls_agnostic,
+                        const float* boxes, const float* pgt_box, const int64_t* labels,
+                        const int64_t* matched_idx, const float* bbox_w_host, float beta, float loss_scale,
+                        float denom, const float* grad_loss, float* dlogits, drn_stream_t stream);
+
+/* Gradient through ReLU + dropout, transposed for the weight-gradient GEMM:
+ *   m[r][c] = grad[r][c] * (mask == NULL || mask[r][c] != 0 ? mul : 0)      (mask = the layer's forward output)
+ *   out_t[c'][r] = m[r][c] for r < R, 0 for R <= r < ld_out;  c' = c, or (c % c49) * 49 + c / c49 when c49 > 0
+ *   (bin-major pooled-feature columns -> the reference's (c, ph, pw) flatten order, box_head.py:87);
+ *   out_masked[r][c] = m[r][c] if non-NULL (operand of the next input-gradient GEMM).
+ * dtype codes per tensor; supported (grad, mask, out): (bf16,bf16,bf16) (f32,bf16,bf16) (bf16,bf16,f32) (f32,f32,f32). */
+int drn_masked_transpose(const void* grad, int ld_grad, int grad_dtype, const void* mask, int ld_mask,
+                         int mask_dtype, float mul, int R, int C, int c49, void* out_t, int ld_out,
+                         void* out_masked, int ld_masked, int out_dtype, drn_stream_t stream);
+
+/* out[row] = sum_i x[row][i], i < cols (bias gradients from a transposed gradient matrix; fixed order). */
+int drn_rowsum(const void* x, int ld, int rows, int cols, int dtype, float* out, drn_stream_t stream);
+
+/* [rows][49*c49] fp32, bin-major columns -> channel-major columns (fc6 weight gradient, exact-fp32 mode). */
+int drn_permute_cols49(const float* in, float* out, int64_t rows, int c49, drn_stream_t stream);
+
 /* dtype / layout helpers used by the weight cache (not on the per-image path). */
 int drn_cast_f32_to_bf16(const float* in, void* out, int64_t n, drn_stream_t stream);
 int drn_cast_bf16_to_f32(const void* in, float* out, int64_t n, drn_stream_t stream);

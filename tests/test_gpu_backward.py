@@ -1,0 +1,128 @@
+"""Backward of the trainable tail on the B200 (-m gpu): parameter gradients of
+`sum(loss_dict.values()).backward()` through the autograd bridge versus (a) gradient fingerprints of the
+unmodified reference (tests/golden/*_grads.npz) and (b) the CPU oracle's autograd on the same seeded inputs;
+then whole SGD steps against the oracle stepped with the same torch optimizer."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+import drn_wsod_pytorch_b200 as drn
+from oracle import wsl_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _build(case, precision):
+    cfg = helpers.case_config(case, device=DEV, precision=precision)
+    model = drn.build_model(cfg)
+    weights = helpers.case_weights(cfg, model)
+    model.load_state_dict({**weights, "pixel_mean": model.pixel_mean, "pixel_std": model.pixel_std}, strict=True)
+    model.train()
+    model.roi_heads.box_head.eval()  # dropout off, as in the golden / oracle runs
+    return cfg, model, weights
+
+
+@pytest.mark.parametrize("case", helpers.GRAD_CASES)
+def test_fp32_gradients_match_reference_golden(case):
+    g = helpers.load_golden(case + "_grads")
+    cfg, model, _ = _build(case, "fp32")
+    batched = helpers.to_batched(helpers.case_inputs(case), drn.Instances, drn.Boxes, device=DEV)
+    losses = model(batched)
+    sum(losses.values()).backward()
+    named = dict(model.named_parameters())
+    trainable = [str(k) for k in g["trainable"]]
+    assert sorted(k for k, p in named.items() if p.requires_grad) == sorted(trainable)
+    for k in trainable:
+        if f"grad/{k}/none" in g:
+            assert named[k].grad is None, k
+            continue
+        assert named[k].grad is not None and named[k].grad.shape == named[k].shape, k
+        helpers.check_grad(named[k].grad, g, f"grad/{k}/", 1e-3, case)
+
+
+@pytest.mark.parametrize("case", ["oicr_r18_small", "oicr_r50_small"])
+def test_bf16_gradients_close_to_reference_golden(case):
+    """Tensor-core mode: bf16 operands (activations, weights, gradients), fp32 accumulation.  Gradients must agree
+    with the fp32 reference to bf16 accuracy: norms and all but 3 % of the sampled elements (ReLU-boundary flips,
+    see helpers.check_grad) within 6 % of the tensor's scale -- provided the bf16 forward mined the same pseudo GT (checked; otherwise the loss surface differs)."""
+    g = helpers.load_golden(case + "_grads")
+    gold = helpers.load_golden(case)
+    cfg, model, _ = _build(case, "bf16")
+    model.roi_heads.keep_trace = True
+    batched = helpers.to_batched(helpers.case_inputs(case), drn.Instances, drn.Boxes, device=DEV)
+    losses = model(batched)
+    sum(losses.values()).backward()
+    tr = model.roi_heads.last_trace[0]
+    same = all(np.array_equal(st["pgt_idx"].cpu().numpy(), gold[f"img0/stage{k}/pgt_idx"]) for k, st in enumerate(tr["stages"]))
+    if not same:
+        pytest.skip("bf16 forward picked a different pseudo-GT proposal than the fp32 reference on this case")
+    named = dict(model.named_parameters())
+    for k in (str(k) for k in g["trainable"]):
+        if f"grad/{k}/none" in g:
+            continue
+        helpers.check_grad(named[k].grad, g, f"grad/{k}/", 6e-2, case, atol=1e-4, bad_frac=0.03)
+
+
+def test_weighted_losses_and_graph_replay_gradients_match_oracle():
+    """Non-uniform upstream gradients (each loss scaled differently), eager and through the captured plan."""
+    case = "oicr_r18_reg"
+    cfg, model, weights = _build(case, "fp32")
+    inputs = helpers.case_inputs(case)
+    spec = O.spec_from_cfg(cfg)
+    lw = [0.5, 2.0, 1.0, 0.25, 3.0, 1.5]
+    ref_losses, ref_grads = O.backward_reference(inputs, dict(weights), spec, loss_weights=lw)
+    batched = helpers.to_batched(inputs, drn.Instances, drn.Boxes, device=DEV)
+    for it in range(3):  # first call eager, then captured + replayed
+        model.zero_grad(set_to_none=True)
+        losses = model(batched)
+        assert list(losses) == list(ref_losses)
+        sum(v * w for v, w in zip(losses.values(), lw)).backward()
+        for k, p in model.named_parameters():
+            if not p.requires_grad:
+                continue
+            r = ref_grads[k]
+            if r is None:
+                assert p.grad is None
+                continue
+            scale = max(float(r.abs().max()), 1e-4)  # floor: det.bias is analytically zero (noise ~1e-8 on both sides)
+            assert float((p.grad.cpu() - r).abs().max()) <= 1e-3 * scale, (it, k)
+    assert model._plans
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_sgd_steps_track_the_oracle(precision):
+    """Four SGD steps (momentum 0.9, weight decay 1e-4: detectron2/solver/build.py defaults of the WSL configs) with
+    torch.optim.SGD on our parameters, through the captured plan: the derived weight layouts must follow the
+    in-place updates (no stale weights, no re-capture), and the loss trajectory must match the oracle stepped with
+    the same optimizer."""
+    case = "oicr_r18_small"
+    cfg, model, weights = _build(case, precision)
+    inputs = helpers.case_inputs(case)
+    spec = O.spec_from_cfg(cfg)
+    lr = 2e-4
+    ours_opt = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=lr, momentum=0.9, weight_decay=1e-4)
+    state = {k: v.clone() for k, v in weights.items()}
+    tr_keys = [k for k in state if k.startswith(O.TRAINABLE_PREFIXES)]
+    ref_params = {k: state[k].clone().requires_grad_(True) for k in tr_keys}
+    ref_opt = torch.optim.SGD(list(ref_params.values()), lr=lr, momentum=0.9, weight_decay=1e-4)
+    batched = helpers.to_batched(inputs, drn.Instances, drn.Boxes, device=DEV)
+    ours_traj, ref_traj = [], []
+    for step in range(4):
+        ours_opt.zero_grad(set_to_none=True)
+        losses = model(batched)
+        sum(losses.values()).backward()
+        ours_opt.step()
+        ours_traj.append({k: v.item() for k, v in losses.items()})
+        ref_opt.zero_grad(set_to_none=True)
+        rl, _ = O.forward_train(inputs, {**state, **ref_params}, spec)
+        sum(rl.values()).backward()
+        ref_opt.step()
+        ref_traj.append({k: v.item() for k, v in rl.items()})
+    assert len(model._plans) == 1  # captured once, replayed across the parameter updates
+    tol = 2e-3 if precision == "fp32" else 5e-2
+    for a, b in zip(ours_traj, ref_traj):
+        for k in b:
+            assert abs(a[k] - b[k]) <= tol * max(abs(b[k]), 1e-3), (precision, k, ours_traj, ref_traj)
+    assert ref_traj[0] != ref_traj[-1]  # the steps really moved the losses

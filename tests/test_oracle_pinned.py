@@ -144,3 +144,24 @@ def test_exact_per_class_inference_tail_matches_reference_function(R, K, nreg_k)
         assert len(a[1]) == spec.detections_per_image or len(a[1]) == len(b[1])
         for x, y in zip(a[:3], b[:3]):
             assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("case", ["wsddn_v16_300", "oicr_r18_reg", "oicr_r18_batch2"])
+def test_oracle_backward_matches_reference_gradients(case):
+    """oracle.backward_reference (autograd through the restated forward, with the reference's detach points) against
+    gradient fingerprints of the unmodified reference's loss.backward() (tests/golden/make_golden_grads.py)."""
+    g = helpers.load_golden(case + "_grads")
+    cfg = helpers.case_config(case)
+    model = __import__("drn_wsod_pytorch_b200").build_model(cfg)
+    state = dict(helpers.case_weights(cfg, model))
+    spec = O.spec_from_cfg(cfg)
+    losses, grads = O.backward_reference(helpers.case_inputs(case), state, spec)
+    for k, v in losses.items():
+        assert helpers.rel_err(v.item(), g["loss/" + k]) < 1e-4
+    trainable = [str(k) for k in g["trainable"]]
+    assert sorted(trainable) == sorted(grads)
+    for k in trainable:
+        if f"grad/{k}/none" in g:
+            assert grads[k] is None or float(grads[k].abs().max()) == 0.0, k  # unused parameter (bbox_pred without REFINE_REG)
+            continue
+        helpers.check_grad(grads[k], g, f"grad/{k}/", 2e-4, case)

@@ -130,6 +130,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="forward", choices=["forward", "train"],
+                    help="forward: forward+loss (BASELINE.json's metric, default); train: forward+loss+backward of the trainable "
+                         "tail+SGD step (+ gradient all-reduce at N>1) -- SURVEY.md §8f row 1, reported as an extra line")
     ap.add_argument("--breakdown", action="store_true", help="also print a per-kernel-family time breakdown to stderr")
     ap.add_argument("--profile-step", action="store_true",
                     help="after warm-up run ONE step between cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`; prints no bench line)")
@@ -212,9 +215,25 @@ def main():
 
     from drn_wsod_pytorch_b200 import distributed as D
 
+    train_mode = args.mode == "train"
+    if train_mode:
+        cfg.SOLVER.BASE_LR = 1e-6  # synthetic data: keep the random-init weights in a sane range over the timed steps
+        optimizer = drn.build_optimizer(cfg, model)  # detectron2/solver/build.py mirrored, fused update kernel
+        sync = D.GradientSynchronizer()
+        if world > 1:
+            model.roi_heads.grad_ready_hook = sync.ready
+
     def step(batched):
-        with torch.no_grad():  # the metric is forward + loss; the backward has its own line (--mode train)
+        if not train_mode:
+            with torch.no_grad():  # the metric is forward + loss; the backward has its own line (--mode train)
+                losses = model(batched)
+        else:
+            optimizer.zero_grad(set_to_none=True)
             losses = model(batched)
+            sum(losses.values()).backward()  # gradient blocks are all-reduced (AVG) as they are produced
+            sync.finish()
+            optimizer.step()
+            losses = {k: v.detach() for k, v in losses.items()}
         losses = D.reduce_dict(losses)  # one packed all-reduce (detectron2/utils/comm.py:234-263 equivalent); identity at N=1
         keys = sorted(losses)
         return torch.stack([losses[k] for k in keys]), keys
@@ -368,7 +387,7 @@ def main():
     total_tflops = 2 * sum(gmac.values()) * 1e9 / (ms_step * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
     out = {
-        "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC if not train_mode else METRIC.replace("forward+loss", "training step (forward+loss+backward+SGD)"), "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic", "config": config,
         "e2e": {"value": world * args.steps / t_e2e.item(), "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -381,6 +400,9 @@ def main():
                      "whole_step_tflops": total_tflops, "whole_step_frac": total_tflops / peak},
         "losses": dict(zip(loss_keys, [round(float(x), 6) for x in vec.tolist()])),
     }
+    if train_mode:
+        out["config"]["mode"] = "train: backward of fc6/fc7/heads (backbone frozen, FREEZE_AT 5) + fused SGD; gradients averaged over ranks"
+        out["grad_allreduce_bytes_per_step"] = sync.bytes // max(1, sync.steps)
     if world == 1 and not args.no_cpu_baseline:
         from oracle import wsl_oracle as O
 

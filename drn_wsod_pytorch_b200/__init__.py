@@ -21,6 +21,7 @@ from .registry import (  # noqa: F401
     ROI_HEADS_REGISTRY,
     register_into_detectron2,
 )
+from .solver import FusedSGD, build_optimizer  # noqa: F401
 from .structures import Boxes, ImageList, Instances  # noqa: F401
 
 __version__ = "0.1.0"

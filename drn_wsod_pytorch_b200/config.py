@@ -174,6 +174,9 @@ def get_cfg():
             },
             "INPUT": {"FORMAT": "BGR"},
             "TEST": {"DETECTIONS_PER_IMAGE": 100},
+            # detectron2/config/defaults.py SOLVER keys read by build_optimizer (solver/build.py:93-137)
+            "SOLVER": {"BASE_LR": 0.001, "MOMENTUM": 0.9, "NESTEROV": False, "WEIGHT_DECAY": 0.0001, "WEIGHT_DECAY_NORM": 0.0,
+                       "BIAS_LR_FACTOR": 1.0, "WEIGHT_DECAY_BIAS": 0.0001, "IMS_PER_BATCH": 16},
             "WSL": {
                 "VIS_TEST": False,
                 "ITER_SIZE": 1,
@@ -216,6 +219,8 @@ _VOC_BASE = {
         },
     },
     "WSL": {"ITER_SIZE": 1, "MEAN_LOSS": True},
+    # projects/WSL/configs/PascalVOC-Detection/oicr_WSR_18_DC5_1x.yaml:40-48 (the same block in every WSL model YAML)
+    "SOLVER": {"IMS_PER_BATCH": 4, "BASE_LR": 0.01, "WEIGHT_DECAY": 0.0005, "BIAS_LR_FACTOR": 2.0, "WEIGHT_DECAY_BIAS": 0.0},
 }
 
 

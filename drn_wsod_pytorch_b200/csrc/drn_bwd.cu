@@ -171,6 +171,67 @@ __global__ void permute_cols49_kernel(const float* __restrict__ in, float* __res
   out[row * ncol + (long long)(c % C49) * 49 + c / C49] = in[i];
 }
 
+// ---- SGD step fused with the refresh of the tensor-core weight copy ------------------------------------------
+// torch.optim.SGD arithmetic (detectron2/solver/build.py builds exactly that optimizer): d = g + wd * w;
+// buf = first ? d : momentum * buf + d;  d = nesterov ? d + momentum * buf : buf;  w -= lr * d.
+// PERM: w is [N][C49 * 49] in the reference's (c, ph, pw) column order and `packed` the bf16 copy in the kernels'
+// bin-major order; one CTA owns 64 channels x 49 bins of one row (contiguous in w), updates them in place and
+// transposes the new values through shared memory so that both sides are coalesced.  grid = (N, C49 / 64).
+__device__ __forceinline__ float sgd_update(float w, float g, float* mom, long long i, float lr, float momentum, float wd,
+                                            int nesterov, int first) {
+  float d = fmaf(wd, w, g);
+  if (momentum != 0.f) {
+    const float b = first ? d : fmaf(momentum, mom[i], d);
+    mom[i] = b;
+    d = nesterov ? fmaf(momentum, b, d) : b;
+  }
+  return fmaf(-lr, d, w);
+}
+
+__global__ void __launch_bounds__(256)
+sgd_pack_perm_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ mom,
+                     __nv_bfloat16* __restrict__ packed, int C49, float lr, float momentum, float wd, int nesterov, int first) {
+  __shared__ float tile[64 * 49];
+  const long long K = (long long)C49 * 49;
+  const long long base = (long long)blockIdx.x * K + (long long)blockIdx.y * 64 * 49;
+  for (int i = threadIdx.x; i < 64 * 49; i += 256) {
+    const float nw = sgd_update(w[base + i], g[base + i], mom, base + i, lr, momentum, wd, nesterov, first);
+    w[base + i] = nw;
+    tile[i] = nw;  // i = cc * 49 + bin
+  }
+  __syncthreads();
+  __nv_bfloat16* prow = packed + (long long)blockIdx.x * K + blockIdx.y * 64;
+  for (int i = threadIdx.x; i < 64 * 49; i += 256) {
+    const int bin = i >> 6, cc = i & 63;
+    prow[(long long)bin * C49 + cc] = __float2bfloat16(tile[cc * 49 + bin]);
+  }
+}
+
+__global__ void sgd_pack_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ mom,
+                                __nv_bfloat16* __restrict__ packed, long long n, float lr, float momentum, float wd,
+                                int nesterov, int first) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float nw = sgd_update(w[i], g[i], mom, i, lr, momentum, wd, nesterov, first);
+  w[i] = nw;
+  if (packed) packed[i] = __float2bfloat16(nw);
+}
+
+// bf16 kernel layout of a linear layer's weight without an optimizer step (weight load / first use)
+__global__ void __launch_bounds__(256)
+pack_perm_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed, int C49) {
+  __shared__ float tile[64 * 49];
+  const long long K = (long long)C49 * 49;
+  const long long base = (long long)blockIdx.x * K + (long long)blockIdx.y * 64 * 49;
+  for (int i = threadIdx.x; i < 64 * 49; i += 256) tile[i] = w[base + i];
+  __syncthreads();
+  __nv_bfloat16* prow = packed + (long long)blockIdx.x * K + blockIdx.y * 64;
+  for (int i = threadIdx.x; i < 64 * 49; i += 256) {
+    const int bin = i >> 6, cc = i & 63;
+    prow[(long long)bin * C49 + cc] = __float2bfloat16(tile[cc * 49 + bin]);
+  }
+}
+
 }  // namespace drn
 
 using namespace drn;
@@ -261,6 +322,38 @@ int drn_permute_cols49(const float* in, float* out, int64_t rows, int c49, drn_s
   permute_cols49_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, out, rows, c49);
   DRN_CHECK_LAUNCH("permute_cols49");
   return 0;
+}
+
+int drn_sgd_step(float* w, const float* grad, float* momentum_buf, void* packed_bf16, int64_t rows, int64_t cols, int c49,
+                 float lr, float momentum, float weight_decay, int nesterov, int first_step, drn_stream_t stream) {
+  DRN_CHECK_ARG(w && grad, "sgd_step: null pointer");
+  DRN_CHECK_ARG(momentum == 0.f || momentum_buf, "sgd_step: momentum without a buffer");
+  const long long n = (long long)rows * cols;
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c49 > 0 && packed_bf16) {
+    DRN_CHECK_ARG(cols == (int64_t)c49 * 49 && c49 % 64 == 0, "sgd_step: cols=%lld is not 49 x %d (c49 %% 64 == 0)", (long long)cols, c49);
+    DRN_CHECK_ARG(rows <= 0x7fffffff, "sgd_step: too many rows");
+    sgd_pack_perm_kernel<<<dim3((unsigned)rows, c49 / 64), 256, 0, st>>>(w, grad, momentum_buf, (__nv_bfloat16*)packed_bf16, c49, lr,
+                                                                          momentum, weight_decay, nesterov, first_step);
+  } else {
+    sgd_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, grad, momentum_buf, (__nv_bfloat16*)packed_bf16, n, lr, momentum,
+                                                                 weight_decay, nesterov, first_step);
+  }
+  DRN_CHECK_LAUNCH("sgd_step");
+  return 0;
+}
+
+int drn_pack_linear_bf16(const float* w, void* packed_bf16, int64_t rows, int64_t cols, int c49, drn_stream_t stream) {
+  DRN_CHECK_ARG(w && packed_bf16, "pack_linear: null pointer");
+  if (rows * cols == 0) return 0;
+  if (c49 > 0) {
+    DRN_CHECK_ARG(cols == (int64_t)c49 * 49 && c49 % 64 == 0, "pack_linear: cols=%lld is not 49 x %d (c49 %% 64 == 0)", (long long)cols, c49);
+    pack_perm_kernel<<<dim3((unsigned)rows, c49 / 64), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)packed_bf16, c49);
+    DRN_CHECK_LAUNCH("pack_linear");
+    return 0;
+  }
+  return drn_cast_f32_to_bf16(w, packed_bf16, rows * cols, stream);
 }
 
 }  // extern "C"

@@ -2,6 +2,9 @@
 step, weights replicated, no data-path collective.  The only exchange of the forward+loss path is
 the mean of the loss dict -- the equivalent of detectron2/utils/comm.py:234-263 `reduce_dict`, done
 as ONE all-reduce of a packed vector (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+A training step adds the mean of the trainable parameters' gradients (what DistributedDataParallel does for the
+reference, detectron2/engine/defaults.py:279-282): `GradientSynchronizer` all-reduces each gradient block the
+moment the backward has produced it, so the transfer of fc6's blocks overlaps the GEMMs of the next ones.
 """
 from typing import Dict, List, Sequence
 
@@ -54,3 +57,40 @@ def gather_counts(values: Sequence[int]) -> List[List[int]]:
     out = [torch.empty_like(t) for _ in range(ws)]
     dist.all_gather(out, t)
     return [o.tolist() for o in out]
+
+
+class GradientSynchronizer:
+    """Data-parallel gradient averaging without DistributedDataParallel: the backward calls `ready(tensor)` for every
+    finished gradient block (a whole parameter gradient, or a row block of fc6's); each call launches an
+    asynchronous all-reduce right away -- NCCL orders it after the kernels already queued on the current stream and
+    runs it on its own stream, next to the backward's remaining GEMMs.  `finish()` waits for all of them and applies
+    the 1/world scale (AVG inside NCCL; SUM then scale with gloo).  Unused parameters (bbox_pred without REFINE_REG)
+    never produce a block, so nothing like find_unused_parameters is needed."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.pending = []
+        self.bytes = 0   # all-reduced so far
+        self.steps = 0   # finish() calls
+
+    def ready(self, tensor):
+        rank, ws = world()
+        if ws == 1:
+            return
+        self.bytes += tensor.numel() * tensor.element_size()
+        if dist.get_backend(self.group) == "nccl":
+            h = dist.all_reduce(tensor, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+            self.pending.append((h, None))
+        else:
+            h = dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self.pending.append((h, tensor))
+
+    def finish(self):
+        rank, ws = world()
+        self.steps += 1
+        for h, t in self.pending:
+            h.wait()
+            if t is not None:
+                t.div_(ws)
+        n, self.pending = len(self.pending), []
+        return n

@@ -48,6 +48,8 @@ _PROTOS = {
     "drn_masked_transpose": [_P, c_int, c_int, _P, c_int, c_int, c_float, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int, _P],
     "drn_rowsum": [_P, c_int, c_int, c_int, c_int, _P, _P],
     "drn_permute_cols49": [_P, _P, c_int64, c_int, _P],
+    "drn_sgd_step": [_P, _P, _P, _P, c_int64, c_int64, c_int, c_float, c_float, c_float, c_int, c_int, _P],
+    "drn_pack_linear_bf16": [_P, _P, c_int64, c_int64, c_int, _P],
     "drn_dropout_inplace": [_P, c_int64, c_int, c_float, c_uint64, _P, _P],
     "drn_cast_f32_to_bf16": [_P, _P, c_int64, _P],
     "drn_cast_bf16_to_f32": [_P, _P, c_int64, _P],

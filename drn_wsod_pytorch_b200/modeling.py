@@ -129,7 +129,20 @@ class Linear(nn.Linear):
         hit = getattr(self, "_cache", {}).get((precision, permute_c49))
         if hit is not None and hit["key"] == key:
             return hit
-        hit = _refresh_in_place(hit, dict(pack_linear([self.weight], [self.bias], precision, permute_c49, pad_to), key=key))
+        n, k = self.weight.shape
+        direct = (precision != "fp32" and self.weight.is_cuda and self.weight.dtype == torch.float32 and n % pad_to == 0
+                  and (permute_c49 is None or (permute_c49 % 64 == 0 and k == 49 * permute_c49)))
+        if direct:
+            # one pass, straight into the (existing) bf16 buffer: fc6 is 205 M weights, the torch route through a
+            # permuted fp32 copy costs 2 ms per optimizer step
+            with torch.no_grad():
+                w = hit["w"] if hit is not None and hit["w"].shape == (n, k) else torch.empty((n, k), device=self.weight.device, dtype=torch.bfloat16)
+                ops.pack_linear_bf16(self.weight.detach().contiguous(), w, permute_c49 or 0)
+                b = self.bias.detach().float().clone()
+            new = {"w": w, "scale": None, "bias": b, "cout": n, "n": n, "key": key}
+        else:
+            new = dict(pack_linear([self.weight], [self.bias], precision, permute_c49, pad_to), key=key)
+        hit = _refresh_in_place(hit, new)
         if not hasattr(self, "_cache"):
             self._cache = {}
         self._cache[(precision, permute_c49)] = hit
@@ -598,6 +611,8 @@ class _WSLROIHeads(nn.Module):
         self.fused_tail = os.environ.get("DRN_B200_FUSED_TAIL", "1") != "0"
         # opt-in: measured gain 0.02-0.05 ms of 2.7 (the GEMM is SM<-L2 feed bound, a co-resident gather starves:
         # profiles/r1_overlap_negative_result.txt), less than the tail split-K schedule of the one-piece fc6 saves
+        self.grad_ready_hook = None   # callable(tensor): a finished gradient block (data-parallel all-reduce, distributed.py)
+        self.wgrad_row_blocks = 4     # fc6 weight gradient in row blocks when a hook is installed (transfer/GEMM overlap)
         self.overlap_pool = os.environ.get("DRN_B200_OVERLAP_POOL", "0") != "0"
         self.pool_ctas_per_sm = int(os.environ.get("DRN_B200_POOL_CTAS_PER_SM", "0"))
         self._gt_cache = {}
@@ -915,9 +930,11 @@ class _WSLROIHeads(nn.Module):
         packed = {"w": w_op, "scale": None, "bias": torch.zeros((n,), device=dy.device, dtype=torch.float32), "cout": n}
         return ops.conv_bf16_tc(dy.view(1, R, 1, Kd), packed, 1, 1, False, out_dtype=out_dtype).view(R, n)
 
-    def _wgrad(self, dy_t, x, R, c49=0):
+    def _wgrad(self, dy_t, x, R, c49=0, row_blocks=1, on_block=None):
         """dW [out, in] (fp32) = dY^T X with dy_t = dY^T [out][Rp] (zero beyond R).  c49 > 0: X's columns are bin-major
-        pooled features and the result's columns are in the parameter's (c, ph, pw) order."""
+        pooled features and the result's columns are in the parameter's (c, ph, pw) order.  row_blocks > 1 (tensor-core
+        mode): the GEMM runs in that many blocks of output rows and `on_block(dW[rows])` is called after each one
+        is queued -- a data-parallel trainer starts the all-reduce of a block while the next one is computed."""
         out_f, Rp = dy_t.shape
         n = x.shape[1]
         bias0 = torch.zeros((n,), device=x.device, dtype=torch.float32)
@@ -926,8 +943,17 @@ class _WSLROIHeads(nn.Module):
             dW = ops.conv_f32(dy_t.view(1, out_f, 1, Rp), {"w": xp, "scale": None, "bias": bias0, "cout": n}, 1, 1, False).view(out_f, n)
             return ops.permute_cols49(dW, c49) if c49 else dW
         x_t, _ = ops.masked_transpose(x, c49=c49, ld_out=Rp)                    # [in][Rp], K-major
-        return ops.conv_bf16_tc(dy_t.view(1, out_f, 1, Rp), {"w": x_t, "scale": None, "bias": bias0, "cout": n}, 1, 1, False,
-                                out_dtype=torch.float32).view(out_f, n)
+        packed = {"w": x_t, "scale": None, "bias": bias0, "cout": n}
+        if row_blocks <= 1 or out_f % (128 * row_blocks) != 0:
+            return ops.conv_bf16_tc(dy_t.view(1, out_f, 1, Rp), packed, 1, 1, False, out_dtype=torch.float32).view(out_f, n)
+        dW = torch.empty((out_f, n), device=x.device, dtype=torch.float32)
+        step = out_f // row_blocks
+        for r0 in range(0, out_f, step):
+            ops.conv_bf16_tc(dy_t[r0:r0 + step].view(1, step, 1, Rp), packed, 1, 1, False, out_dtype=torch.float32,
+                             out=dW[r0:r0 + step].view(1, step, 1, n))
+            if on_block is not None:
+                on_block(dW[r0:r0 + step])
+        return dW
 
     def _backward_device(self, d, grad_vec):
         """Gradients of sum_i grad_vec[i] * loss_i with respect to every trainable parameter: loss -> head
@@ -949,8 +975,12 @@ class _WSLROIHeads(nn.Module):
         fcs = self.box_head.fcs
         grads = {}
 
-        def acc(p, g):
+        hook = self.grad_ready_hook if N == 1 else None  # blocks are final only when one image feeds them
+
+        def acc(p, g, announced=False):
             grads[p] = g if p not in grads else grads[p] + g
+            if hook is not None and not announced:
+                hook(grads[p])
 
         # input-gradient operands: heads W_h transposed (either mode), fc weights ([in][out] bf16 / the parameter itself fp32)
         wh_op, _ = ops.masked_transpose(heads["w"])
@@ -981,19 +1011,27 @@ class _WSLROIHeads(nn.Module):
             dy_t, dy = ops.masked_transpose(dlog, ld_out=Rp, out_dtype=wdt, want_masked=True)
             dW = self._wgrad(dy_t, acts[-1], R)
             db = ops.rowsum(dy_t, cols=R)
+            if hook is not None:  # one block for all heads (the parameters' gradients are row slices of it)
+                hook(dW)
+                hook(db)
             for name, layer in head_layers:
                 o, n = offs[name], layer.out_features
-                acc(layer.weight, dW[o:o + n])
-                acc(layer.bias, db[o:o + n])
+                acc(layer.weight, dW[o:o + n], announced=True)
+                acc(layer.bias, db[o:o + n], announced=True)
             dx = self._dgrad(dy, wh_op, wdt)
             # ---- fc layers, last to first (ReLU + dropout mask = the layer's own output)
             for li in range(len(fcs) - 1, -1, -1):
                 fc, y, x = fcs[li], acts[li + 1], acts[li]
                 dy_t, dy = ops.masked_transpose(dx, mask=y, mul=tr["dropout_mul"], ld_out=Rp, out_dtype=wdt, want_masked=li > 0)
-                acc(fc.weight, self._wgrad(dy_t, x, R, c49=self.in_channels if li == 0 else 0))
+                blocks = self.wgrad_row_blocks if (li == 0 and hook is not None) else 1
+                acc(fc.weight, self._wgrad(dy_t, x, R, c49=self.in_channels if li == 0 else 0, row_blocks=blocks, on_block=hook),
+                    announced=blocks > 1 and not f32 and dy_t.shape[0] % (128 * blocks) == 0)
                 acc(fc.bias, ops.rowsum(dy_t, cols=R))
                 if li > 0:
                     dx = self._dgrad(dy, w_op[li], wdt)
+        if hook is None and self.grad_ready_hook is not None:  # multi-image batches: announce the summed gradients
+            for g in grads.values():
+                self.grad_ready_hook(g)
         return grads
 
     # -- eval ----------------------------------------------------------------------------------------
@@ -1198,27 +1236,44 @@ class GeneralizedRCNNWSL(nn.Module):
     def _apply(self, fn, *a, **k):
         self._plans = {}
         self._sig_tensors = None
+        self._last_sig = None
         return super()._apply(fn, *a, **k)
 
     def _weights_signature(self):
         """Cheap staleness check: in-place updates (load_state_dict, an optimizer step) bump the version
         counters; module-level moves go through _apply and drop the plans."""
         if getattr(self, "_sig_tensors", None) is None:
-            self._sig_tensors = list(self.state_dict(keep_vars=True).values())
-        return tuple(t._version for t in self._sig_tensors)
+            self._sig_tensors, self._sig_owner = [], []
+            for m in self.modules():
+                for t in list(m._parameters.values()) + list(m._buffers.values()):
+                    if t is not None:
+                        self._sig_tensors.append(t)
+                        self._sig_owner.append(m)
+        return [t._version for t in self._sig_tensors]
 
     def _refresh_derived(self):
-        """Bring every derived weight layout (NHWC filters with FrozenBN folded, fc6 K-permutation, concatenated
-        heads, bf16 copies) up to date IN PLACE after a parameter update, on the current stream, so that captured
-        plans -- which hold pointers to those buffers -- stay valid across optimizer steps.  A layout that had to be
-        re-allocated (shape / dtype change) drops the plans."""
+        """Bring the derived weight layouts (NHWC filters with FrozenBN folded, fc6 K-permutation, concatenated
+        heads, bf16 copies) of the modules whose parameters changed up to date IN PLACE, on the current stream, so
+        that captured plans -- which hold pointers to those buffers -- stay valid across optimizer steps.  A layout
+        that had to be re-allocated (shape / dtype change) drops the plans."""
         sig = self._weights_signature()
-        if sig == getattr(self, "_last_sig", None):
+        last = getattr(self, "_last_sig", None)
+        if sig == last:
             return
         self._last_sig = sig
+        if last is None or len(last) != len(sig):
+            changed = None  # first call / structure changed: look at everything
+        else:
+            changed = {id(self._sig_owner[i]) for i, (a, b) in enumerate(zip(sig, last)) if a != b}
         rh = self.roi_heads
         before, after = [], []
+        owners = {}
         for m in self.modules():
+            owners[id(m)] = m
+            if isinstance(m, Conv2d) and m.norm is not None:
+                owners[id(m.norm)] = m  # FrozenBN buffers are folded into the conv's pack
+        todo = list(self.modules()) if changed is None else list({id(owners[c]): owners[c] for c in changed if c in owners}.values())
+        for m in todo:
             cache = getattr(m, "_cache", None)
             if not cache:
                 continue

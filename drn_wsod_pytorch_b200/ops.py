@@ -356,6 +356,26 @@ def permute_cols49(x, c49):
     return out
 
 
+def sgd_step(w, grad, momentum_buf, packed, c49, lr, momentum, weight_decay, nesterov, first_step):
+    """In place: torch.optim.SGD update of `w` (fp32) and, in the same pass, of its bf16 kernel-layout copy `packed`
+    (None: no copy; c49 > 0: the fc6 column permutation)."""
+    _chk(w, "param")
+    _chk(grad, "grad")
+    assert w.dtype == torch.float32 and grad.dtype == torch.float32 and grad.shape == w.shape
+    rows = w.shape[0] if w.dim() > 1 else 1
+    cols = w.numel() // max(rows, 1)
+    call("drn_sgd_step", w, grad, momentum_buf, packed, rows, cols, int(c49 or 0), float(lr), float(momentum), float(weight_decay),
+         int(bool(nesterov)), int(bool(first_step)), current_stream())
+
+
+def pack_linear_bf16(w, out, c49=0):
+    """fp32 [N, K] parameter -> bf16 kernel operand `out` [N, K] (c49 > 0: columns (c, ph, pw) -> (ph, pw, c))."""
+    _chk(w, "weight")
+    _chk(out, "packed")
+    call("drn_pack_linear_bf16", w, out, w.shape[0], w.shape[1], int(c49 or 0), current_stream())
+    return out
+
+
 def to_bf16(x):
     out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
     call("drn_cast_f32_to_bf16", x.contiguous(), out, x.numel(), current_stream())

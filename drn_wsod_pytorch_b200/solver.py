@@ -1,0 +1,106 @@
+"""Optimizer for the trainable tail: detectron2/solver/build.py:93-137 `build_optimizer` mirrored, with the SGD
+update running as one C-ABI kernel per parameter that also rewrites the bf16 kernel-layout copy of the weight
+(drn_sgd_step), so an optimizer step does not trigger a separate re-pack of fc6's 205 M weights.
+
+`FusedSGD` is a torch.optim.Optimizer (param_groups / state_dict / lr schedulers work as usual) with the
+arithmetic of torch.optim.SGD; parameters that are not on a CUDA device take torch's own update."""
+import torch
+
+from . import ops
+
+
+class FusedSGD(torch.optim.Optimizer):
+    def __init__(self, params, lr, momentum=0.0, weight_decay=0.0, nesterov=False, model=None):
+        if nesterov and momentum <= 0:
+            raise ValueError("Nesterov momentum requires a momentum")
+        super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay, nesterov=nesterov))
+        self.model = model
+
+    def _packed_copies(self):
+        """parameter -> (bf16 kernel-layout buffer, c49) for the single-layer tensor-core packs of the model."""
+        out = {}
+        if self.model is None:
+            return out
+        for m in self.model.modules():
+            cache = getattr(m, "_cache", None)
+            if not isinstance(m, torch.nn.Linear) or not cache:
+                continue
+            for (precision, perm), hit in cache.items():
+                w = hit.get("w")
+                if precision != "fp32" and torch.is_tensor(w) and w.dtype == torch.bfloat16 and tuple(w.shape) == tuple(m.weight.shape):
+                    out[m.weight] = (hit, perm or 0, m)
+        return out
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        packed = self._packed_copies()
+        touched = False
+        for group in self.param_groups:
+            lr, mom, wd, nest = group["lr"], group["momentum"], group["weight_decay"], group["nesterov"]
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                first = "momentum_buffer" not in st
+                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+                    d = p.grad.add(p, alpha=wd) if wd != 0 else p.grad
+                    if mom != 0:
+                        buf = st["momentum_buffer"] = torch.clone(d).detach() if first else st["momentum_buffer"].mul_(mom).add_(d)
+                        d = d.add(buf, alpha=mom) if nest else buf
+                    p.add_(d, alpha=-lr)
+                    continue
+                if first and mom != 0:
+                    st["momentum_buffer"] = torch.empty_like(p)
+                hit = packed.get(p)
+                ops.sgd_step(p, p.grad.contiguous(), st.get("momentum_buffer"), hit[0]["w"] if hit else None, hit[1] if hit else 0,
+                             lr, mom, wd, nest, first)
+                touched = True
+        if touched and self.model is not None:
+            self._after_step(packed)
+        return loss
+
+    def _after_step(self, packed):
+        """The kernel wrote the parameters through raw pointers (no autograd version bump): bring the derived
+        layouts it did not rewrite itself up to date, in place -- bias copies of the fused layers, every other pack
+        of a stepped layer (fp32-mode layouts, the concatenated heads)."""
+        fused = {id(hit[0]) for hit in packed.values()}
+        for m in self.model.modules():
+            cache = getattr(m, "_cache", None)
+            if not isinstance(m, torch.nn.Linear) or not cache:
+                continue
+            for (precision, perm), hit in list(cache.items()):
+                if id(hit) in fused:
+                    hit["bias"].copy_(m.bias.detach())
+                else:
+                    hit["key"] = None
+                    m.packed(precision, permute_c49=perm)  # re-packed in place, now
+        rh = getattr(self.model, "roi_heads", None)
+        if rh is not None and getattr(rh, "_heads_cache", None) is not None:
+            rh._heads_cache["key"] = None
+            rh._heads_packed()
+
+
+def build_optimizer(cfg, model):
+    """detectron2/solver/build.py:93-137: one param group per trainable parameter, lr = BASE_LR (x BIAS_LR_FACTOR for
+    biases), weight decay = WEIGHT_DECAY / WEIGHT_DECAY_BIAS / WEIGHT_DECAY_NORM; SGD with MOMENTUM / NESTEROV."""
+    s = cfg.SOLVER
+    norm_types = (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d, torch.nn.BatchNorm3d, torch.nn.SyncBatchNorm, torch.nn.GroupNorm,
+                  torch.nn.InstanceNorm1d, torch.nn.InstanceNorm2d, torch.nn.InstanceNorm3d, torch.nn.LayerNorm,
+                  torch.nn.LocalResponseNorm)
+    params, memo = [], set()
+    for module in model.modules():
+        for key, value in module.named_parameters(recurse=False):
+            if not value.requires_grad or value in memo:
+                continue
+            memo.add(value)
+            lr, wd = s.BASE_LR, s.WEIGHT_DECAY
+            if isinstance(module, norm_types):
+                wd = s.WEIGHT_DECAY_NORM
+            elif key == "bias":
+                lr, wd = s.BASE_LR * s.BIAS_LR_FACTOR, s.WEIGHT_DECAY_BIAS
+            params.append({"params": [value], "lr": lr, "weight_decay": wd})
+    return FusedSGD(params, s.BASE_LR, momentum=s.MOMENTUM, nesterov=s.NESTEROV, model=model)

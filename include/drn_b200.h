@@ -269,6 +269,19 @@ int drn_rowsum(const void* x, int ld, int rows, int cols, int dtype, float* out,
 /* [rows][49*c49] fp32, bin-major columns -> channel-major columns (fc6 weight gradient, exact-fp32 mode). */
 int drn_permute_cols49(const float* in, float* out, int64_t rows, int c49, drn_stream_t stream);
 
+/* One SGD update of a parameter tensor, fused with the refresh of its bf16 kernel-layout copy.
+ * Arithmetic of torch.optim.SGD (the optimizer detectron2/solver/build.py:93-137 builds for the reference):
+ *   d = grad + weight_decay * w;  buf = first_step ? d : momentum * buf + d;  d = nesterov ? d + momentum * buf : buf;
+ *   w -= lr * d.
+ * w/grad/momentum_buf: fp32 [rows][cols] in the parameter's layout, updated in place; packed_bf16 (may be NULL):
+ * the [rows][cols] bf16 operand the GEMM kernels read -- same column order, or with c49 > 0 the fc6 permutation
+ * (parameter columns (c, ph, pw) -> kernel columns (ph, pw, c), cols == 49 * c49, c49 % 64 == 0). */
+int drn_sgd_step(float* w, const float* grad, float* momentum_buf, void* packed_bf16, int64_t rows, int64_t cols,
+                 int c49, float lr, float momentum, float weight_decay, int nesterov, int first_step,
+                 drn_stream_t stream);
+/* The same bf16 kernel layout without an update (weight load / first use). */
+int drn_pack_linear_bf16(const float* w, void* packed_bf16, int64_t rows, int64_t cols, int c49, drn_stream_t stream);
+
 /* dtype / layout helpers used by the weight cache (not on the per-image path). */
 int drn_cast_f32_to_bf16(const float* in, void* out, int64_t n, drn_stream_t stream);
 int drn_cast_bf16_to_f32(const void* in, float* out, int64_t n, drn_stream_t stream);

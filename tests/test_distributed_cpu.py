@@ -27,6 +27,15 @@ def _worker(rank, world, port, out):
         red = D.reduce_dict(losses)
         summed = D.reduce_dict(losses, average=False)
         counts = D.gather_counts([len(mine), 4000 * len(mine)])
+        # gradient blocks announced one by one (as the backward produces them), averaged across ranks
+        sync = D.GradientSynchronizer()
+        g1, g2 = torch.full((4, 3), float(rank + 1)), torch.arange(6, dtype=torch.float32) * (rank + 1)
+        sync.ready(g1[:2])
+        sync.ready(g1[2:])
+        sync.ready(g2)
+        n = sync.finish()
+        assert n == 3 and sync.finish() == 0
+        assert torch.equal(g1, torch.full((4, 3), 1.5)) and torch.equal(g2, torch.arange(6, dtype=torch.float32) * 1.5)
         out.put((rank, mine, {k: float(v) for k, v in red.items()}, {k: float(v) for k, v in summed.items()}, counts))
     finally:
         dist.destroy_process_group()
@@ -55,3 +64,7 @@ def test_single_process_is_identity():
     losses = {"a": torch.tensor(2.0)}
     assert D.reduce_dict(losses)["a"].item() == 2.0
     assert D.shard_indices(3, 0, 1) == [0, 1, 2]
+    sync = D.GradientSynchronizer()
+    g = torch.ones(3)
+    sync.ready(g)
+    assert sync.finish() == 0 and torch.equal(g, torch.ones(3))

@@ -126,3 +126,54 @@ def test_sgd_steps_track_the_oracle(precision):
         for k in b:
             assert abs(a[k] - b[k]) <= tol * max(abs(b[k]), 1e-3), (precision, k, ours_traj, ref_traj)
     assert ref_traj[0] != ref_traj[-1]  # the steps really moved the losses
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fused_sgd_from_build_optimizer_tracks_the_oracle(precision):
+    """drn.build_optimizer (detectron2/solver/build.py:93-137 mirrored: per-parameter groups, BIAS_LR_FACTOR 2,
+    WEIGHT_DECAY_BIAS 0 from the WSL YAMLs) with the fused update kernel, against the oracle stepped by
+    torch.optim.SGD over the same groups; the bf16 kernel copies written by the update kernel must equal a fresh pack
+    of the updated fp32 parameters bit for bit."""
+    case = "oicr_r18_small"
+    cfg, model, weights = _build(case, precision)
+    cfg.SOLVER.BASE_LR = 2e-4
+    inputs = helpers.case_inputs(case)
+    spec = O.spec_from_cfg(cfg)
+    opt = drn.build_optimizer(cfg, model)
+    assert isinstance(opt, drn.FusedSGD) and len(opt.param_groups) == len([p for p in model.parameters() if p.requires_grad])
+    names = {p: k for k, p in model.named_parameters()}
+    state = {k: v.clone() for k, v in weights.items()}
+    ref_params = {k: state[k].clone().requires_grad_(True) for k in state if k.startswith(O.TRAINABLE_PREFIXES)}
+    groups = [{"params": [ref_params[names[g["params"][0]]]], "lr": g["lr"], "weight_decay": g["weight_decay"]} for g in opt.param_groups]
+    assert {g["lr"] for g in groups} == {2e-4, 4e-4} and {g["weight_decay"] for g in groups} == {0.0005, 0.0}
+    ref_opt = torch.optim.SGD(groups, 2e-4, momentum=cfg.SOLVER.MOMENTUM, nesterov=cfg.SOLVER.NESTEROV)
+    batched = helpers.to_batched(inputs, drn.Instances, drn.Boxes, device=DEV)
+    tol = 2e-3 if precision == "fp32" else 5e-2
+    for step in range(4):
+        opt.zero_grad(set_to_none=True)
+        losses = model(batched)
+        sum(losses.values()).backward()
+        opt.step()
+        ref_opt.zero_grad(set_to_none=True)
+        rl, _ = O.forward_train(inputs, {**state, **ref_params}, spec)
+        sum(rl.values()).backward()
+        ref_opt.step()
+        for k in rl:
+            assert abs(losses[k].item() - rl[k].item()) <= tol * max(abs(rl[k].item()), 1e-3), (precision, step, k)
+    assert len(model._plans) == 1
+    # parameter UPDATES after 4 steps (fp32 masters minus the initial weights) close to the oracle's
+    for p, k in names.items():
+        if p.requires_grad and p.grad is not None:
+            d_ref = ref_params[k].detach() - weights[k]
+            d_ours = p.detach().cpu() - weights[k]
+            assert float((d_ours - d_ref).norm()) <= (5e-3 if precision == "fp32" else 6e-2) * float(d_ref.norm()) + 1e-7, k  # floor: det.bias moves by rounding noise only
+    if precision == "bf16":
+        from drn_wsod_pytorch_b200 import ops
+        for fc, perm in ((model.roi_heads.box_head.fc1, model.roi_heads.in_channels), (model.roi_heads.box_head.fc2, None)):
+            hit = fc._cache[("bf16", perm)]
+            fresh = ops.pack_linear_bf16(fc.weight.detach(), torch.empty_like(hit["w"]), perm or 0)
+            assert torch.equal(hit["w"], fresh) and torch.equal(hit["bias"], fc.bias.detach())
+            # and the pack kernel itself against the torch formulation
+            w = fc.weight.detach()
+            ref = w.view(w.shape[0], perm, -1).permute(0, 2, 1).reshape(w.shape) if perm else w
+            assert torch.equal(fresh, ref.to(torch.bfloat16))

@@ -24,7 +24,11 @@ def main():
     model.load_state_dict({**weights, "pixel_mean": model.pixel_mean, "pixel_std": model.pixel_std}, strict=True)
     del weights
     model.train()
-    opt = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=1e-5, momentum=0.9, weight_decay=1e-4)
+    cfg.SOLVER.BASE_LR = 1e-5
+    if os.environ.get("TORCH_SGD") == "1":
+        opt = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=1e-5, momentum=0.9, weight_decay=1e-4)
+    else:
+        opt = drn.build_optimizer(cfg, model)
     batched = bench.make_batched(synth.make_inputs(H, W, R, seed=0), torch.device("cuda:0"), drn)
     ev = lambda: torch.cuda.Event(enable_timing=True)
     tot = {"fwd": 0.0, "bwd": 0.0, "opt": 0.0}

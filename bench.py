@@ -144,8 +144,7 @@ def main():
     config = {"workload": f"{cfg_name} {H}x{W} R={R} {precision} (BASELINE.json configs[{2 if 'r50' in args.workload else 1}])"
               if args.workload in ("r50_bf16", "r18_fp32") else f"{cfg_name} {H}x{W} R={R} {precision}",
               "images_per_gpu": 1, "proposals_per_image": R, "parallelism": f"dp{world}", "dropout": "on (train mode)",
-              "launch": "one CUDA-graph replay per step (captured per input signature by the public forward); ROI pooling and fc6 "
-                        "run in row blocks on two streams inside the graph",
+              "launch": "one CUDA-graph replay per step (captured per input signature by the public forward)",
               "l2": "no flush: per-step working set (fc6 weights 411 MB + ROI features 0.2-0.8 GB) exceeds the 126 MB L2"}
 
     import drn_wsod_pytorch_b200 as drn
@@ -192,6 +191,10 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
+        if args.mode == "train" and os.environ.get("DRN_B200_COMM_SMS", "0") != "0":
+            # opt-in: bound the SMs NCCL takes while gradient all-reduces run next to the backward's GEMMs (whose grids
+            # are then capped to the rest, modeling._wgrad / drn_gemm_set_max_sms)
+            os.environ.setdefault("NCCL_MAX_CTAS", os.environ["DRN_B200_COMM_SMS"])
         dist.init_process_group("nccl", device_id=dev)
     from drn_wsod_pytorch_b200 import lib as drn_lib, ops
 

@@ -773,6 +773,7 @@ static int make_map(CUtensorMap* map, const void* base, int rank, const cuuint64
   return 0;
 }
 
+static int g_max_sms = 0;  // drn_gemm_set_max_sms: leave SMs to a concurrently running kernel (NCCL)
 static int num_sms() {
   static int n = 0;
   if (!n) {
@@ -781,7 +782,7 @@ static int num_sms() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }
-  return n;
+  return (g_max_sms > 0 && g_max_sms < n) ? g_max_sms : n;
 }
 
 constexpr size_t SK_FLAG_BYTES = 4096;
@@ -921,6 +922,11 @@ static void pick_conv_tile(int H, int W, int* tw_out, int* th_out) {
 using namespace drn;
 
 extern "C" size_t drn_gemm_workspace_bytes(void) { return drn::tc::SK_WS_BYTES_MAX; }
+extern "C" int drn_gemm_set_max_sms(int max_sms) {
+  const int prev = drn::tc::g_max_sms;
+  drn::tc::g_max_sms = max_sms > 0 ? (max_sms & ~1) : 0;  // even: CTA pairs
+  return prev;
+}
 extern "C" int drn_gemm_set_tail_split(int enabled) {
   const int prev = drn::tc::g_tail_split;
   drn::tc::g_tail_split = enabled ? 1 : 0;

@@ -86,6 +86,8 @@ def load():
     lib.drn_roipool_workspace_bytes.restype = c_size_t
     lib.drn_detections_workspace_bytes.argtypes = [c_int, c_int]
     lib.drn_detections_workspace_bytes.restype = c_size_t
+    lib.drn_gemm_set_max_sms.argtypes = [c_int]
+    lib.drn_gemm_set_max_sms.restype = c_int
     lib.drn_gemm_set_tail_split.argtypes = [c_int]
     lib.drn_gemm_set_tail_split.restype = c_int
     lib.drn_gemm_workspace_bytes.argtypes = []

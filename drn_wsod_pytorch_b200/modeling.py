@@ -17,7 +17,7 @@ from typing import Dict, List, Optional
 import torch
 from torch import nn
 
-from . import ops
+from . import lib, ops
 from .config import precision_of
 from .registry import BACKBONE_REGISTRY, META_ARCH_REGISTRY, ROI_BOX_HEAD_REGISTRY, ROI_HEADS_REGISTRY
 from .structures import Boxes, ImageList, Instances, detector_postprocess
@@ -612,7 +612,10 @@ class _WSLROIHeads(nn.Module):
         # opt-in: measured gain 0.02-0.05 ms of 2.7 (the GEMM is SM<-L2 feed bound, a co-resident gather starves:
         # profiles/r1_overlap_negative_result.txt), less than the tail split-K schedule of the one-piece fc6 saves
         self.grad_ready_hook = None   # callable(tensor): a finished gradient block (data-parallel all-reduce, distributed.py)
-        self.wgrad_row_blocks = 4     # fc6 weight gradient in row blocks when a hook is installed (transfer/GEMM overlap)
+        self.wgrad_row_blocks = int(os.environ.get("DRN_B200_WGRAD_BLOCKS", "4"))  # fc6 weight gradient in row blocks when a hook is installed
+        # SMs left to the collective during those blocks (pair with NCCL_MAX_CTAS).  0 = off: measured at 2 GPUs 8.42 ms/step
+        # uncapped vs 9.29 (16 SMs) / 8.38 (32 SMs) -- the step is bound by the 858 MB fp32 all-reduce itself
+        self.comm_sms = int(os.environ.get("DRN_B200_COMM_SMS", "0"))
         self.overlap_pool = os.environ.get("DRN_B200_OVERLAP_POOL", "0") != "0"
         self.pool_ctas_per_sm = int(os.environ.get("DRN_B200_POOL_CTAS_PER_SM", "0"))
         self._gt_cache = {}
@@ -948,11 +951,18 @@ class _WSLROIHeads(nn.Module):
             return ops.conv_bf16_tc(dy_t.view(1, out_f, 1, Rp), packed, 1, 1, False, out_dtype=torch.float32).view(out_f, n)
         dW = torch.empty((out_f, n), device=x.device, dtype=torch.float32)
         step = out_f // row_blocks
-        for r0 in range(0, out_f, step):
-            ops.conv_bf16_tc(dy_t[r0:r0 + step].view(1, step, 1, Rp), packed, 1, 1, False, out_dtype=torch.float32,
-                             out=dW[r0:r0 + step].view(1, step, 1, n))
-            if on_block is not None:
-                on_block(dW[r0:r0 + step])
+        # the collective started by on_block holds `comm_sms` SMs while the next block's GEMM runs: keep its grid off them
+        sms = torch.cuda.get_device_properties(x.device).multi_processor_count
+        prev = lib.load().drn_gemm_set_max_sms(sms - self.comm_sms) if (on_block is not None and self.comm_sms > 0) else None
+        try:
+            for r0 in range(0, out_f, step):
+                ops.conv_bf16_tc(dy_t[r0:r0 + step].view(1, step, 1, Rp), packed, 1, 1, False, out_dtype=torch.float32,
+                                 out=dW[r0:r0 + step].view(1, step, 1, n))
+                if on_block is not None:
+                    on_block(dW[r0:r0 + step])
+        finally:
+            if prev is not None:
+                lib.load().drn_gemm_set_max_sms(prev)
         return dW
 
     def _backward_device(self, d, grad_vec):

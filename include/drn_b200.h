@@ -77,6 +77,10 @@ int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int Cin, const v
  * one-piece accumulation).  Both schedules are measured negative results on fc6, kept for other shapes. */
 size_t drn_gemm_workspace_bytes(void);
 int drn_gemm_set_tail_split(int enabled);
+/* Cap the number of SMs the persistent GEMM grids occupy (0 = all; returns the previous cap).  The grids are
+ * one CTA per SM with a static tile schedule: when a collective (NCCL) holds some SMs for its whole duration,
+ * a full-width GEMM grid would wait for them; a capped grid runs beside it. */
+int drn_gemm_set_max_sms(int max_sms);
 
 /* MaxPool2d(kernel 2, stride 1|2, padding 0), NHWC.
  * Replaces nn.MaxPool2d in WSL/backbone/resnet_ws.py:93-94,110-111,403,415 and vgg.py:93-94,108-109. */

@@ -27,7 +27,7 @@ def test_cabi_library_exports_every_header_symbol():
     assert len(syms) >= 15
     for s in syms:
         assert hasattr(handle, s), f"{s} declared in include/drn_b200.h but not exported"
-    assert set(lib._PROTOS) | {"drn_last_error", "drn_roipool_workspace_bytes", "drn_gemm_workspace_bytes", "drn_gemm_set_tail_split",
+    assert set(lib._PROTOS) | {"drn_last_error", "drn_roipool_workspace_bytes", "drn_gemm_workspace_bytes", "drn_gemm_set_tail_split", "drn_gemm_set_max_sms",
                                  "drn_detections_workspace_bytes"} == set(syms), "lib.py prototypes out of sync with the header"
     handle.drn_version.restype = ctypes.c_int
     assert handle.drn_version() >= 100

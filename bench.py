@@ -31,6 +31,9 @@ WORKLOADS = {
 }
 DEFAULT_WORKLOAD = os.environ.get("DRN_BENCH_WORKLOAD", "r50_bf16")  # BASELINE.json configs[2]: the 4k-proposal metric
 METRIC = "images/sec (4k proposals/img) WSOD forward+loss"
+# DRAM bytes of ONE fc6 launch from the ncu capture of a whole step (read 2587.9 MB + write 15.8 MB; algorithmic operand
+# bytes 1.21 GB: the A operand is streamed once per wave of N tiles)
+FC6_DRAM_BYTES = {"r50_bf16": 2587.9e6 + 15.8e6}
 # kernels launched per C-ABI call (for the gpu_launches claim)
 LAUNCHES = {"drn_wsddn_mil_fwd": 3, "drn_wsddn_mil_pgt_fwd": 2, "drn_label_proposals": 2, "drn_roipool_fwd": 2}  # (memset counted as a launch)
 
@@ -399,7 +402,8 @@ def main():
         "roofline": {"bound": "tensor", "kernel": "fc6 GEMM (gemm_tc_kernel)" if precision == "bf16" else "fc6 GEMM (conv_igemm_f32_kernel, SIMT fp32)",
                      "achieved": fc6_tflops, "peak": peak, "unit": "TFLOP/s", "frac": fc6_tflops / peak,
                      "peak_source": f"{peaks['src']} cuBLAS bf16 sustained (kernel timed inside a long step)",
-                     "traffic": None, "kernel_ms": fc6_ms, "share_of_step": fc6_ms / ms_step,
+                     "traffic": FC6_DRAM_BYTES.get(args.workload), "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of the fc6 launch, profiles/r1_ncu_step_v7_per_launch.txt (#62)" if args.workload in FC6_DRAM_BYTES else None,
+                     "algorithmic_flops_per_launch": 2 * gmac["fc6"] * 1e9, "kernel_ms": fc6_ms, "share_of_step": fc6_ms / ms_step,
                      "whole_step_tflops": total_tflops, "whole_step_frac": total_tflops / peak},
         "losses": dict(zip(loss_keys, [round(float(x), 6) for x in vec.tolist()])),
     }

@@ -35,7 +35,6 @@ namespace tc {
 constexpr int BM = 128;      // UMMA M (cta_group::1)
 constexpr int BK = 64;       // one 128-byte swizzle atom of bf16 along K
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
 constexpr int EPI_CHUNK = 64;                    // columns per staging buffer (128 B of bf16)
 constexpr int EPI_BUF_BYTES = 32 * EPI_CHUNK * 2;  // 32 rows x 128 B
 constexpr int IDENT_BYTES = 64 * 64 * 2;           // 64x64 bf16 identity (B operand of the residual MMAs)
@@ -340,14 +339,19 @@ __device__ __forceinline__ void epi_chunk(uint32_t taddr, uint32_t scale_s, uint
 // reads both halves (the peer's through the pair's shared-memory path), so the per-SM operand feed drops
 // from 16 KB + BN*128 B to 16 KB + BN*64 B per k-block -- the SM<-L2 ingest limit (~64 B/clk/SM) is what
 // bounds every GEMM here whose K loop is fed from L2.
-template <int BN, int STAGES, int NBUF, int CG>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// EW = epilogue warps (4 or 8).  A warp may only read the TMEM lanes of its quadrant (warp id % 4), so with 8 warps
+// two warps share a quadrant and split the tile's 64-column chunks between them.  The epilogue of a chunk is a
+// latency chain (tcgen05.ld -> math -> st.shared -> TMA store -> wait for the staging slot); short-K, wide-N layers
+// (1x1 expansion convs: 8 k-blocks of MMA per 128 x 256 tile) are bound by it, and a second set of warps hides it.
+template <int BN, int STAGES, int NBUF, int CG, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_r, const Params p) {
   constexpr uint32_t BROWS = BN / CG;                       // B rows staged by this CTA
   constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BROWS * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  constexpr uint32_t EPI_BYTES = 4 * NBUF * EPI_BUF_BYTES;
+  constexpr uint32_t EPI_BYTES = EW * NBUF * EPI_BUF_BYTES;
+  constexpr int ETHREADS = 32 * EW, ESPLIT = EW / 4;  // epilogue threads; warps per TMEM quadrant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset arithmetic keeps the shared address space
   uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;                        // 1024-aligned (stage sizes are multiples of 1 KB)
@@ -372,7 +376,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (!p.out_f32) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_o) : "memory");
     if (p.has_residual) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_r) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4 * CG); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EW * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -546,8 +550,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ------------------------------------------------------------------ epilogue (warps 2..5, every CTA: its own 128 rows)
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;
-    const int etid = (warp - 2) * 32 + lane;  // 0..127 within the epilogue group
-    uint8_t* my_bufs = epi_smem + quad * (NBUF * EPI_BUF_BYTES);
+    const int etid = (warp - 2) * 32 + lane;  // 0..ETHREADS-1 within the epilogue group
+    const int half = (warp - 2) >> 2;          // which share of the column chunks this warp takes (0 when EW == 4)
+    uint8_t* my_bufs = epi_smem + (warp - 2) * (NBUF * EPI_BUF_BYTES);
     const uint32_t sw_xor = (uint32_t)(lane & 7);
     // warp's 32-row sub-box inside a conv tile
     const int sub_h = (quad * 32) / (p.conv ? p.tile_w : 32), sub_w = (quad * 32) % (p.conv ? p.tile_w : 32);
@@ -561,7 +566,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     auto fetch_sb = [&](int nt_) {
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const int idx = etid + 128 * i, n = nt_ * BN + idx;
+        const int idx = etid + ETHREADS * i, n = nt_ * BN + idx;
         const bool ok = idx < BN && n < p.N;
         pre_sc[i] = (ok && p.scale) ? __ldg(p.scale + n) : 1.f;
         pre_bi[i] = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
@@ -600,10 +605,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       float* s_bias = s_scale + BN;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const int idx = etid + 128 * i;
+        const int idx = etid + ETHREADS * i;
         if (idx < BN) { s_scale[idx] = pre_sc[i]; s_bias[idx] = pre_bi[i]; }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(ETHREADS) : "memory");
       if (have_next) fetch_sb(pc_next.tile / num_mp);  // in flight while this tile is drained
 
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -615,7 +620,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // layout [column][128 rows] so that a warp's 32 lanes (rows) write / read 128 contiguous bytes
         float* wsp = p.sk_ws + (size_t)(pc.slot * CG + cta_rank) * (BN * 128) + row;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = 32 * half; c < BN; c += 32 * ESPLIT) {
           uint32_t v[32];
           tmem_ld32_nowait(taddr + c, v);
           tmem_ld_wait();
@@ -623,7 +628,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int j = 0; j < 32; ++j) __stcg(wsp + (size_t)(c + j) * 128, __uint_as_float(v[j]));
         }
         __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(ETHREADS) : "memory");
         if (etid == 0) {
           unsigned int* flag = p.sk_flags + pc.slot * CG + cta_rank;
           asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(1u) : "memory");
@@ -641,10 +646,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(flag) : "memory");
             } while (f == 0u);
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(ETHREADS) : "memory");
           const float* wsp = p.sk_ws + (size_t)((pc.slot + s) * CG + cta_rank) * (BN * 128) + row;
 #pragma unroll 1
-          for (int c = 0; c < BN; c += 32) {
+          for (int c = 32 * half; c < BN; c += 32 * ESPLIT) {
             uint32_t v[32];
             tmem_ld32_nowait(taddr + c, v);
             tmem_ld_wait();
@@ -652,7 +657,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldcg(wsp + (size_t)(c + j) * 128));
             tmem_st32(taddr + c, v);
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(ETHREADS) : "memory");
           if (etid == 0) *flag = 0u;  // self-resetting: ready for the next launch
         }
       }
@@ -662,9 +667,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       } else if (!p.out_f32) {
         // ---------------------------------------------------------- bf16 output through smem + TMA store
 #pragma unroll 1
-        for (int c = 0; c < NCHUNK; ++c) {
+        uint32_t mine = 0;
+        for (int c = half; c < NCHUNK; c += ESPLIT) {
           if (c >= nchunk) break;
-          const uint32_t g = gchunk + c;
+          const uint32_t g = gchunk + mine;
+          ++mine;
           const int b = g % NBUF;
           uint8_t* buf = my_bufs + b * EPI_BUF_BYTES;
           if (lane == 0) bulk_wait_read<NBUF - 1>();  // the store that last used this slot has drained
@@ -694,11 +701,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           __syncwarp();
         }
-        gchunk += nchunk;
+        gchunk += mine;
       } else {
         // ---------------------------------------------------------- fp32 output, direct stores (head logits)
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = 32 * half; c < BN; c += 32 * ESPLIT) {
           uint32_t v[32];
           tmem_ld32_nowait(taddr + c, v);
           tmem_ld_wait();
@@ -790,15 +797,15 @@ constexpr size_t SK_WS_BYTES = SK_FLAG_BYTES + (size_t)148 * 128 * 256 * sizeof(
 constexpr size_t SK_WS_BYTES_MAX = SK_FLAG_BYTES + (size_t)4 * 148 * 128 * 256 * sizeof(float);  // tail split-K: up to 4 per SM
 static int g_tail_split = 0;  // opt-in (drn_gemm_set_tail_split / DRN_TC_TAILSPLIT=1): measured neutral-to-negative, see launch()
 
-template <int BN, int STAGES, int NBUF, int CG>
+template <int BN, int STAGES, int NBUF, int CG, int EW = 4>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mr, Params p,
                   cudaStream_t st, void* workspace, size_t workspace_bytes) {
-  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + (BN / CG) * BK * 2) + 4 * NBUF * EPI_BUF_BYTES + IDENT_BYTES +
+  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + (BN / CG) * BK * 2) + EW * NBUF * EPI_BUF_BYTES + IDENT_BYTES +
                           4 * BN * sizeof(float) + (2 * STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
   static_assert(smem <= 232448, "gemm_tc: shared memory budget exceeded");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, NBUF, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, NBUF, CG, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_err("gemm_tc: cudaFuncSetAttribute(%zu B smem): %s", smem, cudaGetErrorString(e));
     configured = true;
   }
@@ -863,7 +870,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(CG * (units < max_units ? units : max_units)));
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(64 + 32 * EW);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -878,7 +885,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
   }
   cfg.attrs = attr;
   cfg.numAttrs = pdl_env ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, NBUF, CG>, ma, mb, mo, mr, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, NBUF, CG, EW>, ma, mb, mo, mr, p);
   if (e != cudaSuccess) return set_err("gemm_tc launch: %s", cudaGetErrorString(e));
   return 0;
 }
@@ -1034,6 +1041,28 @@ extern "C" int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int C
     if (make_map(&mb, w, 2, dims, strides, box)) return 1;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  // 8 epilogue warps for short-K layers (the epilogue latency chain, not the MMAs, bounds them); the split-K schedules
+  // keep the 4-warp variant.  DRN_TC_EPI8_KB: largest K-block count that takes it (0 = never).
+  static int epi8_kb = -1;
+  if (epi8_kb < 0) {
+    const char* e = getenv("DRN_TC_EPI8_KB");
+    epi8_kb = e ? atoi(e) : 64;
+  }
+  // measured (tools/layer_bench.py, us warm, 4 -> 8 warps): 64->256 9.4 -> 7.7, 256->1024+res 12.7 -> 11.8, fc7 86 -> 77,
+  // heads 30.7 -> 27.7; but the single-CTA 256-wide tile only has smem for 3 pipeline stages next to 8 staging
+  // slots, which costs more than it gains once a tile streams more than 8 k-blocks (512->2048+res 25.4 -> 27.8)
+  const int eff_kb = p.KB + (p.has_residual ? bn / 64 : 0);
+  const bool epi8 = p.KB <= epi8_kb && !workspace && !(cg == 1 && bn == 256 && eff_kb > 8);
+  if (epi8) {
+    if (cg == 2) {
+      if (bn == 256) return launch<256, 4, 2, 2, 8>(ma, mb, mo, mr, p, st, workspace, workspace_bytes);
+      if (bn == 128) return launch<128, 5, 2, 2, 8>(ma, mb, mo, mr, p, st, workspace, workspace_bytes);
+      return launch<64, 6, 2, 2, 8>(ma, mb, mo, mr, p, st, workspace, workspace_bytes);
+    }
+    if (bn == 256) return launch<256, 3, 1, 1, 8>(ma, mb, mo, mr, p, st, workspace, workspace_bytes);
+    if (bn == 128) return launch<128, 4, 2, 1, 8>(ma, mb, mo, mr, p, st, workspace, workspace_bytes);
+    return launch<64, 5, 2, 1, 8>(ma, mb, mo, mr, p, st, workspace, workspace_bytes);
+  }
   if (cg == 2) {
     if (bn == 256 && p.KB >= 48) return launch<256, 6, 1, 2>(ma, mb, mo, mr, p, st, workspace, workspace_bytes);  // deep K: smem goes to pipeline stages
     if (bn == 256) return launch<256, 5, 2, 2>(ma, mb, mo, mr, p, st, workspace, workspace_bytes);

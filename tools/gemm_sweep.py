@@ -35,6 +35,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--res", action="store_true")
     ap.add_argument("--shapes", default="")
+    ap.add_argument("--dropout", type=float, default=0.0)
     args = ap.parse_args()
     dev = "cuda:0"
     shapes = [(9176, n, k) for n in (256, 512, 2048) for k in (256, 512, 1024, 2048, 4096, 8192)]
@@ -47,7 +48,7 @@ def main():
         w = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
         packed = {"w": w, "scale": None, "bias": torch.zeros(N, device=dev), "cout": N}
         r = torch.randn(M, N, device=dev).bfloat16().view(1, M, 1, N) if args.res else None
-        us = timed(lambda: ops.conv_bf16_tc(a.view(1, M, 1, K), packed, 1, 1, True, r))
+        us = timed(lambda: ops.conv_bf16_tc(a.view(1, M, 1, K), packed, 1, 1, True, r, dropout_p=args.dropout, dropout_seed=3))
         tf = 2.0 * M * N * K / (us * 1e-6) / 1e12
         print(f"{M:6d} {N:5d} {K:6d} {us:9.1f} {tf:8.1f}")
 

@@ -4,6 +4,7 @@ detection hot path behind the reference's registry / config / state_dict surface
     from drn_wsod_pytorch_b200 import builtin_config, build_model
     model = build_model(builtin_config("oicr_WSR_18_DC5_1x"))      # needs libdrn_b200.so + a B200
 """
+from . import data  # noqa: F401  (proposal files, transform_proposals, weight files)
 from .config import CfgNode, builtin_config, get_cfg  # noqa: F401
 from .modeling import (  # noqa: F401
     DiscriminativeAdaptionNeck,

@@ -133,9 +133,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="forward", choices=["forward", "train"],
+    ap.add_argument("--mode", default="forward", choices=["forward", "train", "eval"],
                     help="forward: forward+loss (BASELINE.json's metric, default); train: forward+loss+backward of the trainable "
-                         "tail+SGD step (+ gradient all-reduce at N>1) -- SURVEY.md §8f row 1, reported as an extra line")
+                         "tail+SGD step (+ gradient all-reduce at N>1) -- SURVEY.md §8f row 1; eval: inference forward + on-device "
+                         "threshold/NMS/top-k (§8f row 2).  train / eval are extra lines, not the headline metric")
     ap.add_argument("--breakdown", action="store_true", help="also print a per-kernel-family time breakdown to stderr")
     ap.add_argument("--profile-step", action="store_true",
                     help="after warm-up run ONE step between cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`; prints no bench line)")
@@ -206,6 +207,11 @@ def main():
     model.load_state_dict({**weights, "pixel_mean": model.pixel_mean, "pixel_std": model.pixel_std}, strict=True)
     del weights
     model.train()
+    eval_mode = args.mode == "eval"
+    if eval_mode:
+        model.eval()
+        config["dropout"] = "off (eval mode)"
+        config["mode"] = "eval: inference forward, mean of the refinement softmaxes, threshold 1e-5, per-class NMS 0.3, top-100 on the device"
     inp = synth.make_inputs(H, W, R, seed=rank)  # one distinct image per rank (weak scaling)
     batched_dev = make_batched(inp, dev, drn)
     host = make_batched(inp, None, drn, pinned=True)[0]
@@ -230,7 +236,13 @@ def main():
             model.roi_heads.grad_ready_hook = sync.ready
 
     def step(batched):
-        if not train_mode:
+        if eval_mode:
+            with torch.no_grad():
+                out = model(batched)  # list of {"instances"}: scores / boxes / classes of the kept detections
+            inst = out[0]["instances"]
+            n = torch.tensor([float(len(inst))], device=dev)
+            losses = {"num_detections": n[0], "top_score": inst.scores[0] if len(inst) else n[0] * 0}
+        elif not train_mode:
             with torch.no_grad():  # the metric is forward + loss; the backward has its own line (--mode train)
                 losses = model(batched)
         else:
@@ -393,7 +405,8 @@ def main():
     total_tflops = 2 * sum(gmac.values()) * 1e9 / (ms_step * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
     out = {
-        "metric": METRIC if not train_mode else METRIC.replace("forward+loss", "training step (forward+loss+backward+SGD)"), "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC.replace("forward+loss", "inference (forward + NMS + top-k)") if eval_mode else METRIC if not train_mode
+        else METRIC.replace("forward+loss", "training step (forward+loss+backward+SGD)"), "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic", "config": config,
         "e2e": {"value": world * args.steps / t_e2e.item(), "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -41,7 +41,7 @@ __global__ void nms_row_valid_kernel(const float* __restrict__ scores, const flo
 // grid = K, block = 1024, dynamic smem = P * 8 (keys) + P * 16 (boxes) + P (flags) + 4 * 33, P = next pow2 >= R
 __global__ void __launch_bounds__(NMS_THREADS)
 nms_class_kernel(const float* __restrict__ scores, const float* __restrict__ boxes, const unsigned char* __restrict__ row_ok,
-                 int R, int K, int nreg, int P, float img_h, float img_w, float score_thresh, double nms_thresh,
+                 int R, int K, int nreg, int P, float img_h, float img_w, float score_thresh, double nms_thresh, int cap,
                  unsigned long long* __restrict__ kept_keys, int* __restrict__ kept_count) {
   extern __shared__ __align__(16) unsigned char nms_smem[];
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(nms_smem);
@@ -122,9 +122,13 @@ nms_class_kernel(const float* __restrict__ scores, const float* __restrict__ box
     dead[i] = 0;
   }
   __syncthreads();
-  // ---- greedy suppression in score order: every thread tests box i against its share of the later boxes
+  // ---- greedy suppression in score order: every thread tests box i against its share of the later boxes.
+  // Only the first `cap` kept boxes of a class can reach the image's top-`cap` (they precede every later box of the
+  // class in the final order), so the scan stops there: the cost is bounded by cap barriers, not by R.
+  int stop = n, nkept = 0;
   for (int i = 0; i < n; ++i) {
     if (dead[i]) continue;  // uniform: written before the last barrier
+    if (++nkept >= cap) { stop = i + 1; break; }  // uniform
     const float4 bi = sbox[i];
     const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
     for (int j = i + 1 + tid; j < n; j += NMS_THREADS) {
@@ -142,9 +146,9 @@ nms_class_kernel(const float* __restrict__ scores, const float* __restrict__ box
   // ---- kept keys of this class, still in sorted order (ordered compaction)
   if (tid == 0) s_base = 0;
   __syncthreads();
-  for (int i0 = 0; i0 < n; i0 += NMS_THREADS) {
+  for (int i0 = 0; i0 < stop; i0 += NMS_THREADS) {
     const int i = i0 + tid;
-    const bool keep = i < n && !dead[i];
+    const bool keep = i < stop && !dead[i];
     const unsigned ball = __ballot_sync(0xffffffffu, keep);
     const int in_warp = __popc(ball & ((1u << lane) - 1u));
     if (lane == 0) wsum[wid] = __popc(ball);
@@ -258,7 +262,7 @@ int drn_detections_fwd(const float* all_scores, const float* all_boxes, int R, i
   nms_row_valid_kernel<<<cdiv(R * 32, 256), 256, 0, st>>>(all_scores, all_boxes, R, K, nreg, row_ok);
   DRN_CHECK_LAUNCH("detections row validity");
   nms_class_kernel<<<K, NMS_THREADS, smem, st>>>(all_scores, all_boxes, row_ok, R, K, nreg, P, img_h, img_w, score_thresh,
-                                                 nms_thresh, kept_keys, kept_count);
+                                                 nms_thresh, cap, kept_keys, kept_count);
   DRN_CHECK_LAUNCH("detections per-class nms");
   nms_rank_scatter_kernel<<<dim3(cdiv(R, 256), K), 256, 0, st>>>(kept_keys, kept_count, all_boxes, R, K, nreg, img_h, img_w, cap,
                                                                 out_boxes, out_scores, (long long*)out_classes, (long long*)out_rows, num_out);

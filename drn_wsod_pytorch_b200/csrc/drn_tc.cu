@@ -666,8 +666,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // nothing to store
       } else if (!p.out_f32) {
         // ---------------------------------------------------------- bf16 output through smem + TMA store
-#pragma unroll 1
         uint32_t mine = 0;
+#pragma unroll 1
         for (int c = half; c < NCHUNK; c += ESPLIT) {
           if (c >= nchunk) break;
           const uint32_t g = gchunk + mine;

@@ -150,6 +150,36 @@ __global__ void masked_transpose_kernel(const TI* __restrict__ g, int ldg, const
   }
 }
 
+// Plain bf16 transpose (no mask, no scaling) for the big operands (pooled features: 0.8 GB): every thread moves an
+// 8 x 8 block through registers -- eight 16-byte loads along the columns of eight consecutive rows, byte-permute
+// transpose, eight 16-byte stores along the rows of the output.  A warp reads 4 x 128 contiguous bytes per load
+// instruction and writes 8 x 64; no shared memory.  grid = (ceil(ldo / 256), ceil(C / 64)), block = (8, 32).
+__global__ void __launch_bounds__(256)
+transpose_bf16_8x8_kernel(const uint4* __restrict__ g, int ldg8, int R, int C, int C49, uint4* __restrict__ out, int ldo8) {
+  const int c = (blockIdx.y * 8 + threadIdx.x) * 8;   // first of this thread's 8 input columns
+  const int r = (blockIdx.x * 32 + threadIdx.y) * 8;  // first of this thread's 8 input rows
+  if (c >= C || r >= ldo8 * 8) return;
+  uint32_t in[8][4];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r + k < R) v = __ldg(g + (size_t)(r + k) * ldg8 + (c >> 3));
+    in[k][0] = v.x; in[k][1] = v.y; in[k][2] = v.z; in[k][3] = v.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {  // output row = input column c + j; its 8 elements = column j of rows r .. r + 7
+    const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
+    uint4 o;
+    o.x = __byte_perm(in[0][j >> 1], in[1][j >> 1], sel);
+    o.y = __byte_perm(in[2][j >> 1], in[3][j >> 1], sel);
+    o.z = __byte_perm(in[4][j >> 1], in[5][j >> 1], sel);
+    o.w = __byte_perm(in[6][j >> 1], in[7][j >> 1], sel);
+    const int cc = c + j;
+    const int co = C49 > 0 ? (cc % C49) * 49 + cc / C49 : cc;
+    out[(size_t)co * ldo8 + (r >> 3)] = o;
+  }
+}
+
 // rowsum[c] = sum_r x[c][r]  (bias gradients from a transposed gradient matrix); one warp per row, fixed order
 template <typename T>
 __global__ void rowsum_kernel(const T* __restrict__ x, int ld, int rows, int cols, float* __restrict__ out) {
@@ -295,6 +325,13 @@ int drn_masked_transpose(const void* grad, int ld_grad, int grad_dtype, const vo
   if (ld_out == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const bool gi = grad_dtype == DRN_BF16, mi = mask_dtype == DRN_BF16, oi = out_dtype == DRN_BF16;
+  if (gi && oi && !mask && !out_masked && mul == 1.f && C % 8 == 0 && ld_grad % 8 == 0 && ld_out % 8 == 0 &&
+      (uintptr_t)grad % 16 == 0 && (uintptr_t)out_t % 16 == 0) {
+    transpose_bf16_8x8_kernel<<<dim3(cdiv(ld_out, 256), cdiv(C, 64)), dim3(8, 32), 0, st>>>((const uint4*)grad, ld_grad / 8, R, C, c49,
+                                                                                          (uint4*)out_t, ld_out / 8);
+    DRN_CHECK_LAUNCH("transpose_bf16");
+    return 0;
+  }
 #define DRN_MT(TI, TM, TO) return launch_mt<TI, TM, TO>(grad, ld_grad, mask, ld_mask, mul, R, C, c49, out_t, ld_out, out_masked, ld_masked, st)
   if (gi && mi && oi) DRN_MT(__nv_bfloat16, __nv_bfloat16, __nv_bfloat16);
   if (!gi && mi && oi) DRN_MT(float, __nv_bfloat16, __nv_bfloat16);

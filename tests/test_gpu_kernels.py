@@ -476,3 +476,20 @@ def test_detections_tail_edge_cases():
     # empty proposal list
     b, s, c, r, cnt = ops.detections(torch.zeros(0, 5, device=DEV), torch.zeros(0, 16, device=DEV), (600, 1000), 1e-5, 0.3, 100)
     assert int(cnt.item()) == 0
+
+
+@pytest.mark.parametrize("R,C,c49,ld", [(100, 64, 0, 128), (4000, 49 * 64, 64, 4032), (77, 4096, 0, 128), (333, 49 * 128, 128, 384), (64, 8, 0, 64)])
+def test_bf16_transpose_fast_path_matches_torch(R, C, c49, ld):
+    """drn_masked_transpose's register-transpose path (plain bf16, the pooled-feature operand of the fc6 weight gradient),
+    incl. the bin-major -> (c, ph, pw) row permutation and the zero fill up to the padded K."""
+    g = torch.Generator().manual_seed(R + C)
+    x = torch.randn(R, C, generator=g).bfloat16().to(DEV)
+    out, _ = ops.masked_transpose(x, c49=c49, ld_out=ld)
+    ref = x.t()
+    if c49:
+        ref = x.view(R, 49, c49).permute(2, 1, 0).reshape(C, R)  # row (ch * 49 + bin) <- column (bin * c49 + ch)
+    assert out.shape == (C, ld) and torch.equal(out[:, :R], ref) and bool((out[:, R:] == 0).all())
+    # the general (masked) kernel agrees on the same input
+    mask = torch.ones_like(x)
+    out2, masked = ops.masked_transpose(x, mask=mask, c49=c49, ld_out=ld, want_masked=True)
+    assert torch.equal(out2, out) and torch.equal(masked, x)

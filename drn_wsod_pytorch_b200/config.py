@@ -173,7 +173,11 @@ def get_cfg():
                 },
             },
             "INPUT": {"FORMAT": "BGR"},
-            "TEST": {"DETECTIONS_PER_IMAGE": 100},
+            # detectron2/config/defaults.py:97-104, :569-583 (read by the TTA driver, tta.py)
+            "DATASETS": {"PRECOMPUTED_PROPOSAL_TOPK_TRAIN": 2000, "PRECOMPUTED_PROPOSAL_TOPK_TEST": 1000},
+            "TEST": {"DETECTIONS_PER_IMAGE": 100,
+                     "AUG": {"ENABLED": False, "MIN_SIZES": [400, 500, 600, 700, 800, 900, 1000, 1100, 1200], "MAX_SIZE": 4000,
+                             "FLIP": True}},
             # detectron2/config/defaults.py SOLVER keys read by build_optimizer (solver/build.py:93-137)
             "SOLVER": {"BASE_LR": 0.001, "MOMENTUM": 0.9, "NESTEROV": False, "WEIGHT_DECAY": 0.0001, "WEIGHT_DECAY_NORM": 0.0,
                        "BIAS_LR_FACTOR": 1.0, "WEIGHT_DECAY_BIAS": 0.0001, "IMS_PER_BATCH": 16},
@@ -219,6 +223,9 @@ _VOC_BASE = {
         },
     },
     "WSL": {"ITER_SIZE": 1, "MEAN_LOSS": True},
+    # projects/WSL/configs/PascalVOC-Detection/Base-RCNN-DilatedC5.yaml:2-8, oicr_WSR_18_DC5_1x.yaml:49-53
+    "DATASETS": {"PRECOMPUTED_PROPOSAL_TOPK_TRAIN": 4000, "PRECOMPUTED_PROPOSAL_TOPK_TEST": 4000},
+    "TEST": {"AUG": {"ENABLED": True, "MIN_SIZES": [480, 576, 672, 768, 864, 960, 1056, 1152], "MAX_SIZE": 4000, "FLIP": True}},
     # projects/WSL/configs/PascalVOC-Detection/oicr_WSR_18_DC5_1x.yaml:40-48 (the same block in every WSL model YAML)
     "SOLVER": {"IMS_PER_BATCH": 4, "BASE_LR": 0.01, "WEIGHT_DECAY": 0.0005, "BIAS_LR_FACTOR": 2.0, "WEIGHT_DECAY_BIAS": 0.0},
 }

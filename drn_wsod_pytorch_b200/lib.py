@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdrn_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "drn_b200.h")
 
-DRN_F32, DRN_BF16 = 0, 1
+DRN_F32, DRN_BF16, DRN_U8 = 0, 1, 2
 
 _P = c_void_p
 _FP = POINTER(c_float)
@@ -53,6 +53,8 @@ _PROTOS = {
     "drn_dropout_inplace": [_P, c_int64, c_int, c_float, c_uint64, _P, _P],
     "drn_cast_f32_to_bf16": [_P, _P, c_int64, _P],
     "drn_cast_bf16_to_f32": [_P, _P, c_int64, _P],
+    "drn_resample_u8_fwd": [_P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, c_int, c_int, _P, c_int, _P, c_int, _P],
+    "drn_tta_accumulate": [_P, _P, c_int, c_int, c_int, c_int, _IP, _FP, _FP, _P, _P, c_int, c_int, _P],
 }
 
 _lib = None

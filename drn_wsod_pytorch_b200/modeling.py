@@ -1048,9 +1048,10 @@ class _WSLROIHeads(nn.Module):
         return grads
 
     # -- eval ----------------------------------------------------------------------------------------
-    def _eval_device(self, features, boxes_l, obj_l, image_sizes):
+    def _eval_device(self, features, boxes_l, obj_l, image_sizes, with_detections=True):
         """Device pipeline of the eval forward: (all_scores, all_boxes) and the thresholded / NMS-ed / top-k
-        detections in fixed-size buffers -- capturable like _train_device."""
+        detections in fixed-size buffers -- capturable like _train_device.  with_detections=False stops at
+        (all_scores, all_boxes): the TTA driver averages those over the views and runs the tail once (tta.py)."""
         K, S = self.num_classes, self.refine_K
         layer = self.box_refinery[-1] if S > 0 else self.box_predictor
         scores_l, boxes_out, dets = [], [], []
@@ -1075,7 +1076,7 @@ class _WSLROIHeads(nn.Module):
             boxes_out.append(bx)
             topk = layer.test_topk_per_image
             dets.append(ops.detections(sc, bx, image_sizes[i], layer.test_score_thresh, layer.test_nms_thresh,
-                                       topk if topk >= 0 else sc.shape[0] * K))
+                                       topk if topk >= 0 else sc.shape[0] * K) if with_detections else None)
         return {"scores": scores_l, "boxes": boxes_out, "dets": dets}
 
     def _eval_post(self, d, proposals):
@@ -1085,9 +1086,12 @@ class _WSLROIHeads(nn.Module):
         for i, p in enumerate(proposals):
             sc, bx = d["scores"][i].clone(), d["boxes"][i].clone()  # returned to the caller (TTA): fresh storage
             inst_cls, box_cls = type(p), type(p.proposal_boxes)
-            res, _ = fast_rcnn_inference_single_image(bx, sc, p.image_size, layer.test_score_thresh, layer.test_nms_thresh,
-                                                      layer.test_topk_per_image, inst_cls, box_cls, dets=d["dets"][i])
-            results.append(res)
+            if d["dets"][i] is None:  # inference(..., with_detections=False)
+                results.append(None)
+            else:
+                res, _ = fast_rcnn_inference_single_image(bx, sc, p.image_size, layer.test_score_thresh, layer.test_nms_thresh,
+                                                          layer.test_topk_per_image, inst_cls, box_cls, dets=d["dets"][i])
+                results.append(res)
             all_scores.append(sc.unsqueeze(0))
             all_boxes.append(bx.unsqueeze(0))
         self.iter_test += 1
@@ -1206,7 +1210,7 @@ class _WSLLossBridge(torch.autograd.Function):
 class GeneralizedRCNNWSL(nn.Module):
     """projects/WSL/wsl/modeling/meta_arch/rcnn.py:23-265 with precomputed proposals."""
 
-    MAX_PLANS = 8  # captured graphs kept alive (each owns its activation pool)
+    MAX_PLANS = 24  # captured graphs kept alive (each owns its activation pool; the 8 TTA scales need one each)
     CAPTURE_AFTER = 2  # an input signature is captured the 2nd time it is seen: multi-scale training, where
     #                    (H, W, R) change every iteration, stays on the eager launch path instead of re-capturing
 
@@ -1410,8 +1414,12 @@ class GeneralizedRCNNWSL(nn.Module):
                 losses = {k: vec[i] for i, k in enumerate(keys)}
         return losses
 
-    def inference(self, batched_inputs, detected_instances=None, do_postprocess=True):
+    def inference(self, batched_inputs, detected_instances=None, do_postprocess=True, with_detections=True):
+        """rcnn.py:187-240.  with_detections=False (an addition; needs do_postprocess=False) skips the per-image
+        threshold / NMS / top-k and returns None in place of each Instances -- for callers that only read
+        (all_scores, all_boxes), i.e. the TTA driver."""
         assert not self.training
+        assert with_detections or not do_postprocess
         images, sizes, canvas = self.preprocess_image(batched_inputs)
         if detected_instances is None:
             assert self.load_proposals and "proposals" in batched_inputs[0]
@@ -1422,11 +1430,11 @@ class GeneralizedRCNNWSL(nn.Module):
 
             def fn(flat):
                 g = [flat[i * n:(i + 1) * n] for i in range(3)]
-                return rh._eval_device(self._features(g[0], canvas), g[1], g[2], img_sizes)
+                return rh._eval_device(self._features(g[0], canvas), g[1], g[2], img_sizes, with_detections)
 
             groups = [images, [p.proposal_boxes.tensor.float() for p in proposals],
                       [p.objectness_logits.float() for p in proposals]]
-            dev_out, _ = self._run_device(("eval", tuple(img_sizes)), canvas, groups, fn)
+            dev_out, _ = self._run_device(("eval", tuple(img_sizes), with_detections), canvas, groups, fn)
             proposals = [p.to(self.device) for p in proposals]
             results, all_scores, all_boxes = rh._eval_post(dev_out, proposals)
         else:

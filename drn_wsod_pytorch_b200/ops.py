@@ -8,7 +8,7 @@ import os
 import torch
 
 from . import lib
-from .lib import DRN_BF16, DRN_F32, call, current_stream, fvec, ivec
+from .lib import DRN_BF16, DRN_F32, DRN_U8, call, current_stream, fvec, ivec
 
 
 def _dt(t):
@@ -300,6 +300,41 @@ def detections(all_scores, all_boxes, image_hw, score_thresh, nms_thresh, cap):
     call("drn_detections_fwd", all_scores, all_boxes, R, K, nreg, float(image_hw[0]), float(image_hw[1]), float(score_thresh),
          float(nms_thresh), cap, out_boxes, out_scores, out_classes, out_rows, count, ws, ws.numel(), current_stream())
     return out_boxes, out_scores, out_classes, out_rows, count
+
+
+# ---------------------------------------------------------------- test-time augmentation (tta.py)
+TTA_OP_NOOP, TTA_OP_RESIZE, TTA_OP_HFLIP = 0, 1, 2  # include/drn_b200.h DRN_TTA_OP_*
+TTA_MAX_OPS = 4
+
+
+def resample_u8(img_chw, new_h, new_w, xtab, ytab, flip=False, out_dtype=torch.uint8):
+    """Pillow 8-bit bilinear resize of a uint8 [C,H,W] image (+ flip, + uint8 -> fp32).  xtab / ytab:
+    (bounds int32 [new,2], coeffs int32 [new,ksize], ksize) device tables, or (None, None, 0) for an unchanged axis."""
+    _chk(img_chw, "image")
+    assert img_chw.dtype == torch.uint8 and img_chw.dim() == 3
+    C, H, W = img_chw.shape
+    assert out_dtype in (torch.uint8, torch.float32)
+    out = torch.empty((C, new_h, new_w), device=img_chw.device, dtype=out_dtype)
+    tmp = torch.empty((C, H, new_w), device=img_chw.device, dtype=torch.uint8) if (new_w != W and new_h != H) else None
+    call("drn_resample_u8_fwd", img_chw, C, H, W, xtab[0], xtab[1], int(xtab[2]), ytab[0], ytab[1], int(ytab[2]), int(new_h),
+         int(new_w), tmp, int(bool(flip)), out, DRN_U8 if out_dtype == torch.uint8 else DRN_F32, current_stream())
+    return out
+
+
+def tta_accumulate(all_boxes, all_scores, inverse_ops, acc_boxes, acc_scores, view_index, n_views):
+    """acc += (boxes through `inverse_ops` [(kind, a, b)], scores); overwrite on view 0, divide by n_views on the last."""
+    for t, name in ((all_boxes, "all_boxes"), (all_scores, "all_scores"), (acc_boxes, "acc_boxes"), (acc_scores, "acc_scores")):
+        _chk(t, name)
+        assert t.dtype == torch.float32
+    R, box_cols = all_boxes.shape
+    assert all_scores.shape[0] == R and acc_boxes.shape == all_boxes.shape and acc_scores.shape == all_scores.shape
+    if len(inverse_ops) > TTA_MAX_OPS:
+        raise RuntimeError(f"tta_accumulate: {len(inverse_ops)} transforms per view (max {TTA_MAX_OPS})")
+    kinds = ivec([o[0] for o in inverse_ops] or [0])
+    a = fvec([o[1] for o in inverse_ops] or [0.0])
+    b = fvec([o[2] for o in inverse_ops] or [0.0])
+    call("drn_tta_accumulate", all_boxes, all_scores, R, box_cols, all_scores.shape[1], len(inverse_ops), kinds, a, b, acc_boxes,
+         acc_scores, int(view_index), int(n_views), current_stream())
 
 
 # ---------------------------------------------------------------- backward of the trainable tail

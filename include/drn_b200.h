@@ -24,6 +24,7 @@ extern "C" {
 
 #define DRN_F32 0
 #define DRN_BF16 1
+#define DRN_U8 2 /* images only (drn_resample_u8_fwd) */
 
 typedef void* drn_stream_t;
 
@@ -289,6 +290,38 @@ int drn_pack_linear_bf16(const float* w, void* packed_bf16, int64_t rows, int64_
 /* dtype / layout helpers used by the weight cache (not on the per-image path). */
 int drn_cast_f32_to_bf16(const float* in, void* out, int64_t n, drn_stream_t stream);
 int drn_cast_bf16_to_f32(const void* in, float* out, int64_t n, drn_stream_t stream);
+
+/* ---- test-time augmentation (projects/WSL/wsl/modeling/test_time_augmentation_avg.py) ----
+ *
+ * drn_resample_u8_fwd: PIL Image.resize((new_w, new_h), BILINEAR) on an 8-bit image -- what
+ * ResizeTransform.apply_image does for uint8 input (detectron2/data/transforms/transform.py:105-109, called by
+ * DatasetMapperTTAAVG.__call__ test_time_augmentation_avg.py:121-124) -- fused with HFlipTransform.apply_image
+ * (flip != 0: output column x <- new_w - 1 - x) and, for out_dtype DRN_F32, the uint8 -> float conversion of
+ * GeneralizedRCNNWSL.preprocess_image.  Pillow's algorithm (src/libImaging/Resample.c): horizontal pass into a uint8
+ * intermediate, then the vertical pass; out = clip8((2^21 + sum_k px[min + k] * coef[k]) >> 22).  A pass whose size
+ * does not change is skipped.  Bit-exact (integer arithmetic).
+ *   src_chw: uint8 [C][H][W] (planar);  out_chw: uint8 or fp32 [C][new_h][new_w];
+ *   xbounds/ybounds: int32 [new][2] = (first source index, tap count);  xcoef/ycoef: int32 [new][ksize] fixed-point
+ *   coefficients (host-built in double: precompute_coeffs + normalize_coeffs_8bpc), device pointers, may be NULL for
+ *   a skipped pass;  tmp: uint8 [C][H][new_w] scratch, required when both passes run. */
+int drn_resample_u8_fwd(const void* src_chw, int C, int H, int W, const int* xbounds, const int* xcoef, int xksize,
+                        const int* ybounds, const int* ycoef, int yksize, int new_h, int new_w, void* tmp, int flip,
+                        void* out_chw, int out_dtype, drn_stream_t stream);
+
+/* drn_tta_accumulate: GeneralizedRCNNWithTTAAVG._get_augmented_boxes (test_time_augmentation_avg.py:286-309) for one
+ * view: all_boxes [R][box_cols] go through the view's INVERSE transforms (fvcore Transform.apply_box: the four
+ * corners through apply_coords in fp32 -- DRN_TTA_OP_RESIZE: x *= a, y *= b  (ResizeTransform.apply_coords,
+ * transform.py:124-127, a = w / new_w, b = h / new_h rounded to fp32);  DRN_TTA_OP_HFLIP: x = a - x -- then min / max)
+ * and are added to acc_boxes; all_scores [R][score_cols] are added to acc_scores.  view_index == 0 overwrites the
+ * accumulators, view_index == n_views - 1 also divides by n_views (torch.mean over the views, summed in view order).
+ * op_kind / op_a / op_b: HOST arrays of n_ops <= DRN_TTA_MAX_OPS entries, applied in order. */
+#define DRN_TTA_MAX_OPS 4
+#define DRN_TTA_OP_NOOP 0
+#define DRN_TTA_OP_RESIZE 1
+#define DRN_TTA_OP_HFLIP 2
+int drn_tta_accumulate(const void* all_boxes, const void* all_scores, int R, int box_cols, int score_cols, int n_ops,
+                       const int* op_kind, const float* op_a, const float* op_b, void* acc_boxes, void* acc_scores,
+                       int view_index, int n_views, drn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -302,6 +302,110 @@ def _smooth_l1_loss(input, target, beta, reduction="none"):
 _INSTALLED = False
 
 
+def _fvcore_transforms(names):
+    """Functional restatement of the fvcore (>= 0.1.1, absent here) transform classes the reference's TTA driver
+    uses -- Transform.apply_box (four corners through apply_coords, then min / max), TransformList (sequential
+    application, `+` concatenates, inverse = reversed inverses), HFlipTransform (x -> width - x, np.flip on
+    axis 1), NoOpTransform -- fvcore/transforms/transform.py.  The other names stay inert placeholders."""
+    import numpy as np
+
+    class Transform:
+        def __init__(self, *a, **k):
+            pass
+
+        def _set_attributes(self, params=None):
+            if params:
+                for k, v in params.items():
+                    if k != "self" and not k.startswith("_"):
+                        setattr(self, k, v)
+
+        @classmethod
+        def register_type(cls, *a, **k):
+            pass
+
+        def apply_box(self, box):
+            idxs = np.array([(0, 1), (2, 1), (0, 3), (2, 3)]).flatten()
+            coords = np.asarray(box).reshape(-1, 4)[:, idxs].reshape(-1, 2)
+            coords = self.apply_coords(coords).reshape((-1, 4, 2))
+            minxy = coords.min(axis=1)
+            maxxy = coords.max(axis=1)
+            return np.concatenate((minxy, maxxy), axis=1)
+
+        def apply_segmentation(self, segmentation):
+            return self.apply_image(segmentation)
+
+        def inverse(self):
+            raise NotImplementedError
+
+    class TransformList(Transform):
+        def __init__(self, transforms):
+            super().__init__()
+            self.transforms = list(transforms)
+
+        def _apply(self, x, meth):
+            for t in self.transforms:
+                x = getattr(t, meth)(x)
+            return x
+
+        def __getattribute__(self, name):
+            if name.startswith("apply_"):
+                return lambda x: self._apply(x, name)
+            return super().__getattribute__(name)
+
+        def __add__(self, other):
+            others = other.transforms if isinstance(other, TransformList) else [other]
+            return TransformList(self.transforms + others)
+
+        def __iadd__(self, other):
+            others = other.transforms if isinstance(other, TransformList) else [other]
+            self.transforms.extend(others)
+            return self
+
+        def __radd__(self, other):
+            others = other.transforms if isinstance(other, TransformList) else [other]
+            return TransformList(others + self.transforms)
+
+        def __len__(self):
+            return len(self.transforms)
+
+        def inverse(self):
+            return TransformList([t.inverse() for t in self.transforms[::-1]])
+
+    class HFlipTransform(Transform):
+        def __init__(self, width):
+            super().__init__()
+            self.width = width
+
+        def apply_image(self, img):
+            return np.flip(img, axis=1) if img.ndim <= 3 else np.flip(img, axis=-2)
+
+        def apply_coords(self, coords):
+            coords[:, 0] = self.width - coords[:, 0]
+            return coords
+
+        def inverse(self):
+            return self
+
+    class NoOpTransform(Transform):
+        def apply_image(self, img):
+            return img
+
+        def apply_coords(self, coords):
+            return coords
+
+        def inverse(self):
+            return self
+
+        def __getattr__(self, name):
+            if name.startswith("apply_"):
+                return lambda x: x
+            raise AttributeError(name)
+
+    real = {"Transform": Transform, "TransformList": TransformList, "HFlipTransform": HFlipTransform,
+            "NoOpTransform": NoOpTransform}
+    return {n: real.get(n, type(n, (Transform,), {})) for n in names}
+
+
 def install(with_wsl=True):
     """Install the stubs and import the reference.  Returns (detectron2, wsl).
     with_wsl=False imports detectron2 only (used to test the registry drop-in, where the B200
@@ -324,21 +428,11 @@ def install(with_wsl=True):
     _mod("fvcore.nn.weight_init", c2_msra_fill=_c2_msra_fill, c2_xavier_fill=_c2_xavier_fill)
     _mod("fvcore.nn.precise_bn")
 
-    class _T:
-        def __init__(self, *a, **k):
-            pass
-
-        @classmethod
-        def register_type(cls, *a, **k):
-            pass
-
     names = [
         "BlendTransform", "CropTransform", "GridSampleTransform", "HFlipTransform",
         "VFlipTransform", "NoOpTransform", "ScaleTransform", "Transform", "TransformList",
     ]
-    tattrs = {n: type(n, (_T,), {}) for n in names}
-    tm = _mod("fvcore.transforms.transform_placeholder")
-    del sys.modules["fvcore.transforms.transform_placeholder"]
+    tattrs = _fvcore_transforms(names)
     _mod("fvcore.transforms", **tattrs)
     _mod("fvcore.transforms.transform", __all__=names, **tattrs)
 

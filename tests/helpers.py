@@ -134,3 +134,29 @@ def check_grad(g, gold, prefix, rtol, what="", atol=1e-6, bad_frac=0.005):
     err = np.abs(s["sample"].astype(np.float64) - ref) / scale
     nbad = int((err > rtol).sum())
     assert nbad <= max(1, int(bad_frac * err.size)), (what, prefix, nbad, err.size, float(err.max()))
+
+
+# ---------------------------------------------------------------- test-time augmentation
+# name -> (CASES entry, TEST.AUG.MIN_SIZES, TEST.AUG.MAX_SIZE, TEST.AUG.FLIP, dataset (height, width) or None)
+TTA_CASES = {
+    # three scales x flip; the largest scale hits MAX_SIZE (224 -> 224x314 -> capped to 214x300)
+    "tta_r18_small": ("oicr_r18_small", (128, 160, 224), 300, True, None),
+    # the dataset image is larger than the model input: pre-transform + its inverse on the way back
+    "tta_r18_pre": ("oicr_r18_small", (160, 192), 4000, True, (320, 448)),
+    # WSDDN head (zero background column, identity boxes), no flip
+    "tta_wsddn_v16": ("wsddn_v16_300", (240, 300), 4000, False, None),
+}
+
+
+def tta_input(name):
+    """The CASES entry's first image with a uint8 BGR image (the dataset mapper hands uint8 CHW tensors to the TTA
+    driver): low-frequency pattern + noise, so that the resampling filter matters."""
+    case = TTA_CASES[name][0]
+    inp = dict(case_inputs(case)[0])
+    H, W = inp["height"], inp["width"]
+    rng = np.random.Generator(np.random.PCG64(1000 + len(name)))
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    chans = [128 + 70 * np.sin(xx / (9.0 + 4 * c) + c) * np.cos(yy / (7.0 + 3 * c)) + 45 * (rng.random((H, W)) - 0.5) for c in range(3)]
+    inp["image_u8"] = torch.from_numpy(np.clip(np.stack(chans), 0, 255).astype(np.uint8))
+    inp["image"] = inp["image_u8"].float()
+    return inp

@@ -1,0 +1,252 @@
+"""Test-time augmentation driver (SURVEY.md §8f row 3;
+projects/WSL/wsl/modeling/test_time_augmentation_avg.py).
+
+CPU: `oracle/tta_oracle.py` pinned (a) bit-exact against Pillow itself for the 8-bit bilinear resample, (b) against
+golden vectors of the UNMODIFIED reference TTA classes (tests/golden/tta_*.npz, tests/golden/make_golden_tta.py);
+host logic of drn_wsod_pytorch_b200/tta.py (coefficient tables, shapes, proposal transforms) against the oracle.
+GPU (-m gpu): the CUDA resample / merge kernels and the whole driver through the C ABI against the oracle + goldens.
+"""
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+import drn_wsod_pytorch_b200 as drn
+from drn_wsod_pytorch_b200 import tta
+from oracle import tta_oracle as T
+from oracle import wsl_oracle as O
+
+RESIZE_CASES = [(60, 100, 96, 160), (60, 100, 48, 80), (60, 100, 60, 77), (60, 100, 33, 100), (375, 500, 688, 917),
+                (600, 1000, 480, 800), (37, 53, 111, 29), (100, 100, 100, 100), (7, 5, 300, 2), (333, 500, 1152, 1730)]
+
+
+def _rand_u8(H, W, C, seed):
+    return np.random.Generator(np.random.PCG64(seed)).integers(0, 256, (H, W, C), dtype=np.uint8)
+
+
+# ------------------------------------------------------------------ oracle pins (CPU)
+@pytest.mark.parametrize("H,W,nh,nw", RESIZE_CASES)
+def test_resample_restatement_bit_exact_vs_pillow(H, W, nh, nw):
+    Image = pytest.importorskip("PIL.Image")
+    for C in (3, 1):
+        img = _rand_u8(H, W, C, H * 7 + nw)
+        arr = img if C == 3 else img[:, :, 0]
+        ref = np.asarray(Image.fromarray(arr).resize((nw, nh), Image.BILINEAR))
+        np.testing.assert_array_equal(T.pil_resize_bilinear_u8(arr, nw, nh), ref)
+
+
+def _tta_setup(name):
+    case, min_sizes, max_size, flip, dataset_hw = helpers.TTA_CASES[name]
+    cfg = helpers.case_config(case)
+    model = drn.build_model(cfg)
+    state = helpers.case_weights(cfg, model)
+    return cfg, state, helpers.tta_input(name), (min_sizes, max_size, flip, dataset_hw)
+
+
+def _expand(b, cols):
+    return np.tile(b, (1, cols // b.shape[1])) if b.shape[1] != cols else b
+
+
+@pytest.mark.parametrize("name", list(helpers.TTA_CASES))
+def test_tta_oracle_matches_reference_golden(name):
+    g = helpers.load_golden(name)
+    cfg, state, inp, (min_sizes, max_size, flip, dataset_hw) = _tta_setup(name)
+    spec = O.spec_from_cfg(cfg)
+    out = T.tta_forward(inp, state, spec, min_sizes, max_size, flip, cfg.DATASETS.PRECOMPUTED_PROPOSAL_TOPK_TEST, dataset_hw)
+    assert len(out["views"]) == int(g["n_views"])
+    np.testing.assert_array_equal(out["views"][0]["image"].numpy(), g["view0/image"])
+    for i, v in enumerate(out["views"]):
+        im = np.ascontiguousarray(v["image"].numpy())
+        assert tuple(im.shape) == tuple(g[f"view{i}/image_shape"])
+        assert zlib.crc32(im.tobytes()) == int(g[f"view{i}/image_crc32"]), f"view {i}: resampled image differs from Pillow's"
+        np.testing.assert_array_equal(v["boxes"].numpy(), g[f"view{i}/boxes"])  # float32 transform arithmetic, bit-exact
+        np.testing.assert_array_equal(v["objectness"].numpy(), g[f"view{i}/objectness"])
+        sc, bx = out["per_view"][i]
+        assert helpers.rel_err(sc.numpy(), g[f"view{i}/all_scores"], floor=1e-9) < 1e-3
+        np.testing.assert_allclose(bx.numpy(), _expand(g[f"view{i}/all_boxes"], bx.shape[1]), rtol=1e-6, atol=1e-4)
+    np.testing.assert_allclose(out["mean_boxes"].numpy(), _expand(g["mean_boxes"], out["mean_boxes"].shape[1]), rtol=1e-6, atol=1e-4)
+    assert helpers.rel_err(out["mean_scores"].numpy(), g["mean_scores"], floor=1e-9) < 1e-3
+    boxes, scores, classes, _ = out["det"]
+    np.testing.assert_array_equal(classes.numpy(), g["det_classes"])
+    np.testing.assert_allclose(boxes.numpy(), g["det_boxes"], rtol=1e-6, atol=1e-4)
+    assert helpers.rel_err(scores.numpy(), g["det_scores"], floor=1e-9) < 1e-3
+
+
+# ------------------------------------------------------------------ host logic of tta.py (CPU, no kernels)
+@pytest.mark.parametrize("in_size,out_size", [(100, 160), (100, 48), (1000, 1920), (1000, 800), (5, 2), (7, 300), (600, 600)])
+def test_coefficient_tables_match_oracle(in_size, out_size):
+    b0, k0 = T.pil_bilinear_coeffs(in_size, out_size)
+    b1, k1 = tta.resample_tables(in_size, out_size)
+    np.testing.assert_array_equal(b0, b1)
+    np.testing.assert_array_equal(k0, k1)
+    assert int(k1.sum(1).min()) > 0 and abs(int(k1.sum(1).max()) - (1 << 22)) <= k1.shape[1]
+
+
+def test_view_shapes_and_proposal_transforms_match_oracle():
+    for (h, w, size, mx) in [(600, 1000, 480, 4000), (600, 1000, 1152, 4000), (160, 224, 224, 300), (500, 375, 688, 4000),
+                             (333, 500, 1152, 1200)]:
+        assert tta.ResizeShortestEdge(size, mx).get_shape(h, w) == T.resize_shortest_edge_shape(h, w, size, mx)
+    inp = helpers.tta_input("tta_r18_small")
+    H, W = inp["height"], inp["width"]
+    boxes = torch.cat([inp["boxes"], torch.tensor([[5.0, 5.0, 5.0, 40.0], [-3.0, 2.0, 500.0, 400.0]])])  # empty + out of bounds
+    obj = torch.cat([inp["objectness"], torch.tensor([0.5, 0.25])])
+    for size, do_flip in [(128, False), (224, True)]:
+        nh, nw = T.resize_shortest_edge_shape(H, W, size, 300)
+        rec = [("resize", H, W, nh, nw)] + ([("hflip", nw)] if do_flip else [])
+        tl = tta.TransformList([tta.ResizeTransform(H, W, nh, nw)] + ([tta.HFlipTransform(nw)] if do_flip else []))
+        b0, o0 = T.transform_proposals(boxes, obj, (nh, nw), rec, 60)
+        d = {"proposals": drn.Instances((H, W), proposal_boxes=drn.Boxes(boxes.clone()), objectness_logits=obj.clone())}
+        tta.transform_proposals(d, (nh, nw), tl, proposal_topk=60)
+        np.testing.assert_array_equal(d["proposals"].proposal_boxes.tensor.numpy(), b0.numpy())
+        np.testing.assert_array_equal(d["proposals"].objectness_logits.numpy(), o0.numpy())
+        assert d["proposals"].image_size == (nh, nw)
+        back0 = T.apply_box(b0.numpy().copy(), T.inverse(rec))
+        back1 = tl.inverse().apply_box(b0.numpy().copy())
+        np.testing.assert_array_equal(back0, back1)
+        assert tl.inverse().device_params() == tta.TransformList(tl.inverse().transforms).device_params()
+
+
+def test_tta_wrapper_rejects_other_models_and_float_images():
+    cfg = helpers.case_config("oicr_r18_small")
+    with pytest.raises(AssertionError):
+        tta.GeneralizedRCNNWithTTAAVG(cfg, torch.nn.Linear(2, 2))
+    mapper = tta.DatasetMapperTTAAVG(cfg)
+    assert mapper.proposal_topk == cfg.DATASETS.PRECOMPUTED_PROPOSAL_TOPK_TEST
+    with pytest.raises((RuntimeError, TypeError)):  # float images take F.interpolate in the reference; not on the B200 path
+        mapper({"image": torch.rand(3, 64, 64), "height": 64, "width": 64})
+
+
+# ------------------------------------------------------------------ GPU: kernels + driver through the C ABI
+DEV = "cuda:0"
+RTOL = 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,W,nh,nw", RESIZE_CASES + [(600, 1000, 1152, 1920)])  # last: the largest TTA view of the bench image
+def test_gpu_resample_bit_exact(H, W, nh, nw):
+    img = _rand_u8(H, W, 3, H + 3 * nw)
+    want = T.pil_resize_bilinear_u8(img, nw, nh).transpose(2, 0, 1)  # oracle (itself bit-exact vs Pillow)
+    src = torch.from_numpy(np.ascontiguousarray(img.transpose(2, 0, 1))).to(DEV)
+    for flip in (False, True):
+        ref = want[:, :, ::-1] if flip else want
+        got_u8 = tta.resize_u8(src, nh, nw, flip=flip, out_dtype=torch.uint8)
+        got_f32 = tta.resize_u8(src, nh, nw, flip=flip, out_dtype=torch.float32)
+        assert got_u8.dtype == torch.uint8 and got_f32.dtype == torch.float32
+        np.testing.assert_array_equal(got_u8.cpu().numpy(), ref)
+        np.testing.assert_array_equal(got_f32.cpu().numpy(), ref.astype(np.float32))
+    # property: flipping twice is the identity; a same-size "resize" is a copy
+    same = tta.resize_u8(tta.resize_u8(src, H, W, flip=True), H, W, flip=True)
+    assert torch.equal(same, src)
+
+
+@pytest.mark.gpu
+def test_gpu_resample_rejects_bad_inputs():
+    with pytest.raises(TypeError):
+        tta.resize_u8(torch.zeros(3, 8, 8, device=DEV), 4, 4)
+    with pytest.raises(RuntimeError):
+        tta.resize_u8(torch.zeros(3, 8, 8, dtype=torch.uint8), 4, 4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("R,cols", [(1, 4), (97, 80), (4000, 80), (513, 4)])
+def test_gpu_tta_accumulate_matches_oracle(R, cols):
+    g = torch.Generator().manual_seed(R + cols)
+    H, W = 375, 500
+    views = []
+    for size, do_flip, pre in [(480, False, False), (480, True, False), (688, True, True), (1152, False, True), (333, True, False)]:
+        nh, nw = T.resize_shortest_edge_shape(H, W, size, 1200)
+        rec = ([("resize", 750, 1000, H, W)] if pre else [("noop",)]) + [("resize", H, W, nh, nw)] + ([("hflip", nw)] if do_flip else [])
+        tl = tta.TransformList(([tta.ResizeTransform(750, 1000, H, W)] if pre else [tta.NoOpTransform()])
+                               + [tta.ResizeTransform(H, W, nh, nw)] + ([tta.HFlipTransform(nw)] if do_flip else []))
+        xy = torch.rand(R, cols // 4, 2, generator=g) * torch.tensor([nw * 0.8, nh * 0.8])
+        wh = torch.rand(R, cols // 4, 2, generator=g) * torch.tensor([nw * 0.2, nh * 0.2])
+        boxes = torch.cat([xy, xy + wh], dim=2).reshape(R, cols).contiguous()
+        if R > 1:
+            boxes[1, :4] = torch.tensor([30.0, 20.0, 10.0, 5.0])  # corners out of order: apply_box re-sorts them
+        scores = torch.softmax(torch.randn(R, 21, generator=g), 1)
+        views.append((rec, tl, boxes, scores))
+    # one view: the inverse transform alone, bit-exact (x / 1 is exact)
+    for rec, tl, boxes, scores in views:
+        ab, asc = torch.empty(R, cols, device=DEV), torch.empty(R, 21, device=DEV)
+        drn.ops.tta_accumulate(boxes.to(DEV), scores.to(DEV), tl.inverse().device_params(), ab, asc, 0, 1)
+        want = T.apply_box(boxes.reshape(-1, 4).numpy().copy(), T.inverse(rec)).reshape(R, cols)
+        np.testing.assert_array_equal(ab.cpu().numpy(), want)
+        assert torch.equal(asc.cpu(), scores)
+    # all views: the mean (summed in view order; torch.mean may associate differently -> 1 ulp-level tolerance)
+    ab, asc = torch.empty(R, cols, device=DEV), torch.empty(R, 21, device=DEV)
+    for i, (rec, tl, boxes, scores) in enumerate(views):
+        drn.ops.tta_accumulate(boxes.to(DEV), scores.to(DEV), tl.inverse().device_params(), ab, asc, i, len(views))
+    mb, ms = T.tta_merge([v[2] for v in views], [v[3] for v in views], [v[0] for v in views])
+    np.testing.assert_allclose(ab.cpu().numpy(), mb.numpy(), rtol=1e-6, atol=1e-5)
+    np.testing.assert_allclose(asc.cpu().numpy(), ms.numpy(), rtol=1e-6, atol=1e-9)
+
+
+def _build_gpu(name, precision="fp32", use_graph=True):
+    case, min_sizes, max_size, flip, dataset_hw = helpers.TTA_CASES[name]
+    cfg = helpers.case_config(case, device=DEV, precision=precision)
+    cfg.TEST.AUG.MIN_SIZES, cfg.TEST.AUG.MAX_SIZE, cfg.TEST.AUG.FLIP = list(min_sizes), max_size, flip
+    model = drn.build_model(cfg)
+    weights = helpers.case_weights(cfg, model)
+    model.load_state_dict({**weights, "pixel_mean": model.pixel_mean, "pixel_std": model.pixel_std}, strict=True)
+    model.eval()
+    model.use_cuda_graph = use_graph
+    inp = helpers.tta_input(name)
+    d = helpers.to_batched([inp], drn.Instances, drn.Boxes, device="cpu", train=False)[0]
+    d["image"] = inp["image_u8"]
+    if dataset_hw is not None:
+        d["height"], d["width"] = dataset_hw
+    return cfg, model, d
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(helpers.TTA_CASES))
+def test_gpu_tta_driver_matches_reference_golden(name):
+    g = helpers.load_golden(name)
+    cfg, model, d = _build_gpu(name)
+    # the mapper: resampled views bit-exact vs the reference's Pillow output, proposals bit-exact
+    views = tta.DatasetMapperTTAAVG(cfg)(dict(d))
+    assert len(views) == int(g["n_views"])
+    np.testing.assert_array_equal(views[0]["image"].cpu().numpy(), g["view0/image"])
+    for i, v in enumerate(views):
+        im = np.ascontiguousarray(v["image"].cpu().numpy())
+        assert im.dtype == np.uint8 and tuple(im.shape) == tuple(g[f"view{i}/image_shape"])
+        assert zlib.crc32(im.tobytes()) == int(g[f"view{i}/image_crc32"]), f"view {i}"
+        np.testing.assert_array_equal(v["proposals"].proposal_boxes.tensor.cpu().numpy(), g[f"view{i}/boxes"])
+        np.testing.assert_array_equal(v["proposals"].objectness_logits.cpu().numpy(), g[f"view{i}/objectness"])
+    # the driver, twice: first pass eager (signatures seen once), second pass through the captured plans
+    wrapper = tta.GeneralizedRCNNWithTTAAVG(cfg, model)
+    for rep in range(2):
+        aug, tfms = wrapper._get_augmented_inputs(dict(d))
+        mean_boxes, mean_scores, _ = wrapper._get_augmented_boxes(aug, tfms)
+        np.testing.assert_allclose(mean_boxes.cpu().numpy(), _expand(g["mean_boxes"], mean_boxes.shape[1]), rtol=1e-5, atol=2e-3)
+        err = np.abs(mean_scores.cpu().numpy().astype(np.float64) - g["mean_scores"]) / (np.abs(g["mean_scores"]) + 1e-3 * g["mean_scores"].max(0, keepdims=True) + 1e-30)
+        assert err.max() < RTOL, (rep, err.max())
+        res = wrapper([dict(d)])[0]["instances"]
+        ds, dc = res.scores.cpu().numpy(), res.pred_classes.cpu().numpy()
+        gs, gc = g["det_scores"], g["det_classes"]
+        assert len(ds) == len(gs)
+        np.testing.assert_allclose(ds, gs, rtol=RTOL)
+        gaps = np.abs(np.diff(gs)) / gs[:-1]
+        if len(gs) > 1 and gaps.min() > 10 * RTOL:
+            np.testing.assert_array_equal(dc, gc)
+            np.testing.assert_allclose(res.pred_boxes.tensor.cpu().numpy(), g["det_boxes"], rtol=1e-5, atol=2e-3)
+
+
+@pytest.mark.gpu
+def test_gpu_tta_batched_views_and_skipped_detections_agree():
+    """batch_size > 1 pads the views of one chunk onto a common canvas (ImageList.from_tensors) -- same scores as one
+    view per call within fp32 noise; with_detections=False returns the same (all_scores, all_boxes)."""
+    cfg, model, d = _build_gpu("tta_r18_small", use_graph=False)
+    one = tta.GeneralizedRCNNWithTTAAVG(cfg, model, batch_size=1)
+    two = tta.GeneralizedRCNNWithTTAAVG(cfg, model, batch_size=2)  # (normal, flipped) pairs share their size
+    b1, s1, _ = one._get_augmented_boxes(*one._get_augmented_inputs(dict(d)))
+    b2, s2, _ = two._get_augmented_boxes(*two._get_augmented_inputs(dict(d)))
+    np.testing.assert_allclose(b1.cpu().numpy(), b2.cpu().numpy(), rtol=1e-6, atol=1e-4)
+    np.testing.assert_allclose(s1.cpu().numpy(), s2.cpu().numpy(), rtol=1e-4, atol=1e-8)
+    view = one._get_augmented_inputs(dict(d))[0][0]
+    r_a, sc_a, bx_a = model.inference([view], do_postprocess=False)
+    r_b, sc_b, bx_b = model.inference([view], do_postprocess=False, with_detections=False)
+    assert r_b == [None] and len(r_a[0]) > 0
+    assert torch.equal(sc_a[0], sc_b[0]) and torch.equal(bx_a[0], bx_b[0])

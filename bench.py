@@ -23,6 +23,7 @@ import torch  # noqa: E402
 # workload -> (builtin config, H, W, R, precision, GMAC per image {conv, fc6, fc7, heads} from BASELINE.md §3)
 WORKLOADS = {
     "r18_fp32": ("oicr_WSR_18_DC5_1x", 600, 1000, 2000, "fp32", dict(conv=118.0, fc6=205.5, fc7=33.6, heads=0.85)),
+    "r18_fp32_tc": ("oicr_WSR_18_DC5_1x", 600, 1000, 2000, "fp32_tc", dict(conv=118.0, fc6=205.5, fc7=33.6, heads=0.85)),
     "r18_bf16": ("oicr_WSR_18_DC5_1x", 600, 1000, 2000, "bf16", dict(conv=118.0, fc6=205.5, fc7=33.6, heads=0.85)),
     "r50_bf16": ("oicr_WSR_50_DC5_1x", 600, 1000, 4000, "bf16", dict(conv=232.7, fc6=822.1, fc7=33.6, heads=1.7)),
     "r50_fp32": ("oicr_WSR_50_DC5_1x", 600, 1000, 4000, "fp32", dict(conv=232.7, fc6=822.1, fc7=33.6, heads=1.7)),
@@ -149,7 +150,8 @@ def main():
               if args.workload in ("r50_bf16", "r18_fp32") else f"{cfg_name} {H}x{W} R={R} {precision}",
               "images_per_gpu": 1, "proposals_per_image": R, "parallelism": f"dp{world}", "dropout": "on (train mode)",
               "launch": "one CUDA-graph replay per step (captured per input signature by the public forward)",
-              "l2": "no flush: per-step working set (fc6 weights 411 MB + ROI features 0.2-0.8 GB) exceeds the 126 MB L2"}
+              "l2": "no flush: per-step working set (fc6 weights 411 MB + ROI features 0.2-0.8 GB) exceeds the 126 MB L2",
+              "e2e_read": "loss vector D2H into pinned memory behind every step, read by the host one step later (event-synchronised)"}
 
     import drn_wsod_pytorch_b200 as drn
     from drn_wsod_pytorch_b200 import synth
@@ -272,7 +274,7 @@ def main():
 
     def wrap(fn):
         def inner(x, packed, ksize, dilation, relu, *a, **k):
-            if ksize == 1 and x.shape[-1] == fc6_K and record["on"]:
+            if ksize == 1 and x.shape[-1] in (fc6_K, 3 * fc6_K, 6 * fc6_K) and record["on"]:  # 3x / 6x: fp32_tc term planes
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 out = fn(x, packed, ksize, dilation, relu, *a, **k)
@@ -353,13 +355,27 @@ def main():
     for _ in range(3):
         e2e_step()
     sync_all()
+    # the loss vector of step i is copied to pinned host memory right behind step i on the stream and read by the host
+    # one step later (after step i+1 has been launched), so the host-side launch work of the next step overlaps the
+    # running one: every step's result is still read on the host inside the timed region
+    pinned = [torch.empty(vec.shape, dtype=vec.dtype).pin_memory() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+
+    def read(i):
+        done[i & 1].synchronize()
+        return pinned[i & 1].clone()
+
     t0 = time.perf_counter()
     batches = [[host], [host]]  # two batch objects over the same pinned tensors (prefetch is keyed on the batch object)
     model.prefetch(batches[0])
     for i in range(args.steps):
         v, _ = step(batches[i & 1])
+        pinned[i & 1].copy_(v, non_blocking=True)
+        done[i & 1].record()
         model.prefetch(batches[(i + 1) & 1])
-        loss_host = v.cpu()
+        if i > 0:
+            loss_host = read(i - 1)
+    loss_host = read(args.steps - 1)
     sync_all()
     t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
     if dist is not None:
@@ -412,7 +428,7 @@ def main():
         "e2e": {"value": world * args.steps / t_e2e.item(), "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "fc6 GEMM (gemm_tc_kernel)" if precision == "bf16" else "fc6 GEMM (conv_igemm_f32_kernel, SIMT fp32)",
+        "roofline": {"bound": "tensor", "kernel": "fc6 GEMM (gemm_tc_kernel)" if precision == "bf16" else "fc6 GEMM (gemm_tc_kernel over split-bf16 term planes; fp32-equivalent FLOPs counted once)" if precision == "fp32_tc" else "fc6 GEMM (conv_igemm_f32_kernel, SIMT fp32)",
                      "achieved": fc6_tflops, "peak": peak, "unit": "TFLOP/s", "frac": fc6_tflops / peak,
                      "peak_source": f"{peaks['src']} cuBLAS bf16 sustained (kernel timed inside a long step)",
                      "traffic": FC6_DRAM_BYTES.get(args.workload), "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of the fc6 launch, profiles/r1_ncu_step_v7_per_launch.txt (#62)" if args.workload in FC6_DRAM_BYTES else None,

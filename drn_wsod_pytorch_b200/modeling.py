@@ -65,6 +65,34 @@ def _refresh_in_place(old, new):
 # ------------------------------------------------------------------------------------------------
 # layers (parameter holders with the reference's names)
 # ------------------------------------------------------------------------------------------------
+F32_ACT = ("fp32", "fp32_tc")  # precisions whose activations (and pooled ROI features) are fp32
+
+
+def _split_terms():
+    """(activation terms, weight terms) of the "fp32_tc" precision: DRN_B200_SPLIT_TERMS = 6 (default, fp32-level
+    accuracy) or 3 (~2^-16 per product, half the tensor-core work)."""
+    return ops.SPLIT_TERMS[int(os.environ.get("DRN_B200_SPLIT_TERMS", "6"))]
+
+
+def _weight_planes(w, dim):
+    """fp32 weight -> its bf16 terms stacked as planes along a new axis `dim` in the order WI (csrc/drn_split.cu)."""
+    w1 = w.to(torch.bfloat16)
+    r1 = w - w1.float()
+    w2 = r1.to(torch.bfloat16)
+    w3 = (r1 - w2.float()).to(torch.bfloat16)
+    terms = (w1, w2, w3)
+    return torch.stack([terms[t] for t in _split_terms()[1]], dim=dim)
+
+
+def _split_of(x):
+    """bf16 term planes of an fp32 activation, computed once per tensor (several layers may consume it)."""
+    s = getattr(x, "_drn_split", None)
+    if s is None:
+        s = ops.split_bf16_terms(x, _split_terms()[0])[1]
+        x._drn_split = s
+    return s
+
+
 class FrozenBatchNorm2d(nn.Module):
     """Buffers of detectron2/layers/batch_norm.py:14-65 (eps 1e-5); folded into the conv epilogue."""
 
@@ -112,6 +140,12 @@ class Conv2d(nn.Module):
                 bias = (self.bias.detach().float() if self.bias is not None else torch.zeros(cout, device=w.device)).contiguous()
             if self.in_channels == 3 or precision == "fp32":
                 wp = w.permute(2, 3, 1, 0).reshape(-1, cout).contiguous()  # [(kh,kw,cin)][cout]
+            elif precision == "fp32_tc":
+                # fp32-accurate on the tensor cores: FrozenBN scale folded in fp32, then the bf16 term planes along K
+                if scale is not None:
+                    w = w * scale.view(-1, 1, 1, 1)
+                    scale = None
+                wp = _weight_planes(w.permute(0, 2, 3, 1).contiguous(), dim=3).reshape(cout, -1).contiguous()  # [cout][(kh,kw,p,cin)]
             else:
                 # tensor-core path: FrozenBN scale folded into the bf16 filter (the epilogue is bias-only and
                 # the shortcut can be accumulated by the MMA itself, see csrc/drn_tc.cu)
@@ -133,7 +167,7 @@ class Linear(nn.Linear):
         if hit is not None and hit["key"] == key:
             return hit
         n, k = self.weight.shape
-        direct = (precision != "fp32" and self.weight.is_cuda and self.weight.dtype == torch.float32 and n % pad_to == 0
+        direct = (precision not in F32_ACT and self.weight.is_cuda and self.weight.dtype == torch.float32 and n % pad_to == 0
                   and (permute_c49 is None or (permute_c49 % 64 == 0 and k == 49 * permute_c49)))
         if direct:
             # one pass, straight into the (existing) bf16 buffer: fc6 is 205 M weights, the torch route through a
@@ -167,6 +201,8 @@ def pack_linear(weights, biases, precision, permute_c49=None, pad_to=64):
             b = torch.cat([b, b.new_zeros(npad - n)], dim=0)
         if precision == "fp32":
             wp = w.t().contiguous()  # [K][N]
+        elif precision == "fp32_tc":
+            wp = _weight_planes(w, dim=1).reshape(npad, -1).contiguous()  # [N][(p, k)]
         else:
             wp = w.contiguous().to(torch.bfloat16)  # [N][K]
     return {"w": wp, "scale": None, "bias": b.contiguous(), "cout": npad, "n": n}
@@ -176,6 +212,13 @@ def run_conv(conv: Conv2d, x, precision, relu, residual=None):
     p = conv.packed(precision)
     if precision == "fp32":
         return ops.conv_f32(x, p, conv.kernel_size, conv.dilation, relu, residual)
+    if precision == "fp32_tc":
+        y = ops.conv_bf16_tc(_split_of(x), p, conv.kernel_size, conv.dilation, relu and residual is None, None,
+                             out_dtype=torch.float32)
+        if residual is not None:  # shortcut add + ReLU in fp32, fused with the split the next layer needs
+            y, planes = ops.split_bf16_terms(y, _split_terms()[0], residual=residual, relu=relu, write_f32=True)
+            y._drn_split = planes
+        return y
     return ops.conv_bf16_tc(x, p, conv.kernel_size, conv.dilation, relu, residual)
 
 
@@ -188,6 +231,12 @@ def run_linear(x2d, packed, precision, relu, out_dtype=None, dropout=None, out=N
     x4 = x2d.view(1, M, 1, K)
     if precision == "fp32":
         y = ops.conv_f32(x4, packed, 1, 1, relu)
+        if dropout is not None:
+            ops.dropout_(y, dropout[0], dropout[1], dropout[2])
+    elif precision == "fp32_tc":
+        xs = _split_of(x2d)
+        y = ops.conv_bf16_tc(xs.view(1, M, 1, xs.shape[1]), packed, 1, 1, relu, out_dtype=torch.float32,
+                             out=None if out is None else out.view(1, M, 1, packed["cout"]))
         if dropout is not None:
             ops.dropout_(y, dropout[0], dropout[1], dropout[2])
     else:
@@ -288,7 +337,7 @@ class Backbone(nn.Module):
         }
 
     def _act_dtype(self):
-        return torch.float32 if self.precision == "fp32" else torch.bfloat16
+        return torch.float32 if self.precision in F32_ACT else torch.bfloat16
 
     def forward(self, x):
         """x: N x 3 x H x W fp32, already normalised (reference interface).  Returns
@@ -501,7 +550,7 @@ class DiscriminativeAdaptionNeck(nn.Module):
         if x.dim() > 2:
             x = torch.flatten(x, start_dim=1)
         x = x.contiguous()
-        if self.precision != "fp32" and x.dtype != torch.bfloat16:
+        if self.precision not in F32_ACT and x.dtype != torch.bfloat16:
             x = ops.to_bf16(x)
         return self.run(x, bin_major=False)
 
@@ -652,7 +701,7 @@ class _WSLROIHeads(nn.Module):
     def _features_hwc(self, features, i):
         f = features[self.box_in_features[0]]
         x = f[i].permute(1, 2, 0)  # [h,w,C]; a no-copy view when the backbone wrote NHWC
-        want = torch.float32 if self.precision == "fp32" else torch.bfloat16
+        want = torch.float32 if self.precision in F32_ACT else torch.bfloat16
         if x.dtype != want:
             x = ops.to_bf16(x.contiguous()) if want == torch.bfloat16 else ops.to_f32(x.contiguous())
         return x.contiguous()
@@ -679,7 +728,7 @@ class _WSLROIHeads(nn.Module):
         R = boxes.shape[0]
         fc1 = self.box_head.fcs[0] if hasattr(self.box_head, "fcs") else None
         blocks = [(0, R)]
-        if self.overlap_pool and self.precision != "fp32" and fc1 is not None and R >= 512:
+        if self.overlap_pool and self.precision not in F32_ACT and fc1 is not None and R >= 512:
             blocks = self._row_blocks(R, fc1.out_features)
         tables = ops.roipool_tables(fh) if len(blocks) > 1 else None
         if tables is None:
@@ -974,6 +1023,8 @@ class _WSLROIHeads(nn.Module):
         as GEMMs on the forward's kernels -- dX = dY W, dW = dY^T X -- with drn_masked_transpose applying the
         ReLU/dropout mask and producing the K-major operands.  The backbone is frozen (FREEZE_AT 5), so the chain
         stops at the pooled features.  Returns {parameter: gradient (fp32, parameter layout)}."""
+        if self.precision == "fp32_tc":
+            raise NotImplementedError('B200.PRECISION "fp32_tc" covers forward+loss and inference; train with "bf16" or "fp32"')
         K, S = self.num_classes, self.refine_K
         traces = d["traces"]
         N = len(traces)

@@ -302,6 +302,28 @@ def detections(all_scores, all_boxes, image_hw, score_thresh, nms_thresh, cap):
     return out_boxes, out_scores, out_classes, out_rows, count
 
 
+# ---------------------------------------------------------------- "fp32_tc": fp32-accurate layers on the bf16 tensor cores
+# K-plane layout of the split operands (include/drn_b200.h drn_split_bf16_terms): activation term XI[p] meets weight
+# term WI[p]; 6 planes = every product x_i w_j with i + j <= 4 (fp32-level accuracy), 3 planes = i + j <= 3 (~2^-16)
+SPLIT_TERMS = {6: ((0, 0, 1, 0, 1, 2), (0, 1, 0, 2, 1, 0)), 3: ((0, 0, 1), (0, 1, 0))}
+
+
+def split_bf16_terms(x, act_terms, residual=None, relu=False, write_f32=False):
+    """x: fp32 [..., C] -> (relu?(x + residual?) as fp32 [..., C] or None, bf16 [..., P*C] planes of its bf16 terms)."""
+    _chk(x, "x")
+    assert x.dtype == torch.float32
+    C = x.shape[-1]
+    rows = x.numel() // C
+    P = len(act_terms)
+    if residual is not None:
+        _chk(residual, "residual")
+        assert residual.dtype == torch.float32 and residual.shape == x.shape
+    y = torch.empty_like(x) if write_f32 else None
+    planes = torch.empty(tuple(x.shape[:-1]) + (P * C,), device=x.device, dtype=torch.bfloat16)
+    call("drn_split_bf16_terms", x, residual, int(bool(relu)), rows, C, P, ivec(act_terms), y, planes, current_stream())
+    return y, planes
+
+
 # ---------------------------------------------------------------- test-time augmentation (tta.py)
 TTA_OP_NOOP, TTA_OP_RESIZE, TTA_OP_HFLIP = 0, 1, 2  # include/drn_b200.h DRN_TTA_OP_*
 TTA_MAX_OPS = 4

@@ -323,6 +323,18 @@ int drn_tta_accumulate(const void* all_boxes, const void* all_scores, int R, int
                        const int* op_kind, const float* op_a, const float* op_b, void* acc_boxes, void* acc_scores,
                        int view_index, int n_views, drn_stream_t stream);
 
+/* ---- "fp32_tc" precision: fp32-accurate layers on the bf16 tensor cores ----
+ * drn_split_bf16_terms: v = relu?(x + residual?) (fp32, [rows][C]); y_f32 = v (optional); planes[r][p*C + c] = term
+ * term_idx[p] of v[r][c], where term 0 = bf16(v), term 1 = bf16(v - term0), term 2 = bf16(v - term0 - term1) (the
+ * three-way bf16 split of an fp32 value, exact).  With the weights split the same way and laid out plane by plane
+ * along K, drn_conv_igemm_bf16_tc over the P*C "channels" computes sum_p x_XI[p] * w_WI[p] with fp32 accumulation:
+ * P = 6 (x1w1, x1w2, x2w1, x1w3, x2w2, x3w1) reproduces an fp32 conv / linear layer of WSL/backbone/*.py and
+ * roi_heads/box_head.py:82-91 to ~2^-24 per product; P = 3 (x1w1, x1w2, x2w1) to ~2^-16.
+ * term_idx: HOST array of n_terms <= DRN_SPLIT_MAX_TERMS entries in {0, 1, 2}; C % 4 == 0. */
+#define DRN_SPLIT_MAX_TERMS 6
+int drn_split_bf16_terms(const float* x, const float* residual, int relu, int64_t rows, int C, int n_terms,
+                         const int* term_idx, float* y_f32, void* planes_bf16, drn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -493,3 +493,50 @@ def test_bf16_transpose_fast_path_matches_torch(R, C, c49, ld):
     mask = torch.ones_like(x)
     out2, masked = ops.masked_transpose(x, mask=mask, c49=c49, ld_out=ld, want_masked=True)
     assert torch.equal(out2, out) and torch.equal(masked, x)
+
+
+# ---------------------------------------------------------------- "fp32_tc": split-bf16 operands (csrc/drn_split.cu)
+@pytest.mark.parametrize("rows,C", [(1, 4), (37, 64), (1000, 512), (5, 25088)])
+def test_split_bf16_terms_exact(rows, C):
+    """The three bf16 terms sum back to the fp32 value EXACTLY; shortcut add + ReLU match torch bit for bit; plane p holds
+    term XI[p]."""
+    g = torch.Generator().manual_seed(rows + C)
+    x = (torch.randn(rows, C, generator=g) * torch.exp(torch.randn(rows, C, generator=g) * 3)).to(DEV)
+    res = torch.randn(rows, C, generator=g).to(DEV)
+    for terms in ((0, 0, 1, 0, 1, 2), (0, 0, 1)):
+        for use_res, relu in ((False, False), (True, True), (True, False), (False, True)):
+            y, planes = ops.split_bf16_terms(x, terms, residual=res if use_res else None, relu=relu, write_f32=True)
+            want = x + res if use_res else x
+            want = torch.relu(want) if relu else want
+            assert torch.equal(y, want)
+            pl = planes.view(rows, len(terms), C).float()
+            t0, t1 = pl[:, 0], pl[:, 2]  # XI = (0, 0, 1, ...): planes 0 and 1 hold term 0, plane 2 term 1
+            assert torch.equal(pl[:, 0], pl[:, 1])
+            assert torch.equal(t0, want.to(torch.bfloat16).float())
+            assert torch.equal(t1, (want - t0).to(torch.bfloat16).float())
+            if len(terms) == 6:
+                assert torch.equal(pl[:, 3], t0) and torch.equal(pl[:, 4], t1)
+                assert torch.equal((t0.double() + t1.double() + pl[:, 5].double()).float(), want)  # exact three-way split
+
+
+@pytest.mark.parametrize("M,K,N,nterms", [(300, 512, 128, 6), (300, 512, 128, 3), (2000, 4096, 256, 6), (129, 25088, 64, 6)])
+def test_fp32_tc_linear_accuracy(M, K, N, nterms, monkeypatch):
+    """A linear layer through the split-bf16 GEMM versus float64: 6 planes are as accurate as an fp32 GEMM (error
+    relative to sum_k |x_k w_k| below 1e-6), 3 planes below 3e-5."""
+    from drn_wsod_pytorch_b200 import modeling
+
+    monkeypatch.setenv("DRN_B200_SPLIT_TERMS", str(nterms))
+    g = torch.Generator().manual_seed(M + K)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    packed = modeling.pack_linear([w.to(DEV)], [b.to(DEV)], "fp32_tc")
+    y = modeling.run_linear(x.to(DEV), packed, "fp32_tc", relu=False).cpu().double()
+    ref = x.double() @ w.double().t() + b.double()
+    scale = x.double().abs() @ w.double().abs().t() + b.double().abs()
+    err = ((y - ref).abs() / scale).max().item()
+    assert err < (1e-6 if nterms == 6 else 3e-5), err
+    # plain bf16 on the same layer is ~3 orders of magnitude further away
+    pb = modeling.pack_linear([w.to(DEV)], [b.to(DEV)], "bf16")
+    yb = modeling.run_linear(x.to(DEV).to(torch.bfloat16), pb, "bf16", relu=False, out_dtype=torch.float32).cpu().double()
+    assert ((yb - ref).abs() / scale).max().item() > 30 * err

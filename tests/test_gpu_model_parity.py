@@ -35,10 +35,16 @@ def _score_err(a, b):
     return float(np.max(np.abs(a - b) / (np.abs(b) + floor)))
 
 
+# "fp32": SIMT fp32 kernels; "fp32_tc": the same layers as split-bf16 GEMMs on the tensor cores (csrc/drn_split.cu) --
+# both are held to the fp32 bar (bit-exact indices, 1e-3 scores)
+F32_PRECISIONS = ["fp32", "fp32_tc"]
+
+
+@pytest.mark.parametrize("precision", F32_PRECISIONS)
 @pytest.mark.parametrize("case", CASES)
-def test_train_forward_matches_reference_golden(case):
+def test_train_forward_matches_reference_golden(case, precision):
     g = helpers.load_golden(case)
-    cfg, model, _ = _build(case)
+    cfg, model, _ = _build(case, precision)
     model.train()
     model.roi_heads.box_head.eval()  # dropout off, as in the golden run
     inputs = helpers.case_inputs(case)
@@ -59,10 +65,11 @@ def test_train_forward_matches_reference_golden(case):
             assert helpers.rel_err(st["pgt_weights"].cpu().numpy(), g[p + "pgt_weights"]) < RTOL
 
 
+@pytest.mark.parametrize("precision", F32_PRECISIONS)
 @pytest.mark.parametrize("case", CASES)
-def test_eval_forward_matches_reference_golden(case):
+def test_eval_forward_matches_reference_golden(case, precision):
     g = helpers.load_golden(case)
-    cfg, model, _ = _build(case)
+    cfg, model, _ = _build(case, precision)
     model.eval()
     inputs = helpers.case_inputs(case)
     batched = helpers.to_batched(inputs, drn.Instances, drn.Boxes, device=DEV, train=False)

@@ -34,6 +34,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--cpu-sample", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="after warm-up run ONE image between cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`)")
     args = ap.parse_args()
     cfg_name, H, W, R, precision, _ = bench.WORKLOADS[args.workload]
     dev = "cuda:0"
@@ -58,6 +60,12 @@ def main():
     for _ in range(max(args.warmup, 3)):  # pass 1 eager, pass 2 captures one plan per scale, pass 3+ replays
         n_det = step()
     torch.cuda.synchronize()
+    if args.profile_step:
+        torch.cuda.cudart().cudaProfilerStart()
+        step()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()

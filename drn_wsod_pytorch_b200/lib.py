@@ -54,7 +54,8 @@ _PROTOS = {
     "drn_cast_f32_to_bf16": [_P, _P, c_int64, _P],
     "drn_cast_bf16_to_f32": [_P, _P, c_int64, _P],
     "drn_resample_u8_fwd": [_P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, c_int, c_int, _P, c_int, _P, c_int, _P],
-    "drn_split_bf16_terms": [_P, _P, c_int, c_int64, c_int, c_int, _IP, _P, _P, _P],
+    "drn_f32tc_split": [_P, c_int64, c_int, c_int, _P, _P, _P],
+    "drn_f32tc_reduce": [_P, c_int, c_int64, c_int, _P, _P, c_int, c_int64, c_int, _P, _P],
     "drn_tta_accumulate": [_P, _P, c_int, c_int, c_int, c_int, _IP, _FP, _FP, _P, _P, c_int, c_int, _P],
 }
 

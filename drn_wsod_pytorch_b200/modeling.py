@@ -68,29 +68,67 @@ def _refresh_in_place(old, new):
 F32_ACT = ("fp32", "fp32_tc")  # precisions whose activations (and pooled ROI features) are fp32
 
 
-def _split_terms():
-    """(activation terms, weight terms) of the "fp32_tc" precision: DRN_B200_SPLIT_TERMS = 6 (default, fp32-level
-    accuracy) or 3 (~2^-16 per product, half the tensor-core work)."""
-    return ops.SPLIT_TERMS[int(os.environ.get("DRN_B200_SPLIT_TERMS", "6"))]
+def _kgroup(ksize, C):
+    """K-group size (channels) of the leading-product GEMMs of the "fp32_tc" precision: every group accumulates
+    ksize^2 * Cg / 16 MMA steps in its own accumulator (csrc/drn_split.cu) -- 64 channels for a 3x3 filter (36 steps),
+    ~512 for 1x1 / linear layers (32 steps), more only when that would need over 64 launches (fc6 of the R50 nets)."""
+    if ksize == 3:
+        return 64
+    if C <= 576:
+        return C
+    for m in range(8, C // 64 + 1):
+        if (C // 64) % m == 0 and C // (64 * m) <= 64:
+            return 64 * m
+    return C
 
 
-def _weight_planes(w, dim):
-    """fp32 weight -> its bf16 terms stacked as planes along a new axis `dim` in the order WI (csrc/drn_split.cu)."""
+def _bf16_terms(w):
     w1 = w.to(torch.bfloat16)
     r1 = w - w1.float()
     w2 = r1.to(torch.bfloat16)
     w3 = (r1 - w2.float()).to(torch.bfloat16)
-    terms = (w1, w2, w3)
-    return torch.stack([terms[t] for t in _split_terms()[1]], dim=dim)
+    return w1, w2, w3
 
 
-def _split_of(x):
-    """bf16 term planes of an fp32 activation, computed once per tensor (several layers may consume it)."""
-    s = getattr(x, "_drn_split", None)
-    if s is None:
-        s = ops.split_bf16_terms(x, _split_terms()[0])[1]
-        x._drn_split = s
-    return s
+def _f32tc_pack(w, bias, Cg):
+    """w: fp32 [cout, taps, C] (FrozenBN scale folded in) -> the operands of the "fp32_tc" GEMMs:
+    big [G, cout, taps*Cg] (term w1 per K-group), small [cout, taps*5*C] (planes w2 | w1 | w3 | w2 | w1 per tap)."""
+    cout, taps, C = w.shape
+    t = _bf16_terms(w)
+    G = C // Cg
+    big = t[0].view(cout, taps, G, Cg).permute(2, 0, 1, 3).reshape(G, cout, taps * Cg).contiguous()
+    small = torch.stack([t[i] for i in ops.F32TC_SMALL_W], dim=2).reshape(cout, taps * 5 * C).contiguous()
+    return {"big": big, "small": small, "scale": None, "bias": bias, "zero": torch.zeros_like(bias), "cout": cout,
+            "groups": G, "cg": Cg}
+
+
+def _split_of(x, Cg):
+    """(big, small) bf16 operands of an fp32 activation, computed once per tensor and group size."""
+    cache = getattr(x, "_drn_split", None)
+    if cache is None:
+        cache = {}
+        x._drn_split = cache
+    if Cg not in cache:
+        cache[Cg] = ops.f32tc_split(x, Cg)
+    return cache[Cg]
+
+
+def _f32tc_layer(x, p, ksize, dilation, relu, residual=None, out=None):
+    """One fp32 conv / linear layer as 1 + G bf16 tensor-core GEMMs with fp32 output + a round-to-nearest reduction.
+    x: fp32 [N,H,W,C] NHWC."""
+    N, H, W, C = x.shape
+    big, small = _split_of(x, p["cg"])
+    G, cout = p["groups"], p["cout"]
+    partials = torch.empty((G + 1, N, H, W, cout), device=x.device, dtype=torch.float32)
+    sub = {"scale": None, "bias": p["zero"], "cout": cout}
+    ops.conv_bf16_tc(small, dict(sub, w=p["small"]), ksize, dilation, False, None, out_dtype=torch.float32, out=partials[0])
+    for g in range(G):  # ascending magnitude last: the correction partial first, then the leading-product groups
+        ops.conv_bf16_tc(big[g], dict(sub, w=p["big"][g]), ksize, dilation, False, None, out_dtype=torch.float32, out=partials[g + 1])
+    y = ops.f32tc_reduce(partials, p["bias"], residual, relu)
+    if out is not None:
+        out.view_as(y).copy_(y)
+        return out
+    return y
 
 
 class FrozenBatchNorm2d(nn.Module):
@@ -145,7 +183,11 @@ class Conv2d(nn.Module):
                 if scale is not None:
                     w = w * scale.view(-1, 1, 1, 1)
                     scale = None
-                wp = _weight_planes(w.permute(0, 2, 3, 1).contiguous(), dim=3).reshape(cout, -1).contiguous()  # [cout][(kh,kw,p,cin)]
+                k = self.kernel_size
+                new = dict(_f32tc_pack(w.permute(0, 2, 3, 1).reshape(cout, k * k, -1).contiguous(), bias, _kgroup(k, self.in_channels)), key=key)
+                hit = _refresh_in_place(hit, new)
+                self._cache[precision] = hit
+                return hit
             else:
                 # tensor-core path: FrozenBN scale folded into the bf16 filter (the epilogue is bias-only and
                 # the shortcut can be accumulated by the MMA itself, see csrc/drn_tc.cu)
@@ -202,7 +244,7 @@ def pack_linear(weights, biases, precision, permute_c49=None, pad_to=64):
         if precision == "fp32":
             wp = w.t().contiguous()  # [K][N]
         elif precision == "fp32_tc":
-            wp = _weight_planes(w, dim=1).reshape(npad, -1).contiguous()  # [N][(p, k)]
+            return dict(_f32tc_pack(w.view(npad, 1, k).contiguous(), b.contiguous(), _kgroup(1, k)), n=n)
         else:
             wp = w.contiguous().to(torch.bfloat16)  # [N][K]
     return {"w": wp, "scale": None, "bias": b.contiguous(), "cout": npad, "n": n}
@@ -213,12 +255,7 @@ def run_conv(conv: Conv2d, x, precision, relu, residual=None):
     if precision == "fp32":
         return ops.conv_f32(x, p, conv.kernel_size, conv.dilation, relu, residual)
     if precision == "fp32_tc":
-        y = ops.conv_bf16_tc(_split_of(x), p, conv.kernel_size, conv.dilation, relu and residual is None, None,
-                             out_dtype=torch.float32)
-        if residual is not None:  # shortcut add + ReLU in fp32, fused with the split the next layer needs
-            y, planes = ops.split_bf16_terms(y, _split_terms()[0], residual=residual, relu=relu, write_f32=True)
-            y._drn_split = planes
-        return y
+        return _f32tc_layer(x, p, conv.kernel_size, conv.dilation, relu, residual)
     return ops.conv_bf16_tc(x, p, conv.kernel_size, conv.dilation, relu, residual)
 
 
@@ -234,9 +271,7 @@ def run_linear(x2d, packed, precision, relu, out_dtype=None, dropout=None, out=N
         if dropout is not None:
             ops.dropout_(y, dropout[0], dropout[1], dropout[2])
     elif precision == "fp32_tc":
-        xs = _split_of(x2d)
-        y = ops.conv_bf16_tc(xs.view(1, M, 1, xs.shape[1]), packed, 1, 1, relu, out_dtype=torch.float32,
-                             out=None if out is None else out.view(1, M, 1, packed["cout"]))
+        y = _f32tc_layer(x4, packed, 1, 1, relu, out=None if out is None else out.view(1, M, 1, packed["cout"]))
         if dropout is not None:
             ops.dropout_(y, dropout[0], dropout[1], dropout[2])
     else:
@@ -1486,7 +1521,8 @@ class GeneralizedRCNNWSL(nn.Module):
             groups = [images, [p.proposal_boxes.tensor.float() for p in proposals],
                       [p.objectness_logits.float() for p in proposals]]
             dev_out, _ = self._run_device(("eval", tuple(img_sizes), with_detections), canvas, groups, fn)
-            proposals = [p.to(self.device) for p in proposals]
+            # _eval_post reads only the proposals' classes and image sizes: no device copy (a blocking pageable H2D here
+            # would stall the host behind the replay it has just launched, once per TTA view)
             results, all_scores, all_boxes = rh._eval_post(dev_out, proposals)
         else:
             features = self._features([im.to(self.device).float().contiguous() for im in images], canvas)

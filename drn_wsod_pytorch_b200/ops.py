@@ -303,25 +303,35 @@ def detections(all_scores, all_boxes, image_hw, score_thresh, nms_thresh, cap):
 
 
 # ---------------------------------------------------------------- "fp32_tc": fp32-accurate layers on the bf16 tensor cores
-# K-plane layout of the split operands (include/drn_b200.h drn_split_bf16_terms): activation term XI[p] meets weight
-# term WI[p]; 6 planes = every product x_i w_j with i + j <= 4 (fp32-level accuracy), 3 planes = i + j <= 3 (~2^-16)
-SPLIT_TERMS = {6: ((0, 0, 1, 0, 1, 2), (0, 1, 0, 2, 1, 0)), 3: ((0, 0, 1), (0, 1, 0))}
+# weight planes that meet the "small" activation planes x1 | x2 | x1 | x2 | x3 (include/drn_b200.h drn_f32tc_split)
+F32TC_SMALL_W = (1, 0, 2, 1, 0)
 
 
-def split_bf16_terms(x, act_terms, residual=None, relu=False, write_f32=False):
-    """x: fp32 [..., C] -> (relu?(x + residual?) as fp32 [..., C] or None, bf16 [..., P*C] planes of its bf16 terms)."""
+def f32tc_split(x, Cg):
+    """x: fp32 [..., C] -> (big bf16 [C/Cg, ..., Cg] = term x1 per K-group, small bf16 [..., 5C] = correction planes)."""
     _chk(x, "x")
     assert x.dtype == torch.float32
     C = x.shape[-1]
+    assert C % Cg == 0
     rows = x.numel() // C
-    P = len(act_terms)
+    big = torch.empty((C // Cg,) + tuple(x.shape[:-1]) + (Cg,), device=x.device, dtype=torch.bfloat16)
+    small = torch.empty(tuple(x.shape[:-1]) + (5 * C,), device=x.device, dtype=torch.bfloat16)
+    call("drn_f32tc_split", x, rows, C, Cg, big, small, current_stream())
+    return big, small
+
+
+def f32tc_reduce(partials, bias=None, residual=None, relu=False):
+    """partials: fp32 [n, ..., C] -> relu?(sum_n partials + bias + residual) as fp32 [..., C] (round-to-nearest adds)."""
+    _chk(partials, "partials")
+    assert partials.dtype == torch.float32
+    n, C = partials.shape[0], partials.shape[-1]
+    rows = partials[0].numel() // C
+    y = torch.empty(tuple(partials.shape[1:]), device=partials.device, dtype=torch.float32)
     if residual is not None:
         _chk(residual, "residual")
-        assert residual.dtype == torch.float32 and residual.shape == x.shape
-    y = torch.empty_like(x) if write_f32 else None
-    planes = torch.empty(tuple(x.shape[:-1]) + (P * C,), device=x.device, dtype=torch.bfloat16)
-    call("drn_split_bf16_terms", x, residual, int(bool(relu)), rows, C, P, ivec(act_terms), y, planes, current_stream())
-    return y, planes
+        assert residual.dtype == torch.float32 and residual.numel() == y.numel()
+    call("drn_f32tc_reduce", partials, n, rows * C, C, bias, residual, int(bool(relu)), rows, C, y, current_stream())
+    return y
 
 
 # ---------------------------------------------------------------- test-time augmentation (tta.py)

@@ -229,9 +229,11 @@ def resize_u8(img_chw_u8, new_h, new_w, flip=False, out_dtype=torch.uint8):
 
 
 # ---------------------------------------------------------------------------------------------- mapper
-def transform_proposals(dataset_dict, image_shape, transforms, *, proposal_topk, min_box_size=0):
+def transform_proposals(dataset_dict, image_shape, transforms, *, proposal_topk, min_box_size=0, pin_memory=False):
     """test_time_augmentation_avg.py:27-64: `apply_box` -> clip -> nonempty(min_box_size) -> first top-k (no `unique`
-    step, unlike detection_utils.transform_proposals).  Replaces dataset_dict["proposals"] in place."""
+    step, unlike detection_utils.transform_proposals).  Replaces dataset_dict["proposals"] in place.
+    pin_memory (an addition): page-lock the results, so that the model's H2D copies of them are truly asynchronous
+    (a pageable cudaMemcpyAsync first drains the stream: the host would wait for the previous view to finish)."""
     prop = dataset_dict["proposals"]
     boxes = prop.proposal_boxes.tensor.cpu().numpy()
     boxes = transforms.apply_box(boxes)
@@ -241,9 +243,14 @@ def transform_proposals(dataset_dict, image_shape, transforms, *, proposal_topk,
     keep = boxes.nonempty(threshold=min_box_size)
     boxes = boxes[keep]
     objectness_logits = objectness_logits[keep.to(objectness_logits.device)]
+    boxes, objectness_logits = boxes[:proposal_topk], objectness_logits[:proposal_topk]
+    if pin_memory:
+        boxes = type(boxes)(boxes.tensor.contiguous().pin_memory())
+        if not objectness_logits.is_cuda:
+            objectness_logits = objectness_logits.contiguous().pin_memory()
     proposals = type(prop)(tuple(image_shape))
-    proposals.proposal_boxes = boxes[:proposal_topk]
-    proposals.objectness_logits = objectness_logits[:proposal_topk]
+    proposals.proposal_boxes = boxes
+    proposals.objectness_logits = objectness_logits
     dataset_dict["proposals"] = proposals
 
 
@@ -286,7 +293,7 @@ class DatasetMapperTTAAVG:
                 dic["image"] = resize_u8(image, new_shape[0], new_shape[1], flip=do_flip, out_dtype=self.image_dtype)
                 if self.proposal_topk is not None:
                     dic["proposals"] = dataset_dict["proposals"]
-                    transform_proposals(dic, new_shape, tfms, proposal_topk=self.proposal_topk)
+                    transform_proposals(dic, new_shape, tfms, proposal_topk=self.proposal_topk, pin_memory=self.device.type == "cuda")
                 ret.append(dic)
         return ret
 

@@ -323,17 +323,21 @@ int drn_tta_accumulate(const void* all_boxes, const void* all_scores, int R, int
                        const int* op_kind, const float* op_a, const float* op_b, void* acc_boxes, void* acc_scores,
                        int view_index, int n_views, drn_stream_t stream);
 
-/* ---- "fp32_tc" precision: fp32-accurate layers on the bf16 tensor cores ----
- * drn_split_bf16_terms: v = relu?(x + residual?) (fp32, [rows][C]); y_f32 = v (optional); planes[r][p*C + c] = term
- * term_idx[p] of v[r][c], where term 0 = bf16(v), term 1 = bf16(v - term0), term 2 = bf16(v - term0 - term1) (the
- * three-way bf16 split of an fp32 value, exact).  With the weights split the same way and laid out plane by plane
- * along K, drn_conv_igemm_bf16_tc over the P*C "channels" computes sum_p x_XI[p] * w_WI[p] with fp32 accumulation:
- * P = 6 (x1w1, x1w2, x2w1, x1w3, x2w2, x3w1) reproduces an fp32 conv / linear layer of WSL/backbone/*.py and
- * roi_heads/box_head.py:82-91 to ~2^-24 per product; P = 3 (x1w1, x1w2, x2w1) to ~2^-16.
- * term_idx: HOST array of n_terms <= DRN_SPLIT_MAX_TERMS entries in {0, 1, 2}; C % 4 == 0. */
-#define DRN_SPLIT_MAX_TERMS 6
-int drn_split_bf16_terms(const float* x, const float* residual, int relu, int64_t rows, int C, int n_terms,
-                         const int* term_idx, float* y_f32, void* planes_bf16, drn_stream_t stream);
+/* ---- "fp32_tc" precision: fp32-accurate conv / linear layers on the bf16 tensor cores (csrc/drn_split.cu) ----
+ * An fp32 value is the exact sum of three bf16 terms x1 + x2 + x3; sum_k x[k] w[k] is recovered to ~2^-24 from the six
+ * leading bf16 x bf16 products.  tcgen05.mma truncates when it adds a K = 16 slice into its fp32 accumulator (measured
+ * bias ~2^-25 per step, profiles/r1_fp32_tc_accumulator_truncation_v1.txt), so a layer of WSL/backbone/*.py or
+ * roi_heads/box_head.py:82-91 runs as: ONE drn_conv_igemm_bf16_tc over the five correction products ("small" operand,
+ * accumulator ~2^-8 of the result) + one drn_conv_igemm_bf16_tc per K-GROUP of the leading product x1 w1 ("big"
+ * operand, <= ~64 MMA steps per accumulator), all with fp32 output, summed by drn_f32tc_reduce with round-to-nearest.
+ *
+ * drn_f32tc_split: x fp32 [rows][C] -> big bf16 [C / Cg][rows][Cg] (term x1, one dense matrix per K-group of Cg
+ * channels) and small bf16 [rows][5 C] (planes x1 | x2 | x1 | x2 | x3, to meet weight planes w2 | w1 | w3 | w2 | w1).
+ * drn_f32tc_reduce: y[r][c] = relu?(sum_{i < n_in} partials[i * part_stride + r * ld + c] + bias[c] + residual[r][c]),
+ * fp32 adds in that order (bias / residual may be NULL).  C % 4 == 0. */
+int drn_f32tc_split(const float* x, int64_t rows, int C, int Cg, void* big_bf16, void* small_bf16, drn_stream_t stream);
+int drn_f32tc_reduce(const float* partials, int n_in, int64_t part_stride, int ld, const float* bias,
+                     const float* residual, int relu, int64_t rows, int C, float* y, drn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -496,47 +496,84 @@ def test_bf16_transpose_fast_path_matches_torch(R, C, c49, ld):
 
 
 # ---------------------------------------------------------------- "fp32_tc": split-bf16 operands (csrc/drn_split.cu)
-@pytest.mark.parametrize("rows,C", [(1, 4), (37, 64), (1000, 512), (5, 25088)])
-def test_split_bf16_terms_exact(rows, C):
-    """The three bf16 terms sum back to the fp32 value EXACTLY; shortcut add + ReLU match torch bit for bit; plane p holds
-    term XI[p]."""
+@pytest.mark.parametrize("rows,C,Cg", [(1, 64, 64), (37, 128, 64), (1000, 512, 512), (5, 25088, 512)])
+def test_f32tc_split_exact(rows, C, Cg):
+    """The three bf16 terms sum back to the fp32 value EXACTLY; the big operand is term 1 regrouped [C/Cg][rows][Cg]; the
+    small operand holds the planes x1 | x2 | x1 | x2 | x3."""
     g = torch.Generator().manual_seed(rows + C)
     x = (torch.randn(rows, C, generator=g) * torch.exp(torch.randn(rows, C, generator=g) * 3)).to(DEV)
-    res = torch.randn(rows, C, generator=g).to(DEV)
-    for terms in ((0, 0, 1, 0, 1, 2), (0, 0, 1)):
-        for use_res, relu in ((False, False), (True, True), (True, False), (False, True)):
-            y, planes = ops.split_bf16_terms(x, terms, residual=res if use_res else None, relu=relu, write_f32=True)
-            want = x + res if use_res else x
-            want = torch.relu(want) if relu else want
-            assert torch.equal(y, want)
-            pl = planes.view(rows, len(terms), C).float()
-            t0, t1 = pl[:, 0], pl[:, 2]  # XI = (0, 0, 1, ...): planes 0 and 1 hold term 0, plane 2 term 1
-            assert torch.equal(pl[:, 0], pl[:, 1])
-            assert torch.equal(t0, want.to(torch.bfloat16).float())
-            assert torch.equal(t1, (want - t0).to(torch.bfloat16).float())
-            if len(terms) == 6:
-                assert torch.equal(pl[:, 3], t0) and torch.equal(pl[:, 4], t1)
-                assert torch.equal((t0.double() + t1.double() + pl[:, 5].double()).float(), want)  # exact three-way split
+    big, small = ops.f32tc_split(x, Cg)
+    t0 = x.to(torch.bfloat16).float()
+    t1 = (x - t0).to(torch.bfloat16).float()
+    t2 = (x - t0 - t1).to(torch.bfloat16).float()
+    assert torch.equal((t0.double() + t1.double() + t2.double()).float(), x)  # the split itself is exact
+    assert big.shape == (C // Cg, rows, Cg) and small.shape == (rows, 5 * C)
+    assert torch.equal(big.float().permute(1, 0, 2).reshape(rows, C), t0)
+    pl = small.float().view(rows, 5, C)
+    for p, t in enumerate((t0, t1, t0, t1, t2)):
+        assert torch.equal(pl[:, p], t), p
 
 
-@pytest.mark.parametrize("M,K,N,nterms", [(300, 512, 128, 6), (300, 512, 128, 3), (2000, 4096, 256, 6), (129, 25088, 64, 6)])
-def test_fp32_tc_linear_accuracy(M, K, N, nterms, monkeypatch):
-    """A linear layer through the split-bf16 GEMM versus float64: 6 planes are as accurate as an fp32 GEMM (error
-    relative to sum_k |x_k w_k| below 1e-6), 3 planes below 3e-5."""
+@pytest.mark.parametrize("n,rows,C", [(1, 3, 8), (5, 1000, 64), (50, 129, 4096)])
+def test_f32tc_reduce_matches_torch(n, rows, C):
+    g = torch.Generator().manual_seed(n + rows)
+    parts = torch.randn(n, rows, C, generator=g).to(DEV)
+    bias, res = torch.randn(C, generator=g).to(DEV), torch.randn(rows, C, generator=g).to(DEV)
+    want = parts[0].clone()
+    for k in range(1, n):
+        want = want + parts[k]  # same order, round-to-nearest
+    assert torch.equal(ops.f32tc_reduce(parts), want)
+    assert torch.equal(ops.f32tc_reduce(parts, bias, res, relu=True), torch.relu(want + bias + res))
+    assert torch.equal(ops.f32tc_reduce(parts, bias, None, relu=False), want + bias)
+
+
+@pytest.mark.parametrize("M,K,N", [(300, 512, 128), (2000, 4096, 256), (129, 25088, 64)])
+def test_fp32_tc_linear_accuracy(M, K, N):
+    """A linear layer through the split-bf16 GEMMs versus float64: error relative to sum_k |x_k w_k| below 1e-6 and, on
+    all-positive operands (where the tensor core's truncating accumulator would show as a bias of (K/16) 2^-25 if the
+    leading product ran as ONE chain), a mean signed error below 2e-6."""
     from drn_wsod_pytorch_b200 import modeling
 
-    monkeypatch.setenv("DRN_B200_SPLIT_TERMS", str(nterms))
     g = torch.Generator().manual_seed(M + K)
-    x = torch.randn(M, K, generator=g)
-    w = torch.randn(N, K, generator=g) / K ** 0.5
-    b = torch.randn(N, generator=g)
-    packed = modeling.pack_linear([w.to(DEV)], [b.to(DEV)], "fp32_tc")
-    y = modeling.run_linear(x.to(DEV), packed, "fp32_tc", relu=False).cpu().double()
-    ref = x.double() @ w.double().t() + b.double()
-    scale = x.double().abs() @ w.double().abs().t() + b.double().abs()
-    err = ((y - ref).abs() / scale).max().item()
-    assert err < (1e-6 if nterms == 6 else 3e-5), err
-    # plain bf16 on the same layer is ~3 orders of magnitude further away
-    pb = modeling.pack_linear([w.to(DEV)], [b.to(DEV)], "bf16")
-    yb = modeling.run_linear(x.to(DEV).to(torch.bfloat16), pb, "bf16", relu=False, out_dtype=torch.float32).cpu().double()
-    assert ((yb - ref).abs() / scale).max().item() > 30 * err
+    for positive in (False, True):
+        x = torch.randn(M, K, generator=g)
+        w = torch.randn(N, K, generator=g) / K ** 0.5
+        b = torch.randn(N, generator=g)
+        if positive:
+            x, w, b = x.abs(), w.abs(), b.abs()
+        packed = modeling.pack_linear([w.to(DEV)], [b.to(DEV)], "fp32_tc")
+        y = modeling.run_linear(x.to(DEV), packed, "fp32_tc", relu=False).cpu().double()
+        ref = x.double() @ w.double().t() + b.double()
+        scale = x.double().abs() @ w.double().abs().t() + b.double().abs()
+        err = ((y - ref).abs() / scale).max().item()
+        assert err < 1e-6, (positive, err)
+        if positive:
+            bias_rel = ((y - ref) / ref).mean().item()
+            assert abs(bias_rel) < 2e-6, bias_rel
+            # plain bf16 on the same layer is orders of magnitude further away
+            pb = modeling.pack_linear([w.to(DEV)], [b.to(DEV)], "bf16")
+            yb = modeling.run_linear(x.to(DEV).to(torch.bfloat16), pb, "bf16", relu=False, out_dtype=torch.float32).cpu().double()
+            assert ((yb - ref).abs() / scale).max().item() > 100 * err
+
+
+@pytest.mark.parametrize("cin,cout,dil,H,W,res", [(64, 64, 1, 40, 56, False), (128, 128, 1, 19, 31, True), (512, 512, 2, 20, 28, True)])
+def test_fp32_tc_conv3x3_accuracy(cin, cout, dil, H, W, res):
+    """3x3 conv (+ FrozenBN-style bias, shortcut, ReLU) through the split-bf16 GEMMs versus torch float64."""
+    from drn_wsod_pytorch_b200 import modeling
+
+    g = torch.Generator().manual_seed(cin + H)
+    conv = modeling.Conv2d(cin, cout, 3, dilation=dil, bias=True).to(DEV)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(cout, cin, 3, 3, generator=g) / (9 * cin) ** 0.5)
+        conv.bias.copy_(torch.randn(cout, generator=g))
+    x = torch.randn(1, cin, H, W, generator=g).abs()
+    r = torch.randn(1, cout, H, W, generator=g)
+    ref = F.conv2d(x.double(), conv.weight.detach().cpu().double(), conv.bias.detach().cpu().double(), padding=dil, dilation=dil)
+    mag = F.conv2d(x.double().abs(), conv.weight.detach().cpu().double().abs(), conv.bias.detach().cpu().double().abs(), padding=dil, dilation=dil)
+    if res:
+        ref, mag = ref + r.double(), mag + r.double().abs()
+    ref = torch.relu(ref)
+    y = modeling.run_conv(conv, x.permute(0, 2, 3, 1).contiguous().to(DEV), "fp32_tc", relu=True,
+                          residual=r.permute(0, 2, 3, 1).contiguous().to(DEV) if res else None)
+    err = ((y.permute(0, 3, 1, 2).cpu().double() - ref).abs() / mag).max().item()
+    assert err < 1e-6, err

@@ -274,7 +274,7 @@ def main():
 
     def wrap(fn):
         def inner(x, packed, ksize, dilation, relu, *a, **k):
-            if ksize == 1 and x.shape[-1] in (fc6_K, 3 * fc6_K, 6 * fc6_K) and record["on"]:  # 3x / 6x: fp32_tc term planes
+            if ksize == 1 and x.shape[-1] == fc6_K and record["on"]:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 out = fn(x, packed, ksize, dilation, relu, *a, **k)
@@ -285,6 +285,20 @@ def main():
         return inner
 
     ops.conv_bf16_tc, ops.conv_f32 = wrap(orig_tc), wrap(orig_f32)
+    from drn_wsod_pytorch_b200 import modeling as _modeling
+    orig_layer = _modeling._f32tc_layer
+
+    def layer_wrap(x, pk, ksize, dilation, relu, *a, **k):  # fp32_tc: fc6 = 1 + G GEMM launches + the reduction, timed together
+        if ksize == 1 and x.shape[-1] == fc6_K and record["on"]:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = orig_layer(x, pk, ksize, dilation, relu, *a, **k)
+            e1.record()
+            fc6_events.append((e0, e1))
+            return out
+        return orig_layer(x, pk, ksize, dilation, relu, *a, **k)
+
+    _modeling._f32tc_layer = layer_wrap
     # the roofline kernel is timed as ONE launch on its own (the default path runs it in row blocks that
     # overlap the ROI pooling of the next block on a second stream, which CUDA events cannot separate)
     overlap_default = model.roi_heads.overlap_pool
@@ -299,6 +313,7 @@ def main():
     sync_all()
     record["on"] = False
     ops.conv_bf16_tc, ops.conv_f32 = orig_tc, orig_f32
+    _modeling._f32tc_layer = orig_layer
     model.roi_heads.overlap_pool = overlap_default
     step(batched_dev)
     sync_all()
@@ -428,7 +443,7 @@ def main():
         "e2e": {"value": world * args.steps / t_e2e.item(), "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "fc6 GEMM (gemm_tc_kernel)" if precision == "bf16" else "fc6 GEMM (gemm_tc_kernel over split-bf16 term planes; fp32-equivalent FLOPs counted once)" if precision == "fp32_tc" else "fc6 GEMM (conv_igemm_f32_kernel, SIMT fp32)",
+        "roofline": {"bound": "tensor", "kernel": "fc6 GEMM (gemm_tc_kernel)" if precision == "bf16" else "fc6 layer (1 + G gemm_tc_kernel launches over split-bf16 operands + fp32 reduction; fp32-equivalent FLOPs counted once, 6x that many run on the tensor cores)" if precision == "fp32_tc" else "fc6 GEMM (conv_igemm_f32_kernel, SIMT fp32)",
                      "achieved": fc6_tflops, "peak": peak, "unit": "TFLOP/s", "frac": fc6_tflops / peak,
                      "peak_source": f"{peaks['src']} cuBLAS bf16 sustained (kernel timed inside a long step)",
                      "traffic": FC6_DRAM_BYTES.get(args.workload), "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of the fc6 launch, profiles/r1_ncu_step_v7_per_launch.txt (#62)" if args.workload in FC6_DRAM_BYTES else None,

@@ -71,12 +71,13 @@ F32_ACT = ("fp32", "fp32_tc")  # precisions whose activations (and pooled ROI fe
 def _kgroup(ksize, C):
     """K-group size (channels) of the leading-product GEMMs of the "fp32_tc" precision: every group accumulates
     ksize^2 * Cg / 16 MMA steps in its own accumulator (csrc/drn_split.cu) -- 64 channels for a 3x3 filter (36 steps),
-    ~512 for 1x1 / linear layers (32 steps), more only when that would need over 64 launches (fc6 of the R50 nets)."""
+    896..1024 for 1x1 / linear layers (<= 64 steps: a truncation bias <= 1.6e-6 per layer), more only when that would
+    need over 64 launches (fc6 of the R50 nets)."""
     if ksize == 3:
         return 64
-    if C <= 576:
+    if C <= 1024:
         return C
-    for m in range(8, C // 64 + 1):
+    for m in range(14, C // 64 + 1):
         if (C // 64) % m == 0 and C // (64 * m) <= 64:
             return 64 * m
     return C

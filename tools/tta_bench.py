@@ -34,6 +34,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--cpu-sample", action="store_true")
+    ap.add_argument("--per-view", action="store_true",
+                    help="also report, for one image: host enqueue time, GPU time per view (CUDA events around each model call), "
+                         "mapper GPU time -- tells host-bound gaps from slow kernels")
     ap.add_argument("--profile-step", action="store_true",
                     help="after warm-up run ONE image between cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`)")
     args = ap.parse_args()
@@ -82,6 +85,35 @@ def main():
             "warmup": max(args.warmup, 3), "dtype": precision,
             "config": {"workload": f"{cfg_name} {H}x{W} R={R} {precision}, MIN_SIZES {list(cfg.TEST.AUG.MIN_SIZES)} FLIP {cfg.TEST.AUG.FLIP}"},
             "h2d_bytes_per_image": image_u8.numel() + n_views * R * 20, "mem_gb": torch.cuda.max_memory_allocated() / 1e9}
+    if args.per_view:
+        orig_inf = model.inference
+        evs = []
+
+        def timed_inference(*a, **k):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            out = orig_inf(*a, **k)
+            a1.record()
+            evs.append((a0, a1))
+            return out
+
+        model.inference = timed_inference
+        torch.cuda.synchronize()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        b0.record()
+        with torch.no_grad():
+            aug, tfms = wrapper._get_augmented_inputs(dict(batched[0]))
+            t_map = time.perf_counter() - t0
+            mb, ms_, _ = wrapper._get_augmented_boxes(aug, tfms)
+            t_enq = time.perf_counter() - t0
+            wrapper._merge_detections(mb, ms_, None, (H, W))
+        b1.record()
+        torch.cuda.synchronize()
+        model.inference = orig_inf
+        line["per_view"] = {"host_mapper_ms": t_map * 1e3, "host_enqueue_all_views_ms": t_enq * 1e3, "gpu_total_ms": b0.elapsed_time(b1),
+                            "gpu_ms_per_view": [round(a.elapsed_time(b), 3) for a, b in evs],
+                            "gpu_ms_views_sum": sum(a.elapsed_time(b) for a, b in evs)}
     if args.cpu_sample:
         from oracle import tta_oracle as T
 

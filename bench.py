@@ -126,6 +126,54 @@ def cpu_reference_step(state, spec, inp, R_sample, threads):
     return est, {"backbone_s": tb, "roipool_s": tp, "fc_heads_s": th, "R_sample": R_sample}
 
 
+def _graph_ms(fn, reps=20):
+    """Average duration of `fn`'s kernels captured as one CUDA graph and replayed back to back (warm)."""
+    cur = torch.cuda.current_stream()
+    side = torch.cuda.Stream()
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        fn()
+        fn()
+    cur.wait_stream(side)
+    torch.cuda.synchronize()
+    from drn_wsod_pytorch_b200 import ops as _ops
+    _ops.drop_scratch(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        keep = fn()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    del keep
+    return e0.elapsed_time(e1) / reps
+
+
+def measure_parts(model, batched0, H, W, R, gmac, ops):
+    """Conv stack (whole backbone: first conv + every tcgen05 conv + max-pools) and ROIPool (tables + gather), each as
+    its own graph: ms, achieved TFLOP/s over the conv GMACs, achieved GB/s over the ROIPool's algorithmic bytes
+    (feature map once + rois + output)."""
+    with torch.no_grad():
+        img = batched0["image"].float().contiguous()
+        boxes = batched0["proposals"].proposal_boxes.tensor.float().contiguous()
+        obj = batched0["proposals"].objectness_logits.float().contiguous()
+        bb_ms = _graph_ms(lambda: model._features([img], (H, W)))
+        feats = model._features([img], (H, W))
+        fh = model.roi_heads._features_hwc(feats, 0)
+        scale = model.roi_heads.pooler_scale
+        rp_ms = _graph_ms(lambda: ops.roipool(fh, boxes, obj, scale))
+    h, w, C = fh.shape
+    e = fh.element_size()
+    rp_bytes = h * w * C * e + R * 20 + R * 49 * C * e
+    return {"conv_stack_ms": bb_ms, "conv_stack_gmac": gmac["conv"], "conv_stack_tflops": 2 * gmac["conv"] * 1e9 / (bb_ms * 1e-3) / 1e12,
+            "roipool_ms": rp_ms, "roipool_algorithmic_bytes": rp_bytes, "roipool_gbs": rp_bytes / (rp_ms * 1e-3) / 1e9,
+            "how": "each part captured as its own CUDA graph, 20 back-to-back replays (warm), CUDA events"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -425,6 +473,14 @@ def main():
         print("breakdown (ms, 1 step):", {n: round(sum(a.elapsed_time(b) for a, b in ev), 3) for n, ev in fams.items()},
               file=sys.stderr)
 
+    # ---- parts (rank 0, secondary numbers): the conv stack and the ROIPool as their own CUDA graphs, replayed back to back
+    # (warm), for the north_star's "fraction of the conv roofline" and the HBM-bound piece of SURVEY.md 8(d)
+    parts = None
+    if rank == 0 and precision == "bf16":
+        try:
+            parts = measure_parts(model, batched_dev[0], H, W, R, gmac, ops)
+        except Exception as e:  # never lose the bench line over a secondary measurement
+            parts = {"error": f"{type(e).__name__}: {e}"[:200]}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -451,6 +507,11 @@ def main():
                      "whole_step_tflops": total_tflops, "whole_step_frac": total_tflops / peak},
         "losses": dict(zip(loss_keys, [round(float(x), 6) for x in vec.tolist()])),
     }
+    if parts is not None:
+        if "conv_stack_ms" in parts:
+            parts["conv_stack_frac_of_bf16_peak"] = parts["conv_stack_tflops"] / peak
+            parts["roipool_frac_of_hbm_peak"] = parts["roipool_gbs"] / peaks["hbm_gbs"]
+        out["parts"] = parts
     if train_mode:
         out["config"]["mode"] = "train: backward of fc6/fc7/heads (backbone frozen, FREEZE_AT 5) + fused SGD; gradients averaged over ranks"
         out["grad_allreduce_bytes_per_step"] = sync.bytes // max(1, sync.steps)

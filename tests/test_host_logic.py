@@ -148,3 +148,25 @@ def test_synthetic_data_is_deterministic_and_well_formed():
     w1, w2 = synth.make_weights(shapes, 3), synth.make_weights(shapes, 3)
     assert all(torch.equal(w1[k], w2[k]) for k in w1)
     assert synth.load_calib("resnet_ws18_d2"), "data/calib.json missing"
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract's keys, produced
+    without a GPU.  Smallest workload, one bounded sample."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "r18_bf16",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "images/sec" and line["value"] > 0 and line["vs_baseline"] is None
+    assert line["gpu_launches"] == 0 and "workload" in line["config"] and "model" not in line["config"]
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
+    assert line["e2e"] == {"value": line["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -6,8 +6,8 @@ one threshold / NMS / top-k, host read of the detection count.  GPU box only.  P
 
     python tools/tta_bench.py [--workload r50_bf16] [--steps 5] [--warmup 3] [--cpu-sample]
 
---cpu-sample also times the oracle's Pillow-equivalent resample + proposal transforms of all 16 views on the host (the
-part of the reference's TTA mapper that runs on the CPU even when the model is on a GPU).
+--cpu-sample also times Pillow's 8 resizes (+ flips) of the same image on the host -- the part of the reference's TTA mapper
+that runs on the CPU even when the model is on a GPU.
 """
 import argparse
 import json
@@ -115,12 +115,6 @@ def main():
                             "gpu_ms_per_view": [round(a.elapsed_time(b), 3) for a, b in evs],
                             "gpu_ms_views_sum": sum(a.elapsed_time(b) for a, b in evs)}
     if args.cpu_sample:
-        from oracle import tta_oracle as T
-
-        t0 = time.perf_counter()
-        T.tta_views(image_u8, H, W, inp["boxes"], inp["objectness"], cfg.TEST.AUG.MIN_SIZES, cfg.TEST.AUG.MAX_SIZE, cfg.TEST.AUG.FLIP,
-                    cfg.DATASETS.PRECOMPUTED_PROPOSAL_TOPK_TEST)
-        line["cpu_mapper_ms_oracle_numpy"] = (time.perf_counter() - t0) * 1e3
         try:
             from PIL import Image
 

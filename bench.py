@@ -476,7 +476,7 @@ def main():
     # ---- parts (rank 0, secondary numbers): the conv stack and the ROIPool as their own CUDA graphs, replayed back to back
     # (warm), for the north_star's "fraction of the conv roofline" and the HBM-bound piece of SURVEY.md 8(d)
     parts = None
-    if rank == 0 and precision == "bf16":
+    if world == 1 and precision == "bf16":  # single-GPU runs only: nothing extra between the ranks' teardown at N > 1
         try:
             parts = measure_parts(model, batched_dev[0], H, W, R, gmac, ops)
         except Exception as e:  # never lose the bench line over a secondary measurement

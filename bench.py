@@ -26,6 +26,7 @@ WORKLOADS = {
     "r18_fp32_tc": ("oicr_WSR_18_DC5_1x", 600, 1000, 2000, "fp32_tc", dict(conv=118.0, fc6=205.5, fc7=33.6, heads=0.85)),
     "r18_bf16": ("oicr_WSR_18_DC5_1x", 600, 1000, 2000, "bf16", dict(conv=118.0, fc6=205.5, fc7=33.6, heads=0.85)),
     "r50_bf16": ("oicr_WSR_50_DC5_1x", 600, 1000, 4000, "bf16", dict(conv=232.7, fc6=822.1, fc7=33.6, heads=1.7)),
+    "r50_fp32_tc": ("oicr_WSR_50_DC5_1x", 600, 1000, 4000, "fp32_tc", dict(conv=232.7, fc6=822.1, fc7=33.6, heads=1.7)),
     "r50_fp32": ("oicr_WSR_50_DC5_1x", 600, 1000, 4000, "fp32", dict(conv=232.7, fc6=822.1, fc7=33.6, heads=1.7)),
     "v16_bf16": ("oicr_V_16_DC5_1x", 600, 1000, 2000, "bf16", dict(conv=231.9, fc6=205.5, fc7=33.6, heads=0.85)),
     "r101_coco_bf16": ("oicr_WSR_101_DC5_1x_coco", 800, 1333, 4000, "bf16", dict(conv=723.5, fc6=822.1, fc7=33.6, heads=6.6)),

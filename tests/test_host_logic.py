@@ -170,3 +170,38 @@ def test_bench_reference_arm_prints_the_contract_line():
     cb = line["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
     assert line["e2e"] == {"value": line["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_fp32_tc_operand_packing_reconstructs_the_layer_on_cpu():
+    """Host logic of the "fp32_tc" precision (modeling._f32tc_pack / _kgroup), checked without a GPU: emulate the 1 + G
+    GEMMs in float64 from the packed bf16 operands -- the small planes x1|x2|x1|x2|x3 against w2|w1|w3|w2|w1 plus the
+    K-grouped leading product -- and compare with the fp32 layer (3x3 filter taps and a linear layer)."""
+    import torch
+    from drn_wsod_pytorch_b200 import modeling as M, ops
+
+    assert [M._kgroup(3, c) for c in (64, 128, 512)] == [64, 64, 64]
+    for c, want in ((64, 64), (512, 512), (1024, 1024), (2048, 1024), (4096, 1024), (25088, 896), (100352, 1792)):
+        cg = M._kgroup(1, c)
+        assert cg == want and c % cg == 0 and cg % 64 == 0 and c // cg <= 64, (c, cg)
+    g = torch.Generator().manual_seed(5)
+    for rows, taps, C, cout in ((7, 9, 128, 8), (5, 1, 2048, 16)):
+        w = torch.randn(cout, taps, C, generator=g)
+        b = torch.randn(cout, generator=g)
+        cg = M._kgroup(3 if taps == 9 else 1, C)
+        p = M._f32tc_pack(w, b, cg)
+        G = C // cg
+        assert p["groups"] == G and p["big"].shape == (G, cout, taps * cg) and p["small"].shape == (cout, taps * 5 * C)
+        assert p["big"].dtype == torch.bfloat16 and p["small"].dtype == torch.bfloat16
+        x = torch.randn(rows, taps, C, generator=g)  # im2col'd activation: [rows][tap][channel]
+        t = M._bf16_terms(x)
+        assert torch.equal((t[0].double() + t[1].double() + t[2].double()).float(), x)  # exact three-way split
+        small_x = torch.stack([t[0], t[1], t[0], t[1], t[2]], dim=2).reshape(rows, taps * 5 * C)  # what drn_f32tc_split writes
+        big_x = t[0].view(rows, taps, G, cg).permute(2, 0, 1, 3).reshape(G, rows, taps * cg)
+        y = small_x.double() @ p["small"].double().t()
+        for k in range(G):
+            y = y + big_x[k].double() @ p["big"][k].double().t()
+        y = y + p["bias"].double()
+        ref = x.reshape(rows, -1).double() @ w.reshape(cout, -1).double().t() + b.double()
+        mag = x.reshape(rows, -1).double().abs() @ w.reshape(cout, -1).double().abs().t()
+        assert ((y - ref).abs() / mag).max().item() < 2e-7  # the nine dropped products are <= 2^-24 each
+    assert ops.F32TC_SMALL_W == (1, 0, 2, 1, 0)

@@ -187,6 +187,10 @@ def main():
                     help="forward: forward+loss (BASELINE.json's metric, default); train: forward+loss+backward of the trainable "
                          "tail+SGD step (+ gradient all-reduce at N>1) -- SURVEY.md §8f row 1; eval: inference forward + on-device "
                          "threshold/NMS/top-k (§8f row 2).  train / eval are extra lines, not the headline metric")
+    ap.add_argument("--library-baseline", action="store_true",
+                    help="N=1 only: also time the oracle port on torch's CUDA ops (cuDNN TF32 convolutions, cuBLAS fp32 GEMMs, "
+                         "torchvision roi_pool) -- what the reference's own code runs when MODEL.DEVICE is a GPU (SURVEY.md 8d); "
+                         "adds `library_baseline` to the JSON line")
     ap.add_argument("--breakdown", action="store_true", help="also print a per-kernel-family time breakdown to stderr")
     ap.add_argument("--profile-step", action="store_true",
                     help="after warm-up run ONE step between cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`; prints no bench line)")
@@ -528,9 +532,40 @@ def main():
         out["cpu_baseline"] = {"value": 1.0 / est, "unit": "images/sec", "cores": threads, "kind": "port",
                                "sample": f"full backbone on the {H}x{W} image + ROI stage on {R_sample} of {R} proposals, ROI-stage time "
                                          f"scaled x{R / R_sample:.0f} (linear in R); fp32 torch CPU ops, {threads} threads", "parts": parts}
+    if world == 1 and args.library_baseline:
+        try:
+            out["library_baseline"] = library_baseline(cfg, model, helpers, synth, H, W, R, dev)
+        except Exception as e:
+            out["library_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def library_baseline(cfg, model, helpers, synth, H, W, R, dev, reps=5):
+    """The baseline leg on the GPU: the oracle's restatement of the reference forward+loss (dropout off) executed by
+    torch's own CUDA kernels in fp32, as the reference does on a GPU (no AMP in detectron2 v0.2; cuDNN may use TF32
+    for the convolutions, matmuls stay fp32).  Baseline only -- never part of the product path."""
+    from oracle import wsl_oracle as O
+
+    state = {k: v.to(dev) for k, v in helpers.case_weights(cfg, model).items()}
+    spec = O.spec_from_cfg(cfg)
+    inp = synth.make_inputs(H, W, R, seed=0)
+    b = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in inp.items()}
+    with torch.device(dev), torch.no_grad():
+        for _ in range(2):
+            O.forward_train([b], state, spec)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            losses, _ = O.forward_train([b], state, spec)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {"value": 1e3 / ms, "unit": "images/sec", "ms_per_step": ms, "kind": "oracle port on torch CUDA ops (cuDNN / cuBLAS / torchvision roi_pool), fp32, dropout off",
+            "cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32), "matmul_allow_tf32": bool(torch.backends.cuda.matmul.allow_tf32),
+            "losses": {k: round(float(v), 6) for k, v in losses.items()}}
 
 
 if __name__ == "__main__":

@@ -187,9 +187,10 @@ def main():
                     help="forward: forward+loss (BASELINE.json's metric, default); train: forward+loss+backward of the trainable "
                          "tail+SGD step (+ gradient all-reduce at N>1) -- SURVEY.md §8f row 1; eval: inference forward + on-device "
                          "threshold/NMS/top-k (§8f row 2).  train / eval are extra lines, not the headline metric")
-    ap.add_argument("--library-baseline", action="store_true",
+    ap.add_argument("--library-baseline", nargs="?", const="fp32", default=None, choices=["fp32", "bf16"],
                     help="N=1 only: also time the oracle port on torch's CUDA ops (cuDNN TF32 convolutions, cuBLAS fp32 GEMMs, "
                          "torchvision roi_pool) -- what the reference's own code runs when MODEL.DEVICE is a GPU (SURVEY.md 8d); "
+                         "bf16: the same under torch.autocast(bfloat16), the closest library-only equivalent of this tree's bf16 mode; "
                          "adds `library_baseline` to the JSON line")
     ap.add_argument("--breakdown", action="store_true", help="also print a per-kernel-family time breakdown to stderr")
     ap.add_argument("--profile-step", action="store_true",
@@ -534,7 +535,7 @@ def main():
                                          f"scaled x{R / R_sample:.0f} (linear in R); fp32 torch CPU ops, {threads} threads", "parts": parts}
     if world == 1 and args.library_baseline:
         try:
-            out["library_baseline"] = library_baseline(cfg, model, helpers, synth, H, W, R, dev)
+            out["library_baseline"] = library_baseline(cfg, model, helpers, synth, H, W, R, dev, autocast=args.library_baseline == "bf16")
         except Exception as e:
             out["library_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     print(json.dumps(out))
@@ -542,7 +543,7 @@ def main():
         dist.destroy_process_group()
 
 
-def library_baseline(cfg, model, helpers, synth, H, W, R, dev, reps=5):
+def library_baseline(cfg, model, helpers, synth, H, W, R, dev, reps=5, autocast=False):
     """The baseline leg on the GPU: the oracle's restatement of the reference forward+loss (dropout off) executed by
     torch's own CUDA kernels in fp32, as the reference does on a GPU (no AMP in detectron2 v0.2; cuDNN may use TF32
     for the convolutions, matmuls stay fp32).  Baseline only -- never part of the product path."""
@@ -552,7 +553,7 @@ def library_baseline(cfg, model, helpers, synth, H, W, R, dev, reps=5):
     spec = O.spec_from_cfg(cfg)
     inp = synth.make_inputs(H, W, R, seed=0)
     b = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in inp.items()}
-    with torch.device(dev), torch.no_grad():
+    with torch.device(dev), torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
         for _ in range(2):
             O.forward_train([b], state, spec)
         torch.cuda.synchronize()
@@ -563,7 +564,7 @@ def library_baseline(cfg, model, helpers, synth, H, W, R, dev, reps=5):
         e1.record()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    return {"value": 1e3 / ms, "unit": "images/sec", "ms_per_step": ms, "kind": "oracle port on torch CUDA ops (cuDNN / cuBLAS / torchvision roi_pool), fp32, dropout off",
+    return {"value": 1e3 / ms, "unit": "images/sec", "ms_per_step": ms, "kind": "oracle port on torch CUDA ops (cuDNN / cuBLAS / torchvision roi_pool), " + ("bf16 autocast" if autocast else "fp32") + ", dropout off",
             "cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32), "matmul_allow_tf32": bool(torch.backends.cuda.matmul.allow_tf32),
             "losses": {k: round(float(v), 6) for k, v in losses.items()}}
 

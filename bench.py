@@ -553,7 +553,23 @@ def library_baseline(cfg, model, helpers, synth, H, W, R, dev, reps=5, autocast=
     spec = O.spec_from_cfg(cfg)
     inp = synth.make_inputs(H, W, R, seed=0)
     b = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in inp.items()}
-    with torch.device(dev), torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+    orig_features = O.forward_features
+    if autocast:  # backbone -> ROIPool -> fc6/fc7 under bf16 autocast; heads and losses stay fp32 (BCE refuses autocast)
+        def features(*a, **k):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                t = orig_features(*a, **k)
+            t["feat"] = t["feat"].float()
+            return t
+
+        O.forward_features = features
+    try:
+        return _library_baseline_run(O, b, state, spec, dev, reps, autocast)
+    finally:
+        O.forward_features = orig_features
+
+
+def _library_baseline_run(O, b, state, spec, dev, reps, autocast):
+    with torch.device(dev), torch.no_grad():
         for _ in range(2):
             O.forward_train([b], state, spec)
         torch.cuda.synchronize()

@@ -14,7 +14,7 @@ import torch
 
 import helpers
 import drn_wsod_pytorch_b200 as drn
-from drn_wsod_pytorch_b200 import modeling, ops
+from drn_wsod_pytorch_b200 import modeling
 
 DEV = "cuda:0"
 

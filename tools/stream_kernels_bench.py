@@ -8,7 +8,6 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import numpy as np
 import torch
 
 from drn_wsod_pytorch_b200 import ops, tta

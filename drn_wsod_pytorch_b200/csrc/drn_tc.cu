@@ -703,27 +703,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         gchunk += mine;
       } else {
-        // ---------------------------------------------------------- fp32 output, direct stores (head logits)
+        // ---------------------------------------------------------- fp32 output (head logits, fp32_tc partials)
+        // Each 32 x 32 block goes through this warp's staging slot (unused on this path: no TMA stores) so that one store
+        // instruction writes 4 rows x 128 contiguous bytes; the first version stored 32 rows x 16 B per instruction.
+        const uint32_t stage_s = smem_u32(my_bufs);
+        const int q4 = lane & 7, rsub = lane >> 3;
+        long long mrow[8];  // global row of staging row rr = 4 i + rsub (owned by lane rr), -1 when out of range
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + rsub;
+          const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)(m_global & 0xffffffffll), rr);
+          const unsigned hi = __shfl_sync(0xffffffffu, (unsigned)((unsigned long long)m_global >> 32), rr);
+          const int ok = __shfl_sync(0xffffffffu, (int)row_ok, rr);
+          mrow[i] = ok ? (long long)(((unsigned long long)hi << 32) | lo) : -1ll;
+        }
 #pragma unroll 1
         for (int c = 32 * half; c < BN; c += 32 * ESPLIT) {
           uint32_t v[32];
           tmem_ld32_nowait(taddr + c, v);
           tmem_ld_wait();
           const int n0 = nt * BN + c;
-          if (row_ok && n0 < p.N) {
+          if (n0 < p.N) {  // warp-uniform
             const int nvalid = min(32, p.N - n0);  // multiple of 8 (host checks N % 8 == 0)
-            float* op = reinterpret_cast<float*>(p.out) + m_global * p.ldo + n0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (j < nvalid) {
-                float4 o;
-                o.x = fmaf(__uint_as_float(v[j + 0]), s_scale[c + j + 0], s_bias[c + j + 0]);
-                o.y = fmaf(__uint_as_float(v[j + 1]), s_scale[c + j + 1], s_bias[c + j + 1]);
-                o.z = fmaf(__uint_as_float(v[j + 2]), s_scale[c + j + 2], s_bias[c + j + 2]);
-                o.w = fmaf(__uint_as_float(v[j + 3]), s_scale[c + j + 3], s_bias[c + j + 3]);
-                if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                *reinterpret_cast<float4*>(op + j) = o;
+            for (int j = 0; j < 32; j += 4) {
+              float4 o;
+              o.x = fmaf(__uint_as_float(v[j + 0]), s_scale[c + j + 0], s_bias[c + j + 0]);
+              o.y = fmaf(__uint_as_float(v[j + 1]), s_scale[c + j + 1], s_bias[c + j + 1]);
+              o.z = fmaf(__uint_as_float(v[j + 2]), s_scale[c + j + 2], s_bias[c + j + 2]);
+              o.w = fmaf(__uint_as_float(v[j + 3]), s_scale[c + j + 3], s_bias[c + j + 3]);
+              if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              sts128(stage_s + lane * 128 + ((((uint32_t)j >> 2) ^ sw_xor) << 4), __float_as_uint(o.x), __float_as_uint(o.y),
+                     __float_as_uint(o.z), __float_as_uint(o.w));
+            }
+            __syncwarp();
+            if (4 * q4 < nvalid) {
+              float* ocol = reinterpret_cast<float*>(p.out) + n0 + 4 * q4;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (mrow[i] >= 0) {
+                  const int rr = 4 * i + rsub;
+                  const float4 val = lds128f(stage_s + rr * 128 + (((uint32_t)q4 ^ (uint32_t)(rr & 7)) << 4));
+                  *reinterpret_cast<float4*>(ocol + mrow[i] * p.ldo) = val;
+                }
               }
+            }
+            __syncwarp();  // the slot is rewritten by the next column block
           }
         }
       }

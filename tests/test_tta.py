@@ -250,3 +250,91 @@ def test_gpu_tta_batched_views_and_skipped_detections_agree():
     r_b, sc_b, bx_b = model.inference([view], do_postprocess=False, with_detections=False)
     assert r_b == [None] and len(r_a[0]) > 0
     assert torch.equal(sc_a[0], sc_b[0]) and torch.equal(bx_a[0], bx_b[0])
+
+
+# ------------------------------------------------------------------ wrapper orchestration on the CPU (kernels emulated)
+def _emulate_device_kernels(monkeypatch, state, spec):
+    """Replace the three device entry points the wrapper reaches (resample, merge, detection tail) and the model's eval
+    pipeline by CPU emulations built from the oracle, so that the HOST logic of tta.py -- view streaming, batching, the
+    pairing of every view with its inverse transform parameters, the view count, the final call -- runs without a GPU."""
+    from drn_wsod_pytorch_b200 import ops
+
+    def resize_u8(img, nh, nw, flip=False, out_dtype=torch.uint8):
+        out = T.pil_resize_bilinear_u8(np.ascontiguousarray(img.permute(1, 2, 0).numpy()), nw, nh)
+        out = np.flip(out, axis=1) if flip else out
+        return torch.from_numpy(np.ascontiguousarray(out.transpose(2, 0, 1))).to(out_dtype)
+
+    def tta_accumulate(bx, sc, params, acc_b, acc_s, idx, n):
+        b = bx.numpy().reshape(-1, 4).copy()
+        for kind, a, c in params:  # the (kind, a, b) records drn_tta_accumulate receives
+            x0, y0, x1, y1 = b[:, 0].copy(), b[:, 1].copy(), b[:, 2].copy(), b[:, 3].copy()
+            if kind == ops.TTA_OP_RESIZE:
+                x0, x1, y0, y1 = x0 * np.float32(a), x1 * np.float32(a), y0 * np.float32(c), y1 * np.float32(c)
+            elif kind == ops.TTA_OP_HFLIP:
+                x0, x1 = np.float32(a) - x0, np.float32(a) - x1
+            b = np.stack([np.minimum(x0, x1), np.minimum(y0, y1), np.maximum(x0, x1), np.maximum(y0, y1)], axis=1)
+        b = torch.from_numpy(b.reshape(bx.shape))
+        if idx == 0:
+            acc_b.copy_(b), acc_s.copy_(sc)
+        else:
+            acc_b.add_(b), acc_s.add_(sc)
+        if idx == n - 1:
+            acc_b.div_(n), acc_s.div_(n)
+
+    def tail(all_boxes, all_scores, image_shape, score_thresh, nms_thresh, topk, inst_cls, box_cls, dets=None):
+        boxes, scores, classes, rows = O.inference_single_image(all_boxes, all_scores, image_shape, spec)
+        res = inst_cls(image_shape)
+        res.pred_boxes, res.scores, res.pred_classes = box_cls(boxes), scores, classes
+        return res, rows
+
+    calls = []
+
+    def inference(batched, detected=None, do_postprocess=True, with_detections=True):
+        assert detected is None and not do_postprocess and not with_detections
+        calls.append(len(batched))
+        canvas = (max(b["image"].shape[1] for b in batched), max(b["image"].shape[2] for b in batched))
+        scs, bxs = [], []
+        for b in batched:
+            assert "transforms" not in b  # popped before the model sees the view
+            with torch.no_grad():
+                t = O.forward_eval_scores({"image": b["image"].float(), "boxes": b["proposals"].proposal_boxes.tensor,
+                                           "objectness": b["proposals"].objectness_logits}, state, spec, canvas)
+            scs.append(t["all_scores"][None]), bxs.append(t["all_boxes"][None])
+        return [None] * len(batched), scs, bxs
+
+    monkeypatch.setattr(tta, "resize_u8", resize_u8)
+    monkeypatch.setattr(ops, "tta_accumulate", tta_accumulate)
+    monkeypatch.setattr(tta, "fast_rcnn_inference_single_image", tail)
+    return inference, calls
+
+
+@pytest.mark.parametrize("batch_size", [1, 2, 4])
+def test_tta_wrapper_host_flow_matches_reference_golden(monkeypatch, batch_size):
+    name = "tta_r18_small"
+    g = helpers.load_golden(name)
+    cfg, state, inp, (min_sizes, max_size, flip, dataset_hw) = _tta_setup(name)
+    cfg.TEST.AUG.MIN_SIZES, cfg.TEST.AUG.MAX_SIZE, cfg.TEST.AUG.FLIP = list(min_sizes), max_size, flip
+    model = drn.build_model(cfg)
+    model.eval()
+    spec = O.spec_from_cfg(cfg)
+    inference, calls = _emulate_device_kernels(monkeypatch, state, spec)
+    monkeypatch.setattr(model, "inference", inference)
+    d = helpers.to_batched([inp], drn.Instances, drn.Boxes, device="cpu", train=False)[0]
+    d["image"] = inp["image_u8"]
+    wrapper = tta.GeneralizedRCNNWithTTAAVG(cfg, model, batch_size=batch_size)
+    # streamed path (what __call__ uses) and the reference's list API give the same merge
+    mean_boxes, mean_scores, _ = wrapper._get_augmented_boxes(*wrapper._get_augmented_inputs(dict(d)))
+    n_views = int(g["n_views"])
+    assert calls == [batch_size] * (n_views // batch_size) + ([n_views % batch_size] if n_views % batch_size else [])
+    np.testing.assert_allclose(mean_boxes.numpy(), _expand(g["mean_boxes"], mean_boxes.shape[1]), rtol=1e-6, atol=1e-4)
+    if batch_size == 1:  # larger batches pad the views of a chunk to a common canvas, as the reference would with batch_size > 1
+        assert helpers.rel_err(mean_scores.numpy(), g["mean_scores"], floor=1e-9) < 1e-3
+    del calls[:]
+    res = wrapper([dict(d)])[0]["instances"]
+    assert sum(calls) == n_views
+    assert res.image_size == (inp["height"], inp["width"])
+    if batch_size == 1:
+        np.testing.assert_array_equal(res.pred_classes.numpy(), g["det_classes"])
+        np.testing.assert_allclose(res.pred_boxes.tensor.numpy(), g["det_boxes"], rtol=1e-6, atol=1e-4)
+        assert helpers.rel_err(res.scores.numpy(), g["det_scores"], floor=1e-9) < 1e-3
+    assert "transforms" not in d and d["image"] is inp["image_u8"]  # the caller's dict is left alone

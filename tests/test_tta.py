@@ -338,3 +338,21 @@ def test_tta_wrapper_host_flow_matches_reference_golden(monkeypatch, batch_size)
         np.testing.assert_allclose(res.pred_boxes.tensor.numpy(), g["det_boxes"], rtol=1e-6, atol=1e-4)
         assert helpers.rel_err(res.scores.numpy(), g["det_scores"], floor=1e-9) < 1e-3
     assert "transforms" not in d and d["image"] is inp["image_u8"]  # the caller's dict is left alone
+
+
+def test_resample_restatement_random_sizes_vs_pillow():
+    """60 seeded random size pairs (1..90 px, up- and down-scaling by up to ~20x, single rows / columns): the oracle's
+    resampler and the product's coefficient tables against Pillow itself."""
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.Generator(np.random.PCG64(2024))
+    for _ in range(60):
+        H, W, nh, nw = (int(v) for v in rng.integers(1, 91, 4))
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        ref = np.asarray(Image.fromarray(img).resize((nw, nh), Image.BILINEAR))
+        np.testing.assert_array_equal(T.pil_resize_bilinear_u8(img, nw, nh), ref, err_msg=f"{H}x{W} -> {nh}x{nw}")
+        for a, b in ((W, nw), (H, nh)):
+            b0, k0 = T.pil_bilinear_coeffs(a, b)
+            b1, k1 = tta.resample_tables(a, b)
+            np.testing.assert_array_equal(b0, b1)
+            np.testing.assert_array_equal(k0, k1)
+            assert (b1[:, 0] >= 0).all() and (b1[:, 0] + b1[:, 1] <= a).all() and (b1[:, 1] >= 1).all()

@@ -33,9 +33,13 @@ WORKLOADS = {
 }
 DEFAULT_WORKLOAD = os.environ.get("DRN_BENCH_WORKLOAD", "r50_bf16")  # BASELINE.json configs[2]: the 4k-proposal metric
 METRIC = "images/sec (4k proposals/img) WSOD forward+loss"
-# DRAM bytes of ONE fc6 launch from the ncu capture of a whole step (read 2587.9 MB + write 15.8 MB; algorithmic operand
-# bytes 1.21 GB: the A operand is streamed once per wave of N tiles)
-FC6_DRAM_BYTES = {"r50_bf16": 2587.9e6 + 15.8e6}
+# the reference's own YAML (relative to projects/WSL/configs) of each builtin config, for the reference arm
+REF_YAML = {"oicr_WSR_18_DC5_1x": "PascalVOC-Detection/oicr_WSR_18_DC5_1x.yaml", "oicr_WSR_50_DC5_1x": "PascalVOC-Detection/oicr_WSR_50_DC5_1x.yaml",
+            "oicr_V_16_DC5_1x": "PascalVOC-Detection/oicr_V_16_DC5_1x.yaml", "oicr_WSR_101_DC5_1x_coco": "COCO-Detection/oicr_WSR_101_DC5_1x.yaml"}
+BASELINE_CONFIG_INDEX = {"r18_fp32": 1, "r18_fp32_tc": 1, "r50_bf16": 2, "v16_bf16": 3, "r101_coco_bf16": 4}
+# DRAM bytes of ONE launch of the roofline kernel: read from the ncu capture of the CURRENT tree that tools/ncu_traffic.py
+# summarises into profiles/ (never a literal here); null when no capture of this workload is committed
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r2_fc6_traffic.json")
 # kernels launched per C-ABI call (for the gpu_launches claim)
 LAUNCHES = {"drn_wsddn_mil_fwd": 3, "drn_wsddn_mil_pgt_fwd": 2, "drn_label_proposals": 2, "drn_roipool_fwd": 2}  # (memset counted as a launch)
 
@@ -91,40 +95,92 @@ class ClockSampler:
 
 
 def make_batched(inp, device, drn, pinned=False):
+    """device given: image / proposals / objectness / GT boxes resident in HBM; the (two) GT class ids stay a host tensor, as a
+    dataloader hands them over -- their count sizes kernel launches, so device-resident class ids cost a D2H sync per step."""
     H, W = inp["height"], inp["width"]
     t = {k: (v.pin_memory() if pinned and torch.is_tensor(v) else v) for k, v in inp.items()}
     if device is not None:
-        t = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in t.items()}
+        t = {k: (v.to(device) if torch.is_tensor(v) and k != "gt_classes" else v) for k, v in t.items()}
     p = drn.Instances((H, W), proposal_boxes=drn.Boxes(t["boxes"]), objectness_logits=t["objectness"])
     g = drn.Instances((H, W), gt_boxes=drn.Boxes(t["gt_boxes"]), gt_classes=t["gt_classes"])
     return [{"image": t["image"], "proposals": p, "instances": g, "height": H, "width": W}]
 
 
-def cpu_reference_step(state, spec, inp, R_sample, threads):
-    """One bounded sample of the reference CPU path (oracle port): full backbone on the full image,
-    ROI stage on the first R_sample proposals; per-image time extrapolated linearly in R for the
-    ROI stage (ROIPool + fc6/fc7 + heads are linear in R).  Returns (est. seconds per full image, parts)."""
-    from oracle import wsl_oracle as O
+def _roofline_traffic(workload):
+    if not os.path.exists(TRAFFIC_FILE):
+        return None, None
+    with open(TRAFFIC_FILE) as f:
+        t = json.load(f)
+    e = t.get(workload)
+    if not e:
+        return None, None
+    return e["dram_bytes_per_launch"], e.get("source")
 
-    torch.set_num_threads(threads)
-    R = inp["boxes"].shape[0]
-    with torch.no_grad():
+
+class CpuReference:
+    """The reference's CPU implementation of the path, timed on this box's host cores with every thread torch can use,
+    on the FULL workload (whole image, all R proposals, every stage incl. pseudo-GT mining / labelling / weighted CE) --
+    no sampling, no extrapolation.
+    kind "reference": the UNMODIFIED reference model (projects/WSL GeneralizedRCNNWSL built by the reference's own
+    build_model from its own YAML, imported under oracle/refstub.py's stub layer), `model(inputs)` in train mode inside an
+    EventStorage -- used whenever /root/reference exists (this container).
+    kind "port": oracle/wsl_oracle.forward_train, the restatement pinned to the reference's goldens -- the GPU box has no
+    /root/reference.  Both run dropout-free (box_head.eval()), fp32, torch CPU ops + torchvision roi_pool."""
+
+    def __init__(self, cfg_name, cfg, H, W, R, threads, num_classes):
+        from drn_wsod_pytorch_b200 import synth
+        from oracle import refstub
+
+        torch.set_num_threads(threads)
+        self.threads = threads
+        self.inp = synth.make_inputs(H, W, R, seed=0, num_classes=num_classes)
+        self.kind = "reference" if (refstub.reference_available() and cfg_name in REF_YAML and
+                                    os.environ.get("DRN_BENCH_REFERENCE_KIND", "") != "port") else "port"
+        if self.kind == "reference":
+            _, self.model = refstub.build_reference_model(REF_YAML[cfg_name])
+            sd = self.model.state_dict()
+            w = dict(synth.calibrated_weights(cfg, {k: tuple(v.shape) for k, v in sd.items()}))
+            w["pixel_mean"], w["pixel_std"] = sd["pixel_mean"], sd["pixel_std"]
+            self.model.load_state_dict(w, strict=True)
+            self.model.train()
+            self.model.roi_heads.box_head.eval()
+            from detectron2.structures import Boxes, Instances
+
+            i = self.inp
+            p = Instances((H, W))
+            p.proposal_boxes, p.objectness_logits = Boxes(i["boxes"].clone()), i["objectness"].clone()
+            g = Instances((H, W))
+            g.gt_boxes, g.gt_classes = Boxes(i["gt_boxes"].clone()), i["gt_classes"].clone()
+            self.batched = [{"image": i["image"], "height": H, "width": W, "proposals": p, "instances": g}]
+        else:
+            from oracle import wsl_oracle as O
+
+            self.O, self.spec = O, O.spec_from_cfg(cfg)
+            self.state = None  # set_state(): the same calibrated weights the B200 model runs
+
+    def set_state(self, state):
+        self.state = dict(state)
+
+    def step(self):
+        """One full image; returns (seconds, losses)."""
         t0 = time.perf_counter()
-        x = O.preprocess_image(inp["image"], spec)
-        fmap = O.backbone_forward(x, state, spec)
-        t1 = time.perf_counter()
-        sub = dict(inp, boxes=inp["boxes"][:R_sample], objectness=inp["objectness"][:R_sample])
-        pooled = O.roi_pool(fmap, sub["boxes"], 1.0 / spec.stride) * (sub["objectness"] + 1).view(-1, 1, 1, 1)
-        t2 = time.perf_counter()
-        feat = O.dan_forward(pooled, state)
-        scores = O.wsddn_scores(feat, state)
-        for k in range(spec.refine_num):
-            pre = f"roi_heads.box_refinery_{k}."
-            torch.softmax(torch.nn.functional.linear(feat, state[pre + "cls_score.weight"], state[pre + "cls_score.bias"]), -1)
-        t3 = time.perf_counter()
-    tb, tp, th = t1 - t0, t2 - t1, t3 - t2
-    est = tb + (tp + th) * (R / R_sample)
-    return est, {"backbone_s": tb, "roipool_s": tp, "fc_heads_s": th, "R_sample": R_sample}
+        with torch.no_grad():
+            if self.kind == "reference":
+                from detectron2.utils.events import EventStorage
+
+                with EventStorage():
+                    losses = self.model(self.batched)
+            else:
+                losses, _ = self.O.forward_train([self.inp], self.state, self.spec)
+        dt = time.perf_counter() - t0
+        return dt, {k: round(float(v), 6) for k, v in losses.items()}
+
+    def describe(self, reps):
+        what = ("the unmodified reference model (refstub import), model(inputs) in EventStorage" if self.kind == "reference"
+                else "oracle/wsl_oracle.forward_train (restatement pinned to the reference's goldens; /root/reference is absent on this box)")
+        i = self.inp
+        return (f"{reps} full image(s): whole {i['height']}x{i['width']} image, all {i['boxes'].shape[0]} proposals, every stage, "
+                f"no extrapolation; {what}; fp32 torch {torch.__version__} CPU ops, {self.threads} threads, dropout off")
 
 
 def _graph_ms(fn, reps=20):
@@ -187,11 +243,11 @@ def main():
                     help="forward: forward+loss (BASELINE.json's metric, default); train: forward+loss+backward of the trainable "
                          "tail+SGD step (+ gradient all-reduce at N>1) -- SURVEY.md §8f row 1; eval: inference forward + on-device "
                          "threshold/NMS/top-k (§8f row 2).  train / eval are extra lines, not the headline metric")
-    ap.add_argument("--library-baseline", nargs="?", const="fp32", default=None, choices=["fp32", "bf16"],
-                    help="N=1 only: also time the oracle port on torch's CUDA ops (cuDNN TF32 convolutions, cuBLAS fp32 GEMMs, "
-                         "torchvision roi_pool) -- what the reference's own code runs when MODEL.DEVICE is a GPU (SURVEY.md 8d); "
-                         "bf16: the same under torch.autocast(bfloat16), the closest library-only equivalent of this tree's bf16 mode; "
-                         "adds `library_baseline` to the JSON line")
+    ap.add_argument("--library-baseline", nargs="?", const="both", default="both", choices=["both", "fp32", "bf16", "none"],
+                    help="N=1 only (default: both): also time the oracle port on torch's CUDA ops (cuDNN TF32 convolutions, cuBLAS "
+                         "fp32 GEMMs, torchvision roi_pool) -- what the reference's own code runs when MODEL.DEVICE is a GPU "
+                         "(SURVEY.md 8d, BASELINE.md 4.5); bf16: the same under torch.autocast(bfloat16), the closest library-only "
+                         "equivalent of this tree's bf16 mode; adds `library_baseline` {fp32, bf16} to the JSON line")
     ap.add_argument("--breakdown", action="store_true", help="also print a per-kernel-family time breakdown to stderr")
     ap.add_argument("--profile-step", action="store_true",
                     help="after warm-up run ONE step between cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`; prints no bench line)")
@@ -200,8 +256,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cfg_name, H, W, R, precision, gmac = WORKLOADS[args.workload]
-    config = {"workload": f"{cfg_name} {H}x{W} R={R} {precision} (BASELINE.json configs[{2 if 'r50' in args.workload else 1}])"
-              if args.workload in ("r50_bf16", "r18_fp32") else f"{cfg_name} {H}x{W} R={R} {precision}",
+    config = {"workload": f"{cfg_name} {H}x{W} R={R} {precision}" + (f" (BASELINE.json configs[{BASELINE_CONFIG_INDEX[args.workload]}])"
+                                                                      if args.workload in BASELINE_CONFIG_INDEX else ""),
               "images_per_gpu": 1, "proposals_per_image": R, "parallelism": f"dp{world}", "dropout": "on (train mode)",
               "launch": "one CUDA-graph replay per step (captured per input signature by the public forward)",
               "l2": "no flush: per-step working set (fc6 weights 411 MB + ROI features 0.2-0.8 GB) exceeds the 126 MB L2",
@@ -209,8 +265,6 @@ def main():
 
     import drn_wsod_pytorch_b200 as drn
     from drn_wsod_pytorch_b200 import synth
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import helpers
 
     cfg = drn.builtin_config(cfg_name, ["MODEL.DEVICE", "cpu" if args.impl == "reference" else f"cuda:{local_rank}",
                                         "B200.PRECISION", precision])
@@ -220,27 +274,25 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        from oracle import wsl_oracle as O
-
-        model = drn.build_model(cfg)  # parameter shapes only (CPU); arithmetic below is the oracle's
-        state = dict(helpers.case_weights(cfg, model))
-        spec = O.spec_from_cfg(cfg)
-        inp = synth.make_inputs(H, W, R, seed=0)
-        R_sample = min(R, 250)
-        for _ in range(min(args.warmup, 1)):
-            cpu_reference_step(state, spec, inp, min(R_sample, 50), threads)
-        ests = [cpu_reference_step(state, spec, inp, R_sample, threads) for _ in range(max(1, min(args.steps, 3)))]
-        est = sum(e for e, _ in ests) / len(ests)
+        ref = CpuReference(cfg_name, cfg, H, W, R, threads, cfg.MODEL.ROI_HEADS.NUM_CLASSES)
+        if ref.kind == "port":
+            ref.set_state(synth.calibrated_weights(cfg, drn.build_model(cfg)))  # parameter shapes only; arithmetic is the oracle's
+        nwarm, nsteps = min(args.warmup, 1), max(1, min(args.steps, 2))
+        for _ in range(nwarm):
+            ref.step()
+        times = []
+        for _ in range(nsteps):
+            dt, losses = ref.step()
+            times.append(dt)
+        est = sum(times) / len(times)
         val = 1.0 / est
-        sample = (f"full backbone on the {H}x{W} image + ROI stage on {R_sample} of {R} proposals, ROI-stage time "
-                  f"scaled x{R / R_sample:.0f} (linear in R); {len(ests)} reps; torch {torch.__version__} CPU ops")
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": "images/sec", "n_gpus": args.gpus,
-                          "steps": len(ests), "warmup": min(args.warmup, 1), "ms_per_step": est * 1e3, "higher_is_better": True,
+                          "steps": nsteps, "warmup": nwarm, "ms_per_step": est * 1e3, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                          "cpu_baseline": {"value": val, "unit": "images/sec", "cores": threads, "kind": "port", "sample": sample,
-                                           "parts": ests[-1][1]},
+                          "cpu_baseline": {"value": val, "unit": "images/sec", "cores": threads, "kind": ref.kind,
+                                           "sample": ref.describe(nsteps), "step_seconds": [round(t, 3) for t in times]},
                           "e2e": {"value": val, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                          "gpu_launches": 0}))
+                          "losses": losses, "gpu_launches": 0}))
         return
 
     # ------------------------------------------------------------------ our arm (B200)
@@ -259,7 +311,7 @@ def main():
     from drn_wsod_pytorch_b200 import lib as drn_lib, ops
 
     model = drn.build_model(cfg)
-    weights = helpers.case_weights(cfg, model)
+    weights = synth.calibrated_weights(cfg, model)
     model.load_state_dict({**weights, "pixel_mean": model.pixel_mean, "pixel_std": model.pixel_std}, strict=True)
     del weights
     model.train()
@@ -284,12 +336,11 @@ def main():
     from drn_wsod_pytorch_b200 import distributed as D
 
     train_mode = args.mode == "train"
+    reducer = D.LossReducer()
     if train_mode:
         cfg.SOLVER.BASE_LR = 1e-6  # synthetic data: keep the random-init weights in a sane range over the timed steps
         optimizer = drn.build_optimizer(cfg, model)  # detectron2/solver/build.py mirrored, fused update kernel
-        sync = D.GradientSynchronizer()
-        if world > 1:
-            model.roi_heads.grad_ready_hook = sync.ready
+        sync = D.GradientSynchronizer().attach(model)  # gradients averaged across ranks; p.grad is written by sync.finish()
 
     def step(batched):
         if eval_mode:
@@ -308,9 +359,16 @@ def main():
             sync.finish()
             optimizer.step()
             losses = {k: v.detach() for k, v in losses.items()}
-        losses = D.reduce_dict(losses)  # one packed all-reduce (detectron2/utils/comm.py:234-263 equivalent); identity at N=1
+        # one packed all-reduce per step (detectron2/utils/comm.py:234-263 equivalent; identity at N=1), launched on a side
+        # stream behind the step and handed out one step late, so the next step's kernels never wait for it
+        losses = reducer.submit(losses)
         keys = sorted(losses)
         return torch.stack([losses[k] for k in keys]), keys
+
+    def drain():
+        """Join the last step's loss all-reduce (inside the timed region); returns its vector."""
+        last = reducer.flush()
+        return None if last is None else torch.stack([last[k] for k in sorted(last)])
 
     def sync_all():
         if dist is not None:
@@ -403,6 +461,8 @@ def main():
     e0.record()
     for _ in range(args.steps):
         vec, _ = step(batched_dev)
+    last = drain()
+    vec = vec if last is None else last
     e1.record()
     sync_all()
     launches = launches_per_step * args.steps
@@ -445,6 +505,7 @@ def main():
         if i > 0:
             loss_host = read(i - 1)
     loss_host = read(args.steps - 1)
+    drain()
     sync_all()
     t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
     if dist is not None:
@@ -492,6 +553,7 @@ def main():
             dist.destroy_process_group()
         return
     peaks = _peaks()
+    traffic, traffic_src = _roofline_traffic(args.workload)
     ms_step = ms_total / args.steps
     value = world * args.steps / (ms_total / 1e3)
     fc6_tflops = 2 * gmac["fc6"] * 1e9 / (fc6_ms * 1e-3) / 1e12 if fc6_ms > 0 else 0.0
@@ -508,7 +570,7 @@ def main():
         "roofline": {"bound": "tensor", "kernel": "fc6 GEMM (gemm_tc_kernel)" if precision == "bf16" else "fc6 layer (1 + G gemm_tc_kernel launches over split-bf16 operands + fp32 reduction; fp32-equivalent FLOPs counted once, 6x that many run on the tensor cores)" if precision == "fp32_tc" else "fc6 GEMM (conv_igemm_f32_kernel, SIMT fp32)",
                      "achieved": fc6_tflops, "peak": peak, "unit": "TFLOP/s", "frac": fc6_tflops / peak,
                      "peak_source": f"{peaks['src']} cuBLAS bf16 sustained (kernel timed inside a long step)",
-                     "traffic": FC6_DRAM_BYTES.get(args.workload), "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of the fc6 launch, profiles/r1_ncu_step_v7_per_launch.txt (#62)" if args.workload in FC6_DRAM_BYTES else None,
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_flops_per_launch": 2 * gmac["fc6"] * 1e9, "kernel_ms": fc6_ms, "share_of_step": fc6_ms / ms_step,
                      "whole_step_tflops": total_tflops, "whole_step_frac": total_tflops / peak},
         "losses": dict(zip(loss_keys, [round(float(x), 6) for x in vec.tolist()])),
@@ -522,36 +584,38 @@ def main():
         out["config"]["mode"] = "train: backward of fc6/fc7/heads (backbone frozen, FREEZE_AT 5) + fused SGD; gradients averaged over ranks"
         out["grad_allreduce_bytes_per_step"] = sync.bytes // max(1, sync.steps)
     if world == 1 and not args.no_cpu_baseline:
-        from oracle import wsl_oracle as O
-
-        state = dict(helpers.case_weights(cfg, model))
-        spec = O.spec_from_cfg(cfg)
-        cinp = synth.make_inputs(H, W, R, seed=0)
-        R_sample = min(R, 250)
-        cpu_reference_step(state, spec, cinp, 50, threads)
-        est, parts = cpu_reference_step(state, spec, cinp, R_sample, threads)
-        out["cpu_baseline"] = {"value": 1.0 / est, "unit": "images/sec", "cores": threads, "kind": "port",
-                               "sample": f"full backbone on the {H}x{W} image + ROI stage on {R_sample} of {R} proposals, ROI-stage time "
-                                         f"scaled x{R / R_sample:.0f} (linear in R); fp32 torch CPU ops, {threads} threads", "parts": parts}
-    if world == 1 and args.library_baseline:
-        try:
-            out["library_baseline"] = library_baseline(cfg, model, helpers, synth, H, W, R, dev, autocast=args.library_baseline == "bf16")
-        except Exception as e:
-            out["library_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        # one full image on the host cores (the bounded sample: ~20-50 s of CPU work), after a small warm-up that only
+        # spins up the thread pool; the driver's reference arm (--impl reference) repeats it with a full warm-up step
+        ref = CpuReference(cfg_name, cfg, H, W, R, threads, cfg.MODEL.ROI_HEADS.NUM_CLASSES)
+        if ref.kind == "port":
+            ref.set_state(synth.calibrated_weights(cfg, model))
+        torch.nn.functional.conv2d(torch.zeros(1, 8, 64, 64), torch.zeros(8, 8, 3, 3))
+        dt, closs = ref.step()
+        out["cpu_baseline"] = {"value": 1.0 / dt, "unit": "images/sec", "cores": threads, "kind": ref.kind,
+                               "sample": ref.describe(1), "losses": closs}
+        del ref
+    if world == 1 and args.library_baseline != "none" and args.mode == "forward":
+        out["library_baseline"] = {}
+        for which in (("fp32", "bf16") if args.library_baseline == "both" else (args.library_baseline,)):
+            try:
+                out["library_baseline"][which] = library_baseline(cfg, model, synth, H, W, R, dev, autocast=which == "bf16")
+            except Exception as e:
+                out["library_baseline"][which] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            torch.cuda.empty_cache()
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
 
 
-def library_baseline(cfg, model, helpers, synth, H, W, R, dev, reps=5, autocast=False):
+def library_baseline(cfg, model, synth, H, W, R, dev, reps=5, autocast=False):
     """The baseline leg on the GPU: the oracle's restatement of the reference forward+loss (dropout off) executed by
     torch's own CUDA kernels in fp32, as the reference does on a GPU (no AMP in detectron2 v0.2; cuDNN may use TF32
     for the convolutions, matmuls stay fp32).  Baseline only -- never part of the product path."""
     from oracle import wsl_oracle as O
 
-    state = {k: v.to(dev) for k, v in helpers.case_weights(cfg, model).items()}
+    state = {k: v.to(dev) for k, v in synth.calibrated_weights(cfg, model).items()}
     spec = O.spec_from_cfg(cfg)
-    inp = synth.make_inputs(H, W, R, seed=0)
+    inp = synth.make_inputs(H, W, R, seed=0, num_classes=cfg.MODEL.ROI_HEADS.NUM_CLASSES)
     b = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in inp.items()}
     orig_features = O.forward_features
     if autocast:  # backbone -> ROIPool -> fc6/fc7 under bf16 autocast; heads and losses stay fp32 (BCE refuses autocast)

@@ -24,6 +24,6 @@ from .registry import (  # noqa: F401
 )
 from .solver import FusedSGD, build_optimizer  # noqa: F401
 from .structures import Boxes, ImageList, Instances  # noqa: F401
-from .tta import DatasetMapperTTAAVG, GeneralizedRCNNWithTTAAVG  # noqa: F401
+from .tta import DatasetMapperTTAAVG, DatasetMapperTTAUNION, GeneralizedRCNNWithTTAAVG, GeneralizedRCNNWithTTAUNION  # noqa: F401
 
 __version__ = "0.1.0"

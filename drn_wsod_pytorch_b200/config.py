@@ -180,7 +180,9 @@ def get_cfg():
                              "FLIP": True}},
             # detectron2/config/defaults.py SOLVER keys read by build_optimizer (solver/build.py:93-137)
             "SOLVER": {"BASE_LR": 0.001, "MOMENTUM": 0.9, "NESTEROV": False, "WEIGHT_DECAY": 0.0001, "WEIGHT_DECAY_NORM": 0.0,
-                       "BIAS_LR_FACTOR": 1.0, "WEIGHT_DECAY_BIAS": 0.0001, "IMS_PER_BATCH": 16},
+                       "BIAS_LR_FACTOR": 1.0, "WEIGHT_DECAY_BIAS": 0.0001, "IMS_PER_BATCH": 16,
+                       # detectron2/config/defaults.py:549-559 (solver/build.py:19-92 maybe_add_gradient_clipping)
+                       "CLIP_GRADIENTS": {"ENABLED": False, "CLIP_TYPE": "value", "CLIP_VALUE": 1.0, "NORM_TYPE": 2.0}},
             "WSL": {
                 "VIS_TEST": False,
                 "ITER_SIZE": 1,

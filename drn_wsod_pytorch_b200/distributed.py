@@ -46,6 +46,56 @@ def reduce_dict(losses: Dict[str, torch.Tensor], average: bool = True) -> Dict[s
     return {k: vec[i] for i, k in enumerate(keys)}
 
 
+class LossReducer:
+    """`reduce_dict` off the critical path: the mean of step i's loss dict is launched on a side stream behind step i
+    and handed out when step i+1 submits (one step late -- what the reference's metric writer tolerates: it gathers the
+    metrics of a step after the optimizer has moved on, detectron2/engine/train_loop.py:237-289).  The compute stream
+    never waits for the collective, so a step costs what it costs on one GPU; `flush()` joins the last one."""
+
+    def __init__(self, average: bool = True):
+        self.average = average
+        self.stream = None
+        self.prev = None  # (keys, reduced vector, work handle or None)
+
+    def _take(self):
+        if self.prev is None:
+            return None
+        keys, vec, work = self.prev
+        self.prev = None
+        if work is not None:
+            work.wait()
+            if self.average and not vec.is_cuda:
+                vec = vec / world()[1]
+        elif vec.is_cuda:
+            torch.cuda.current_stream(vec.device).wait_stream(self.stream)
+        return {k: vec[i] for i, k in enumerate(keys)}
+
+    def submit(self, losses: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Start the reduction of `losses`; returns the reduced dict of the PREVIOUS submit (this rank's own values on
+        the first call and at world size 1)."""
+        rank, ws = world()
+        if ws == 1:
+            return dict(losses)
+        out = self._take()
+        keys, vec = pack_losses({k: v.detach() for k, v in losses.items()})
+        if vec.is_cuda:
+            if self.stream is None or self.stream.device != vec.device:
+                self.stream = torch.cuda.Stream(vec.device)
+            self.stream.wait_stream(torch.cuda.current_stream(vec.device))
+            vec.record_stream(self.stream)
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(vec, op=dist.ReduceOp.AVG if self.average else dist.ReduceOp.SUM)
+            self.prev = (keys, vec, None)
+        else:
+            work = dist.all_reduce(vec, op=dist.ReduceOp.SUM, async_op=True)
+            self.prev = (keys, vec, work)
+        return out if out is not None else dict(losses)
+
+    def flush(self):
+        """Reduced dict of the last submit (None if there is none pending); the current stream waits for it."""
+        return self._take()
+
+
 def gather_counts(values: Sequence[int]) -> List[List[int]]:
     """All-gather small per-rank integer tuples (images processed, proposals seen) for throughput accounting."""
     rank, ws = world()
@@ -63,15 +113,27 @@ class GradientSynchronizer:
     """Data-parallel gradient averaging without DistributedDataParallel: the backward calls `ready(tensor)` for every
     finished gradient block (a whole parameter gradient, or a row block of fc6's); each call launches an
     asynchronous all-reduce right away -- NCCL orders it after the kernels already queued on the current stream and
-    runs it on its own stream, next to the backward's remaining GEMMs.  `finish()` waits for all of them and applies
-    the 1/world scale (AVG inside NCCL; SUM then scale with gloo).  Unused parameters (bbox_pred without REFINE_REG)
-    never produce a block, so nothing like find_unused_parameters is needed."""
+    runs it on its own stream, next to the backward's remaining GEMMs.  The backward then `bind`s every parameter to
+    the buffer its blocks live in; `finish()` waits for the collectives, applies the 1/world scale (AVG inside NCCL;
+    SUM then scale with gloo) and only THEN hands the averaged buffers to `p.grad` (accumulating, like
+    DistributedDataParallel does across ITER_SIZE backward passes).  Handing them to autograd earlier would let
+    AccumulateGrad clone the local, un-averaged values while the collective is still in flight.  Unused parameters
+    (bbox_pred without REFINE_REG) never produce a block, so nothing like find_unused_parameters is needed.
+
+    Install with `attach(model)`; call `finish()` after `backward()` and before `optimizer.step()`."""
 
     def __init__(self, group=None):
         self.group = group
         self.pending = []
+        self.bound = []  # (parameter, averaged gradient buffer) pairs of the backward passes since the last finish()
         self.bytes = 0   # all-reduced so far
         self.steps = 0   # finish() calls
+
+    def attach(self, model):
+        """Route the gradients of `model`'s trainable tail through this synchronizer (identity at world size 1)."""
+        rh = getattr(model, "roi_heads", model)
+        rh.grad_sync = self if world()[1] > 1 else None
+        return self
 
     def ready(self, tensor):
         rank, ws = world()
@@ -85,6 +147,10 @@ class GradientSynchronizer:
             h = dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             self.pending.append((h, tensor))
 
+    def bind(self, param, grad):
+        """`grad` (all of whose blocks were announced through `ready`) becomes `param.grad` in `finish()`."""
+        self.bound.append((param, grad))
+
     def finish(self):
         rank, ws = world()
         self.steps += 1
@@ -93,4 +159,11 @@ class GradientSynchronizer:
             if t is not None:
                 t.div_(ws)
         n, self.pending = len(self.pending), []
+        bound, self.bound = self.bound, []
+        with torch.no_grad():
+            for p, g in bound:
+                if p.grad is None:
+                    p.grad = g
+                else:
+                    p.grad.add_(g)
         return n

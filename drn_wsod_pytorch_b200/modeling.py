@@ -699,7 +699,7 @@ class _WSLROIHeads(nn.Module):
         self.fused_tail = os.environ.get("DRN_B200_FUSED_TAIL", "1") != "0"
         # opt-in: measured gain 0.02-0.05 ms of 2.7 (the GEMM is SM<-L2 feed bound, a co-resident gather starves:
         # profiles/r1_overlap_negative_result.txt), less than the tail split-K schedule of the one-piece fc6 saves
-        self.grad_ready_hook = None   # callable(tensor): a finished gradient block (data-parallel all-reduce, distributed.py)
+        self.grad_sync = None   # distributed.GradientSynchronizer (data-parallel training): .ready(block) / .bind(param, grad)
         self.wgrad_row_blocks = int(os.environ.get("DRN_B200_WGRAD_BLOCKS", "4"))  # fc6 weight gradient in row blocks when a hook is installed
         # SMs left to the collective during those blocks (pair with NCCL_MAX_CTAS).  0 = off: measured at 2 GPUs 8.42 ms/step
         # uncapped vs 9.29 (16 SMs) / 8.38 (32 SMs) -- the step is bound by the 858 MB fp32 all-reduce itself
@@ -803,22 +803,18 @@ class _WSLROIHeads(nn.Module):
 
     def _image_level_gt(self, targets):
         """roi_heads.py:137-153: sorted distinct GT classes per image + one-hot.  G (their number) sizes
-        kernel launches, so it has to be known on the host: computed with numpy when the GT arrives on
-        the CPU (the dataloader case, no device sync); for device-resident GT the result is cached on
-        the tensor's (data_ptr, version) so a repeated batch does not sync either."""
+        kernel launches, so it has to be known on the host: the classes are read with numpy when the GT arrives
+        on the CPU (the dataloader case, no device sync) and with one small D2H copy when it is device-resident.
+        Only the DEVICE copies of (classes, one-hot) are cached, and only by content (the class set): a pointer-keyed
+        cache would hand the next image the previous image's labels whenever the caching allocator reuses the address."""
         K = self.num_classes
         out = []
         for t in targets:
             gc = t.gt_classes
             dev = self._device if gc.device.type == "cpu" else gc.device
-            if gc.is_cuda:
-                key = ("dev", gc.data_ptr(), gc._version, gc.numel(), str(gc.device))
-                hit = self._gt_cache.get(key)
-                classes = None if hit is not None else sorted(set(int(c) for c in gc.tolist()))  # one D2H sync
-            else:
-                classes = sorted(set(int(c) for c in gc.tolist()))
-                key = ("set", tuple(classes), str(dev))  # device copies are cached per class set: no H2D per step
-                hit = self._gt_cache.get(key)
+            classes = sorted(set(int(c) for c in gc.tolist()))  # CUDA GT: one D2H sync per image
+            key = ("set", tuple(classes), str(dev))  # device copies are cached per class set: no H2D per step
+            hit = self._gt_cache.get(key)
             if hit is None:
                 gt = torch.tensor(classes, dtype=torch.int64).to(dev)
                 oh_host = torch.zeros((K,), dtype=torch.float32)
@@ -1075,7 +1071,8 @@ class _WSLROIHeads(nn.Module):
         fcs = self.box_head.fcs
         grads = {}
 
-        hook = self.grad_ready_hook if N == 1 else None  # blocks are final only when one image feeds them
+        sync = self.grad_sync
+        hook = sync.ready if (sync is not None and N == 1) else None  # blocks are final only when one image feeds them
 
         def acc(p, g, announced=False):
             grads[p] = g if p not in grads else grads[p] + g
@@ -1129,9 +1126,12 @@ class _WSLROIHeads(nn.Module):
                 acc(fc.bias, ops.rowsum(dy_t, cols=R))
                 if li > 0:
                     dx = self._dgrad(dy, w_op[li], wdt)
-        if hook is None and self.grad_ready_hook is not None:  # multi-image batches: announce the summed gradients
-            for g in grads.values():
-                self.grad_ready_hook(g)
+        if sync is not None:
+            if hook is None:  # multi-image batches: announce the summed gradients
+                for g in grads.values():
+                    sync.ready(g)
+            for p, g in grads.items():  # p.grad is written by sync.finish(), after the collectives have completed
+                sync.bind(p, g)
         return grads
 
     # -- eval ----------------------------------------------------------------------------------------
@@ -1235,6 +1235,7 @@ class _GraphPlan:
         self.staged_event = None
         self.staged_key = None
         self.refill_done = None
+        self.generation = 0  # bumped by every replay: the static outputs of generation g are gone at g + 1
 
     @staticmethod
     def _ident(inputs):
@@ -1272,6 +1273,7 @@ class _GraphPlan:
             if self.refill_done is None:
                 self.refill_done = torch.cuda.Event()
             self.refill_done.record()
+        self.generation += 1
         self.graph.replay()
         return self.out
 
@@ -1283,23 +1285,34 @@ class _WSLLossBridge(torch.autograd.Function):
     as with the reference model (tools/train_net.py / detectron2/engine/train_loop.py:215-240)."""
 
     @staticmethod
-    def forward(ctx, roi_heads, dev_out, loss_vec, *params):
+    def forward(ctx, roi_heads, dev_out, plan, generation, loss_vec, *params):
         ctx.roi_heads, ctx.dev_out, ctx.params = roi_heads, dev_out, params
+        ctx.plan, ctx.generation = plan, generation  # dev_out are the plan's static buffers: valid until its next replay
         return loss_vec.clone()
 
     @staticmethod
     def backward(ctx, grad_vec):
+        if ctx.plan is not None and ctx.plan.generation != ctx.generation:
+            raise RuntimeError("backward() of a loss whose captured forward buffers were overwritten by a later forward with the "
+                               "same input signature: run one backward per forward (as tools/train_net.py's ITER_SIZE loop does), "
+                               "or disable the CUDA-graph plans (B200.CUDA_GRAPH False / DRN_B200_CUDA_GRAPH=0)")
         grads = ctx.roi_heads._backward_device(ctx.dev_out, grad_vec.contiguous().float())
-        return (None, None, None) + tuple(grads.get(p) if p.requires_grad else None for p in ctx.params)
+        if ctx.roi_heads.grad_sync is not None:
+            # data-parallel: the averaged gradients reach p.grad in GradientSynchronizer.finish(); handing the buffers to
+            # autograd here would let AccumulateGrad read them while their all-reduce is still in flight
+            return (None,) * (5 + len(ctx.params))
+        return (None,) * 5 + tuple(grads.get(p) if p.requires_grad else None for p in ctx.params)
 
 
 @META_ARCH_REGISTRY.register()
 class GeneralizedRCNNWSL(nn.Module):
     """projects/WSL/wsl/modeling/meta_arch/rcnn.py:23-265 with precomputed proposals."""
 
-    MAX_PLANS = 24  # captured graphs kept alive (each owns its activation pool; the 8 TTA scales need one each)
+    MAX_PLANS = 24  # captured graphs kept alive, least recently used evicted (each owns its activation pool; the 8 TTA scales need one each)
     CAPTURE_AFTER = 2  # an input signature is captured the 2nd time it is seen: multi-scale training, where
     #                    (H, W, R) change every iteration, stays on the eager launch path instead of re-capturing
+    CAPTURE_AFTER_EVAL = 3  # eval signatures: a TTA image shows every (size, scale) twice (flipped + unflipped view), so
+    #                         two sightings say nothing about the NEXT image; the third one does
 
     def __init__(self, cfg):
         super().__init__()
@@ -1321,10 +1334,15 @@ class GeneralizedRCNNWSL(nn.Module):
             self.use_cuda_graph = os.environ["DRN_B200_CUDA_GRAPH"] not in ("0", "false", "False")
         self._plans = {}
         self._seen = {}
+        self._last_plan = None
 
     @property
     def device(self):
         return self.pixel_mean.device
+
+    def _mean_std_key(self):
+        mean, std = self._mean_std()
+        return (tuple(mean), tuple(std))
 
     def _mean_std(self):
         key = (self.pixel_mean._version, self.pixel_std._version, self.pixel_mean.device)
@@ -1413,17 +1431,22 @@ class GeneralizedRCNNWSL(nn.Module):
     def _plan_for(self, kind, canvas, groups, fn, force=False):
         flat = [t for g in groups for t in g]
         self._refresh_derived()
-        key = (kind, canvas, self.roi_heads.keep_trace, self.roi_heads.box_head.training, tuple((tuple(t.shape), t.dtype) for t in flat))
+        # pixel mean / std and the canvas are baked into the captured first-conv launch
+        key = (kind, canvas, self._mean_std_key(), self.roi_heads.keep_trace, self.roi_heads.box_head.training,
+               tuple((tuple(t.shape), t.dtype) for t in flat))
         plan = self._plans.get(key)
-        if plan is None:
+        if plan is not None:
+            self._plans[key] = self._plans.pop(key)  # most recently used last
+        else:
             seen = self._seen.get(key, 0) + 1
             if len(self._seen) > 4096:
                 self._seen.clear()
             self._seen[key] = seen
-            if seen < self.CAPTURE_AFTER and not force:
+            after = self.CAPTURE_AFTER if kind == "train" else self.CAPTURE_AFTER_EVAL
+            if seen < after and not force:
                 return None, flat
             if len(self._plans) >= self.MAX_PLANS:
-                self._plans.pop(next(iter(self._plans)))
+                self._plans.pop(next(iter(self._plans)))  # least recently used
             img_n = len(groups[0])
             proto = [t.to(torch.float32) if i < img_n else t for i, t in enumerate(flat)]
             dev = self.device
@@ -1438,6 +1461,7 @@ class GeneralizedRCNNWSL(nn.Module):
         plan = None
         if self.use_cuda_graph:
             plan, flat = self._plan_for(kind, canvas, groups, fn)
+        self._last_plan = plan
         if plan is None:  # graphs disabled, or a signature seen for the first time: eager launches
             flat = [t for g in groups for t in g]
             dev = self.device
@@ -1497,7 +1521,9 @@ class GeneralizedRCNNWSL(nn.Module):
                     raise NotImplementedError("the B200 backward covers the ROI heads; the WSL configs freeze the whole backbone "
                                               "(MODEL.BACKBONE.FREEZE_AT: 5) -- freeze it or run under torch.no_grad()")
                 keys = list(losses)
-                vec = _WSLLossBridge.apply(self.roi_heads, dev_out, torch.stack([losses[k] for k in keys]), *params)
+                plan = self._last_plan
+                vec = _WSLLossBridge.apply(self.roi_heads, dev_out, plan, plan.generation if plan is not None else 0,
+                                           torch.stack([losses[k] for k in keys]), *params)
                 losses = {k: vec[i] for i, k in enumerate(keys)}
         return losses
 

@@ -10,11 +10,27 @@ from . import ops
 
 
 class FusedSGD(torch.optim.Optimizer):
-    def __init__(self, params, lr, momentum=0.0, weight_decay=0.0, nesterov=False, model=None):
+    """`model` (optional) lets the update kernel rewrite the model's bf16 kernel-layout weight copies in the same pass.
+    Without it the parameters are still updated correctly: every stepped parameter's autograd version is bumped, so the
+    model's derived layouts (keyed on the versions) re-pack themselves on the next forward.
+    `clip` = (type, value, norm_type): per-parameter gradient clipping before the update, as
+    detectron2/solver/build.py:19-92 wraps the optimizer when SOLVER.CLIP_GRADIENTS.ENABLED."""
+
+    def __init__(self, params, lr, momentum=0.0, weight_decay=0.0, nesterov=False, model=None, clip=None):
         if nesterov and momentum <= 0:
             raise ValueError("Nesterov momentum requires a momentum")
         super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay, nesterov=nesterov))
         self.model = model
+        if clip is not None and clip[0] not in ("value", "norm"):
+            raise ValueError(f"SOLVER.CLIP_GRADIENTS.CLIP_TYPE must be 'value' or 'norm', got {clip[0]!r}")
+        self.clip = clip
+
+    def _clip(self, p):
+        kind, value, norm_type = self.clip
+        if kind == "value":
+            torch.nn.utils.clip_grad_value_(p, value)
+        else:
+            torch.nn.utils.clip_grad_norm_(p, value, norm_type)
 
     def _packed_copies(self):
         """parameter -> (bf16 kernel-layout buffer, c49) for the single-layer tensor-core packs of the model."""
@@ -44,6 +60,8 @@ class FusedSGD(torch.optim.Optimizer):
             for p in group["params"]:
                 if p.grad is None:
                     continue
+                if self.clip is not None:
+                    self._clip(p)
                 st = self.state[p]
                 first = "momentum_buffer" not in st
                 if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
@@ -58,15 +76,20 @@ class FusedSGD(torch.optim.Optimizer):
                 hit = packed.get(p)
                 ops.sgd_step(p, p.grad.contiguous(), st.get("momentum_buffer"), hit[0]["w"] if hit else None, hit[1] if hit else 0,
                              lr, mom, wd, nest, first)
+                # the kernel wrote through raw pointers: tell autograd (and every cache keyed on the version) so
+                torch.autograd.graph.increment_version(p)
                 touched = True
         if touched and self.model is not None:
             self._after_step(packed)
         return loss
 
     def _after_step(self, packed):
-        """The kernel wrote the parameters through raw pointers (no autograd version bump): bring the derived
-        layouts it did not rewrite itself up to date, in place -- bias copies of the fused layers, every other pack
-        of a stepped layer (fp32-mode layouts, the concatenated heads)."""
+        """Bring the derived layouts the kernel did not rewrite itself up to date, in place and now (on the step's
+        stream) -- bias copies of the fused layers, every other pack of a stepped layer (fp32-mode layouts, the
+        concatenated heads) -- and re-key the fused packs to the bumped parameter versions so that the next forward
+        does not pack fc6's 205 M weights a second time."""
+        from .modeling import _versions
+
         fused = {id(hit[0]) for hit in packed.values()}
         for m in self.model.modules():
             cache = getattr(m, "_cache", None)
@@ -75,6 +98,7 @@ class FusedSGD(torch.optim.Optimizer):
             for (precision, perm), hit in list(cache.items()):
                 if id(hit) in fused:
                     hit["bias"].copy_(m.bias.detach())
+                    hit["key"] = (precision, perm, _versions([m.weight, m.bias]))
                 else:
                     hit["key"] = None
                     m.packed(precision, permute_c49=perm)  # re-packed in place, now
@@ -103,4 +127,8 @@ def build_optimizer(cfg, model):
             elif key == "bias":
                 lr, wd = s.BASE_LR * s.BIAS_LR_FACTOR, s.WEIGHT_DECAY_BIAS
             params.append({"params": [value], "lr": lr, "weight_decay": wd})
-    return FusedSGD(params, s.BASE_LR, momentum=s.MOMENTUM, nesterov=s.NESTEROV, model=model)
+    clip = None
+    cg = s.get("CLIP_GRADIENTS") if hasattr(s, "get") else getattr(s, "CLIP_GRADIENTS", None)
+    if cg is not None and cg.ENABLED:  # solver/build.py:65-92 maybe_add_gradient_clipping
+        clip = (cg.CLIP_TYPE, cg.CLIP_VALUE, cg.NORM_TYPE)
+    return FusedSGD(params, s.BASE_LR, momentum=s.MOMENTUM, nesterov=s.NESTEROV, model=model, clip=clip)

@@ -107,6 +107,20 @@ def make_weights(shapes, seed=0, calib=None):
     return out
 
 
+def arch_key(cfg):
+    """Key of the calibration table (data/calib.json) for a config's backbone."""
+    m = cfg.MODEL
+    if "vgg" in m.BACKBONE.NAME:
+        return f"vgg16_d{m.VGG.CONV5_DILATION}"
+    return f"resnet_ws{m.RESNETS.DEPTH}_d{m.RESNETS.RES5_DILATION}"
+
+
+def calibrated_weights(cfg, model_or_shapes, seed=0):
+    """The seeded, calibrated state_dict every bench and parity case uses for `cfg`'s architecture."""
+    shapes = model_or_shapes if isinstance(model_or_shapes, dict) else state_shapes(model_or_shapes)
+    return make_weights(shapes, seed=seed, calib=load_calib(arch_key(cfg)))
+
+
 def state_shapes(model):
     return OrderedDict((k, tuple(v.shape)) for k, v in model.state_dict().items())
 

@@ -17,8 +17,6 @@ What runs where:
 There is no CPU path: a missing library, a CPU model or a float image raises.
 """
 import copy
-from contextlib import contextmanager
-from itertools import count
 
 import numpy as np
 import torch
@@ -28,7 +26,7 @@ from . import ops
 from .modeling import GeneralizedRCNNWSL, fast_rcnn_inference_single_image
 from .structures import Boxes, Instances
 
-__all__ = ["DatasetMapperTTAAVG", "GeneralizedRCNNWithTTAAVG", "transform_proposals", "resample_tables", "resize_u8",
+__all__ = ["DatasetMapperTTAAVG", "GeneralizedRCNNWithTTAAVG", "DatasetMapperTTAUNION", "GeneralizedRCNNWithTTAUNION", "transform_proposals", "resample_tables", "resize_u8",
            "NoOpTransform", "HFlipTransform", "ResizeTransform", "TransformList", "ResizeShortestEdge"]
 
 PRECISION_BITS = 32 - 8 - 2  # Pillow Resample.c
@@ -235,34 +233,37 @@ def resize_u8(img_chw_u8, new_h, new_w, flip=False, out_dtype=torch.uint8):
 
 # ---------------------------------------------------------------------------------------------- mapper
 def transform_proposals(dataset_dict, image_shape, transforms, *, proposal_topk, min_box_size=0, pin_memory=False):
-    """test_time_augmentation_avg.py:27-64: `apply_box` -> clip -> nonempty(min_box_size) -> first top-k (no `unique`
-    step, unlike detection_utils.transform_proposals).  Replaces dataset_dict["proposals"] in place.
-    pin_memory (an addition): page-lock the results, so that the model's H2D copies of them are truly asynchronous
+    """What test_time_augmentation_avg.py:27-64 does to a view's proposals, as array arithmetic: boxes through the view's
+    transforms (numpy float32, like `apply_box` there), clamped to the view, boxes whose width or height does not exceed
+    `min_box_size` dropped, the first `proposal_topk` survivors kept in their original order (no `unique` step, unlike
+    detection_utils.transform_proposals).  dataset_dict["proposals"] is replaced by a new Instances of the view's size.
+    pin_memory (an addition): page-lock the results, so the model's H2D copies of them are truly asynchronous
     (a pageable cudaMemcpyAsync first drains the stream: the host would wait for the previous view to finish)."""
-    prop = dataset_dict["proposals"]
-    boxes = prop.proposal_boxes.tensor.cpu().numpy()
-    boxes = transforms.apply_box(boxes)
-    boxes = type(prop.proposal_boxes)(torch.from_numpy(np.ascontiguousarray(boxes)))
-    objectness_logits = prop.objectness_logits
-    boxes.clip(image_shape)
-    keep = boxes.nonempty(threshold=min_box_size)
-    boxes = boxes[keep]
-    objectness_logits = objectness_logits[keep.to(objectness_logits.device)]
-    boxes, objectness_logits = boxes[:proposal_topk], objectness_logits[:proposal_topk]
+    src = dataset_dict["proposals"]
+    view_h, view_w = image_shape
+    xyxy = torch.from_numpy(np.ascontiguousarray(transforms.apply_box(src.proposal_boxes.tensor.cpu().numpy())))
+    xyxy[:, 0::2] = xyxy[:, 0::2].clamp(min=0, max=view_w)
+    xyxy[:, 1::2] = xyxy[:, 1::2].clamp(min=0, max=view_h)
+    alive = ((xyxy[:, 2] - xyxy[:, 0]) > min_box_size) & ((xyxy[:, 3] - xyxy[:, 1]) > min_box_size)
+    rows = torch.nonzero(alive).flatten()[:proposal_topk]
+    xyxy = xyxy[rows]
+    logits = src.objectness_logits[rows.to(src.objectness_logits.device)]
     if pin_memory:
-        boxes = type(boxes)(boxes.tensor.contiguous().pin_memory())
-        if not objectness_logits.is_cuda:
-            objectness_logits = objectness_logits.contiguous().pin_memory()
-    proposals = type(prop)(tuple(image_shape))
-    proposals.proposal_boxes = boxes
-    proposals.objectness_logits = objectness_logits
-    dataset_dict["proposals"] = proposals
+        xyxy = xyxy.contiguous().pin_memory()
+        if not logits.is_cuda:
+            logits = logits.contiguous().pin_memory()
+    out = type(src)(tuple(image_shape))
+    out.proposal_boxes = type(src.proposal_boxes)(xyxy)
+    out.objectness_logits = logits
+    dataset_dict["proposals"] = out
 
 
 class DatasetMapperTTAAVG:
     """test_time_augmentation_avg.py:67-136.  Takes one dataset dict (image: uint8 C x H x W tensor, host or device)
     and returns `len(MIN_SIZES) * (2 if FLIP else 1)` dicts whose `image` is the resampled (and flipped) view ON THE
     DEVICE, `transforms` the TransformList that produced it and `proposals` the transformed proposals."""
+
+    transforms_proposals = True
 
     def __init__(self, cfg, image_dtype=torch.uint8):
         self.min_sizes = cfg.TEST.AUG.MIN_SIZES
@@ -272,8 +273,12 @@ class DatasetMapperTTAAVG:
         self.device = torch.device(cfg.MODEL.DEVICE)
         self.image_dtype = image_dtype  # torch.float32: the conversion preprocess_image would do is fused into the resample
         self.proposal_topk = None
-        if cfg.MODEL.LOAD_PROPOSALS:
+        if cfg.MODEL.LOAD_PROPOSALS and self.transforms_proposals:
             self.proposal_topk = cfg.DATASETS.PRECOMPUTED_PROPOSAL_TOPK_TEST
+
+    @property
+    def num_views(self):
+        return len(self.min_sizes) * (2 if self.flip else 1)
 
     def __call__(self, dataset_dict):
         return list(self.iter_views(dataset_dict))
@@ -283,7 +288,7 @@ class DatasetMapperTTAAVG:
         prepares view i+1 (resample launch + proposal transform), so the mapper's host work is hidden behind the GPU."""
         image = dataset_dict["image"]
         if image.dtype != torch.uint8:
-            raise TypeError(f"DatasetMapperTTAAVG: uint8 image expected (the dataset mapper's output), got {image.dtype}")
+            raise TypeError(f"{type(self).__name__}: uint8 image expected (the dataset mapper's output), got {image.dtype}")
         image = image.to(self.device, non_blocking=True)  # one H2D per image, every view is made on the device
         shape = tuple(image.shape[-2:])
         orig_shape = (dataset_dict["height"], dataset_dict["width"])
@@ -300,123 +305,144 @@ class DatasetMapperTTAAVG:
                 dic = copy.copy(rest)
                 dic["transforms"] = pre_tfm + tfms
                 dic["image"] = resize_u8(image, new_shape[0], new_shape[1], flip=do_flip, out_dtype=self.image_dtype)
-                if self.proposal_topk is not None:
+                if "proposals" in dataset_dict:
                     dic["proposals"] = dataset_dict["proposals"]
-                    transform_proposals(dic, new_shape, tfms, proposal_topk=self.proposal_topk, pin_memory=self.device.type == "cuda")
+                    if self.proposal_topk is not None:
+                        transform_proposals(dic, new_shape, tfms, proposal_topk=self.proposal_topk, pin_memory=self.device.type == "cuda")
                 yield dic
 
 
-# ---------------------------------------------------------------------------------------------- wrapper
-class GeneralizedRCNNWithTTAAVG(nn.Module):
-    """test_time_augmentation_avg.py:139-325 (box branch; the WSL detection configs have MASK_ON False).
-    `__call__` has the interface of `GeneralizedRCNNWSL.forward` in eval mode."""
+class DatasetMapperTTAUNION(DatasetMapperTTAAVG):
+    """test_time_augmentation_union.py:27-82.  Same views as the AVG mapper, but -- exactly as in the reference -- the
+    proposals are handed to every view UNCHANGED (in the coordinates of the mapper's input image; the reference deep-copies
+    the dataset dict and never calls transform_proposals), so with precomputed proposals only the un-resized,
+    un-flipped view pools the regions the proposals were computed for."""
+
+    transforms_proposals = False
+
+
+# ---------------------------------------------------------------------------------------------- wrappers
+class _TTADriver(nn.Module):
+    """Shared part of the two TTA wrappers: one image in, its views streamed through the model chunk by chunk.
+    The host prepares view i+1 (resample launch, proposal transform) while the device runs view i; nothing is kept per
+    view beyond what `consume` stores."""
+
+    mapper_cls = DatasetMapperTTAAVG
+    per_view_detections = False  # run the per-view threshold / NMS / top-k tail of the model?
 
     def __init__(self, cfg, model, tta_mapper=None, batch_size=1):
         super().__init__()
-        if isinstance(model, nn.parallel.DistributedDataParallel):
-            model = model.module
-        assert isinstance(model, GeneralizedRCNNWSL), \
-            "TTA is only supported on GeneralizedRCNNWSL. Got a model of type {}".format(type(model))
+        model = getattr(model, "module", model) if isinstance(model, nn.parallel.DistributedDataParallel) else model
+        if not isinstance(model, GeneralizedRCNNWSL):
+            raise AssertionError(f"TTA is only supported on GeneralizedRCNNWSL. Got a model of type {type(model)}")
+        if cfg.MODEL.KEYPOINT_ON or cfg.MODEL.MASK_ON:
+            raise NotImplementedError("the B200 TTA driver covers the box branch (the WSL detection configs: no masks / keypoints)")
         self.cfg = cfg.clone()
-        assert not self.cfg.MODEL.KEYPOINT_ON, "TTA for keypoint is not supported yet"
-        if self.cfg.MODEL.MASK_ON:
-            raise NotImplementedError("the B200 TTA driver covers the box branch (the WSL detection configs)")
         self.model = model
-        if tta_mapper is None:
-            tta_mapper = DatasetMapperTTAAVG(cfg, image_dtype=torch.float32)
-        self.tta_mapper = tta_mapper
-        self.batch_size = batch_size
-
-    @contextmanager
-    def _turn_off_roi_heads(self, attrs):
-        roi_heads = self.model.roi_heads
-        old = {a: getattr(roi_heads, a) for a in attrs if hasattr(roi_heads, a)}
-        for a in old:
-            setattr(roi_heads, a, False)
-        try:
-            yield
-        finally:
-            for a, v in old.items():
-                setattr(roi_heads, a, v)
-
-    def _batch_inference(self, batched_inputs, detected_instances=None):
-        """:200-225 -- `batch_size` views per model call; the per-view thresholding / NMS, whose result the box
-        branch never reads, is skipped (outputs holds None per view)."""
-        if detected_instances is None:
-            detected_instances = [None] * len(batched_inputs)
-        outputs, all_scores, all_boxes = [], [], []
-        inputs, instances = [], []
-        for idx, input, instance in zip(count(), batched_inputs, detected_instances):
-            inputs.append(input)
-            instances.append(instance)
-            if len(inputs) == self.batch_size or idx == len(batched_inputs) - 1:
-                output, all_score, all_box = self.model.inference(
-                    inputs, instances if instances[0] is not None else None, do_postprocess=False,
-                    with_detections=instances[0] is not None)
-                outputs.extend(output)
-                all_scores.extend(all_score)
-                all_boxes.extend(all_box)
-                inputs, instances = [], []
-        return outputs, all_scores, all_boxes
+        self.tta_mapper = tta_mapper if tta_mapper is not None else self.mapper_cls(cfg, image_dtype=torch.float32)
+        self.batch_size = max(1, int(batch_size))
 
     def __call__(self, batched_inputs):
-        def _maybe_read_image(dataset_dict):
-            ret = copy.copy(dataset_dict)
-            if "image" not in ret:
-                ret["image"] = read_image(ret.pop("file_name"), self.tta_mapper.image_format)
-            if "height" not in ret and "width" not in ret:
-                ret["height"] = ret["image"].shape[1]
-                ret["width"] = ret["image"].shape[2]
-            return ret
+        return [self.run_image(x) for x in batched_inputs]
 
-        return [self._inference_one_image(_maybe_read_image(x)) for x in batched_inputs]
+    def _with_image(self, dataset_dict):
+        d = dict(dataset_dict)  # the caller's dict is left alone
+        if "image" not in d:
+            d["image"] = read_image(d.pop("file_name"), self.tta_mapper.image_format)
+        if "height" not in d and "width" not in d:
+            d["height"], d["width"] = int(d["image"].shape[1]), int(d["image"].shape[2])
+        return d
 
-    def _inference_one_image(self, input):
-        orig_shape = (input["height"], input["width"])
-        if hasattr(self.tta_mapper, "iter_views"):  # stream the views: host preparation of view i+1 overlaps view i on the GPU
-            augmented_inputs, tfms = self.tta_mapper.iter_views(input), None
-        else:
-            augmented_inputs, tfms = self._get_augmented_inputs(input)
-        with self._turn_off_roi_heads(["mask_on", "keypoint_on"]):
-            all_boxes, all_scores, all_classes = self._get_augmented_boxes(augmented_inputs, tfms)
-        merged_instances = self._merge_detections(all_boxes, all_scores, all_classes, orig_shape)
-        return {"instances": merged_instances}
+    def stream_views(self, dataset_dict, consume):
+        """Run every view of `dataset_dict` through the model, `batch_size` views per call, and hand each view's
+        (instances or None, all_scores [R, K+1], all_boxes [R, 4K], TransformList) to `consume(i, n, ...)` in view order
+        (n = number of views).  Returns n."""
+        mapper = self.tta_mapper
+        if hasattr(mapper, "iter_views"):
+            views, n = mapper.iter_views(dataset_dict), mapper.num_views
+        else:  # a user-supplied mapper with the reference's list interface
+            made = mapper(dataset_dict)
+            views, n = iter(made), len(made)
+        for first in range(0, n, self.batch_size):
+            chunk = [next(views) for _ in range(min(self.batch_size, n - first))]
+            tfms = [v.pop("transforms") for v in chunk]
+            res, scores, boxes = self.model.inference(chunk, do_postprocess=False, with_detections=self.per_view_detections)
+            for j, (r, sc, bx, tfm) in enumerate(zip(res, scores, boxes, tfms)):
+                if bx.shape[0] != 1:
+                    raise AssertionError("one image per view expected")
+                consume(first + j, n, r, sc[0], bx[0], tfm)
+        return n
 
-    def _get_augmented_inputs(self, input):
-        augmented_inputs = self.tta_mapper(input)
-        tfms = [x.pop("transforms") for x in augmented_inputs]
-        return augmented_inputs, tfms
 
-    def _get_augmented_boxes(self, augmented_inputs, tfms):
-        """:286-309 -- boxes of every view back to the original image (inverse transforms), mean of boxes and scores over
-        the views; the inverse transform, the sum and the division run in drn_tta_accumulate, view by view."""
-        if tfms is None:  # an iterator of views that still carry their "transforms" (DatasetMapperTTAAVG.iter_views)
-            n = len(self.tta_mapper.min_sizes) * (2 if self.tta_mapper.flip else 1)
-            views = iter(augmented_inputs)
-        else:
-            n = len(augmented_inputs)
-            views = iter([dict(v, transforms=t) for v, t in zip(augmented_inputs, tfms)])
-        acc_boxes = acc_scores = None
-        done = 0
-        while done < n:  # merge as the views arrive: nothing but the accumulators is kept
-            chunk = [next(views) for _ in range(min(self.batch_size, n - done))]
-            chunk_tfms = [v.pop("transforms") for v in chunk]
-            _, all_scores, all_boxes = self._batch_inference(chunk)
-            for sc, bx, tfm in zip(all_scores, all_boxes, chunk_tfms):
-                num_img, num_pred, num_col = bx.shape
-                assert num_img == 1
-                if acc_boxes is None:
-                    acc_boxes, acc_scores = torch.empty_like(bx[0]), torch.empty_like(sc[0])
-                assert bx[0].shape == acc_boxes.shape, "every view must keep the same proposals (torch.cat in the reference)"
-                ops.tta_accumulate(bx[0], sc[0], tfm.inverse().device_params(), acc_boxes, acc_scores, done, n)
-                done += 1
-        return acc_boxes, acc_scores, None
+class GeneralizedRCNNWithTTAAVG(_TTADriver):
+    """test_time_augmentation_avg.py:139-325 (box branch).  `__call__` has the interface of `GeneralizedRCNNWSL.forward`
+    in eval mode.  Every view's all_boxes go back to the original image through the view's inverse transforms and are
+    averaged with the all_scores over the views by `drn_tta_accumulate` as the views arrive (running sums in two device
+    buffers, divided on the last view); threshold / per-class NMS / top-k run once, on the means."""
 
-    def _merge_detections(self, all_boxes, all_scores, all_classes, shape_hw):
-        merged_instances, _ = fast_rcnn_inference_single_image(
-            all_boxes, all_scores, shape_hw, self.cfg.MODEL.ROI_HEADS.SCORE_THRESH_TEST,
-            self.cfg.MODEL.ROI_HEADS.NMS_THRESH_TEST, self.cfg.TEST.DETECTIONS_PER_IMAGE, Instances, Boxes)
-        return merged_instances
+    mapper_cls = DatasetMapperTTAAVG
+    per_view_detections = False  # the reference computes per-view detections here and never reads them
+
+    def merged_views(self, dataset_dict):
+        """(mean all_boxes [R, 4K], mean all_scores [R, K+1]) over the views of one image."""
+        acc = {}
+
+        def consume(i, n, _res, scores, boxes, tfm):
+            if not acc:
+                acc["boxes"], acc["scores"] = torch.empty_like(boxes), torch.empty_like(scores)
+            elif boxes.shape != acc["boxes"].shape:
+                raise AssertionError("every view must keep the same proposals (the reference concatenates the views' outputs)")
+            ops.tta_accumulate(boxes, scores, tfm.inverse().device_params(), acc["boxes"], acc["scores"], i, n)
+
+        self.stream_views(dataset_dict, consume)
+        return acc["boxes"], acc["scores"]
+
+    def run_image(self, dataset_dict):
+        d = self._with_image(dataset_dict)
+        boxes, scores = self.merged_views(d)
+        m = self.cfg.MODEL.ROI_HEADS
+        inst, _ = fast_rcnn_inference_single_image(boxes, scores, (d["height"], d["width"]), m.SCORE_THRESH_TEST, m.NMS_THRESH_TEST,
+                                                   self.cfg.TEST.DETECTIONS_PER_IMAGE, Instances, Boxes)
+        return {"instances": inst}
+
+
+class GeneralizedRCNNWithTTAUNION(_TTADriver):
+    """test_time_augmentation_union.py:85-262 (box branch): every view keeps its OWN detections (threshold, per-class NMS,
+    top-k inside the model), their boxes go back to the original image through the inverse transforms, and the union of all
+    views' detections -- one row per detection, its score in its class column of an otherwise zero [n, K+1] matrix -- goes
+    through threshold 1e-8 / per-class NMS / top-k once more (:246-262)."""
+
+    mapper_cls = DatasetMapperTTAUNION
+    per_view_detections = True
+    UNION_SCORE_THRESH = 1e-8  # test_time_augmentation_union.py:259
+
+    def union_of_views(self, dataset_dict):
+        """(boxes [n, 4] on the original image, scores [n], classes [n]) of all views' detections, in view order."""
+        parts = []
+
+        def consume(i, n, res, _scores, _boxes, tfm):
+            b = res.pred_boxes.tensor.contiguous()
+            if b.shape[0]:
+                back, dummy = torch.empty_like(b), torch.empty_like(res.scores)
+                ops.tta_accumulate(b, res.scores.contiguous(), tfm.inverse().device_params(), back, dummy, 0, 1)
+                b = back
+            parts.append((b, res.scores, res.pred_classes))
+
+        self.stream_views(dataset_dict, consume)
+        return tuple(torch.cat([p[j] for p in parts], dim=0) for j in range(3))
+
+    def run_image(self, dataset_dict):
+        d = self._with_image(dataset_dict)
+        boxes, scores, classes = self.union_of_views(d)
+        K = self.cfg.MODEL.ROI_HEADS.NUM_CLASSES
+        if boxes.shape[0] == 0:  # no view detected anything
+            return {"instances": Instances((d["height"], d["width"]), pred_boxes=Boxes(boxes), scores=scores, pred_classes=classes)}
+        table = torch.zeros((boxes.shape[0], K + 1), dtype=torch.float32, device=boxes.device)
+        table[torch.arange(boxes.shape[0], device=boxes.device), classes] = scores
+        inst, _ = fast_rcnn_inference_single_image(boxes, table, (d["height"], d["width"]), self.UNION_SCORE_THRESH,
+                                                   self.cfg.MODEL.ROI_HEADS.NMS_THRESH_TEST, self.cfg.TEST.DETECTIONS_PER_IMAGE,
+                                                   Instances, Boxes)
+        return {"instances": inst}
 
 
 def read_image(file_name, format=None):

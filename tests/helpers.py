@@ -31,11 +31,7 @@ CASES = {
 OURS_ONLY = {"oicr_r18_reg"}
 
 
-def arch_key(cfg):
-    m = cfg.MODEL
-    if "vgg" in m.BACKBONE.NAME:
-        return f"vgg16_d{m.VGG.CONV5_DILATION}"
-    return f"resnet_ws{m.RESNETS.DEPTH}_d{m.RESNETS.RES5_DILATION}"
+arch_key = synth.arch_key
 
 
 def case_inputs(case):
@@ -52,9 +48,7 @@ def case_config(case, device="cpu", precision=None):
     return drn.builtin_config(name, ov)
 
 
-def case_weights(cfg, model_or_shapes, seed=0):
-    shapes = model_or_shapes if isinstance(model_or_shapes, dict) else synth.state_shapes(model_or_shapes)
-    return synth.make_weights(shapes, seed=seed, calib=synth.load_calib(arch_key(cfg)))
+case_weights = synth.calibrated_weights
 
 
 def to_batched(inputs, inst_cls, box_cls, device="cpu", train=True):

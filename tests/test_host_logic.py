@@ -152,24 +152,34 @@ def test_synthetic_data_is_deterministic_and_well_formed():
 
 def test_bench_reference_arm_prints_the_contract_line():
     """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract's keys, produced
-    without a GPU.  Smallest workload, one bounded sample."""
+    without a GPU, timing one FULL image of the workload (no sampling / extrapolation).  Here (with /root/reference) it runs the
+    unmodified reference model; forced to the oracle port (what the GPU box runs) it must report the same losses."""
     import json
     import subprocess
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "r18_bf16",
-                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root)
-    assert out.returncode == 0, out.stderr[-2000:]
-    line = json.loads(out.stdout.strip().splitlines()[-1])
-    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
-              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
-        assert k in line, k
-    assert line["impl"] == "reference" and line["unit"] == "images/sec" and line["value"] > 0 and line["vs_baseline"] is None
-    assert line["gpu_launches"] == 0 and "workload" in line["config"] and "model" not in line["config"]
-    cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
-    assert line["e2e"] == {"value": line["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    lines = {}
+    for kind in (("reference", "port") if refstub.reference_available() else ("port",)):
+        env = dict(os.environ, DRN_BENCH_REFERENCE_KIND="port" if kind == "port" else "")
+        out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "r18_bf16",
+                              "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=900, cwd=root, env=env)
+        assert out.returncode == 0, out.stderr[-2000:]
+        line = json.loads(out.stdout.strip().splitlines()[-1])
+        for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                  "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+            assert k in line, k
+        assert line["impl"] == "reference" and line["unit"] == "images/sec" and line["value"] > 0 and line["vs_baseline"] is None
+        assert line["gpu_launches"] == 0 and "workload" in line["config"] and "model" not in line["config"]
+        cb = line["cpu_baseline"]
+        assert cb["kind"] == kind and cb["cores"] >= 1 and cb["value"] == line["value"]
+        assert "no extrapolation" in cb["sample"] and "all 2000 proposals" in cb["sample"]
+        assert abs(line["steps"] * line["ms_per_step"] / 1e3 - sum(cb["step_seconds"])) < 0.01  # claimed time = measured time
+        assert line["e2e"] == {"value": line["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        lines[kind] = line
+    if len(lines) == 2:  # the port the GPU box times computes what the unmodified reference computes, at the full size
+        for k, v in lines["reference"]["losses"].items():
+            assert abs(lines["port"]["losses"][k] - v) <= 1e-4 * abs(v) + 1e-6, (k, lines["port"]["losses"][k], v)
 
 
 def test_fp32_tc_operand_packing_reconstructs_the_layer_on_cpu():
@@ -205,3 +215,40 @@ def test_fp32_tc_operand_packing_reconstructs_the_layer_on_cpu():
         mag = x.reshape(rows, -1).double().abs() @ w.reshape(cout, -1).double().abs().t()
         assert ((y - ref).abs() / mag).max().item() < 2e-7  # the nine dropped products are <= 2^-24 each
     assert ops.F32TC_SMALL_W == (1, 0, 2, 1, 0)
+
+
+@pytest.mark.parametrize("clip", [None, ("value", 0.05, 2.0), ("norm", 0.3, 2.0)])
+def test_fused_sgd_host_branch_matches_torch_sgd_with_gradient_clipping(clip):
+    """solver.FusedSGD on CPU parameters (torch's own arithmetic) incl. the per-parameter clipping of
+    detectron2/solver/build.py:19-92, and build_optimizer's param groups (BIAS_LR_FACTOR, WEIGHT_DECAY_BIAS)."""
+    from drn_wsod_pytorch_b200.solver import FusedSGD, build_optimizer
+
+    torch.manual_seed(0)
+    a = [torch.nn.Parameter(torch.randn(5, 4)), torch.nn.Parameter(torch.randn(5))]
+    b = [torch.nn.Parameter(p.detach().clone()) for p in a]
+    oa = FusedSGD(a, lr=0.1, momentum=0.9, weight_decay=1e-3, clip=clip)
+    ob = torch.optim.SGD(b, lr=0.1, momentum=0.9, weight_decay=1e-3)
+    for it in range(3):
+        for pa, pb in zip(a, b):
+            g = torch.randn_like(pa)
+            pa.grad, pb.grad = g.clone(), g.clone()
+            if clip is not None:
+                if clip[0] == "value":
+                    torch.nn.utils.clip_grad_value_(pb, clip[1])
+                else:
+                    torch.nn.utils.clip_grad_norm_(pb, clip[1], clip[2])
+        v0 = a[0]._version
+        oa.step()
+        ob.step()
+        assert a[0]._version > v0  # caches keyed on the version see the update
+        for pa, pb in zip(a, b):
+            assert torch.equal(pa, pb)
+    with pytest.raises(ValueError):
+        FusedSGD(a, lr=0.1, clip=("median", 1.0, 2.0))
+    cfg = drn.builtin_config("oicr_WSR_18_DC5_1x", ["MODEL.DEVICE", "cpu"])
+    cfg.SOLVER.CLIP_GRADIENTS.ENABLED = True
+    cfg.SOLVER.CLIP_GRADIENTS.CLIP_TYPE = "norm"
+    opt = build_optimizer(cfg, torch.nn.Linear(3, 2))
+    assert opt.clip == ("norm", 1.0, 2.0)
+    lrs = sorted(g["lr"] for g in opt.param_groups)
+    assert lrs == [cfg.SOLVER.BASE_LR, cfg.SOLVER.BASE_LR * cfg.SOLVER.BIAS_LR_FACTOR]

@@ -218,8 +218,7 @@ def test_gpu_tta_driver_matches_reference_golden(name):
     # the driver, twice: first pass eager (signatures seen once), second pass through the captured plans
     wrapper = tta.GeneralizedRCNNWithTTAAVG(cfg, model)
     for rep in range(2):
-        aug, tfms = wrapper._get_augmented_inputs(dict(d))
-        mean_boxes, mean_scores, _ = wrapper._get_augmented_boxes(aug, tfms)
+        mean_boxes, mean_scores = wrapper.merged_views(dict(d))
         np.testing.assert_allclose(mean_boxes.cpu().numpy(), _expand(g["mean_boxes"], mean_boxes.shape[1]), rtol=1e-5, atol=2e-3)
         err = np.abs(mean_scores.cpu().numpy().astype(np.float64) - g["mean_scores"]) / (np.abs(g["mean_scores"]) + 1e-3 * g["mean_scores"].max(0, keepdims=True) + 1e-30)
         assert err.max() < RTOL, (rep, err.max())
@@ -241,11 +240,12 @@ def test_gpu_tta_batched_views_and_skipped_detections_agree():
     cfg, model, d = _build_gpu("tta_r18_small", use_graph=False)
     one = tta.GeneralizedRCNNWithTTAAVG(cfg, model, batch_size=1)
     two = tta.GeneralizedRCNNWithTTAAVG(cfg, model, batch_size=2)  # (normal, flipped) pairs share their size
-    b1, s1, _ = one._get_augmented_boxes(*one._get_augmented_inputs(dict(d)))
-    b2, s2, _ = two._get_augmented_boxes(*two._get_augmented_inputs(dict(d)))
+    b1, s1 = one.merged_views(dict(d))
+    b2, s2 = two.merged_views(dict(d))
     np.testing.assert_allclose(b1.cpu().numpy(), b2.cpu().numpy(), rtol=1e-6, atol=1e-4)
     np.testing.assert_allclose(s1.cpu().numpy(), s2.cpu().numpy(), rtol=1e-4, atol=1e-8)
-    view = one._get_augmented_inputs(dict(d))[0][0]
+    view = one.tta_mapper(dict(d))[0]
+    view.pop("transforms")
     r_a, sc_a, bx_a = model.inference([view], do_postprocess=False)
     r_b, sc_b, bx_b = model.inference([view], do_postprocess=False, with_detections=False)
     assert r_b == [None] and len(r_a[0]) > 0
@@ -323,7 +323,7 @@ def test_tta_wrapper_host_flow_matches_reference_golden(monkeypatch, batch_size)
     d["image"] = inp["image_u8"]
     wrapper = tta.GeneralizedRCNNWithTTAAVG(cfg, model, batch_size=batch_size)
     # streamed path (what __call__ uses) and the reference's list API give the same merge
-    mean_boxes, mean_scores, _ = wrapper._get_augmented_boxes(*wrapper._get_augmented_inputs(dict(d)))
+    mean_boxes, mean_scores = wrapper.merged_views(dict(d))
     n_views = int(g["n_views"])
     assert calls == [batch_size] * (n_views // batch_size) + ([n_views % batch_size] if n_views % batch_size else [])
     np.testing.assert_allclose(mean_boxes.numpy(), _expand(g["mean_boxes"], mean_boxes.shape[1]), rtol=1e-6, atol=1e-4)

@@ -22,7 +22,7 @@ from .registry import (  # noqa: F401
     ROI_HEADS_REGISTRY,
     register_into_detectron2,
 )
-from .solver import FusedSGD, build_optimizer  # noqa: F401
+from .solver import FusedSGD, build_optimizer, run_step  # noqa: F401
 from .structures import Boxes, ImageList, Instances  # noqa: F401
 from .tta import DatasetMapperTTAAVG, DatasetMapperTTAUNION, GeneralizedRCNNWithTTAAVG, GeneralizedRCNNWithTTAUNION  # noqa: F401
 

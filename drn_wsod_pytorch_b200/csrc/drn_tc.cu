@@ -25,6 +25,7 @@
 // is TMA (full 128 B lines) and clipping of partial tiles is done by the TMA unit.  fp32 output (head
 // logits, a few hundred KB) keeps a direct register->global path.
 #include "common.cuh"
+#pragma nv_diag_suppress 128  // "loop is not reachable": the `if constexpr (HALO) { ...; continue; }` branches of gemm_tc_kernel
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -38,6 +39,15 @@ constexpr int UMMA_K = 16;
 constexpr int EPI_CHUNK = 64;                    // columns per staging buffer (128 B of bf16)
 constexpr int EPI_BUF_BYTES = 32 * EPI_CHUNK * 2;  // 32 rows x 128 B
 constexpr int IDENT_BYTES = 64 * 64 * 2;           // 64x64 bf16 identity (B operand of the residual MMAs)
+// HALO mode (3x3 convs without shortcut): the output tile is one image row of 128 pixels; per 64-channel block the three
+// input rows h-d, h, h+d (128 + 2d pixels each, zero-filled outside the map by TMA) are staged ONCE and all nine filter
+// taps read them through UMMA descriptors whose start address is shifted by the tap (dy: whole row buffers, dx: d pixels
+// = d * 128 B inside the 128B-swizzled row), so every input pixel crosses L2->SM ~3x instead of 9x.  Only the weights
+// stream through the STAGES ring.
+constexpr int HALO_MAX_DIL = 4;
+constexpr int HALO_ROW_BYTES = ((BM + 2 * HALO_MAX_DIL) * 128 + 1023) / 1024 * 1024;  // one input row: (128 + 2d) px x 128 B, 1 KB aligned
+constexpr int HALO_SLOT_BYTES = 3 * HALO_ROW_BYTES;
+constexpr int HALO_SLOTS = 2;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -212,6 +222,9 @@ struct Params {
   float drop_inv_keep;
   unsigned long long drop_seed;
   const unsigned long long* drop_seed_dev;  // optional device-resident addend (fresh masks under graph replay)
+  int rotate;   // every unit walks its k-blocks from a different starting block (see kb_rot): concurrently running CTAs then ask
+                // L2 for DIFFERENT weight tiles instead of all 148 for the same 64 lines at the same time
+  int halo_bo;  // HALO mode: also set the descriptor's base-offset field to the start's 128 B row phase (hardware probe switch)
   int debug;  // DRN_TC_DEBUG (profiling experiments only): 1 = skip TMA stores, 2 = skip epilogue math, 4 = skip tcgen05.ld
   // stream-K (deep-K GEMMs whose tile count does not fill whole waves): every unit gets an equal share of the
   // tiles x K-blocks iteration space; a unit that starts inside a tile dumps that partial accumulator to sk_ws
@@ -279,6 +292,16 @@ struct Sched {
   }
 };
 
+// k-block visited at step i of a piece [kb0, kb1) by unit `unit`: the walk starts at a unit-dependent block and wraps.
+// Every CTA of a layer reads the SAME weight tiles; marching through them in lockstep makes all SMs hit the same few L2
+// lines at once and the k-block step then costs ~0.4 us whatever its size (measured: skipping the A loads, 3/4 of the MMAs,
+// the epilogue math or the stores left the conv layers' times unchanged -- profiles/r2_conv_ablation.txt).
+__device__ __forceinline__ int kb_rot(int i, int kb0, int n, int rot) {
+  int j = i + rot;
+  if (j >= n) j -= n;
+  return kb0 + j;
+}
+
 __device__ __forceinline__ float4 lds128f(uint32_t saddr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
@@ -343,25 +366,30 @@ __device__ __forceinline__ void epi_chunk(uint32_t taddr, uint32_t scale_s, uint
 // two warps share a quadrant and split the tile's 64-column chunks between them.  The epilogue of a chunk is a
 // latency chain (tcgen05.ld -> math -> st.shared -> TMA store -> wait for the staging slot); short-K, wide-N layers
 // (1x1 expansion convs: 8 k-blocks of MMA per 128 x 256 tile) are bound by it, and a second set of warps hides it.
-template <int BN, int STAGES, int NBUF, int CG, int EW>
+template <int BN, int STAGES, int NBUF, int CG, int EW, bool HALO = false>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_r, const Params p) {
+  static_assert(!HALO || CG == 1, "HALO mode is single-CTA");
   constexpr uint32_t BROWS = BN / CG;                       // B rows staged by this CTA
-  constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BROWS * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t A_BYTES = HALO ? 0 : BM * BK * 2, B_BYTES = BROWS * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t HALO_BYTES = HALO ? HALO_SLOTS * HALO_SLOT_BYTES : 0;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   constexpr uint32_t EPI_BYTES = EW * NBUF * EPI_BUF_BYTES;
   constexpr int ETHREADS = 32 * EW, ESPLIT = EW / 4;  // epilogue threads; warps per TMEM quadrant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset arithmetic keeps the shared address space
-  uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;                        // 1024-aligned (stage sizes are multiples of 1 KB)
+  uint8_t* halo_smem = smem + STAGES * STAGE_BYTES;                       // 1024-aligned (stage sizes are multiples of 1 KB)
+  uint8_t* epi_smem = halo_smem + HALO_BYTES;
   uint8_t* ident = epi_smem + EPI_BYTES;                                  // 8 KB, 1024-aligned
-  float* sb_smem = reinterpret_cast<float*>(ident + IDENT_BYTES);         // [2 acc stages][scale BN | bias BN]
+  float* sb_smem = reinterpret_cast<float*>(ident + (HALO ? 0 : IDENT_BYTES));  // [2 acc stages][scale BN | bias BN]; HALO has no shortcut, no identity
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sb_smem + 4 * BN);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* hfull_bar = tempty_bar + 2;   // HALO: input rows of a channel block staged / consumed
+  uint64_t* hempty_bar = hfull_bar + HALO_SLOTS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hempty_bar + HALO_SLOTS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta_rank = (CG == 2) ? (int)cluster_ctarank() : 0;
@@ -377,6 +405,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (p.has_residual) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_r) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EW * CG); }
+    for (int s = 0; s < HALO_SLOTS; ++s) { mbar_init(&hfull_bar[s], 1); mbar_init(&hempty_bar[s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -424,6 +453,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int cblocks = p.conv ? (p.Cin / BK) : 1;
       Sched sched(unit, num_units, num_tiles, p);
       Piece pc;
+      int hs = 0;
+      uint32_t hphase = 0;
       while (sched.next(pc)) {
         const int tile = pc.tile;
         const int mt = (tile % num_mp) * CG + cta_rank, nt = tile / num_mp;
@@ -435,7 +466,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           h0 = (r / p.tiles_w) * p.tile_h;
           w0 = (r % p.tiles_w) * p.tile_w;
         }
-        for (int kb = pc.kb0; kb < pc.kb1; ++kb) {
+        if constexpr (HALO) {
+          // per channel block: three input rows into a halo slot, then the nine taps' weight tiles through the ring
+          const uint32_t row_load = (uint32_t)(BM + 2 * p.dil) * 128u;
+          const int rot_t = p.rotate ? unit % 9 : 0, rot_c = p.rotate ? (unit / 9) % cblocks : 0;
+          for (int ci = 0; ci < cblocks; ++ci) {
+            const int cb = kb_rot(ci, 0, cblocks, rot_c);
+            mbar_wait(&hempty_bar[hs], hphase ^ 1);
+            mbar_arrive_expect_tx(&hfull_bar[hs], 3 * row_load);
+            uint8_t* slot = halo_smem + hs * HALO_SLOT_BYTES;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+              tma_load_4d(&map_a, &hfull_bar[hs], slot + dy * HALO_ROW_BYTES, cb * BK, w0 - p.dil, h0 + (dy - 1) * p.dil, img);
+            if (++hs == HALO_SLOTS) { hs = 0; hphase ^= 1; }
+            for (int ti = 0; ti < 9; ++ti) {
+              const int tap = kb_rot(ti, 0, 9, rot_t);
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&full_bar[stage], B_BYTES);
+              tma_load_2d(&map_b, &full_bar[stage], smem + stage * STAGE_BYTES, (tap * cblocks + cb) * BK, nt * BN);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+          continue;
+        }
+        const int nkb = pc.kb1 - pc.kb0, rot = p.rotate ? (int)(((long long)unit * nkb) / num_units) % nkb : 0;
+        for (int ki = 0; ki < nkb; ++ki) {
+          const int kb = kb_rot(ki, pc.kb0, nkb, rot);
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const bool skip_a = (p.debug & 32) != 0;
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], CG * (skip_a ? B_BYTES : STAGE_BYTES));
@@ -494,6 +550,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      int hs = 0;
+      uint32_t hphase = 0;
       auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t id, uint32_t accum) {
         if constexpr (CG == 2) umma2_bf16(d, ad, bd, id, accum); else umma_bf16(d, ad, bd, id, accum);
       };
@@ -508,7 +566,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = pc.kb0; kb < pc.kb1; ++kb) {
+        if constexpr (HALO) {
+          const int cblocks = p.Cin / BK;
+          const int rot_t = p.rotate ? unit % 9 : 0;
+          for (int cb = 0; cb < cblocks; ++cb) {  // cb, ti count steps; the producer decides which block / tap arrives
+            mbar_wait(&hfull_bar[hs], hphase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t slot = smem_u32(halo_smem + hs * HALO_SLOT_BYTES);
+            for (int ti = 0; ti < 9; ++ti) {
+              const int tap = kb_rot(ti, 0, 9, rot_t);
+              mbar_wait(&full_bar[stage], phase);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              // output pixel m of the row tile reads input pixel m + (dx + 1) * d of input row dy: shifted start, SBO stays 1024
+              const uint32_t a_start = slot + (uint32_t)(tap / 3) * HALO_ROW_BYTES + (uint32_t)((tap % 3) * p.dil) * 128u;
+              uint64_t adesc = make_smem_desc(a_start);
+              if (p.halo_bo) adesc |= (uint64_t)((a_start >> 7) & 7u) << 49;
+              const uint64_t bdesc = make_smem_desc(smem_u32(smem + stage * STAGE_BYTES));
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) mma(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (cb > 0 || ti > 0 || k > 0) ? 1u : 0u);
+              commit(&empty_bar[stage]);  // frees the weight slot once these MMAs retire
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            commit(&hempty_bar[hs]);      // all nine taps have read the rows
+            if (cb == cblocks - 1) commit(&tfull_bar[acc]);
+            if (++hs == HALO_SLOTS) { hs = 0; hphase ^= 1; }
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
+        const int nkb = pc.kb1 - pc.kb0;
+        for (int ki = 0; ki < nkb; ++ki) {  // the producer's (rotated) order: which k-block sits in the slot does not matter here
           mbar_wait(&full_bar[stage], phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
@@ -522,10 +609,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the >>4 encoded address
-            if (!(p.debug & 64) || k == 0) mma(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > pc.kb0 || k > 0) ? 1u : 0u);
+            if (!(p.debug & 64) || k == 0) mma(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
           }
           commit(&empty_bar[stage]);  // frees the smem slot (in both CTAs) once these MMAs retire
-          if (kb == pc.kb1 - 1 && !with_res) commit(&tfull_bar[acc]);
+          if (ki == nkb - 1 && !with_res) commit(&tfull_bar[acc]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (with_res) {
@@ -822,15 +909,16 @@ constexpr size_t SK_WS_BYTES = SK_FLAG_BYTES + (size_t)148 * 128 * 256 * sizeof(
 constexpr size_t SK_WS_BYTES_MAX = SK_FLAG_BYTES + (size_t)4 * 148 * 128 * 256 * sizeof(float);  // tail split-K: up to 4 per SM
 static int g_tail_split = 0;  // opt-in (drn_gemm_set_tail_split / DRN_TC_TAILSPLIT=1): measured neutral-to-negative, see launch()
 
-template <int BN, int STAGES, int NBUF, int CG, int EW = 4>
+template <int BN, int STAGES, int NBUF, int CG, int EW = 4, bool HALO = false>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mr, Params p,
                   cudaStream_t st, void* workspace, size_t workspace_bytes) {
-  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + (BN / CG) * BK * 2) + EW * NBUF * EPI_BUF_BYTES + IDENT_BYTES +
-                          4 * BN * sizeof(float) + (2 * STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
+  constexpr size_t smem = (size_t)STAGES * ((HALO ? 0 : BM * BK * 2) + (BN / CG) * BK * 2) + (HALO ? HALO_SLOTS * HALO_SLOT_BYTES : 0) +
+                          EW * NBUF * EPI_BUF_BYTES + (HALO ? 0 : IDENT_BYTES) + 4 * BN * sizeof(float) +
+                          (2 * STAGES + 4 + 2 * HALO_SLOTS) * sizeof(uint64_t) + 16 + 1024;
   static_assert(smem <= 232448, "gemm_tc: shared memory budget exceeded");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, NBUF, CG, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, NBUF, CG, EW, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_err("gemm_tc: cudaFuncSetAttribute(%zu B smem): %s", smem, cudaGetErrorString(e));
     configured = true;
   }
@@ -910,7 +998,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
   }
   cfg.attrs = attr;
   cfg.numAttrs = pdl_env ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, NBUF, CG, EW>, ma, mb, mo, mr, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, NBUF, CG, EW, HALO>, ma, mb, mo, mr, p);
   if (e != cudaSuccess) return set_err("gemm_tc launch: %s", cudaGetErrorString(e));
   return 0;
 }
@@ -929,6 +1017,25 @@ static int pick_bn(int m_tiles, int N, int KB, int cg) {
     const double mma = 2.0 * bn, feed = (16384.0 + bn * 128.0 / cg) / 64.0;
     const double per_tile = KB * (mma > feed ? mma : feed) + 6.0 * bn;
     const double cost = waves * per_tile + 1500.0;
+    if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+// HALO mode tile width: per 64-channel block a tile moves 3 (128 + 2d) x 128 B of input rows + 9 BN x 128 B of weights
+// into the SM (~64 B/clk) and issues 9 x 4 MMAs of BN / 2 clocks
+static int pick_bn_halo(int m_tiles, int N, int cblocks, int dil) {
+  const int units_max = num_sms();
+  int best = 64;
+  double best_cost = 1e30;
+  const int cands[3] = {256, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    if (bn > 64 && N < bn) continue;
+    const int units = m_tiles * ((N + bn - 1) / bn);
+    const int waves = (units + units_max - 1) / units_max;
+    const double mma = 18.0 * bn, feed = (3.0 * (BM + 2 * dil) * 128.0 + 9.0 * bn * 128.0) / 64.0;
+    const double cost = waves * (cblocks * (mma > feed ? mma : feed) + 6.0 * bn) + 1500.0;
     if (cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
@@ -1005,14 +1112,39 @@ extern "C" int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int C
   CUtensorMap ma, mb, mo, mr;
   memset(&mo, 0, sizeof(mo));
   memset(&mr, 0, sizeof(mr));
+  // HALO mode (see HALO_ROW_BYTES): 3x3 convs without shortcut whose rows fill most of a 128-pixel tile.
+  // DRN_TC_HALO: 0 = never, 1 = wherever it is legal, unset = the measured rule below; DRN_TC_HALO_BO=1 sets the
+  // descriptor base-offset field (hardware probe).
+  static int halo_env = -2, halo_bo_env = 0;
+  if (halo_env == -2) {
+    const char* e = getenv("DRN_TC_HALO");
+    halo_env = e ? atoi(e) : -1;
+    const char* b = getenv("DRN_TC_HALO_BO");
+    halo_bo_env = (b && b[0] == '1') ? 1 : 0;
+  }
+  bool halo = false;
+  if (ksize == 3 && !residual && out_dtype != DRN_F32 && dropout_p == 0.f && dilation >= 1 && dilation <= HALO_MAX_DIL && halo_env != 0) {
+    const double fill = (double)W / (128.0 * ((W + 127) / 128));
+    halo = halo_env == 1 ? true : (fill >= 0.7 && Cin <= 256);
+  }
+  p.halo_bo = halo_bo_env;
+  static int rot_env = -1;
+  if (rot_env < 0) {
+    const char* e = getenv("DRN_TC_ROT");
+    rot_env = (e && e[0] == '0') ? 0 : 1;
+  }
+  // only while both operands stay L2-resident: CTAs at different K offsets no longer meet on the same tiles, so a GEMM whose
+  // operands stream from HBM (fc6: 0.8 GB + 0.4 GB) would fetch every tile once per CTA instead of once (the stream-K result)
+  p.rotate = rot_env && ((double)Mll * Cin + (double)Cout * Ktot) * 2.0 <= 48.0 * 1024 * 1024;
   if (ksize == 3) {
     p.conv = 1; p.NB = N; p.H = H; p.W = W; p.Cin = Cin; p.dil = dilation;
-    pick_conv_tile(H, W, &p.tile_w, &p.tile_h);
+    if (halo) { p.tile_w = 128; p.tile_h = 1; }
+    else pick_conv_tile(H, W, &p.tile_w, &p.tile_h);
     p.tiles_h = (H + p.tile_h - 1) / p.tile_h; p.tiles_w = (W + p.tile_w - 1) / p.tile_w;
     p.num_m_tiles = N * p.tiles_h * p.tiles_w;
     const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
-    const cuuint32_t box[4] = {BK, (cuuint32_t)p.tile_w, (cuuint32_t)p.tile_h, 1};
+    const cuuint32_t box[4] = {BK, (cuuint32_t)(halo ? BM + 2 * dilation : p.tile_w), (cuuint32_t)p.tile_h, 1};
     if (make_map(&ma, in, 4, dims, strides, box)) return 1;
     if (!p.out_f32) {
       const int bw = p.tile_w < 32 ? p.tile_w : 32;
@@ -1056,8 +1188,8 @@ extern "C" int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int C
     cg_env = (e && e[0] == '1') ? 1 : (e && e[0] == '2') ? 2 : 0;
   }
   const long long work = (long long)p.num_m_tiles * ((Cout + 255) / 256) * p.KB;
-  const int cg = (p.num_m_tiles >= 2 && (cg_env == 2 || (cg_env == 0 && work >= 9000))) ? 2 : 1;
-  const int bn = pick_bn(p.num_m_tiles, Cout, p.KB, cg);
+  const int cg = halo ? 1 : (p.num_m_tiles >= 2 && (cg_env == 2 || (cg_env == 0 && work >= 9000))) ? 2 : 1;
+  const int bn = halo ? pick_bn_halo(p.num_m_tiles, Cout, Cin / BK, dilation) : pick_bn(p.num_m_tiles, Cout, p.KB, cg);
   p.num_n_tiles = (Cout + bn - 1) / bn;
   {
     const cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
@@ -1066,6 +1198,11 @@ extern "C" int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int C
     if (make_map(&mb, w, 2, dims, strides, box)) return 1;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (halo) {
+    if (bn == 256) return launch<256, 3, 1, 1, 4, true>(ma, mb, mo, mr, p, st, nullptr, 0);
+    if (bn == 128) return launch<128, 5, 2, 1, 4, true>(ma, mb, mo, mr, p, st, nullptr, 0);
+    return launch<64, 8, 2, 1, 4, true>(ma, mb, mo, mr, p, st, nullptr, 0);
+  }
   // 8 epilogue warps for short-K layers (the epilogue latency chain, not the MMAs, bounds them); the split-K schedules
   // keep the 4-warp variant.  DRN_TC_EPI8_KB: largest K-block count that takes it (0 = never).
   static int epi8_kb = -1;

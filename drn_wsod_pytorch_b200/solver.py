@@ -132,3 +132,29 @@ def build_optimizer(cfg, model):
     if cg is not None and cg.ENABLED:  # solver/build.py:65-92 maybe_add_gradient_clipping
         clip = (cg.CLIP_TYPE, cg.CLIP_VALUE, cg.NORM_TYPE)
     return FusedSGD(params, s.BASE_LR, momentum=s.MOMENTUM, nesterov=s.NESTEROV, model=model, clip=clip)
+
+
+def run_step(model, optimizer, batched_inputs, iteration, iter_size=1, start_iter=0, grad_sync=None):
+    """One iteration of projects/WSL/tools/train_net.py:65-117 (`Trainer.run_step`) around the B200 model: forward, the sum
+    of the loss dict divided by `WSL.ITER_SIZE`, backward, and -- only on iterations that are a multiple of ITER_SIZE --
+    the optimizer step followed by zero_grad; gradients accumulate in `p.grad` over the iterations in between
+    (zero_grad also runs once before the first iteration, as there).  With a captured forward plan the backward of
+    iteration i has to run before the forward of iteration i+1 (it reads the plan's buffers): this order does.
+    grad_sync: a distributed.GradientSynchronizer attached to the model (data-parallel runs) -- its `finish()` hands the
+    averaged gradients of THIS backward to `p.grad` (accumulating) before the step, as DistributedDataParallel would.
+    Returns the (un-divided) loss dict, detached."""
+    assert model.training, "[run_step] model was changed to eval mode!"
+    assert iter_size >= 1
+    loss_dict = model(batched_inputs)
+    losses = sum(loss_dict.values())
+    if not torch.isfinite(losses).all():  # detectron2/engine/train_loop.py:_detect_anomaly
+        raise FloatingPointError(f"Loss became infinite or NaN at iteration={iteration}!\nloss_dict = {loss_dict}")
+    if iteration == start_iter:
+        optimizer.zero_grad()
+    (losses / iter_size).backward()
+    if grad_sync is not None:
+        grad_sync.finish()
+    if iteration % iter_size == 0:
+        optimizer.step()
+        optimizer.zero_grad()
+    return {k: v.detach() for k, v in loss_dict.items()}

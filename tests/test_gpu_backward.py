@@ -177,3 +177,44 @@ def test_fused_sgd_from_build_optimizer_tracks_the_oracle(precision):
             w = fc.weight.detach()
             ref = w.view(w.shape[0], perm, -1).permute(0, 2, 1).reshape(w.shape) if perm else w
             assert torch.equal(fresh, ref.to(torch.bfloat16))
+
+
+def test_iter_size_accumulation_and_stale_plan_guard():
+    """WSL.ITER_SIZE (projects/WSL/tools/train_net.py:100-113): `run_step` with ITER_SIZE 2 over two different images
+    accumulates (g1 + g2) / 2 in p.grad and steps once; the parameters must equal one plain SGD step on that mean gradient.
+    Also: a second forward with the same signature before backward() overwrites the captured plan's buffers -- the bridge
+    must refuse to run the stale backward instead of silently using the other image's activations."""
+    case = "oicr_r18_small"
+    cfg, model, weights = _build(case, "fp32")
+    (H, W, R, G, seed) = helpers.CASES[case][3][0]
+    inp_a = helpers.case_inputs(case)
+    inp_b = [helpers.synth.make_inputs(H, W, R, seed=seed + 7, num_gt=G)]
+    ba = helpers.to_batched(inp_a, drn.Instances, drn.Boxes, device=DEV)
+    bb = helpers.to_batched(inp_b, drn.Instances, drn.Boxes, device=DEV)
+    params = [p for p in model.parameters() if p.requires_grad]
+    # reference: separate gradients of the two images
+    grads = []
+    for b in (ba, bb):
+        model.zero_grad(set_to_none=True)
+        sum(model(b).values()).backward()
+        grads.append([None if p.grad is None else p.grad.clone() for p in params])
+    before = [p.detach().clone() for p in params]
+    lr = 1e-3
+    opt = torch.optim.SGD(params, lr=lr)
+    model.zero_grad(set_to_none=True)
+    for it, b in ((1, ba), (2, bb)):  # iteration counts from 1 like the trainer's self.iter after start_iter... the step fires at it % 2 == 0
+        drn.run_step(model, opt, b, it, iter_size=2, start_iter=1)
+    for p, p0, g1, g2 in zip(params, before, grads[0], grads[1]):
+        if g1 is None:
+            assert torch.equal(p.detach(), p0)
+            continue
+        want = p0 - lr * (g1 + g2) / 2
+        assert float((p.detach() - want).abs().max()) <= 1e-6 * max(1.0, float(want.abs().max())) + 1e-3 * lr * float((g1 + g2).abs().max())
+        assert p.grad is None or float(p.grad.abs().max()) == 0.0  # zero_grad after the step
+    # stale-plan guard (the captured plan exists by now: same signature seen more than twice)
+    assert model._plans
+    l1 = model(ba)
+    l2 = model(ba)  # same signature: replays the plan, overwriting the buffers l1's backward would read
+    with pytest.raises(RuntimeError, match="overwritten by a later forward"):
+        sum(l1.values()).backward()
+    sum(l2.values()).backward()  # the latest forward is fine

@@ -181,7 +181,11 @@ def test_tc_gemm_bf16(M, K, N, relu, res, f32out):
 
 @pytest.mark.parametrize("cin,cout,dil,H,W,res", [(64, 64, 1, 16, 32, False), (128, 256, 2, 21, 35, True), (64, 128, 1, 74, 124, False),
                                                    (256, 64, 2, 9, 17, True), (512, 512, 2, 74, 124, True), (64, 64, 1, 5, 300, True),
-                                                   (64, 64, 1, 150, 40, False)])
+                                                   (64, 64, 1, 150, 40, False),
+                                                   # rows that fill a 128-pixel tile and no shortcut: the HALO variant (three input rows
+                                                   # staged once per channel block, nine taps through shifted UMMA descriptors)
+                                                   (256, 256, 2, 74, 124, False), (128, 128, 1, 75, 125, False), (64, 64, 1, 12, 500, False),
+                                                   (64, 192, 4, 20, 100, False), (256, 64, 2, 37, 250, False), (192, 320, 1, 3, 127, False)])
 def test_tc_conv3x3_bf16(cin, cout, dil, H, W, res):
     g = torch.Generator().manual_seed(cin + cout + dil + H)
     N = 2

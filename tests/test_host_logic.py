@@ -252,3 +252,36 @@ def test_fused_sgd_host_branch_matches_torch_sgd_with_gradient_clipping(clip):
     assert opt.clip == ("norm", 1.0, 2.0)
     lrs = sorted(g["lr"] for g in opt.param_groups)
     assert lrs == [cfg.SOLVER.BASE_LR, cfg.SOLVER.BASE_LR * cfg.SOLVER.BIAS_LR_FACTOR]
+
+
+def test_run_step_iter_size_schedule_on_cpu():
+    """solver.run_step = projects/WSL/tools/train_net.py:65-117: zero_grad once at start_iter, loss / ITER_SIZE, the optimizer
+    steps (and zeroes) only on iterations that are a multiple of ITER_SIZE, non-finite losses raise FloatingPointError."""
+    from drn_wsod_pytorch_b200.solver import run_step
+
+    class Toy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.tensor([1.0, -2.0]))
+
+        def forward(self, x):
+            return {"loss_a": (self.w * x).sum(), "loss_b": (self.w ** 2).sum() * 0.5}
+
+    m = Toy().train()
+    opt = torch.optim.SGD(m.parameters(), lr=0.1)
+    m.w.grad = torch.tensor([9.0, 9.0])  # stale gradient: must be cleared at start_iter
+    xs = [torch.tensor([1.0, 0.0]), torch.tensor([0.0, 2.0]), torch.tensor([1.0, 1.0])]
+    w0 = m.w.detach().clone()
+    out = run_step(m, opt, xs[0], 1, iter_size=3, start_iter=1)
+    assert set(out) == {"loss_a", "loss_b"} and not out["loss_a"].requires_grad
+    run_step(m, opt, xs[1], 2, iter_size=3, start_iter=1)
+    assert torch.equal(m.w.detach(), w0)  # no step yet
+    assert torch.allclose(m.w.grad, (xs[0] + xs[1] + 2 * w0) / 3)
+    run_step(m, opt, xs[2], 3, iter_size=3, start_iter=1)
+    assert torch.allclose(m.w.detach(), w0 - 0.1 * (sum(xs) + 3 * w0) / 3)
+    assert m.w.grad is None or float(m.w.grad.abs().max()) == 0.0
+    with pytest.raises(FloatingPointError):
+        run_step(m, opt, torch.tensor([float("inf"), 0.0]), 4, iter_size=3, start_iter=1)
+    m.eval()
+    with pytest.raises(AssertionError):
+        run_step(m, opt, xs[0], 5)

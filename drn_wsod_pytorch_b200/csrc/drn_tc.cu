@@ -35,7 +35,7 @@ namespace tc {
 
 constexpr int BM = 128;      // UMMA M (cta_group::1)
 constexpr int BK = 64;       // one 128-byte swizzle atom of bf16 along K
-constexpr int UMMA_K = 16;
+constexpr int UMMA_K = 16;  // (the four K = 16 steps of a k-block are spelled out in umma_kblock)
 constexpr int EPI_CHUNK = 64;                    // columns per staging buffer (128 B of bf16)
 constexpr int EPI_BUF_BYTES = 32 * EPI_CHUNK * 2;  // 32 rows x 128 B
 constexpr int IDENT_BYTES = 64 * 64 * 2;           // 64x64 bf16 identity (B operand of the residual MMAs)
@@ -94,6 +94,22 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// One lane of a converged warp (PTX elect.sync).  The TMA / MMA role warps run their loops with all 32 lanes in
+// warp-uniform control flow and guard only the issuing instructions with this: ptxas then feeds the instructions'
+// uniform-register operands straight from the elected lane.  Under a plain `if (lane == 0)` it cannot prove that one
+// thread is active and wraps EVERY tcgen05.mma / cp.async.bulk.tensor in an ELECT + 5x R2UR.BROADCAST + BRA.U.ANY
+// waterfall loop: ~127 SASS instructions per k-block in the single issuing thread, ~0.4 us per k-block whatever the tile
+// (profiles/r2_conv_ablation.txt, r2_ncu_mma_issue_loop.txt) -- that, not loads or MMAs, bounded every conv layer.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- CTA-pair (cta_group::2) variants.  In a 2-CTA cluster the even CTA (rank 0) is the MMA leader; the
@@ -136,34 +152,126 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 
+// The same descriptor as two 32-bit words: only the low word (start address, LBO) varies, the high word (SBO, version,
+// swizzle mode) is a constant.  The issue loops do all descriptor arithmetic in 32 bits so that it stays on the uniform
+// datapath (64-bit shifts / ors are vector-only and cost an R2UR pair per operand and MMA).
+constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+
 // kind::f16 instruction descriptor: D=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16 [10,13)=1, K-major A/B,
 // N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t make_idesc(int n, int m = BM) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(a_hi), "r"(DESC_HI) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %6};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(a_hi), "r"(DESC_HI) : "memory");
 }
 __device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {  // arrive on `bar` in BOTH CTAs of the pair
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// The four K = 16 MMAs of one 64-wide k-block in ONE asm block: the descriptor low words advance by 2 (32 bytes along K inside
+// the swizzle atom) in place, so the issuing thread marshals five operands per k-block instead of per MMA.
+template <int CG>
+__device__ __forceinline__ void umma_kblock(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 2) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, t;\n\t"
+        ".reg .b64 da, db;\n\t"
+        ".reg .b32 al, bl;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %6};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t"
+        "add.u32 al, %1, 2;\n\t"
+        "add.u32 bl, %2, 2;\n\t"
+        "mov.b64 da, {al, %5};\n\t"
+        "mov.b64 db, {bl, %6};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, t;\n\t"
+        "add.u32 al, %1, 4;\n\t"
+        "add.u32 bl, %2, 4;\n\t"
+        "mov.b64 da, {al, %5};\n\t"
+        "mov.b64 db, {bl, %6};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, t;\n\t"
+        "add.u32 al, %1, 6;\n\t"
+        "add.u32 bl, %2, 6;\n\t"
+        "mov.b64 da, {al, %5};\n\t"
+        "mov.b64 db, {bl, %6};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, t;\n\t"
+        "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(a_hi), "r"(DESC_HI) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, t;\n\t"
+        ".reg .b64 da, db;\n\t"
+        ".reg .b32 al, bl;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %6};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+        "add.u32 al, %1, 2;\n\t"
+        "add.u32 bl, %2, 2;\n\t"
+        "mov.b64 da, {al, %5};\n\t"
+        "mov.b64 db, {bl, %6};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, t;\n\t"
+        "add.u32 al, %1, 4;\n\t"
+        "add.u32 bl, %2, 4;\n\t"
+        "mov.b64 da, {al, %5};\n\t"
+        "mov.b64 db, {bl, %6};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, t;\n\t"
+        "add.u32 al, %1, 6;\n\t"
+        "add.u32 bl, %2, 6;\n\t"
+        "mov.b64 da, {al, %5};\n\t"
+        "mov.b64 db, {bl, %6};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, t;\n\t"
+        "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(a_hi), "r"(DESC_HI) : "memory");
+  }
+}
+// wait / commit on a barrier given by its shared-space address (the issue loops keep running addresses instead of indexing)
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar) {
+  if constexpr (CG == 2)
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -222,8 +330,6 @@ struct Params {
   float drop_inv_keep;
   unsigned long long drop_seed;
   const unsigned long long* drop_seed_dev;  // optional device-resident addend (fresh masks under graph replay)
-  int rotate;   // every unit walks its k-blocks from a different starting block (see kb_rot): concurrently running CTAs then ask
-                // L2 for DIFFERENT weight tiles instead of all 148 for the same 64 lines at the same time
   int halo_bo;  // HALO mode: also set the descriptor's base-offset field to the start's 128 B row phase (hardware probe switch)
   int debug;  // DRN_TC_DEBUG (profiling experiments only): 1 = skip TMA stores, 2 = skip epilogue math, 4 = skip tcgen05.ld
   // stream-K (deep-K GEMMs whose tile count does not fill whole waves): every unit gets an equal share of the
@@ -291,16 +397,6 @@ struct Sched {
     return true;
   }
 };
-
-// k-block visited at step i of a piece [kb0, kb1) by unit `unit`: the walk starts at a unit-dependent block and wraps.
-// Every CTA of a layer reads the SAME weight tiles; marching through them in lockstep makes all SMs hit the same few L2
-// lines at once and the k-block step then costs ~0.4 us whatever its size (measured: skipping the A loads, 3/4 of the MMAs,
-// the epilogue math or the stores left the conv layers' times unchanged -- profiles/r2_conv_ablation.txt).
-__device__ __forceinline__ int kb_rot(int i, int kb0, int n, int rot) {
-  int j = i + rot;
-  if (j >= n) j -= n;
-  return kb0 + j;
-}
 
 __device__ __forceinline__ float4 lds128f(uint32_t saddr) {
   float4 v;
@@ -391,8 +487,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* hempty_bar = hfull_bar + HALO_SLOTS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hempty_bar + HALO_SLOTS);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cta_rank = (CG == 2) ? (int)cluster_ctarank() : 0;
+  // warp-uniform by construction, and shuffled from lane 0 so that ptxas KNOWS it: branches on them become uniform branches
+  // and the role loops below run on the uniform datapath (no divergence bookkeeping, operands in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int cta_rank = (CG == 2) ? __shfl_sync(0xffffffffu, (int)cluster_ctarank(), 0) : 0;
   const bool leader = cta_rank == 0;
   const int unit = blockIdx.x / CG, num_units = gridDim.x / CG;   // a unit = one CTA (CG=1) or one CTA pair
   const int num_mp = (p.num_m_tiles + CG - 1) / CG;               // M tiles per unit step (pairs for CG=2)
@@ -439,15 +537,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   if constexpr (CG == 2) cluster_sync_all();  // peer barriers initialised before any remote arrive / 2-SM TMA
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   // Programmatic dependent launch: everything above (barrier init, TMEM alloc, descriptor prefetch) may run
   // while the previous kernel of the stream is still draining; global memory is only touched after this point.
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (every CTA)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (every CTA): all 32 lanes walk the
+    // schedule in warp-uniform control flow, one elected lane issues (see elect_one)
+    {
       int stage = 0;
       uint32_t phase = 0;
       const int cblocks = p.conv ? (p.Cin / BK) : 1;
@@ -469,56 +568,69 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if constexpr (HALO) {
           // per channel block: three input rows into a halo slot, then the nine taps' weight tiles through the ring
           const uint32_t row_load = (uint32_t)(BM + 2 * p.dil) * 128u;
-          const int rot_t = p.rotate ? unit % 9 : 0, rot_c = p.rotate ? (unit / 9) % cblocks : 0;
-          for (int ci = 0; ci < cblocks; ++ci) {
-            const int cb = kb_rot(ci, 0, cblocks, rot_c);
+          for (int cb = 0; cb < cblocks; ++cb) {
             mbar_wait(&hempty_bar[hs], hphase ^ 1);
-            mbar_arrive_expect_tx(&hfull_bar[hs], 3 * row_load);
-            uint8_t* slot = halo_smem + hs * HALO_SLOT_BYTES;
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&hfull_bar[hs], 3 * row_load);
+              uint8_t* slot = halo_smem + hs * HALO_SLOT_BYTES;
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy)
-              tma_load_4d(&map_a, &hfull_bar[hs], slot + dy * HALO_ROW_BYTES, cb * BK, w0 - p.dil, h0 + (dy - 1) * p.dil, img);
+              for (int dy = 0; dy < 3; ++dy)
+                tma_load_4d(&map_a, &hfull_bar[hs], slot + dy * HALO_ROW_BYTES, cb * BK, w0 - p.dil, h0 + (dy - 1) * p.dil, img);
+            }
+            __syncwarp();
             if (++hs == HALO_SLOTS) { hs = 0; hphase ^= 1; }
-            for (int ti = 0; ti < 9; ++ti) {
-              const int tap = kb_rot(ti, 0, 9, rot_t);
+            int kcol = cb * BK;                      // weight K order is (tap, channel): tap t of this block at (t * cblocks + cb) * 64
+            const int kstep = cblocks * BK;
+            for (int tap = 0; tap < 9; ++tap) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
-              mbar_arrive_expect_tx(&full_bar[stage], B_BYTES);
-              tma_load_2d(&map_b, &full_bar[stage], smem + stage * STAGE_BYTES, (tap * cblocks + cb) * BK, nt * BN);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(&full_bar[stage], B_BYTES);
+                tma_load_2d(&map_b, &full_bar[stage], smem + stage * STAGE_BYTES, kcol, nt * BN);
+              }
+              __syncwarp();
+              kcol += kstep;
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
           }
           continue;
         }
-        const int nkb = pc.kb1 - pc.kb0, rot = p.rotate ? (int)(((long long)unit * nkb) / num_units) % nkb : 0;
+        // The issuing warps are single instruction streams: every instruction in this loop is paid once per k-block by the
+        // whole pipeline (measured: ~100 SASS instructions with an integer division per k-block held every conv layer at
+        // ~0.3 us per k-block after the MMA loop had been fixed), so the (tap, channel block) walk is kept in counters.
+        const int nkb = pc.kb1 - pc.kb0;
+        const int brow = nt * BN + cta_rank * (int)BROWS;
+        const bool skip_a = (p.debug & 32) != 0;
+        const int a_row = mt * BM;
+        int kcol = pc.kb0 * BK;                      // K offset of the weight tile (and of A in GEMM mode)
+        int cb = 0, tx = 0, ty = 0;                  // conv mode: channel block, filter tap (tx, ty)
+        if (p.conv && pc.kb0 != 0) { const int tap0 = pc.kb0 / cblocks; cb = pc.kb0 - tap0 * cblocks; ty = tap0 / 3; tx = tap0 - 3 * ty; }
+        int dw = (tx - 1) * p.dil, dh = (ty - 1) * p.dil;
         for (int ki = 0; ki < nkb; ++ki) {
-          const int kb = kb_rot(ki, pc.kb0, nkb, rot);
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          const bool skip_a = (p.debug & 32) != 0;
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], CG * (skip_a ? B_BYTES : STAGE_BYTES));
-          uint8_t* sa = smem + stage * STAGE_BYTES;
-          uint8_t* sb = sa + A_BYTES;
-          const int brow = nt * BN + cta_rank * (int)BROWS;
-          if (skip_a) {
-            if constexpr (CG == 2) tma2_load_2d(&map_b, &full_bar[stage], sb, kb * BK, brow);
-            else tma_load_2d(&map_b, &full_bar[stage], sb, kb * BK, brow);
-          } else if constexpr (CG == 2) {
-            if (p.conv) {
-              const int tap = kb / cblocks, cb = kb - tap * cblocks;
-              const int dh = (tap / 3 - 1) * p.dil, dw = (tap % 3 - 1) * p.dil;
-              tma2_load_4d(&map_a, &full_bar[stage], sa, cb * BK, w0 + dw, h0 + dh, img);
+          if (elect_one()) {
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], CG * (skip_a ? B_BYTES : STAGE_BYTES));
+            uint8_t* sa = smem + stage * STAGE_BYTES;
+            uint8_t* sb = sa + A_BYTES;
+            if constexpr (CG == 2) {
+              if (!skip_a) {
+                if (p.conv) tma2_load_4d(&map_a, &full_bar[stage], sa, cb * BK, w0 + dw, h0 + dh, img);
+                else tma2_load_2d(&map_a, &full_bar[stage], sa, kcol, a_row);
+              }
+              tma2_load_2d(&map_b, &full_bar[stage], sb, kcol, brow);
             } else {
-              tma2_load_2d(&map_a, &full_bar[stage], sa, kb * BK, mt * BM);
+              if (!skip_a) {
+                if (p.conv) tma_load_4d(&map_a, &full_bar[stage], sa, cb * BK, w0 + dw, h0 + dh, img);
+                else tma_load_2d(&map_a, &full_bar[stage], sa, kcol, a_row);
+              }
+              tma_load_2d(&map_b, &full_bar[stage], sb, kcol, brow);
             }
-            tma2_load_2d(&map_b, &full_bar[stage], sb, kb * BK, brow);
-          } else {
-            if (p.conv) {
-              const int tap = kb / cblocks, cb = kb - tap * cblocks;
-              const int dh = (tap / 3 - 1) * p.dil, dw = (tap % 3 - 1) * p.dil;
-              tma_load_4d(&map_a, &full_bar[stage], sa, cb * BK, w0 + dw, h0 + dh, img);
-            } else {
-              tma_load_2d(&map_a, &full_bar[stage], sa, kb * BK, mt * BM - ((p.debug & 8) ? ((p.debug >> 8) & 15) : 0));
-            }
-            tma_load_2d(&map_b, &full_bar[stage], sb, kb * BK, brow);
+          }
+          __syncwarp();
+          kcol += BK;
+          if (++cb == cblocks) {                     // next filter tap (GEMM mode: cblocks == 1, the counters are unused)
+            cb = 0;
+            if (++tx == 3) { tx = 0; ++ty; dh += p.dil; }
+            dw = (tx - 1) * p.dil;
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -526,38 +638,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int nchunk = (min(BN, p.N - nt * BN) + EPI_CHUNK - 1) / EPI_CHUNK;
           for (int c = 0; c < nchunk; ++c) {  // shortcut tile as extra "k-blocks": 128 rows x 64 output columns each
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (leader) mbar_arrive_expect_tx(&full_bar[stage], CG * A_BYTES);
-            uint8_t* sa = smem + stage * STAGE_BYTES;
-            if constexpr (CG == 2) {
-              if (p.conv) tma2_load_4d(&map_r, &full_bar[stage], sa, nt * BN + c * EPI_CHUNK, w0, h0, img);
-              else tma2_load_2d(&map_r, &full_bar[stage], sa, nt * BN + c * EPI_CHUNK, mt * BM);
-            } else {
-              if (p.conv) tma_load_4d(&map_r, &full_bar[stage], sa, nt * BN + c * EPI_CHUNK, w0, h0, img);
-              else tma_load_2d(&map_r, &full_bar[stage], sa, nt * BN + c * EPI_CHUNK, mt * BM);
+            if (elect_one()) {
+              if (leader) mbar_arrive_expect_tx(&full_bar[stage], CG * A_BYTES);
+              uint8_t* sa = smem + stage * STAGE_BYTES;
+              if constexpr (CG == 2) {
+                if (p.conv) tma2_load_4d(&map_r, &full_bar[stage], sa, nt * BN + c * EPI_CHUNK, w0, h0, img);
+                else tma2_load_2d(&map_r, &full_bar[stage], sa, nt * BN + c * EPI_CHUNK, mt * BM);
+              } else {
+                if (p.conv) tma_load_4d(&map_r, &full_bar[stage], sa, nt * BN + c * EPI_CHUNK, w0, h0, img);
+                else tma_load_2d(&map_r, &full_bar[stage], sa, nt * BN + c * EPI_CHUNK, mt * BM);
+              }
             }
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread of the leader CTA)
-    if (lane == 0 && leader) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA): the whole warp walks the
+    // schedule, one elected lane issues the tcgen05.mma / tcgen05.commit instructions
+    if (leader) {
       constexpr uint32_t idesc = make_idesc(BN, BM * CG);
       constexpr uint32_t idesc64 = make_idesc(64, BM * CG);
-      const uint64_t ident_desc = make_smem_desc(smem_u32(ident));
+      const uint32_t ident_lo = smem_desc_lo(smem_u32(ident));
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       int hs = 0;
       uint32_t hphase = 0;
-      auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t id, uint32_t accum) {
-        if constexpr (CG == 2) umma2_bf16(d, ad, bd, id, accum); else umma_bf16(d, ad, bd, id, accum);
-      };
-      auto commit = [&](uint64_t* bar) {
-        if constexpr (CG == 2) umma2_commit_both(bar); else umma_commit(bar);
-      };
+      const uint32_t smem_base = smem_u32(smem);
+      const uint32_t full_base = smem_u32(full_bar);
+      constexpr uint32_t EMPTY_OFF = STAGES * 8;  // empty_bar = full_bar + STAGES
       Sched sched(unit, num_units, num_tiles, p);
       Piece pc;
       while (sched.next(pc)) {
@@ -568,52 +681,63 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t tmem_d = tmem_base + acc * BN;
         if constexpr (HALO) {
           const int cblocks = p.Cin / BK;
-          const int rot_t = p.rotate ? unit % 9 : 0;
-          for (int cb = 0; cb < cblocks; ++cb) {  // cb, ti count steps; the producer decides which block / tap arrives
+          const uint32_t dx_bytes = (uint32_t)p.dil * 128u;
+          for (int cb = 0; cb < cblocks; ++cb) {
             mbar_wait(&hfull_bar[hs], hphase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t slot = smem_u32(halo_smem + hs * HALO_SLOT_BYTES);
+            const uint32_t slot = smem_base + (uint32_t)(halo_smem - smem) + hs * HALO_SLOT_BYTES;
+            uint32_t a_start = slot;
+            int tx = 0;
             for (int ti = 0; ti < 9; ++ti) {
-              const int tap = kb_rot(ti, 0, 9, rot_t);
               mbar_wait(&full_bar[stage], phase);
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               // output pixel m of the row tile reads input pixel m + (dx + 1) * d of input row dy: shifted start, SBO stays 1024
-              const uint32_t a_start = slot + (uint32_t)(tap / 3) * HALO_ROW_BYTES + (uint32_t)((tap % 3) * p.dil) * 128u;
-              uint64_t adesc = make_smem_desc(a_start);
-              if (p.halo_bo) adesc |= (uint64_t)((a_start >> 7) & 7u) << 49;
-              const uint64_t bdesc = make_smem_desc(smem_u32(smem + stage * STAGE_BYTES));
+              const uint32_t adesc = smem_desc_lo(a_start);
+              const uint32_t a_hi = p.halo_bo ? (DESC_HI | (((a_start >> 7) & 7u) << 17)) : DESC_HI;  // base-offset field [49,52)
+              const uint32_t bdesc = smem_desc_lo(smem_base + stage * STAGE_BYTES);
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < BK / UMMA_K; ++k) mma(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (cb > 0 || ti > 0 || k > 0) ? 1u : 0u);
-              commit(&empty_bar[stage]);  // frees the weight slot once these MMAs retire
+                umma_kblock<CG>(tmem_d, adesc, bdesc, a_hi, idesc, (cb > 0 || ti > 0) ? 1u : 0u);
+                umma_commit_addr<CG>(smem_u32(&empty_bar[stage]));  // frees the weight slot once these MMAs retire
+                if (ti == 8) {
+                  umma_commit_addr<CG>(smem_u32(&hempty_bar[hs]));  // all nine taps have read the rows
+                  if (cb == cblocks - 1) umma_commit_addr<CG>(smem_u32(&tfull_bar[acc]));
+                }
+              }
+              __syncwarp();
+              a_start += dx_bytes;
+              if (++tx == 3) { tx = 0; a_start += HALO_ROW_BYTES - 3 * dx_bytes; }  // next input row
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
-            commit(&hempty_bar[hs]);      // all nine taps have read the rows
-            if (cb == cblocks - 1) commit(&tfull_bar[acc]);
             if (++hs == HALO_SLOTS) { hs = 0; hphase ^= 1; }
           }
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
           continue;
         }
+        // One k-block per iteration; this warp is a single instruction stream, so every instruction here is paid per k-block
+        // by the whole CTA: running descriptor / barrier addresses (no per-iteration multiplies), one asm block for the four
+        // MMAs, the accumulator hand-over peeled out of the loop.
         const int nkb = pc.kb1 - pc.kb0;
-        for (int ki = 0; ki < nkb; ++ki) {  // the producer's (rotated) order: which k-block sits in the slot does not matter here
-          mbar_wait(&full_bar[stage], phase);
+        constexpr uint32_t STAGE_DESC = STAGE_BYTES >> 4, B_DESC_OFF = A_BYTES >> 4;
+        uint32_t a_lo = smem_desc_lo(smem_base + stage * STAGE_BYTES);
+        uint32_t full_addr = full_base + stage * 8;
+        uint32_t accum = 0;
+        for (int ki = 0; ki < nkb; ++ki) {
+          mbar_wait_addr(full_addr, phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          uint64_t adesc = make_smem_desc(sa);
-          const uint64_t bdesc = make_smem_desc(sa + A_BYTES);
-          if (p.debug & 8) {  // hardware probe: shifted (non-1024-aligned) descriptor start, optional base_offset field [49,52)
-            const uint32_t shift = (p.debug >> 8) & 15;
-            adesc = make_smem_desc(sa + shift * 128);
-            if (p.debug & 16) adesc |= (uint64_t)(shift & 7) << 49;
+          if (elect_one()) {
+            umma_kblock<CG>(tmem_d, a_lo, a_lo + B_DESC_OFF, DESC_HI, idesc, accum);
+            umma_commit_addr<CG>(full_addr + EMPTY_OFF);  // frees the smem slot (in both CTAs) once these MMAs retire
           }
-#pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the >>4 encoded address
-            if (!(p.debug & 64) || k == 0) mma(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
-          }
-          commit(&empty_bar[stage]);  // frees the smem slot (in both CTAs) once these MMAs retire
-          if (ki == nkb - 1 && !with_res) commit(&tfull_bar[acc]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          __syncwarp();
+          accum = 1;
+          a_lo += STAGE_DESC;
+          full_addr += 8;
+          if (++stage == STAGES) { stage = 0; phase ^= 1; a_lo -= STAGES * STAGE_DESC; full_addr -= STAGES * 8; }
+        }
+        if (!with_res) {
+          if (elect_one()) umma_commit_addr<CG>(smem_u32(&tfull_bar[acc]));
+          __syncwarp();
         }
         if (with_res) {
           const int nt = tile / num_mp;
@@ -621,12 +745,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int c = 0; c < nchunk; ++c) {
             mbar_wait(&full_bar[stage], phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint64_t adesc = make_smem_desc(smem_u32(smem + stage * STAGE_BYTES));
-#pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k)
-              mma(tmem_d + c * EPI_CHUNK, adesc + 2 * k, ident_desc + 2 * k, idesc64, 1u);
-            commit(&empty_bar[stage]);
-            if (c == nchunk - 1) commit(&tfull_bar[acc]);
+            const uint32_t adesc = smem_desc_lo(smem_base + stage * STAGE_BYTES);
+            if (elect_one()) {
+              umma_kblock<CG>(tmem_d + c * EPI_CHUNK, adesc, ident_lo, DESC_HI, idesc64, 1u);
+              umma_commit_addr<CG>(smem_u32(&empty_bar[stage]));
+              if (c == nchunk - 1) umma_commit_addr<CG>(smem_u32(&tfull_bar[acc]));
+            }
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -1128,14 +1253,6 @@ extern "C" int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int C
     halo = halo_env == 1 ? true : (fill >= 0.7 && Cin <= 256);
   }
   p.halo_bo = halo_bo_env;
-  static int rot_env = -1;
-  if (rot_env < 0) {
-    const char* e = getenv("DRN_TC_ROT");
-    rot_env = (e && e[0] == '0') ? 0 : 1;
-  }
-  // only while both operands stay L2-resident: CTAs at different K offsets no longer meet on the same tiles, so a GEMM whose
-  // operands stream from HBM (fc6: 0.8 GB + 0.4 GB) would fetch every tile once per CTA instead of once (the stream-K result)
-  p.rotate = rot_env && ((double)Mll * Cin + (double)Cout * Ktot) * 2.0 <= 48.0 * 1024 * 1024;
   if (ksize == 3) {
     p.conv = 1; p.NB = N; p.H = H; p.W = W; p.Cin = Cin; p.dil = dilation;
     if (halo) { p.tile_w = 128; p.tile_h = 1; }

@@ -35,7 +35,6 @@ namespace tc {
 
 constexpr int BM = 128;      // UMMA M (cta_group::1)
 constexpr int BK = 64;       // one 128-byte swizzle atom of bf16 along K
-constexpr int UMMA_K = 16;  // (the four K = 16 steps of a k-block are spelled out in umma_kblock)
 constexpr int EPI_CHUNK = 64;                    // columns per staging buffer (128 B of bf16)
 constexpr int EPI_BUF_BYTES = 32 * EPI_CHUNK * 2;  // 32 rows x 128 B
 constexpr int IDENT_BYTES = 64 * 64 * 2;           // 64x64 bf16 identity (B operand of the residual MMAs)
@@ -330,6 +329,7 @@ struct Params {
   float drop_inv_keep;
   unsigned long long drop_seed;
   const unsigned long long* drop_seed_dev;  // optional device-resident addend (fresh masks under graph replay)
+  int bres;     // HALO mode, Cin = 64, one N tile: the nine weight tiles (72 KB) are loaded once per CTA and stay in the ring's nine slots
   int halo_bo;  // HALO mode: also set the descriptor's base-offset field to the start's 128 B row phase (hardware probe switch)
   int debug;  // DRN_TC_DEBUG (profiling experiments only): 1 = skip TMA stores, 2 = skip epilogue math, 4 = skip tcgen05.ld
   // stream-K (deep-K GEMMs whose tile count does not fill whole waves): every unit gets an equal share of the
@@ -554,6 +554,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       Piece pc;
       int hs = 0;
       uint32_t hphase = 0;
+      bool b_loaded = false;
       while (sched.next(pc)) {
         const int tile = pc.tile;
         const int mt = (tile % num_mp) * CG + cta_rank, nt = tile / num_mp;
@@ -568,6 +569,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if constexpr (HALO) {
           // per channel block: three input rows into a halo slot, then the nine taps' weight tiles through the ring
           const uint32_t row_load = (uint32_t)(BM + 2 * p.dil) * 128u;
+          if (p.bres && !b_loaded) {  // weights of all nine taps: one slot and one barrier each, loaded once per CTA
+            b_loaded = true;
+            if (elect_one()) {
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                mbar_arrive_expect_tx(&full_bar[tap], B_BYTES);
+                tma_load_2d(&map_b, &full_bar[tap], smem + tap * STAGE_BYTES, tap * BK, nt * BN);
+              }
+            }
+            __syncwarp();
+          }
           for (int cb = 0; cb < cblocks; ++cb) {
             mbar_wait(&hempty_bar[hs], hphase ^ 1);
             if (elect_one()) {
@@ -579,6 +591,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             __syncwarp();
             if (++hs == HALO_SLOTS) { hs = 0; hphase ^= 1; }
+            if (p.bres) continue;
             int kcol = cb * BK;                      // weight K order is (tap, channel): tap t of this block at (t * cblocks + cb) * 64
             const int kstep = cblocks * BK;
             for (int tap = 0; tap < 9; ++tap) {
@@ -689,16 +702,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint32_t a_start = slot;
             int tx = 0;
             for (int ti = 0; ti < 9; ++ti) {
-              mbar_wait(&full_bar[stage], phase);
+              // resident weights: tap ti lives in slot ti for the whole kernel (its barrier completed once, phase 0)
+              const int bslot = p.bres ? ti : stage;
+              mbar_wait(&full_bar[bslot], p.bres ? 0u : phase);
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               // output pixel m of the row tile reads input pixel m + (dx + 1) * d of input row dy: shifted start, SBO stays 1024
               const uint32_t adesc = smem_desc_lo(a_start);
               const uint32_t a_hi = p.halo_bo ? (DESC_HI | (((a_start >> 7) & 7u) << 17)) : DESC_HI;  // base-offset field [49,52)
-              const uint32_t bdesc = smem_desc_lo(smem_base + stage * STAGE_BYTES);
+              const uint32_t bdesc = smem_desc_lo(smem_base + bslot * STAGE_BYTES);
               if (elect_one()) {
-#pragma unroll
                 umma_kblock<CG>(tmem_d, adesc, bdesc, a_hi, idesc, (cb > 0 || ti > 0) ? 1u : 0u);
-                umma_commit_addr<CG>(smem_u32(&empty_bar[stage]));  // frees the weight slot once these MMAs retire
+                if (!p.bres) umma_commit_addr<CG>(smem_u32(&empty_bar[stage]));  // frees the weight slot once these MMAs retire
                 if (ti == 8) {
                   umma_commit_addr<CG>(smem_u32(&hempty_bar[hs]));  // all nine taps have read the rows
                   if (cb == cblocks - 1) umma_commit_addr<CG>(smem_u32(&tfull_bar[acc]));
@@ -707,7 +721,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               __syncwarp();
               a_start += dx_bytes;
               if (++tx == 3) { tx = 0; a_start += HALO_ROW_BYTES - 3 * dx_bytes; }  // next input row
-              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              if (!p.bres && ++stage == STAGES) { stage = 0; phase ^= 1; }
             }
             if (++hs == HALO_SLOTS) { hs = 0; hphase ^= 1; }
           }
@@ -1250,7 +1264,10 @@ extern "C" int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int C
   bool halo = false;
   if (ksize == 3 && !residual && out_dtype != DRN_F32 && dropout_p == 0.f && dilation >= 1 && dilation <= HALO_MAX_DIL && halo_env != 0) {
     const double fill = (double)W / (128.0 * ((W + 127) / 128));
-    halo = halo_env == 1 ? true : (fill >= 0.7 && Cin <= 256);
+    // measured (tools/layer_bench.py, R50-WS and VGG16 maps): wins up to 128 input channels, and at 256 while the map has no more
+    // row tiles than SMs (res4: 74 x 124); wider / larger layers are better off as CTA pairs with 256-wide tiles
+    const long row_tiles = (long)N * H * ((W + 127) / 128);
+    halo = halo_env == 1 ? true : (fill >= 0.7 && (Cin <= 128 || (Cin <= 256 && row_tiles <= 148)));
   }
   p.halo_bo = halo_bo_env;
   if (ksize == 3) {
@@ -1316,6 +1333,15 @@ extern "C" int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int C
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (halo) {
+    // resident weights (DRN_TC_BRES=0 disables): every tile of such a layer would otherwise re-read the same 72 KB of weights,
+    // more than the 50 KB of input rows it needs (stem conv2 / conv3, res2 3x3, VGG conv1_2)
+    static int bres_env = -1;
+    if (bres_env < 0) {
+      const char* e = getenv("DRN_TC_BRES");
+      bres_env = (e && e[0] == '0') ? 0 : 1;
+    }
+    p.bres = (bres_env && Cin == BK && bn == 64 && p.num_n_tiles == 1) ? 1 : 0;
+    if (p.bres) return launch<64, 9, 2, 1, 4, true>(ma, mb, mo, mr, p, st, nullptr, 0);
     if (bn == 256) return launch<256, 3, 1, 1, 4, true>(ma, mb, mo, mr, p, st, nullptr, 0);
     if (bn == 128) return launch<128, 5, 2, 1, 4, true>(ma, mb, mo, mr, p, st, nullptr, 0);
     return launch<64, 8, 2, 1, 4, true>(ma, mb, mo, mr, p, st, nullptr, 0);

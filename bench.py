@@ -341,6 +341,14 @@ def main():
         cfg.SOLVER.BASE_LR = 1e-6  # synthetic data: keep the random-init weights in a sane range over the timed steps
         optimizer = drn.build_optimizer(cfg, model)  # detectron2/solver/build.py mirrored, fused update kernel
         sync = D.GradientSynchronizer().attach(model)  # gradients averaged across ranks; p.grad is written by sync.finish()
+        sharder = None
+        if world > 1 and precision == "bf16" and os.environ.get("DRN_B200_SHARDED", "1") != "0":
+            # fc6.weight (95 % of the gradient bytes): reduce-scatter fused into the weight-gradient GEMM's epilogue (peer stores
+            # over NVLink), sharded optimizer step, bf16 rows all-gathered by the update kernel; DRN_B200_SHARDED=0 = all-reduce
+            fc6 = model.roi_heads.box_head.fc1
+            sharder = D.ShardedLinearTrainer(fc6, precision, model.roi_heads.in_channels)
+            model.roi_heads.fc6_sharder = sharder
+            optimizer.attach_sharded(fc6.weight, sharder)
 
     def step(batched):
         if eval_mode:
@@ -583,6 +591,10 @@ def main():
     if train_mode:
         out["config"]["mode"] = "train: backward of fc6/fc7/heads (backbone frozen, FREEZE_AT 5) + fused SGD; gradients averaged over ranks"
         out["grad_allreduce_bytes_per_step"] = sync.bytes // max(1, sync.steps)
+        out["config"]["fc6_gradient"] = ("reduce-scatter fused into the weight-gradient GEMM epilogue (peer stores over NVLink) + sharded SGD + "
+                                         "bf16 all-gather by the update kernel" if sharder is not None else "all-reduce (NCCL)" if world > 1 else "local")
+        if sharder is not None:
+            out["fc6_scatter_bytes_per_step"] = sharder.bytes_scattered // max(1, sync.steps)
     if world == 1 and not args.no_cpu_baseline:
         # one full image on the host cores (the bounded sample: ~20-50 s of CPU work), after a small warm-up that only
         # spins up the thread pool; the driver's reference arm (--impl reference) repeats it with a full warm-up step

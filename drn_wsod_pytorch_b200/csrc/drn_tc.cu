@@ -329,6 +329,10 @@ struct Params {
   float drop_inv_keep;
   unsigned long long drop_seed;
   const unsigned long long* drop_seed_dev;  // optional device-resident addend (fresh masks under graph replay)
+  // reduce-scatter epilogue (fp32 output, data-parallel weight gradient): output row m belongs to rank m / rows_per_peer and
+  // is stored straight into THAT rank's accumulation window, slot `my_rank` -- peer memory mapped over NVLink
+  float* peer_out[8];
+  int n_peers, my_rank, rows_per_peer;
   int bres;     // HALO mode, Cin = 64, one N tile: the nine weight tiles (72 KB) are loaded once per CTA and stay in the ring's nine slots
   int halo_bo;  // HALO mode: also set the descriptor's base-offset field to the start's 128 B row phase (hardware probe switch)
   int debug;  // DRN_TC_DEBUG (profiling experiments only): 1 = skip TMA stores, 2 = skip epilogue math, 4 = skip tcgen05.ld
@@ -934,6 +938,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // instruction writes 4 rows x 128 contiguous bytes; the first version stored 32 rows x 16 B per instruction.
         const uint32_t stage_s = smem_u32(my_bufs);
         const int q4 = lane & 7, rsub = lane >> 3;
+        float* obase = reinterpret_cast<float*>(p.out);
+        if (p.n_peers > 0) {  // the whole 128-row tile has one owner (rows_per_peer % 128 == 0)
+          const int owner = (mt * BM) / p.rows_per_peer;
+          obase = p.peer_out[owner] + ((long long)p.my_rank - owner) * (long long)p.rows_per_peer * p.ldo;
+        }
         long long mrow[8];  // global row of staging row rr = 4 i + rsub (owned by lane rr), -1 when out of range
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -964,7 +973,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             __syncwarp();
             if (4 * q4 < nvalid) {
-              float* ocol = reinterpret_cast<float*>(p.out) + n0 + 4 * q4;
+              float* ocol = obase + n0 + 4 * q4;
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 if (mrow[i] >= 0) {
@@ -1211,13 +1220,14 @@ extern "C" int drn_gemm_set_tail_split(int enabled) {
   return prev;
 }
 
-extern "C" int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int Cin, const void* w, int ksize,
-                                      int dilation, const float* scale, const float* bias, const void* residual,
-                                      int relu, void* out, int out_dtype, int Cout, int ldo, float dropout_p,
-                                      uint64_t dropout_seed, const uint64_t* dropout_seed_dev, void* workspace,
-                                      size_t workspace_bytes, drn_stream_t stream) {
+static int conv_igemm_bf16_tc_impl(const void* in, int N, int H, int W, int Cin, const void* w, int ksize,
+                                   int dilation, const float* scale, const float* bias, const void* residual,
+                                   int relu, void* out, int out_dtype, int Cout, int ldo, float dropout_p,
+                                   uint64_t dropout_seed, const uint64_t* dropout_seed_dev, void* workspace,
+                                   size_t workspace_bytes, drn_stream_t stream, void* const* peer_out, int n_peers,
+                                   int my_rank, int rows_per_peer) {
   using namespace drn::tc;
-  DRN_CHECK_ARG(in && w && out, "conv_igemm_bf16_tc: null pointer");
+  DRN_CHECK_ARG(in && w && (out || n_peers > 0), "conv_igemm_bf16_tc: null pointer");
   DRN_CHECK_ARG(ksize == 1 || ksize == 3, "conv_igemm_bf16_tc: ksize %d", ksize);
   DRN_CHECK_ARG(Cin % 64 == 0, "conv_igemm_bf16_tc: Cin=%d must be a multiple of 64", Cin);
   DRN_CHECK_ARG(Cout % 8 == 0, "conv_igemm_bf16_tc: Cout=%d must be a multiple of 8", Cout);
@@ -1225,6 +1235,13 @@ extern "C" int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int C
   DRN_CHECK_ARG(((uintptr_t)in % 16 == 0) && ((uintptr_t)w % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
                     ((uintptr_t)residual % 16 == 0),
                 "conv_igemm_bf16_tc: operands must be 16-byte aligned");
+  if (n_peers > 0) {
+    DRN_CHECK_ARG(n_peers <= 8 && my_rank >= 0 && my_rank < n_peers, "gemm_scatter: %d peers, rank %d", n_peers, my_rank);
+    DRN_CHECK_ARG(ksize == 1 && out_dtype == DRN_F32 && !residual && !scale, "gemm_scatter: fp32-output linear layers only");
+    DRN_CHECK_ARG(rows_per_peer % 128 == 0 && (long long)rows_per_peer * n_peers == (long long)N * H * W,
+                  "gemm_scatter: %lld rows do not split into %d blocks of %d rows (multiple of 128)", (long long)N * H * W, n_peers, rows_per_peer);
+    for (int i = 0; i < n_peers; ++i) DRN_CHECK_ARG(peer_out[i] && (uintptr_t)peer_out[i] % 16 == 0, "gemm_scatter: peer window %d", i);
+  }
   DRN_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "conv_igemm_bf16_tc: dropout p=%f", dropout_p);
   DRN_CHECK_ARG(!(residual && scale), "conv_igemm_bf16_tc: fold the per-channel scale into the weights when a residual is given");
   DRN_CHECK_ARG(!(dropout_p > 0.f && out_dtype == DRN_F32), "conv_igemm_bf16_tc: fused dropout needs bf16 output");
@@ -1235,6 +1252,8 @@ extern "C" int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int C
   p.N = Cout;
   p.scale = scale; p.bias = bias; p.has_residual = residual != nullptr;
   p.out = out; p.out_f32 = (out_dtype == DRN_F32); p.ldo = ldo; p.relu = relu;
+  p.n_peers = n_peers; p.my_rank = my_rank; p.rows_per_peer = rows_per_peer;
+  for (int i = 0; i < 8; ++i) p.peer_out[i] = (i < n_peers) ? (float*)peer_out[i] : nullptr;
   if (dropout_p > 0.f) {
     const double keep = 1.0 - (double)dropout_p;
     p.drop_keep_thresh = (uint32_t)(keep * 4294967295.0);
@@ -1377,4 +1396,20 @@ extern "C" int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int C
   if (bn == 256) return launch<256, 4, 1, 1>(ma, mb, mo, mr, p, st, workspace, workspace_bytes);
   if (bn == 128) return launch<128, 5, 2, 1>(ma, mb, mo, mr, p, st, workspace, workspace_bytes);
   return launch<64, 7, 2, 1>(ma, mb, mo, mr, p, st, workspace, workspace_bytes);
+}
+
+extern "C" int drn_conv_igemm_bf16_tc(const void* in, int N, int H, int W, int Cin, const void* w, int ksize,
+                                      int dilation, const float* scale, const float* bias, const void* residual,
+                                      int relu, void* out, int out_dtype, int Cout, int ldo, float dropout_p,
+                                      uint64_t dropout_seed, const uint64_t* dropout_seed_dev, void* workspace,
+                                      size_t workspace_bytes, drn_stream_t stream) {
+  return conv_igemm_bf16_tc_impl(in, N, H, W, Cin, w, ksize, dilation, scale, bias, residual, relu, out, out_dtype, Cout, ldo,
+                                 dropout_p, dropout_seed, dropout_seed_dev, workspace, workspace_bytes, stream, nullptr, 0, 0, 0);
+}
+
+extern "C" int drn_gemm_bf16_tc_scatter(const void* a, int M, int K, const void* b, int Nout, const float* bias,
+                                        void* const* peer_windows, int n_peers, int my_rank, int ldo, drn_stream_t stream) {
+  DRN_CHECK_ARG(n_peers > 0 && M % n_peers == 0, "gemm_scatter: %d rows over %d peers", M, n_peers);
+  return conv_igemm_bf16_tc_impl(a, 1, M, 1, K, b, 1, 1, nullptr, bias, nullptr, 0, nullptr, DRN_F32, Nout, ldo, 0.f, 0, nullptr,
+                                 nullptr, 0, stream, peer_windows, n_peers, my_rank, M / n_peers);
 }

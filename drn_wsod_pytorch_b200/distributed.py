@@ -167,3 +167,107 @@ class GradientSynchronizer:
                 else:
                     p.grad.add_(g)
         return n
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fc6.weight without an all-reduce: gradient tiles scattered into the owners' windows by the weight-gradient GEMM itself,
+# sharded optimizer step, refreshed bf16 rows stored into every rank's weight buffer (csrc/drn_dist.cu, drn_tc.cu)
+# ------------------------------------------------------------------------------------------------------------------
+def _map_peers(tensor, group=None):
+    """Raw device pointers of `tensor` on every rank of the group, as seen from THIS process: the local pointer for this
+    rank, CUDA-IPC mappings (drn_peer_open) of the peers' allocations for the others.  Every rank must call this with a
+    tensor of the same shape.  Returns (pointers, bases to close)."""
+    import ctypes
+
+    from . import lib
+
+    L = lib.load()
+    rank, ws = dist.get_rank(group), dist.get_world_size(group)
+    handle = ctypes.create_string_buffer(L.drn_peer_handle_bytes())
+    off = ctypes.c_uint64(0)
+    lib.call("drn_peer_get_handle", tensor, handle, ctypes.byref(off))
+    mine = (rank, bytes(handle.raw), int(off.value), tuple(tensor.shape), str(tensor.dtype))
+    everyone = [None] * ws
+    dist.all_gather_object(everyone, mine, group=group)
+    ptrs, opened = [], []
+    for r, h, o, shape, dt in everyone:
+        assert shape == tuple(tensor.shape) and dt == str(tensor.dtype), "peer windows must match in shape and dtype"
+        if r == rank:
+            ptrs.append(tensor.data_ptr())
+            continue
+        base = ctypes.c_void_p(0)
+        lib.call("drn_peer_open", ctypes.create_string_buffer(h, len(h)), ctypes.byref(base))
+        opened.append(base.value)
+        ptrs.append(base.value + o)
+    return ptrs, opened
+
+
+class ShardedLinearTrainer:
+    """Data-parallel training of ONE big linear layer (fc6) whose weight gradient never goes through a collective.
+
+    Rank r owns rows [r * rows/n, (r+1) * rows/n) of the weight.  Per step:
+      1. backward: `wgrad(dy_t, x_t)` runs the weight-gradient GEMM dW = dY^T X with the reduce-scatter epilogue -- every rank's
+         tiles land in the owners' `slots` windows over NVLink while the GEMM is still computing the next tiles;
+      2. `fence()`: a 4-byte all-reduce on the compute stream -- when it has completed, every rank's GEMM has (its stores are
+         performed at kernel completion), so the slots are final;
+      3. `step(...)`: the owner sums its slots, updates its shard of the fp32 master weight and of the momentum, and stores the
+         refreshed bf16 kernel-layout rows into EVERY rank's weight buffer (1/n of the optimizer traffic per rank, the all-gather
+         rides the update);
+      4. `fence()` again before the next forward reads the weight buffers (and before anyone overwrites slots).
+    The fp32 master is current only on its owner; `gather_master()` all-gathers it (checkpointing).  Everything else of the
+    model (fc7, heads: < 5 % of the gradient bytes) stays on the GradientSynchronizer's all-reduce, which doubles as the
+    reference implementation this path is checked against (tools/train_sharded_check.py)."""
+
+    def __init__(self, linear, precision, c49, group=None):
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.linear, self.c49 = linear, int(c49)
+        rows, cols = linear.weight.shape
+        assert rows % (128 * self.world) == 0, f"{rows} weight rows do not split into {self.world} blocks of whole 128-row tiles"
+        assert 1 <= self.world <= 8
+        self.rows_per = rows // self.world
+        self.row0 = self.rank * self.rows_per
+        dev = linear.weight.device
+        self.packed = linear.packed(precision, permute_c49=self.c49)["w"]  # the bf16 [rows, cols] buffer the forward reads
+        self.slots = torch.zeros((self.world, self.rows_per, cols), dtype=torch.float32, device=dev)
+        self.momentum = None
+        self.first = True
+        self.slot_ptrs, self._opened = _map_peers(self.slots, group)
+        self.packed_ptrs, opened = _map_peers(self.packed, group)
+        self._opened += opened
+        self._token = torch.zeros((1,), dtype=torch.float32, device=dev)
+        self.bytes_scattered = 0
+        self.fence()
+
+    def wgrad(self, dy_t, x_t):
+        """dW = dY^T X scattered: dy_t [rows, Rp] bf16 (zero beyond R), x_t [cols, Rp] bf16, both K-major."""
+        from . import ops
+
+        ops.gemm_scatter(dy_t, x_t, self.slot_ptrs, self.rank)
+        self.bytes_scattered += (self.world - 1) * self.rows_per * x_t.shape[0] * 4
+
+    def fence(self):
+        dist.all_reduce(self._token, group=self.group)
+
+    def step(self, lr, momentum, weight_decay, nesterov):
+        from . import ops
+
+        w = self.linear.weight
+        if momentum != 0 and self.momentum is None:
+            self.momentum = torch.empty((self.rows_per, w.shape[1]), dtype=torch.float32, device=w.device)
+        with torch.no_grad():
+            ops.sgd_step_sharded(w.detach(), self.momentum, self.slots, self.packed_ptrs, self.row0, self.rows_per, self.c49, lr,
+                                 momentum, weight_decay, nesterov, self.first)
+        self.first = False
+
+    def gather_master(self):
+        """All-gather the fp32 master shards so that `linear.weight` is complete on every rank (state_dict / checkpoint)."""
+        w = self.linear.weight.detach()
+        dist.all_gather_into_tensor(w, w[self.row0:self.row0 + self.rows_per].clone(), group=self.group)
+
+    def close(self):
+        from . import lib
+
+        for b in self._opened:
+            lib.call("drn_peer_close", b)
+        self._opened = []

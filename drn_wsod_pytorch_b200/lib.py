@@ -50,6 +50,13 @@ _PROTOS = {
     "drn_permute_cols49": [_P, _P, c_int64, c_int, _P],
     "drn_sgd_step": [_P, _P, _P, _P, c_int64, c_int64, c_int, c_float, c_float, c_float, c_int, c_int, _P],
     "drn_pack_linear_bf16": [_P, _P, c_int64, c_int64, c_int, _P],
+    "drn_peer_handle_bytes": [],
+    "drn_peer_get_handle": [_P, _P, POINTER(c_uint64)],
+    "drn_peer_open": [_P, POINTER(c_void_p)],
+    "drn_peer_close": [_P],
+    "drn_gemm_bf16_tc_scatter": [_P, c_int, c_int, _P, c_int, _P, POINTER(c_void_p), c_int, c_int, c_int, _P],
+    "drn_sgd_step_sharded": [_P, _P, _P, c_int, POINTER(c_void_p), c_int, c_int64, c_int64, c_int64, c_int, c_float, c_float,
+                             c_float, c_int, c_int, _P],
     "drn_dropout_inplace": [_P, c_int64, c_int, c_float, c_uint64, _P, _P],
     "drn_cast_f32_to_bf16": [_P, _P, c_int64, _P],
     "drn_cast_bf16_to_f32": [_P, _P, c_int64, _P],
@@ -112,6 +119,11 @@ def fvec(vals):
 
 def ivec(vals):
     return (c_int * len(vals))(*[int(v) for v in vals])
+
+
+def pvec(ptrs):
+    """Host array of device pointers (void* const*)."""
+    return (c_void_p * len(ptrs))(*[int(p) for p in ptrs])
 
 
 def call(name, *args):

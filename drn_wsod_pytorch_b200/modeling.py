@@ -699,6 +699,7 @@ class _WSLROIHeads(nn.Module):
         self.fused_tail = os.environ.get("DRN_B200_FUSED_TAIL", "1") != "0"
         # opt-in: measured gain 0.02-0.05 ms of 2.7 (the GEMM is SM<-L2 feed bound, a co-resident gather starves:
         # profiles/r1_overlap_negative_result.txt), less than the tail split-K schedule of the one-piece fc6 saves
+        self.fc6_sharder = None  # distributed.ShardedLinearTrainer: fc6's weight gradient reduce-scattered by the wgrad GEMM itself
         self.grad_sync = None   # distributed.GradientSynchronizer (data-parallel training): .ready(block) / .bind(param, grad)
         self.wgrad_row_blocks = int(os.environ.get("DRN_B200_WGRAD_BLOCKS", "4"))  # fc6 weight gradient in row blocks when a hook is installed
         # SMs left to the collective during those blocks (pair with NCCL_MAX_CTAS).  0 = off: measured at 2 GPUs 8.42 ms/step
@@ -1017,7 +1018,7 @@ class _WSLROIHeads(nn.Module):
         packed = {"w": w_op, "scale": None, "bias": torch.zeros((n,), device=dy.device, dtype=torch.float32), "cout": n}
         return ops.conv_bf16_tc(dy.view(1, R, 1, Kd), packed, 1, 1, False, out_dtype=out_dtype).view(R, n)
 
-    def _wgrad(self, dy_t, x, R, c49=0, row_blocks=1, on_block=None):
+    def _wgrad(self, dy_t, x, R, c49=0, row_blocks=1, on_block=None, sharder=None):
         """dW [out, in] (fp32) = dY^T X with dy_t = dY^T [out][Rp] (zero beyond R).  c49 > 0: X's columns are bin-major
         pooled features and the result's columns are in the parameter's (c, ph, pw) order.  row_blocks > 1 (tensor-core
         mode): the GEMM runs in that many blocks of output rows and `on_block(dW[rows])` is called after each one
@@ -1030,6 +1031,9 @@ class _WSLROIHeads(nn.Module):
             dW = ops.conv_f32(dy_t.view(1, out_f, 1, Rp), {"w": xp, "scale": None, "bias": bias0, "cout": n}, 1, 1, False).view(out_f, n)
             return ops.permute_cols49(dW, c49) if c49 else dW
         x_t, _ = ops.masked_transpose(x, c49=c49, ld_out=Rp)                    # [in][Rp], K-major
+        if sharder is not None:  # distributed.ShardedLinearTrainer: the GEMM's epilogue reduce-scatters the tiles into the owners' windows
+            sharder.wgrad(dy_t, x_t)
+            return None
         packed = {"w": x_t, "scale": None, "bias": bias0, "cout": n}
         if row_blocks <= 1 or out_f % (128 * row_blocks) != 0:
             return ops.conv_bf16_tc(dy_t.view(1, out_f, 1, Rp), packed, 1, 1, False, out_dtype=torch.float32).view(out_f, n)
@@ -1121,8 +1125,12 @@ class _WSLROIHeads(nn.Module):
                 fc, y, x = fcs[li], acts[li + 1], acts[li]
                 dy_t, dy = ops.masked_transpose(dx, mask=y, mul=tr["dropout_mul"], ld_out=Rp, out_dtype=wdt, want_masked=li > 0)
                 blocks = self.wgrad_row_blocks if (li == 0 and hook is not None) else 1
-                acc(fc.weight, self._wgrad(dy_t, x, R, c49=self.in_channels if li == 0 else 0, row_blocks=blocks, on_block=hook),
-                    announced=blocks > 1 and not f32 and dy_t.shape[0] % (128 * blocks) == 0)
+                sharder = self.fc6_sharder if (li == 0 and not f32) else None
+                if sharder is not None:
+                    assert N == 1, "the sharded fc6 path takes one image per rank and step (IMS_PER_BATCH == world size)"
+                gw = self._wgrad(dy_t, x, R, c49=self.in_channels if li == 0 else 0, row_blocks=blocks, on_block=hook, sharder=sharder)
+                if gw is not None:  # (sharded: the gradient lives in the owners' windows, the optimizer steps it there)
+                    acc(fc.weight, gw, announced=blocks > 1 and not f32 and dy_t.shape[0] % (128 * blocks) == 0)
                 acc(fc.bias, ops.rowsum(dy_t, cols=R))
                 if li > 0:
                     dx = self._dgrad(dy, w_op[li], wdt)

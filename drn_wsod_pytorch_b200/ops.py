@@ -435,6 +435,27 @@ def sgd_step(w, grad, momentum_buf, packed, c49, lr, momentum, weight_decay, nes
          int(bool(nesterov)), int(bool(first_step)), current_stream())
 
 
+def gemm_scatter(a, b, peer_windows, my_rank):
+    """dW tile-scattered: a [M, K] bf16 (dY^T), b [N, K] bf16 (X^T) -> row block m // (M / n) of a @ b^T stored into rank
+    (m // (M / n))'s window `peer_windows[that rank]` (raw device pointers of mapped peer memory), slot `my_rank`."""
+    _chk(a, "a")
+    _chk(b, "b")
+    M, K = a.shape
+    N = b.shape[0]
+    call("drn_gemm_bf16_tc_scatter", a, M, K, b, N, None, lib.pvec(peer_windows), len(peer_windows), int(my_rank), N, current_stream())
+
+
+def sgd_step_sharded(w, momentum_shard, slots, packed_ptrs, row0, rows, c49, lr, momentum, weight_decay, nesterov, first_step):
+    """Owner's optimizer step on rows [row0, row0 + rows) of `w` from the gradient slots [n_src, rows, cols]; refreshed bf16
+    kernel-layout rows go to every rank's weight buffer (raw device pointers)."""
+    _chk(w, "param")
+    _chk(slots, "slots")
+    assert w.dtype == torch.float32 and slots.dtype == torch.float32 and slots.dim() == 3 and slots.shape[1] == rows
+    call("drn_sgd_step_sharded", w, momentum_shard, slots, slots.shape[0], lib.pvec(packed_ptrs), len(packed_ptrs), int(row0), int(rows),
+         w.shape[1], int(c49), float(lr), float(momentum), float(weight_decay), int(bool(nesterov)), int(bool(first_step)),
+         current_stream())
+
+
 def pack_linear_bf16(w, out, c49=0):
     """fp32 [N, K] parameter -> bf16 kernel operand `out` [N, K] (c49 > 0: columns (c, ph, pw) -> (ph, pw, c))."""
     _chk(w, "weight")

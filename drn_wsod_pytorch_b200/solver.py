@@ -21,9 +21,18 @@ class FusedSGD(torch.optim.Optimizer):
             raise ValueError("Nesterov momentum requires a momentum")
         super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay, nesterov=nesterov))
         self.model = model
+        self._sharded = {}  # parameter -> distributed.ShardedLinearTrainer (its gradient never reaches p.grad)
         if clip is not None and clip[0] not in ("value", "norm"):
             raise ValueError(f"SOLVER.CLIP_GRADIENTS.CLIP_TYPE must be 'value' or 'norm', got {clip[0]!r}")
         self.clip = clip
+
+    def attach_sharded(self, param, sharder):
+        """`param` (fc6.weight) is stepped shard by shard by `sharder` (distributed.ShardedLinearTrainer): its gradient was
+        reduce-scattered into the owners' windows by the weight-gradient GEMM, every rank updates the rows it owns and
+        broadcasts the refreshed bf16 kernel rows."""
+        if self.clip is not None:
+            raise NotImplementedError("gradient clipping of a sharded parameter needs its global norm; not implemented")
+        self._sharded[param] = sharder
 
     def _clip(self, p):
         kind, value, norm_type = self.clip
@@ -55,9 +64,18 @@ class FusedSGD(torch.optim.Optimizer):
                 loss = closure()
         packed = self._packed_copies()
         touched = False
+        stepped_shards = []
         for group in self.param_groups:
             lr, mom, wd, nest = group["lr"], group["momentum"], group["weight_decay"], group["nesterov"]
             for p in group["params"]:
+                sharder = self._sharded.get(p)
+                if sharder is not None:
+                    sharder.fence()  # every rank's weight-gradient GEMM has finished: the slots are final
+                    sharder.step(lr, mom, wd, nest)
+                    torch.autograd.graph.increment_version(p)
+                    stepped_shards.append(sharder)
+                    touched = True
+                    continue
                 if p.grad is None:
                     continue
                 if self.clip is not None:
@@ -79,6 +97,8 @@ class FusedSGD(torch.optim.Optimizer):
                 # the kernel wrote through raw pointers: tell autograd (and every cache keyed on the version) so
                 torch.autograd.graph.increment_version(p)
                 touched = True
+        for sharder in stepped_shards:
+            sharder.fence()  # every rank's refreshed rows have landed in this rank's weight buffer (and its slots are free again)
         if touched and self.model is not None:
             self._after_step(packed)
         return loss

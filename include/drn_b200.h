@@ -284,6 +284,30 @@ int drn_permute_cols49(const float* in, float* out, int64_t rows, int c49, drn_s
 int drn_sgd_step(float* w, const float* grad, float* momentum_buf, void* packed_bf16, int64_t rows, int64_t cols,
                  int c49, float lr, float momentum, float weight_decay, int nesterov, int first_step,
                  drn_stream_t stream);
+/* ---- data-parallel training of fc6.weight without an all-reduce (replaces the DistributedDataParallel
+ * gradient all-reduce of detectron2/engine/defaults.py:279-282 + the replicated optimizer step of solver/build.py:93-137
+ * for the one parameter that is 95 % of the gradient bytes) ----
+ * drn_peer_get_handle: CUDA IPC handle (drn_peer_handle_bytes() bytes) of the cudaMalloc allocation `ptr` lives in, and
+ *   ptr's byte offset inside it.  drn_peer_open / drn_peer_close: map / unmap another rank's allocation from such a
+ *   handle; *base is the allocation's base address in this process (add the offset).
+ * drn_gemm_bf16_tc_scatter: out[m][n] = sum_k a[m][k] * b[n][k] (+ bias[n]), bf16 operands, fp32 result, as
+ *   drn_conv_igemm_bf16_tc (ksize 1, DRN_F32) -- but row m is owned by rank m / (M / n_peers) and every 128-row tile is
+ *   stored by the GEMM's epilogue straight into the OWNER's window peer_windows[owner] (mapped peer memory, NVLink),
+ *   slot my_rank: window layout [n_peers][M / n_peers][ldo] fp32.  M / n_peers % 128 == 0.  The weight gradient
+ *   dW = dY^T X of a linear layer computed this way is reduce-scattered by the time the kernel (on every rank) has finished.
+ * drn_sgd_step_sharded: the owner's part of the optimizer step: grad = (sum over the n_src slots, slot order) / n_src,
+ *   torch.optim.SGD arithmetic (see drn_sgd_step) on rows [row0, row0 + rows) of the fp32 master w [*, cols] and on the
+ *   momentum shard [rows][cols], then the refreshed bf16 kernel-layout rows (fc6 permutation, c49 > 0) stored into
+ *   every rank's weight buffer packed_bf16[0 .. n_dst) (the all-gather of the update). */
+int drn_peer_handle_bytes(void);
+int drn_peer_get_handle(const void* ptr, void* ipc_handle, uint64_t* offset);
+int drn_peer_open(const void* ipc_handle, void** base);
+int drn_peer_close(void* base);
+int drn_gemm_bf16_tc_scatter(const void* a, int M, int K, const void* b, int Nout, const float* bias,
+                             void* const* peer_windows, int n_peers, int my_rank, int ldo, drn_stream_t stream);
+int drn_sgd_step_sharded(float* w, float* momentum_shard, const float* slots, int n_src, void* const* packed_bf16,
+                         int n_dst, int64_t row0, int64_t rows, int64_t cols, int c49, float lr, float momentum,
+                         float weight_decay, int nesterov, int first_step, drn_stream_t stream);
 /* The same bf16 kernel layout without an update (weight load / first use). */
 int drn_pack_linear_bf16(const float* w, void* packed_bf16, int64_t rows, int64_t cols, int c49, drn_stream_t stream);
 

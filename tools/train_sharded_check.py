@@ -1,0 +1,112 @@
+#!/usr/bin/env python
+"""2..8-rank check of the fused reduce-scatter training path (torchrun, one rank per GPU; GPU box only).
+
+Trains the same model twice from the same weights on the same per-rank images: (A) gradients all-reduced by NCCL
+(distributed.GradientSynchronizer, the DistributedDataParallel-equivalent reference path), (B) fc6.weight through
+distributed.ShardedLinearTrainer (weight-gradient GEMM with the reduce-scatter epilogue over NVLink peer memory, sharded SGD,
+bf16 rows all-gathered by the update kernel).  Reports per-step losses of both, the largest difference of the refreshed bf16 fc6
+kernel weights (A vs B, and across ranks), and ms/step of both paths.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/train_sharded_check.py
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    dist.init_process_group("nccl", device_id=dev)
+    import drn_wsod_pytorch_b200 as drn
+    from drn_wsod_pytorch_b200 import distributed as D, synth
+    import bench
+
+    H, W, R = (int(x) for x in os.environ.get("CHECK_SHAPE", "600,1000,4000").split(","))
+    steps = int(os.environ.get("CHECK_STEPS", "4"))
+    timed = int(os.environ.get("CHECK_TIMED", "10"))
+    cfg = drn.builtin_config("oicr_WSR_50_DC5_1x", ["MODEL.DEVICE", f"cuda:{local}", "B200.PRECISION", "bf16"])
+    cfg.SOLVER.BASE_LR = 1e-3
+    inp = synth.make_inputs(H, W, R, seed=rank)
+    batched = bench.make_batched(inp, dev, drn)
+
+    def run(sharded):
+        model = drn.build_model(cfg)
+        weights = synth.calibrated_weights(cfg, model)
+        model.load_state_dict({**weights, "pixel_mean": model.pixel_mean, "pixel_std": model.pixel_std}, strict=True)
+        model.train()
+        model.roi_heads.box_head.eval()  # no dropout: both runs see the same activations
+        opt = drn.build_optimizer(cfg, model)
+        sync = D.GradientSynchronizer().attach(model)
+        fc6 = model.roi_heads.box_head.fc1
+        sh = None
+        if sharded:
+            sh = D.ShardedLinearTrainer(fc6, "bf16", model.roi_heads.in_channels)
+            model.roi_heads.fc6_sharder = sh
+            opt.attach_sharded(fc6.weight, sh)
+        losses = []
+
+        def one():
+            opt.zero_grad(set_to_none=True)
+            l = model(batched)
+            sum(l.values()).backward()
+            sync.finish()
+            opt.step()
+            return {k: float(v) for k, v in l.items()}
+
+        for _ in range(steps):
+            losses.append(one())
+        packed = fc6.packed("bf16", permute_c49=model.roi_heads.in_channels)["w"].clone()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(timed):
+            one()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / timed], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if sh is not None:
+            sh.gather_master()
+            master = fc6.weight.detach().clone()
+            sh.close()
+        else:
+            master = fc6.weight.detach().clone()
+        del model, opt
+        torch.cuda.empty_cache()
+        return losses, packed, master, float(ms)
+
+    la, pa, ma, ms_a = run(False)
+    lb, pb, mb, ms_b = run(True)
+    diff = (pa.float() - pb.float()).abs()
+    # across ranks: every rank must hold the same refreshed weights
+    chk = torch.stack([pb.float().sum(), pb.float().abs().sum(), pb.float()[::997].flatten()[::131].sum()])
+    allchk = [torch.empty_like(chk) for _ in range(world)]
+    dist.all_gather(allchk, chk)
+    same_across_ranks = all(torch.equal(allchk[0], c) for c in allchk)
+    out = {"world": world, "shape": [H, W, R], "steps": steps, "losses_allreduce": la, "losses_sharded": lb,
+           "fc6_bf16_max_abs_diff": float(diff.max()), "fc6_bf16_frac_different": float((diff > 0).float().mean()),
+           "fc6_bf16_scale": float(pa.float().abs().max()),
+           "fc6_master_max_abs_diff": float((ma - mb).abs().max()), "fc6_master_scale": float(ma.abs().max()),
+           "sharded_weights_identical_across_ranks": bool(same_across_ranks),
+           "ms_per_step_allreduce": ms_a, "ms_per_step_sharded": ms_b}
+    if rank == 0:
+        print(json.dumps(out))
+        ok = (out["sharded_weights_identical_across_ranks"] and out["fc6_master_max_abs_diff"] <= 1e-5 * out["fc6_master_scale"] + 1e-9)
+        for a, b in zip(la, lb):
+            for k in a:
+                ok = ok and abs(a[k] - b[k]) <= 2e-2 * max(abs(a[k]), 1e-3)
+        print("SHARDED_CHECK", "OK" if ok else "FAILED")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -74,6 +74,28 @@ def test_tta_oracle_matches_reference_golden(name):
     assert helpers.rel_err(scores.numpy(), g["det_scores"], floor=1e-9) < 1e-3
 
 
+def test_tta_union_oracle_matches_reference_golden():
+    """oracle.tta_forward_union against the UNMODIFIED reference GeneralizedRCNNWithTTAUNION (tests/golden/
+    make_golden_tta_union.py): per-view detections, their union on the original image, the final detections."""
+    name = "tta_r18_small"
+    g = helpers.load_golden("tta_union_r18_small")
+    cfg, state, inp, (min_sizes, max_size, flip, dataset_hw) = _tta_setup(name)
+    spec = O.spec_from_cfg(cfg)
+    out = T.tta_forward_union(inp, state, spec, min_sizes, max_size, flip, dataset_hw)
+    assert len(out["per_view"]) == int(g["n_views"])
+    for i, (b, s, c) in enumerate(out["per_view"]):
+        np.testing.assert_array_equal(c.numpy(), g[f"view{i}/det_classes"])
+        np.testing.assert_allclose(s.numpy(), g[f"view{i}/det_scores"], rtol=1e-4, atol=1e-9)
+        np.testing.assert_allclose(b.numpy(), g[f"view{i}/det_boxes"], rtol=1e-6, atol=1e-4)
+    ub, us, uc = out["union"]
+    np.testing.assert_allclose(ub.numpy(), g["union_boxes"], rtol=1e-6, atol=1e-4)
+    np.testing.assert_array_equal(uc.numpy(), g["union_classes"])
+    db, ds, dc = out["det"]
+    np.testing.assert_array_equal(dc.numpy(), g["det_classes"])
+    np.testing.assert_allclose(ds.numpy(), g["det_scores"], rtol=1e-4, atol=1e-9)
+    np.testing.assert_allclose(db.numpy(), g["det_boxes"], rtol=1e-6, atol=1e-4)
+
+
 # ------------------------------------------------------------------ host logic of tta.py (CPU, no kernels)
 @pytest.mark.parametrize("in_size,out_size", [(100, 160), (100, 48), (1000, 1920), (1000, 800), (5, 2), (7, 300), (600, 600)])
 def test_coefficient_tables_match_oracle(in_size, out_size):
@@ -231,6 +253,40 @@ def test_gpu_tta_driver_matches_reference_golden(name):
         if len(gs) > 1 and gaps.min() > 10 * RTOL:
             np.testing.assert_array_equal(dc, gc)
             np.testing.assert_allclose(res.pred_boxes.tensor.cpu().numpy(), g["det_boxes"], rtol=1e-5, atol=2e-3)
+
+
+@pytest.mark.gpu
+def test_gpu_tta_union_driver_matches_reference_golden():
+    """GeneralizedRCNNWithTTAUNION on the B200 (views resampled on the device, per-view detections by the on-device tail,
+    inverse transforms by drn_tta_accumulate, final tail at threshold 1e-8) against the reference's golden."""
+    name = "tta_r18_small"
+    g = helpers.load_golden("tta_union_r18_small")
+    cfg, model, d = _build_gpu(name)
+    views = tta.DatasetMapperTTAUNION(cfg)(dict(d))
+    assert len(views) == int(g["n_views"])
+    for i, v in enumerate(views):  # the UNION mapper hands the proposals over untouched
+        assert tuple(v["image"].shape) == tuple(g[f"view{i}/image_shape"])
+        np.testing.assert_array_equal(v["proposals"].proposal_boxes.tensor.cpu().numpy(), g[f"view{i}/boxes"])
+    wrapper = tta.GeneralizedRCNNWithTTAUNION(cfg, model)
+    ub, us, uc = wrapper.union_of_views(dict(d))
+    assert ub.shape[0] == g["union_boxes"].shape[0]
+    # same candidates per view (order inside a view follows the scores: compare as sorted sets per view)
+    off = 0
+    for i in range(int(g["n_views"])):
+        n = len(g[f"view{i}/det_scores"])
+        gs, gc = g["union_scores"][off:off + n], g["union_classes"][off:off + n]
+        np.testing.assert_allclose(np.sort(us[off:off + n].cpu().numpy()), np.sort(gs), rtol=RTOL)
+        assert sorted(uc[off:off + n].cpu().tolist()) == sorted(gc.tolist())
+        off += n
+    res = wrapper([dict(d)])[0]["instances"]
+    ds, dc = res.scores.cpu().numpy(), res.pred_classes.cpu().numpy()
+    gs, gc = g["det_scores"], g["det_classes"]
+    assert len(ds) == len(gs)
+    np.testing.assert_allclose(ds, gs, rtol=RTOL)
+    gaps = np.abs(np.diff(gs)) / gs[:-1]
+    if len(gs) > 1 and gaps.min() > 10 * RTOL:
+        np.testing.assert_array_equal(dc, gc)
+        np.testing.assert_allclose(res.pred_boxes.tensor.cpu().numpy(), g["det_boxes"], rtol=1e-5, atol=2e-3)
 
 
 @pytest.mark.gpu

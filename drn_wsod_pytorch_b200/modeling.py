@@ -1321,6 +1321,10 @@ class GeneralizedRCNNWSL(nn.Module):
     #                    (H, W, R) change every iteration, stays on the eager launch path instead of re-capturing
     CAPTURE_AFTER_EVAL = 3  # eval signatures: a TTA image shows every (size, scale) twice (flipped + unflipped view), so
     #                         two sightings say nothing about the NEXT image; the third one does
+    CAPTURE_MIN_SHARE = 0.05  # ... and only a signature that makes up >= 5 % of the calls since it was first seen is worth a
+    #                           capture (an eager warm-up + a sync + the capture itself cost ~100 ms): multi-scale training draws
+    #                           ~90 distinct (H, W) and runs at 2.75 ms / step eagerly -- GPU-bound, as fast as a replay -- but at
+    #                           8.5 ms / step when every second sighting is captured (profiles/r2_multiscale_r50.json)
 
     def __init__(self, cfg):
         super().__init__()
@@ -1342,6 +1346,7 @@ class GeneralizedRCNNWSL(nn.Module):
             self.use_cuda_graph = os.environ["DRN_B200_CUDA_GRAPH"] not in ("0", "false", "False")
         self._plans = {}
         self._seen = {}
+        self._calls = 0
         self._last_plan = None
 
     @property
@@ -1443,15 +1448,21 @@ class GeneralizedRCNNWSL(nn.Module):
         key = (kind, canvas, self._mean_std_key(), self.roi_heads.keep_trace, self.roi_heads.box_head.training,
                tuple((tuple(t.shape), t.dtype) for t in flat))
         plan = self._plans.get(key)
+        self._calls += 1
         if plan is not None:
             self._plans[key] = self._plans.pop(key)  # most recently used last
         else:
-            seen = self._seen.get(key, 0) + 1
+            seen, first = self._seen.get(key, (0, self._calls))
+            seen += 1
             if len(self._seen) > 4096:
                 self._seen.clear()
-            self._seen[key] = seen
+            self._seen[key] = (seen, first)
             after = self.CAPTURE_AFTER if kind == "train" else self.CAPTURE_AFTER_EVAL
-            if seen < after and not force:
+            share = seen / float(self._calls - first + 1)
+            # dominant signature (fixed-shape training, a benchmark): capture at once; a recurring one among others (the 8 TTA
+            # scales): after 4 sightings; one of many (multi-scale training): never -- the eager path is GPU-bound anyway
+            worth = seen >= after and share >= self.CAPTURE_MIN_SHARE and (share >= 0.5 or seen >= 4)
+            if not worth and not force:
                 return None, flat
             if len(self._plans) >= self.MAX_PLANS:
                 self._plans.pop(next(iter(self._plans)))  # least recently used

@@ -423,8 +423,9 @@ class GeneralizedRCNNWithTTAUNION(_TTADriver):
         def consume(i, n, res, _scores, _boxes, tfm):
             b = res.pred_boxes.tensor.contiguous()
             if b.shape[0]:
-                back, dummy = torch.empty_like(b), torch.empty_like(res.scores)
-                ops.tta_accumulate(b, res.scores.contiguous(), tfm.inverse().device_params(), back, dummy, 0, 1)
+                sc = res.scores.contiguous().view(-1, 1)
+                back, dummy = torch.empty_like(b), torch.empty_like(sc)
+                ops.tta_accumulate(b, sc, tfm.inverse().device_params(), back, dummy, 0, 1)
                 b = back
             parts.append((b, res.scores, res.pred_classes))
 

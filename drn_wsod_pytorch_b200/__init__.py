@@ -10,6 +10,7 @@ from .modeling import (  # noqa: F401
     DiscriminativeAdaptionNeck,
     GeneralizedRCNNWSL,
     OICRROIHeads,
+    PCLROIHeads,
     WSDDNROIHeads,
     build_model,
     build_vgg_backbone,

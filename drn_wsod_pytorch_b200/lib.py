@@ -50,6 +50,8 @@ _PROTOS = {
     "drn_permute_cols49": [_P, _P, c_int64, c_int, _P],
     "drn_sgd_step": [_P, _P, _P, _P, c_int64, c_int64, c_int, c_float, c_float, c_float, c_int, c_int, _P],
     "drn_pack_linear_bf16": [_P, _P, c_int64, c_int64, c_int, _P],
+    "drn_pcl_stage_fwd": [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "drn_pcl_stage_bwd": [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, c_float, _P, c_int, c_int, _P, _P],
     "drn_peer_handle_bytes": [],
     "drn_peer_get_handle": [_P, _P, POINTER(c_uint64)],
     "drn_peer_open": [_P, POINTER(c_void_p)],

@@ -699,6 +699,8 @@ class _WSLROIHeads(nn.Module):
         self.fused_tail = os.environ.get("DRN_B200_FUSED_TAIL", "1") != "0"
         # opt-in: measured gain 0.02-0.05 ms of 2.7 (the GEMM is SM<-L2 feed bound, a co-resident gather starves:
         # profiles/r1_overlap_negative_result.txt), less than the tail split-K schedule of the one-piece fc6 saves
+        self.pcl = False              # PCLROIHeads: refinement stages trained with proposal-cluster mining + pcl_loss
+        self.train_capturable = True  # the train pipeline has no host step (PCL mines its clusters on the host: eager launches)
         self.fc6_sharder = None  # distributed.ShardedLinearTrainer: fc6's weight gradient reduce-scattered by the wgrad GEMM itself
         self.grad_sync = None   # distributed.GradientSynchronizer (data-parallel training): .ready(block) / .bind(param, grad)
         self.wgrad_row_blocks = int(os.environ.get("DRN_B200_WGRAD_BLOCKS", "4"))  # fc6 weight gradient in row blocks when a hook is installed
@@ -809,7 +811,7 @@ class _WSLROIHeads(nn.Module):
         Only the DEVICE copies of (classes, one-hot) are cached, and only by content (the class set): a pointer-keyed
         cache would hand the next image the previous image's labels whenever the caching allocator reuses the address."""
         K = self.num_classes
-        out = []
+        out, host = [], []
         for t in targets:
             gc = t.gt_classes
             dev = self._device if gc.device.type == "cpu" else gc.device
@@ -825,6 +827,8 @@ class _WSLROIHeads(nn.Module):
                     self._gt_cache.clear()
                 self._gt_cache[key] = hit
             out.append(hit)
+            host.append(classes)
+        self._gt_classes_host = host
         self.gt_classes_img = [g for g, _ in out]
         self.gt_classes_img_int = self.gt_classes_img
         self.gt_classes_img_oh = torch.stack([o for _, o in out], dim=0) if out else None
@@ -870,6 +874,8 @@ class _WSLROIHeads(nn.Module):
         dev = boxes_l[0].device
         if self._counter is None or self._counter.device != dev:
             self._counter = torch.zeros((1,), dtype=torch.int32, device=dev)
+        if self.pcl:
+            return self._train_device_pcl(features, boxes_l, obj_l, gtb_l, gtc_l, gt_int_l, gt_oh_l)
         nloss = 1 + S + sum(self.refine_reg)
         loss_buf = torch.zeros((N, nloss), dtype=torch.float32, device=dev)
         stage_stats = [[None] * N for _ in range(S)]
@@ -941,6 +947,40 @@ class _WSLROIHeads(nn.Module):
         return {"loss_buf": loss_buf, "img_scores": torch.stack(img_scores, dim=0), "label_counts": label_counts,
                 "stage_stats": stage_stats, "lab0": lab0_l, "midx0": midx0_l, "traces": traces}
 
+    def _train_device_pcl(self, features, boxes_l, obj_l, gtb_l, gtc_l, gt_int_l, gt_oh_l):
+        """roi_heads_pcl.py:291-352 for one image: WSDDN MIL head, then per refinement stage the cluster centres mined on the host
+        from the previous stage's scores (pcl.mine_cluster_centres: one small D2H of the image classes' score columns, as the
+        reference's `.cpu().numpy()`), and assignment / cluster statistics / pcl_loss on the device (ops.pcl_stage)."""
+        from . import pcl as pcl_host
+
+        K, N, S = self.num_classes, len(boxes_l), self.refine_K
+        assert N == 1, "the PCL head mines clusters for one image at a time (third_party/pcl.py asserts batch size 1)"
+        assert not any(self.refine_reg), "PCL configs have no box regression stage"
+        dev = boxes_l[0].device
+        boxes, obj = boxes_l[0], obj_l[0]
+        loss_buf = torch.zeros((1, 1 + S), dtype=torch.float32, device=dev)
+        feat, logits, heads = self._roi_logits(features, boxes, obj, 0)
+        offs = heads["offs"]
+        lab0, midx0, cnt0 = ops.label_proposals(boxes, gtb_l[0], gtc_l[0], K, self.iou_thresholds, self.iou_labels)
+        scores, img_score = ops.wsddn_mil(logits, K, offs["cls"], offs["det"], gt_oh_l[0], self.box_predictor.mean_loss,
+                                          1.0, loss_buf[0, 0:1])
+        classes = list(self._gt_classes_host[0])
+        cols = gt_int_l[0]
+        boxes_host = boxes.cpu().numpy()
+        tr = {"scores": scores, "img_score": img_score, "logits": logits, "feat": feat, "stages": [], "acts": self._acts, "boxes": boxes,
+              "gt_onehot": gt_oh_l[0], "dropout_mul": 2.0 if self.box_head.training else 1.0, "labels_gt": lab0}
+        prev_cols = torch.index_select(scores, 1, cols)
+        for k in range(S):
+            host_scores = prev_cols.clamp(1e-9, 1 - 1e-9).cpu().numpy()          # third_party/pcl.py:36-39 (host sync, as there)
+            cb, cc, cs = pcl_host.mine_cluster_centres(boxes_host, host_scores, classes)
+            st = ops.pcl_stage(logits, offs[f"cls_score_{k}"], K, boxes, torch.from_numpy(cb).to(dev), torch.from_numpy(cc).to(dev),
+                               torch.from_numpy(cs).to(dev), 1.0, loss_buf[0, 1 + k:2 + k], self._counter)
+            st.update(center_boxes=cb, center_classes=cc, center_scores=cs)
+            tr["stages"].append(st)
+            prev_cols = torch.index_select(st["probs"], 1, cols + 1)               # background is column 0 of a PCL stage
+        return {"loss_buf": loss_buf, "img_scores": torch.stack([img_score], 0), "label_counts": [[cnt0]], "stage_stats": [],
+                "lab0": [lab0], "midx0": [midx0], "traces": [tr], "pcl": True}
+
     def _train_post(self, d, proposals, targets, attach=True):
         """Host side of the train forward: loss dict (keys/normalisation of fast_rcnn.py:317-329,
         :1128-1144, :1146-1211), the attributes/fields the reference sets, EventStorage scalars."""
@@ -980,7 +1020,13 @@ class _WSLROIHeads(nn.Module):
                     losses[f"loss_box_reg_r{k}"] = (loss_buf[:, col] * rs).sum() / Rtot; col += 1
 
         storage = _event_storage()
-        if storage is not None:  # the reference's scalars (roi_heads.py:346-349, roi_heads_oicr.py:345-348, fast_rcnn.py:1098-1126)
+        if storage is not None and d.get("pcl"):  # PCLOutputs.pcl_loss logs nothing per stage: only the labelling against the real GT
+            c = torch.stack(label_counts[0], 0).float().mean(0).tolist()
+            obj1 = torch.cat([p.objectness_logits.float() + 1 for p in proposals])
+            self._put_scalars(storage, [("roi_head/num_fg_samples", c[0]), ("roi_head/num_bg_samples", c[1]), ("roi_head/num_ig_samples", c[2]),
+                                        ("proposals/objectness_logits+1 mean", obj1.mean()), ("proposals/objectness_logits+1 max", obj1.max()),
+                                        ("proposals/objectness_logits+1 min", obj1.min())])
+        elif storage is not None:  # the reference's scalars (roi_heads.py:346-349, roi_heads_oicr.py:345-348, fast_rcnn.py:1098-1126)
             pend = []
             for s, suffix in enumerate([""] + [f"_r{k}" for k in range(S)]):
                 c = torch.stack(label_counts[s], 0).float().mean(0).tolist()
@@ -1071,7 +1117,7 @@ class _WSLROIHeads(nn.Module):
         pad = 16 if f32 else 64
         mil_scale = (1.0 / (N * N)) if self.box_predictor.mean_loss else (1.0 / N)
         Rtot = sum(tr["logits"].shape[0] for tr in traces)
-        nvalid = [torch.stack([tr["stages"][k]["stats"] for tr in traces], 0)[:, 5].sum().reshape(1) for k in range(S)]
+        nvalid = [] if self.pcl else [torch.stack([tr["stages"][k]["stats"] for tr in traces], 0)[:, 5].sum().reshape(1) for k in range(S)]
         fcs = self.box_head.fcs
         grads = {}
 
@@ -1099,6 +1145,10 @@ class _WSLROIHeads(nn.Module):
             col = 1
             for k in range(S):
                 st = tr["stages"][k]
+                if self.pcl:
+                    ops.pcl_stage_bwd(st, K, 1.0, grad_vec[col:col + 1], offs[f"cls_score_{k}"], dlog)
+                    col += 1
+                    continue
                 ops.oicr_stage_bwd(st["probs"], st["labels"], st["weights"], nvalid[k], 1.0, grad_vec[col:col + 1], K,
                                    offs[f"cls_score_{k}"], dlog)
                 col += 1
@@ -1160,6 +1210,8 @@ class _WSLROIHeads(nn.Module):
                 nreg = 1 if self.cls_agnostic_bbox_reg else K
                 sc, bx = ops.oicr_infer(logits, K, [offs[f"cls_score_{k}"] for k in ks],
                                         [offs[f"bbox_pred_{k}"] for k in ks], boxes, bw, nreg)
+                if self.pcl:  # background is column 0 of a PCL stage: rotated to the back before the detection tail (fast_rcnn.py:1463-1465)
+                    sc = torch.cat((sc[:, 1:], sc[:, :1]), dim=1).contiguous()
             else:
                 gt_oh = torch.zeros((K,), dtype=torch.float32, device=boxes.device)
                 dummy = torch.empty((1,), dtype=torch.float32, device=boxes.device)
@@ -1207,6 +1259,17 @@ class OICRROIHeads(_WSLROIHeads):
 
     def __init__(self, cfg, input_shape):
         super().__init__(cfg, input_shape, with_refinery=True)
+
+
+@ROI_HEADS_REGISTRY.register()
+class PCLROIHeads(_WSLROIHeads):
+    """projects/WSL/wsl/modeling/roi_heads/roi_heads_pcl.py (box branch): the OICR head's parameters, refinement stages trained
+    by proposal-cluster learning (third_party/pcl.py + the pcl_loss op), background in column 0 of every refinement head."""
+
+    def __init__(self, cfg, input_shape):
+        super().__init__(cfg, input_shape, with_refinery=True)
+        self.pcl = True
+        self.train_capturable = False  # cluster mining is a host step between the stages (as in the reference)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -1460,8 +1523,8 @@ class GeneralizedRCNNWSL(nn.Module):
             after = self.CAPTURE_AFTER if kind == "train" else self.CAPTURE_AFTER_EVAL
             share = seen / float(self._calls - first + 1)
             # dominant signature (fixed-shape training, a benchmark): capture at once; a recurring one among others (the 8 TTA
-            # scales): after 4 sightings; one of many (multi-scale training): never -- the eager path is GPU-bound anyway
-            worth = seen >= after and share >= self.CAPTURE_MIN_SHARE and (share >= 0.5 or seen >= 4)
+            # scales): after 8 sightings; one of many (multi-scale training): never -- the eager path is GPU-bound anyway
+            worth = seen >= after and share >= self.CAPTURE_MIN_SHARE and (share >= 0.5 or seen >= 8)
             if not worth and not force:
                 return None, flat
             if len(self._plans) >= self.MAX_PLANS:
@@ -1478,7 +1541,7 @@ class GeneralizedRCNNWSL(nn.Module):
         """Run `fn(flat tensor list)` eagerly or through the captured plan for this input signature.
         groups: list of equally long tensor lists (one entry per image).  Returns (outputs, device inputs)."""
         plan = None
-        if self.use_cuda_graph:
+        if self.use_cuda_graph and (kind != "train" or self.roi_heads.train_capturable):
             plan, flat = self._plan_for(kind, canvas, groups, fn)
         self._last_plan = plan
         if plan is None:  # graphs disabled, or a signature seen for the first time: eager launches
@@ -1515,7 +1578,7 @@ class GeneralizedRCNNWSL(nn.Module):
     def prefetch(self, batched_inputs):
         """Optional: start moving the NEXT batch to the device while the current step runs (train mode,
         CUDA-graph path).  Call it with the same `batched_inputs` object you will pass to forward next."""
-        if not (self.training and self.use_cuda_graph):
+        if not (self.training and self.use_cuda_graph and self.roi_heads.train_capturable):
             return
         prep = self._train_groups(batched_inputs)
         canvas, groups, fn, _, _ = prep

@@ -369,6 +369,30 @@ def tta_accumulate(all_boxes, all_scores, inverse_ops, acc_boxes, acc_scores, vi
          acc_scores, int(view_index), int(n_views), current_stream())
 
 
+# ---------------------------------------------------------------- PCL refinement stage
+def pcl_stage(logits, col_off, K, boxes, center_boxes, center_classes, center_scores, loss_scale, loss_out, counter):
+    """One PCL stage on the device from host-mined cluster centres -> dict(probs, labels, weights, assignment, pc_probs,
+    pc_count, img_w) (third_party/pcl.py:148-200 + the pcl_loss op forward)."""
+    R, ld = logits.shape
+    P = center_boxes.shape[0]
+    dev = logits.device
+    f32 = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
+    i32 = lambda *s: torch.empty(s, device=dev, dtype=torch.int32)
+    o = dict(probs=f32(R, K + 1), labels=i32(R), weights=f32(R), assignment=i32(R), pc_probs=f32(P), pc_count=f32(P), img_w=f32(P))
+    ws = f32(P + 1)
+    assert center_classes.dtype == torch.int32 and center_boxes.dtype == torch.float32 and counter.dtype == torch.int32
+    call("drn_pcl_stage_fwd", logits, ld, R, K, int(col_off), boxes, center_boxes, center_classes, center_scores, P, float(loss_scale),
+         o["probs"], o["labels"], o["weights"], o["assignment"], o["pc_probs"], o["pc_count"], o["img_w"], loss_out, ws, counter,
+         current_stream())
+    return o
+
+
+def pcl_stage_bwd(st, K, loss_scale, grad_loss, col_off, dlogits):
+    R = st["probs"].shape[0]
+    call("drn_pcl_stage_bwd", st["probs"], R, K, st["labels"], st["weights"], st["assignment"], st["pc_probs"], st["pc_count"], st["img_w"],
+         float(loss_scale), grad_loss, int(col_off), dlogits.shape[1], dlogits, current_stream())
+
+
 # ---------------------------------------------------------------- backward of the trainable tail
 def wsddn_mil_bwd(logits, K, cls_off, det_off, scores, gt_onehot, mean_loss, loss_scale, grad_loss, dlogits):
     R, ld = logits.shape

@@ -284,6 +284,24 @@ int drn_permute_cols49(const float* in, float* out, int64_t rows, int c49, drn_s
 int drn_sgd_step(float* w, const float* grad, float* momentum_buf, void* packed_bf16, int64_t rows, int64_t cols,
                  int c49, float lr, float momentum, float weight_decay, int nesterov, int first_step,
                  drn_stream_t stream);
+/* ---- PCL refinement stage: projects/WSL/wsl/modeling/roi_heads/third_party/pcl.py:148-200
+ * `_get_proposal_clusters` + wsl/layers/csrc/pcl_loss/pcl_loss_cpu.cpp:8-62 / :64-115 (the op behind wsl/layers/pcl_loss.py;
+ * scaling :52,119) + the softmax of fast_rcnn.py PCLOutputs.predict_probs.  The cluster centres (k-means + IoU-graph cover,
+ * third_party/pcl.py:62-145) are mined on the host, as in the reference, and passed in: center_boxes [P][4], center_classes [P]
+ * (1-based: column of the refinement head, 0 = background), center_scores [P].
+ * fwd: probs [R][K+1] = softmax(logits[:, col_off : col_off+K+1]); labels / assignment [R] int32 (0 / -1 below IoU 0.5),
+ *   weights [R] (0 below IoU 0.1); per cluster pc_probs (mean clipped probability of its class over its members), pc_count,
+ *   img_cls_loss_weights; loss[0] = loss_scale * (background term + cluster terms) / R.  terms_ws: P + 1 floats; counter: one
+ *   zero-initialised uint32 (left at zero).
+ * bwd: dlogits[:, col_off : col_off+K+1] = grad_loss[0] * d loss / d logits (overwrites those columns). */
+int drn_pcl_stage_fwd(const float* logits, int ld, int R, int K, int col_off, const float* boxes, const float* center_boxes,
+                      const int* center_classes, const float* center_scores, int P, float loss_scale, float* probs, int* labels,
+                      float* weights, int* assignment, float* pc_probs, float* pc_count, float* img_cls_loss_weights, float* loss,
+                      float* terms_ws, unsigned int* counter, drn_stream_t stream);
+int drn_pcl_stage_bwd(const float* probs, int R, int K, const int* labels, const float* weights, const int* assignment,
+                      const float* pc_probs, const float* pc_count, const float* img_cls_loss_weights, float loss_scale,
+                      const float* grad_loss, int col_off, int ld, float* dlogits, drn_stream_t stream);
+
 /* ---- data-parallel training of fc6.weight without an all-reduce (replaces the DistributedDataParallel
  * gradient all-reduce of detectron2/engine/defaults.py:279-282 + the replicated optimizer step of solver/build.py:93-137
  * for the one parameter that is 95 % of the gradient bytes) ----

@@ -470,6 +470,21 @@ def install(with_wsl=True):
     sys.modules["wsl"] = wsl
     wc = _mod("wsl._C")
     wsl._C = wc
+    # the one compiled op on a path this repo covers: the PCL loss (wsl/layers/pcl_loss.py:41-50, :90-102), compiled from the
+    # reference's own pcl_loss_cpu.cpp by oracle/build_ref.py into oracle/_ref/
+    try:
+        from oracle.build_ref import load_pcl_ref
+
+        pcl = load_pcl_ref()
+    except Exception:  # no compiler / no reference sources: the PCL configs then fail at the first loss call
+        pcl = None
+    if pcl is not None:
+        wc.pcl_loss_forward = pcl.pcl_loss_forward
+        wc.pcl_loss_backward = pcl.pcl_loss_backward
+    if not torch.cuda.is_available():
+        # wsl/layers/pcl_loss.py:52,121 moves the op's CPU result back with `.cuda(device_id)` (device_id = -1 for CPU
+        # tensors): on a box without CUDA that call is made the identity -- a placement shim, no arithmetic
+        torch.Tensor.cuda = lambda self, *a, **k: self
     spec.loader.exec_module(wsl)
     _INSTALLED = True
     return detectron2, wsl

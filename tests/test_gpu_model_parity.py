@@ -222,7 +222,11 @@ def test_graph_plan_replay_tracks_new_inputs_and_matches_eager():
             assert got[k] == v, (name, k, got[k], v)  # same kernels, same order: bit-identical
         for x, y in zip(idx, eager[name][1]):
             assert torch.equal(x, y)
-    assert len(model._plans) == 2  # (a, b) share one plan, c has its own
+    assert len(model._plans) == 1  # (a, b) share one plan; c was 2 of the 5 calls since its first sighting: not dominant, stays eager
+    for _ in range(3):             # ... until it makes up half of the calls since it was first seen
+        got, _ = run(inp_c, True)
+        assert got == eager["c"][0]
+    assert len(model._plans) == 2
     got, _ = run(inp_b, True, device="cpu")  # host tensors: copied H2D into the plan's static buffers
     assert got == eager["b"][0]
     # prefetch: inputs staged on a side stream ahead of the call, picked up by identity; unrelated inputs ignore the stage

@@ -6,9 +6,6 @@
 Reports ms/step (forward + loss, device-timed over the whole sequence, host launch time included) for
   * "eager":   CUDA graphs off -- every step is ~75 C-ABI launches from Python;
   * "plans":   the default (a signature is captured the 2nd time it is seen, LRU of MAX_PLANS graphs);
-  * "bucketed": plans + B200.CANVAS_BUCKET-style padding of the canvas to multiples of 64 px (an image smaller than the canvas
-     sits on a zero canvas exactly as ImageList.from_tensors pads the smaller images of a batch), which folds the
-     sequence's distinct shapes into a few dozen signatures;
 and the fixed-shape replay time of the largest view for comparison.
 
     python tools/multiscale_bench.py [--steps 120] [--workload r18|r50]
@@ -58,26 +55,10 @@ def main():
     # pinned host batches, one per distinct shape (what a dataloader hands over)
     batches = {hw: bench.make_batched(synth.make_inputs(hw[0], hw[1], R, seed=hw[0] * 7 + hw[1]), None, drn, pinned=True) for hw in distinct}
 
-    def bucketed(b, q=64):
-        """The same image on a zero canvas whose sides are multiples of q: done here by batching it with an empty second
-        entry is not possible, so the image tensor itself is padded (after the dataloader, before the model)."""
-        d = dict(b[0])
-        im = d["image"]
-        H, W = im.shape[-2:]
-        Hp, Wp = -(-H // q) * q, -(-W // q) * q
-        if (Hp, Wp) != (H, W):
-            pad = torch.nn.functional.pad(im, (0, Wp - W, 0, Hp - H), value=0.0)
-            # the canvas is zero AFTER normalisation in the reference (ImageList pads the normalised image): pre-compensate
-            mean = model.pixel_mean.flatten().cpu()
-            pad[:, H:, :] = mean.view(3, 1, 1)
-            pad[:, :, W:] = mean.view(3, 1, 1)
-            d["image"] = pad.pin_memory()
-        return [d]
-
     def run(mode):
         model.invalidate_plans()
         model.use_cuda_graph = mode != "eager"
-        seq = [(bucketed(batches[hw]) if mode == "bucketed" else batches[hw]) for hw in shapes]
+        seq = [batches[hw] for hw in shapes]
         with torch.no_grad():
             for b in seq[:3]:
                 model(b)
@@ -93,8 +74,7 @@ def main():
         return {"ms_per_step_device": e0.elapsed_time(e1) / len(seq), "ms_per_step_wall": wall * 1e3 / len(seq), "plans": len(model._plans),
                 "signatures": len({tuple(b[0]["image"].shape) for b in seq})}
 
-    res = {"workload": f"{name} bf16 R={R}, {args.steps} steps, {len(distinct)} distinct (H, W)", "eager": run("eager"), "plans": run("plans"),
-           "bucketed": run("bucketed")}
+    res = {"workload": f"{name} bf16 R={R}, {args.steps} steps, {len(distinct)} distinct (H, W)", "eager": run("eager"), "plans": run("plans")}
     # fixed shape for reference: the mean-size image replayed
     hw = distinct[len(distinct) // 2]
     model.invalidate_plans()

@@ -600,11 +600,122 @@ roipool_gather_body(const typename V::T* __restrict__ feat, const typename V::T*
   }  // items
 }
 
-template <typename V>
-__global__ void __launch_bounds__(224)
+// Per-ROI bin geometry (torchvision roi_pool, see roi_geometry above) into shared memory, by threads 0..13
+struct RoiBinTable {
+  int y0[7], ylast[7], nrow[7], i[7];   // per bin row: first window row, last window row, #windows, y level
+  int x0[7], x1[7], j[7], wd[7];        // per bin col: first / right-aligned window col, x level, width
+};
+__device__ __forceinline__ void roi_bin_table(const float* __restrict__ box, float scale, int h, int w, RoiBinTable& s) {
+  if (threadIdx.x < 14) {
+    const bool is_y = threadIdx.x < 7;
+    const int p = is_y ? threadIdx.x : threadIdx.x - 7;
+    const int lim = is_y ? h : w;
+    const int s0 = (int)roundf(__fmul_rn(box[is_y ? 1 : 0], scale));
+    const int e0 = (int)roundf(__fmul_rn(box[is_y ? 3 : 2], scale));
+    const int rl = max(e0 - s0 + 1, 1);
+    const float bs = __fdiv_rn((float)rl, 7.f);
+    const int lo = min(max((int)floorf(__fmul_rn((float)p, bs)) + s0, 0), lim);
+    const int hi = min(max((int)ceilf(__fmul_rn((float)(p + 1), bs)) + s0, 0), lim);
+    const int len = hi - lo;  // <= 0: empty bin
+    if (is_y) {
+      const int i = len >= 2 ? 1 : 0;
+      s.i[p] = i;
+      s.y0[p] = lo;
+      s.ylast[p] = hi - (1 << i);
+      s.nrow[p] = len > 0 ? (len + (1 << i) - 1) >> i : 0;
+    } else {
+      int j = len > 0 ? 31 - __clz(len) : 0;
+      if (j > XT_LEVELS) j = XT_LEVELS;
+      s.j[p] = j;
+      s.x0[p] = lo;
+      s.x1[p] = hi - (1 << j);
+      s.wd[p] = len;
+    }
+  }
+}
+
+// Default gather: one CTA per (ROI, 512-byte channel chunk), 14 warps: warp (ph, half) owns bins pw = 4 half .. of bin
+// ROW ph and walks the row's table windows ONCE for all of them: the row offset, the bins' table pointers and the
+// one-or-two-lookups decision are set up once per warp, so a lookup costs an address add, the 16-byte load and the vector
+// max, and up to 16 loads are in flight per lane.  The first table version looped (bin, window row) the other way round and
+// spent ~48 issued instructions per lookup (260 M warp instructions per launch at the bench workload: issue-bound, 0.33 ms;
+// profiles/r2_ncu_step_per_launch.txt); a 7-bins-per-warp variant needed 98 registers and was latency-bound at 14 warps
+// per SM (0.70 ms).  Bins wider than two table windows (> 32 cells: maps wider than ~230 cells) step full windows.
+constexpr int GATHER_THREADS = 448;
+template <typename V, int MINB>
+__global__ void __launch_bounds__(GATHER_THREADS, MINB)
 roipool_gather_kernel(const typename V::T* __restrict__ feat, const typename V::T* __restrict__ tables, int h, int w,
                       int CV, const float* __restrict__ boxes, const float* __restrict__ obj, float scale,
                       typename V::T* __restrict__ out, int R, int nitems) {
+  typedef typename V::T T;
+  __shared__ RoiBinTable g;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ph = warp >> 1, pw0 = (warp & 1) * 4, nb = (warp & 1) ? 3 : 4;
+  const int r = (int)blockIdx.x, cv = (int)blockIdx.y * 32 + lane;
+  roi_bin_table(boxes + 4 * (size_t)r, scale, h, w, g);
+  __syncthreads();
+  if (cv >= CV) return;
+  const float mul = obj ? __fadd_rn(__ldg(obj + r), 1.f) : 1.f;
+  const int i = g.i[ph], y0 = g.y0[ph], ylast = g.ylast[ph], nrow = g.nrow[ph];
+  const int ystep = 1 << i;
+  const unsigned plane = (unsigned)h * w * CV;       // vectors per table (< 2^27 for any map that fits the builder)
+  const unsigned rowpitch = (unsigned)w * CV;
+  const T* p0[4];     // first window of the bin in its table, at row 0
+  unsigned d1[4];     // distance to the right-aligned second window
+  unsigned one = 0, two = 0, wide = 0;  // bit b: bin non-empty / needs the second lookup / wider than two windows
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int pw = min(pw0 + b, 6);
+    const int j = g.j[pw], wd = (b < nb) ? g.wd[pw] : 0, x0 = g.x0[pw], x1 = g.x1[pw];
+    p0[b] = ((i | j) == 0 ? feat : tables + (size_t)xt_index(i, j) * plane) + cv + (unsigned)x0 * CV;
+    d1[b] = (unsigned)max(x1 - x0, 0) * CV;
+    if (wd > 0) one |= 1u << b;
+    if (wd > (1 << j)) two |= 1u << b;
+    if (wd > (2 << j)) wide |= 1u << b;
+  }
+  T acc[4];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) acc[b] = V::lowest();
+  if (wide == 0) {
+#pragma unroll 1
+    for (int k = 0; k < nrow; ++k) {
+      const unsigned ro = (unsigned)min(y0 + k * ystep, ylast) * rowpitch;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if (one & (1u << b)) {   // warp-uniform
+          acc[b] = V::vmax(acc[b], __ldg(p0[b] + ro));
+          if (two & (1u << b)) acc[b] = V::vmax(acc[b], __ldg(p0[b] + ro + d1[b]));
+        }
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int k = 0; k < nrow; ++k) {
+      const unsigned ro = (unsigned)min(y0 + k * ystep, ylast) * rowpitch;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if (one & (1u << b)) {
+          const unsigned step = (unsigned)(1 << g.j[min(pw0 + b, 6)]) * CV;
+          acc[b] = V::vmax(acc[b], __ldg(p0[b] + ro + d1[b]));
+          for (unsigned xo = 0; xo < d1[b]; xo += step) acc[b] = V::vmax(acc[b], __ldg(p0[b] + ro + xo));
+        }
+      }
+    }
+  }
+  T* orow = out + ((size_t)r * 49 + ph * 7 + pw0) * CV + cv;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    if (b < nb) {
+      const T m = (nrow > 0 && (one & (1u << b))) ? acc[b] : V::zero();
+      __stcs(orow + (size_t)b * CV, V::scale(m, mul));
+    }
+  }
+}
+template <typename V>
+__global__ void __launch_bounds__(224)
+roipool_gather_binmajor_kernel(const typename V::T* __restrict__ feat, const typename V::T* __restrict__ tables, int h, int w,
+                               int CV, const float* __restrict__ boxes, const float* __restrict__ obj, float scale,
+                               typename V::T* __restrict__ out, int R, int nitems) {
   roipool_gather_body<V, false>(feat, tables, h, w, CV, boxes, obj, scale, out, R, nitems);
 }
 // persistent variant: capped at 40 registers so that one or two of its CTAs fit next to a resident GEMM CTA
@@ -662,9 +773,25 @@ static int roipool_v2(const void* feat, int h, int w, int CV, const float* boxes
       }
       roipool_gather_persistent_kernel<V><<<grid, 224, 0, st>>>((const T*)feat, (const T*)ws, h, w, CV, boxes, objectness,
                                                            spatial_scale, (T*)out, R, (int)nitems);
-    } else
-      roipool_gather_kernel<V><<<dim3(R, cdiv(CV, 32)), 224, 0, st>>>((const T*)feat, (const T*)ws, h, w, CV, boxes, objectness,
-                                                            spatial_scale, (T*)out, R, (int)nitems);
+    } else {
+      // DRN_ROIPOOL_GATHER (measurement switch): 0 = the first, bin-major table kernel; 2 / 3 = row-major kernel compiled for
+      // 2 / 3 CTAs of 14 warps per SM
+      static int variant = -1;
+      if (variant < 0) {
+        const char* e = getenv("DRN_ROIPOOL_GATHER");
+        variant = e ? atoi(e) : 2;
+      }
+      const dim3 grid2(R, cdiv(CV, 32));
+      if (variant == 0)
+        roipool_gather_binmajor_kernel<V><<<grid2, 224, 0, st>>>((const T*)feat, (const T*)ws, h, w, CV, boxes, objectness,
+                                                                  spatial_scale, (T*)out, R, (int)nitems);
+      else if (variant == 3)
+        roipool_gather_kernel<V, 3><<<grid2, GATHER_THREADS, 0, st>>>((const T*)feat, (const T*)ws, h, w, CV, boxes, objectness,
+                                                                       spatial_scale, (T*)out, R, (int)nitems);
+      else
+        roipool_gather_kernel<V, 2><<<grid2, GATHER_THREADS, 0, st>>>((const T*)feat, (const T*)ws, h, w, CV, boxes, objectness,
+                                                                       spatial_scale, (T*)out, R, (int)nitems);
+    }
     DRN_CHECK_LAUNCH("roipool gather");
   }
   return 0;

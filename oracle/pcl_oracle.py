@@ -115,6 +115,12 @@ def pcl_mine(boxes, last_scores, im_labels, probs_new):
     return out
 
 
+def _fmaxf(x, lo):
+    """C fmaxf(x, lo): a NaN operand is DROPPED (an empty cluster's mean probability is NaN; the reference's loop then
+    uses eps, pcl_loss_cpu.cpp:43,51) -- torch.clamp would propagate it."""
+    return torch.where(torch.isnan(x), torch.full_like(x, lo), torch.clamp(x, min=lo))
+
+
 class _PCLLoss(torch.autograd.Function):
     """pcl_loss_cpu.cpp forward (:8-62) and backward (:64-115) with the scaling of wsl/layers/pcl_loss.py:52,119."""
 
@@ -126,14 +132,14 @@ class _PCLLoss(torch.autograd.Function):
         w = torch.from_numpy(m["cls_loss_weights"].astype(np.float32))
         out = torch.zeros(C)
         bg = lab == 0
-        out[0] = -(w[bg] * torch.log(torch.clamp(p[bg, 0], min=1e-6))).sum()  # im_labels_real[0] == 1 always
+        out[0] = -(w[bg] * torch.log(_fmaxf(p[bg, 0], 1e-6))).sum()  # im_labels_real[0] == 1 always
         pcl = torch.from_numpy(m["pc_labels"].astype(np.int64))
         pcp = torch.from_numpy(m["pc_probs"].astype(np.float32))
         imgw = torch.from_numpy(m["img_cls_loss_weights"].astype(np.float32))
         for c in range(1, C):
             if im_labels_real[c] != 0:
                 sel = pcl == c
-                out[c] = -(imgw[sel] * torch.log(torch.clamp(pcp[sel], min=1e-6))).sum()
+                out[c] = -(imgw[sel] * torch.log(_fmaxf(pcp[sel], 1e-6))).sum()
         ctx.save_for_backward(p, lab, w, torch.from_numpy(m["gt_assignment"].astype(np.int64)), pcl, pcp,
                               torch.from_numpy(m["pc_count"].astype(np.float32)), imgw, torch.as_tensor(im_labels_real))
         return out.sum() / R
@@ -144,11 +150,11 @@ class _PCLLoss(torch.autograd.Function):
         R, C = p.shape
         grad = torch.zeros(R, C)
         bg = lab == 0
-        grad[bg, 0] = -w[bg] / torch.clamp(p[bg, 0], min=1e-5)
+        grad[bg, 0] = -w[bg] / _fmaxf(p[bg, 0], 1e-5)
         fg = (lab > 0) & (iml[lab.clamp(min=0)] != 0)
         rows = torch.nonzero(fg).flatten()
         a = assign[rows]
-        grad[rows, lab[rows]] = -imgw[a] / torch.clamp(pcn[a] * pcp[a], min=1e-5)
+        grad[rows, lab[rows]] = -imgw[a] / _fmaxf(pcn[a] * pcp[a], 1e-5)
         return grad * (g / R), None, None
 
 

@@ -71,9 +71,10 @@ def test_pcl_loss_restatement_matches_the_compiled_reference_op():
     probs = torch.softmax(torch.randn(R, K + 1, generator=g) * 3, 1)
     probs[5, 0] = 1e-8
     m = {"labels": np.zeros(R, np.int32), "cls_loss_weights": torch.rand(R, generator=g).numpy(), "gt_assignment": -np.ones(R, np.int64),
-         "pc_labels": np.array([3, 3, 8, 8, 12, 15], np.int32), "pc_probs": np.array([0.3, 1e-9, 0.5, 0.2, 0.9, 0.4], np.float32),
+         "pc_labels": np.array([3, 3, 8, 8, 12, 15], np.int32), "pc_probs": np.array([0.3, 1e-9, 0.5, 0.2, 0.9, np.nan], np.float32),
          "pc_count": np.zeros(Pn, np.int32), "img_cls_loss_weights": torch.rand(Pn, generator=g).numpy()}
     rows = torch.randperm(R, generator=g)[:120].numpy()
+    m["pc_labels"][5] = 12  # the empty cluster (NaN mean, as np.average gives) carries a class that IS in the image: fmaxf drops the NaN
     for j, r in enumerate(rows):
         c = j % 5  # cluster 5 stays empty
         m["gt_assignment"][r], m["labels"][r] = c, m["pc_labels"][c]

@@ -113,6 +113,109 @@ conv3x3_c3_kernel(const float* __restrict__ img, int H, int W, float m0, float m
   }
 }
 
+// Tiled variant for Cout == 64 (every stem on the path): one CTA = C3_TH x C3_TW output pixels, 128 threads.  The input patch
+// under the tile is normalised ONCE into shared memory ((img - mean) / std with IEEE division, zero outside the valid image:
+// the same values the kernel above computes per thread) -- the kernel above normalises each input value 4 x ~3 times (once per
+// channel group and per overlapping pixel group, ~900 of its ~3100 instructions per thread) and re-stages the filter per 128
+// output pixels.  The FMA order per output (kh, c, kw) is unchanged: results are bit-identical.
+constexpr int C3_TW = 64, C3_TH = 4;  // tile: 16 pixel groups of 4 wide x 2 rows per pass, 2 passes
+
+template <typename OutT, int STRIDE>
+__global__ void __launch_bounds__(128)
+conv3x3_c3_tile_kernel(const float* __restrict__ img, int H, int W, float m0, float m1, float m2, float s0, float s1, float s2,
+                       const float* __restrict__ wp, const float* __restrict__ scale, const float* __restrict__ bias,
+                       int relu, int Ho, int Wo, OutT* __restrict__ out) {
+  constexpr int Cout = 64;
+  constexpr int PR = (C3_TH - 1) * STRIDE + 3, PC = (C3_TW - 1) * STRIDE + 3, PCP = (PC + 3) & ~3;
+  constexpr int NCOL = (C3_NPX - 1) * STRIDE + 3;
+  __shared__ __align__(16) float sw[27 * Cout];
+  __shared__ __align__(16) float sx[3][PR][PCP];
+  for (int i = threadIdx.x; i < 27 * Cout / 4; i += 128) reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(wp) + i);
+  const int oh_t = blockIdx.y * C3_TH, ow_t = blockIdx.x * C3_TW;
+  const int ih0 = oh_t * STRIDE - 1, iw0 = ow_t * STRIDE - 1;
+  const float mean[3] = {m0, m1, m2};
+  const float stdv[3] = {s0, s1, s2};
+  for (int i = threadIdx.x; i < 3 * PR * PCP; i += 128) {
+    const int pc = i % PCP, pr = (i / PCP) % PR, c = i / (PCP * PR);
+    const int ih = ih0 + pr, iw = iw0 + pc;
+    float v = 0.f;  // rows / cols outside the valid H x W image are ImageList zero padding
+    if (pc < PC && ih >= 0 && ih < H && iw >= 0 && iw < W)
+      v = __fdiv_rn(__fsub_rn(__ldg(img + ((long long)c * H + ih) * W + iw), mean[c]), stdv[c]);
+    sx[c][pr][pc] = v;
+  }
+  __syncthreads();
+  const int cg = threadIdx.x & 3, pg = threadIdx.x >> 2;   // 16 output channels; pixel group: 16 across x 2 rows
+  const int gx = pg & 15, gy = pg >> 4;
+  const float* wrow = sw + cg * 16;
+  float sc[16], bi[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    sc[j] = scale ? __ldg(scale + cg * 16 + j) : 1.f;
+    bi[j] = __ldg(bias + cg * 16 + j);
+  }
+#pragma unroll 1
+  for (int pass = 0; pass < C3_TH / 2; ++pass) {
+    const int orow = pass * 2 + gy;                       // output row inside the tile
+    const int oh = oh_t + orow, ow0 = ow_t + gx * C3_NPX;
+    if (oh >= Ho || ow0 >= Wo) continue;
+    float acc[C3_NPX][16];
+#pragma unroll
+    for (int p = 0; p < C3_NPX; ++p)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[p][j] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float x[NCOL];
+        const float* xr = &sx[c][orow * STRIDE + kh][gx * C3_NPX * STRIDE];
+#pragma unroll
+        for (int i = 0; i < NCOL; ++i) x[i] = xr[i];
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float4* w4 = reinterpret_cast<const float4*>(wrow + ((kh * 3 + kw) * 3 + c) * Cout);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 wv = w4[q];
+#pragma unroll
+            for (int p = 0; p < C3_NPX; ++p) {
+              const float xv = x[p * STRIDE + kw];
+              acc[p][q * 4 + 0] = fmaf(xv, wv.x, acc[p][q * 4 + 0]);
+              acc[p][q * 4 + 1] = fmaf(xv, wv.y, acc[p][q * 4 + 1]);
+              acc[p][q * 4 + 2] = fmaf(xv, wv.z, acc[p][q * 4 + 2]);
+              acc[p][q * 4 + 3] = fmaf(xv, wv.w, acc[p][q * 4 + 3]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < C3_NPX; ++p) {
+      const int ow = ow0 + p;
+      if (ow >= Wo) break;
+      OutT* o = out + ((long long)oh * Wo + ow) * Cout + cg * 16;
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float t = scale ? acc[p][j] * sc[j] : acc[p][j];  // same rounding sequence as the reference: conv, *scale, +bias
+        t += bi[j];
+        v[j] = relu ? fmaxf(t, 0.f) : t;
+      }
+      if constexpr (sizeof(OutT) == 4) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
+        uint4 pk[2];
+        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(pk);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h2[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        *reinterpret_cast<uint4*>(o) = pk[0];
+        *reinterpret_cast<uint4*>(o + 8) = pk[1];
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // SIMT fp32 implicit GEMM: out[m][n] = act(sum_k A[m][k] * Wt[k][n] * scale[n] + bias[n] + res[m][n])
 // m = output pixel (NHWC, stride 1, "same" padding), k = (kh, kw, cin), n = cout.
@@ -413,8 +516,20 @@ constexpr int XT_TABLES = (YT_LEVELS + 1) * (XT_LEVELS + 1) - 1;  // every (i, j
 constexpr int XT_SLOTS = 8;         // 16-byte channel vectors per build CTA (128 B of channels)
 __host__ __device__ constexpr int xt_index(int i, int j) { return i * (XT_LEVELS + 1) + j - 1; }
 
+// 16-byte read-only load that is skipped (and leaves `v`) when `pred` is false: no branch, so a run of them is issued
+// back to back and all their latencies overlap (the gather's bins are warp-uniformly present / absent)
+__device__ __forceinline__ uint4 ldg128_if(const void* p, bool pred, uint4 v) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+               : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w) : "l"(p), "r"((unsigned)pred));
+  return v;
+}
+
 struct VecF32 {
   typedef float4 T;
+  static __device__ __forceinline__ T ldg_if(const T* p, bool pred, T init) {
+    const uint4 u = ldg128_if(p, pred, make_uint4(__float_as_uint(init.x), __float_as_uint(init.y), __float_as_uint(init.z), __float_as_uint(init.w)));
+    return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+  }
   static __device__ __forceinline__ T vmax(T a, T b) {
     return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
   }
@@ -426,6 +541,7 @@ struct VecF32 {
 };
 struct VecBF16 {
   typedef uint4 T;
+  static __device__ __forceinline__ T ldg_if(const T* p, bool pred, T init) { return ldg128_if(p, pred, init); }
   static __device__ __forceinline__ T vmax(T a, T b) { return max8bf(a, b); }
   static __device__ __forceinline__ T lowest() { return make_uint4(0xFF7FFF7Fu, 0xFF7FFF7Fu, 0xFF7FFF7Fu, 0xFF7FFF7Fu); }
   static __device__ __forceinline__ T zero() { return make_uint4(0u, 0u, 0u, 0u); }
@@ -605,10 +721,11 @@ struct RoiBinTable {
   int y0[7], ylast[7], nrow[7], i[7];   // per bin row: first window row, last window row, #windows, y level
   int x0[7], x1[7], j[7], wd[7];        // per bin col: first / right-aligned window col, x level, width
 };
-__device__ __forceinline__ void roi_bin_table(const float* __restrict__ box, float scale, int h, int w, RoiBinTable& s) {
-  if (threadIdx.x < 14) {
-    const bool is_y = threadIdx.x < 7;
-    const int p = is_y ? threadIdx.x : threadIdx.x - 7;
+__device__ __forceinline__ void roi_bin_table(const float* __restrict__ box, float scale, int h, int w, RoiBinTable& s,
+                                              int tid = threadIdx.x) {
+  if (tid < 14) {
+    const bool is_y = tid < 7;
+    const int p = is_y ? tid : tid - 7;
     const int lim = is_y ? h : w;
     const int s0 = (int)roundf(__fmul_rn(box[is_y ? 1 : 0], scale));
     const int e0 = (int)roundf(__fmul_rn(box[is_y ? 3 : 2], scale));
@@ -634,83 +751,99 @@ __device__ __forceinline__ void roi_bin_table(const float* __restrict__ box, flo
   }
 }
 
-// Default gather: one CTA per (ROI, 512-byte channel chunk), 14 warps: warp (ph, half) owns bins pw = 4 half .. of bin
+// Default gather: one CTA per (8 ROIs, 512-byte channel chunk), 14 warps: warp (ph, half) owns bins pw = 4 half .. of bin
 // ROW ph and walks the row's table windows ONCE for all of them: the row offset, the bins' table pointers and the
-// one-or-two-lookups decision are set up once per warp, so a lookup costs an address add, the 16-byte load and the vector
-// max, and up to 16 loads are in flight per lane.  The first table version looped (bin, window row) the other way round and
-// spent ~48 issued instructions per lookup (260 M warp instructions per launch at the bench workload: issue-bound, 0.33 ms;
-// profiles/r2_ncu_step_per_launch.txt); a 7-bins-per-warp variant needed 98 registers and was latency-bound at 14 warps
-// per SM (0.70 ms).  Bins wider than two table windows (> 32 cells: maps wider than ~230 cells) step full windows.
+// one-or-two-lookups decision are set up once per warp and ROI, the eight lookups of a window row are predicated loads with
+// no branch in between (all in flight together), then folded in.  The first table version looped (bin, window row) the
+// other way round and spent ~48 issued instructions per lookup (260 M warp instructions per launch at the bench workload;
+// profiles/r2_ncu_step_per_launch.txt).  Measured steps (R50 bench workload, tables + gather, warm): bin-major 410 us;
+// row-major with branches around the loads 608 us (the loads of a row serialise); predicated loads 482 us; + 8 ROIs per
+// CTA 389 us; cp.async into shared memory (28 lookups per lane in flight) 439 us.  All variants move the same ~2.8 GB
+// L2 -> SM and sit at 9-11 TB/s: the lookups, not the instructions, are the floor of this design.
+// Bins wider than two table windows (> 32 cells: maps wider than ~230 cells) step full windows.
 constexpr int GATHER_THREADS = 448;
+constexpr int GATHER_NR = 8;   // ROIs per CTA: one geometry pass + barrier per 8 ROIs; a CTA that lives for one ROI spends ~40 % of
+                               // its ~5 us on launch, box load and the barrier with no lookups in flight (measured: 2 CTAs / SM, 0.54 ms)
 template <typename V, int MINB>
 __global__ void __launch_bounds__(GATHER_THREADS, MINB)
 roipool_gather_kernel(const typename V::T* __restrict__ feat, const typename V::T* __restrict__ tables, int h, int w,
                       int CV, const float* __restrict__ boxes, const float* __restrict__ obj, float scale,
                       typename V::T* __restrict__ out, int R, int nitems) {
   typedef typename V::T T;
-  __shared__ RoiBinTable g;
+  __shared__ RoiBinTable gs[GATHER_NR];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ph = warp >> 1, pw0 = (warp & 1) * 4, nb = (warp & 1) ? 3 : 4;
-  const int r = (int)blockIdx.x, cv = (int)blockIdx.y * 32 + lane;
-  roi_bin_table(boxes + 4 * (size_t)r, scale, h, w, g);
+  const int r0 = (int)blockIdx.x * GATHER_NR, cv = (int)blockIdx.y * 32 + lane;
+  {
+    const int q = threadIdx.x / 14;
+    if (q < GATHER_NR && r0 + q < R) roi_bin_table(boxes + 4 * (size_t)(r0 + q), scale, h, w, gs[q], threadIdx.x - 14 * q);
+  }
   __syncthreads();
   if (cv >= CV) return;
-  const float mul = obj ? __fadd_rn(__ldg(obj + r), 1.f) : 1.f;
-  const int i = g.i[ph], y0 = g.y0[ph], ylast = g.ylast[ph], nrow = g.nrow[ph];
-  const int ystep = 1 << i;
   const unsigned plane = (unsigned)h * w * CV;       // vectors per table (< 2^27 for any map that fits the builder)
   const unsigned rowpitch = (unsigned)w * CV;
-  const T* p0[4];     // first window of the bin in its table, at row 0
-  unsigned d1[4];     // distance to the right-aligned second window
-  unsigned one = 0, two = 0, wide = 0;  // bit b: bin non-empty / needs the second lookup / wider than two windows
-#pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    const int pw = min(pw0 + b, 6);
-    const int j = g.j[pw], wd = (b < nb) ? g.wd[pw] : 0, x0 = g.x0[pw], x1 = g.x1[pw];
-    p0[b] = ((i | j) == 0 ? feat : tables + (size_t)xt_index(i, j) * plane) + cv + (unsigned)x0 * CV;
-    d1[b] = (unsigned)max(x1 - x0, 0) * CV;
-    if (wd > 0) one |= 1u << b;
-    if (wd > (1 << j)) two |= 1u << b;
-    if (wd > (2 << j)) wide |= 1u << b;
-  }
-  T acc[4];
-#pragma unroll
-  for (int b = 0; b < 4; ++b) acc[b] = V::lowest();
-  if (wide == 0) {
+  const T low = V::lowest();
 #pragma unroll 1
-    for (int k = 0; k < nrow; ++k) {
-      const unsigned ro = (unsigned)min(y0 + k * ystep, ylast) * rowpitch;
+  for (int q = 0; q < GATHER_NR && r0 + q < R; ++q) {
+    const RoiBinTable& g = gs[q];
+    const int r = r0 + q;
+    const float mul = obj ? __fadd_rn(__ldg(obj + r), 1.f) : 1.f;
+    const int i = g.i[ph], y0 = g.y0[ph], ylast = g.ylast[ph], nrow = g.nrow[ph];
+    const int ystep = 1 << i;
+    const T* p0[4];     // first window of the bin in its table, at row 0
+    unsigned d1[4];     // distance to the right-aligned second window
+    unsigned one = 0, two = 0, wide = 0;  // bit b: bin non-empty / needs the second lookup / wider than two windows
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        if (one & (1u << b)) {   // warp-uniform
-          acc[b] = V::vmax(acc[b], __ldg(p0[b] + ro));
-          if (two & (1u << b)) acc[b] = V::vmax(acc[b], __ldg(p0[b] + ro + d1[b]));
+    for (int b = 0; b < 4; ++b) {
+      const int pw = min(pw0 + b, 6);
+      const int j = g.j[pw], wd = (b < nb) ? g.wd[pw] : 0, x0 = g.x0[pw], x1 = g.x1[pw];
+      p0[b] = ((i | j) == 0 ? feat : tables + (size_t)xt_index(i, j) * plane) + cv + (unsigned)x0 * CV;
+      d1[b] = (unsigned)max(x1 - x0, 0) * CV;
+      if (wd > 0) one |= 1u << b;
+      if (wd > (1 << j)) two |= 1u << b;
+      if (wd > (2 << j)) wide |= 1u << b;
+    }
+    T acc[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[b] = low;
+    if (wide == 0) {
+#pragma unroll 1
+      for (int k = 0; k < nrow; ++k) {
+        const unsigned ro = (unsigned)min(y0 + k * ystep, ylast) * rowpitch;
+        T v0[4], v1[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {   // eight loads in flight, no branches in between
+          v0[b] = V::ldg_if(p0[b] + ro, (one >> b) & 1u, low);
+          v1[b] = V::ldg_if(p0[b] + ro + d1[b], (two >> b) & 1u, low);
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[b] = V::vmax(acc[b], V::vmax(v0[b], v1[b]));
+      }
+    } else {
+#pragma unroll 1
+      for (int k = 0; k < nrow; ++k) {
+        const unsigned ro = (unsigned)min(y0 + k * ystep, ylast) * rowpitch;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          if (one & (1u << b)) {
+            const unsigned step = (unsigned)(1 << g.j[min(pw0 + b, 6)]) * CV;
+            acc[b] = V::vmax(acc[b], __ldg(p0[b] + ro + d1[b]));
+            for (unsigned xo = 0; xo < d1[b]; xo += step) acc[b] = V::vmax(acc[b], __ldg(p0[b] + ro + xo));
+          }
         }
       }
     }
-  } else {
-#pragma unroll 1
-    for (int k = 0; k < nrow; ++k) {
-      const unsigned ro = (unsigned)min(y0 + k * ystep, ylast) * rowpitch;
+    T* orow = out + ((size_t)r * 49 + ph * 7 + pw0) * CV + cv;
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        if (one & (1u << b)) {
-          const unsigned step = (unsigned)(1 << g.j[min(pw0 + b, 6)]) * CV;
-          acc[b] = V::vmax(acc[b], __ldg(p0[b] + ro + d1[b]));
-          for (unsigned xo = 0; xo < d1[b]; xo += step) acc[b] = V::vmax(acc[b], __ldg(p0[b] + ro + xo));
-        }
+    for (int b = 0; b < 4; ++b) {
+      if (b < nb) {
+        const T m = (nrow > 0 && (one & (1u << b))) ? acc[b] : V::zero();
+        __stcs(orow + (size_t)b * CV, V::scale(m, mul));
       }
-    }
-  }
-  T* orow = out + ((size_t)r * 49 + ph * 7 + pw0) * CV + cv;
-#pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    if (b < nb) {
-      const T m = (nrow > 0 && (one & (1u << b))) ? acc[b] : V::zero();
-      __stcs(orow + (size_t)b * CV, V::scale(m, mul));
     }
   }
 }
+
 template <typename V>
 __global__ void __launch_bounds__(224)
 roipool_gather_binmajor_kernel(const typename V::T* __restrict__ feat, const typename V::T* __restrict__ tables, int h, int w,
@@ -774,22 +907,18 @@ static int roipool_v2(const void* feat, int h, int w, int CV, const float* boxes
       roipool_gather_persistent_kernel<V><<<grid, 224, 0, st>>>((const T*)feat, (const T*)ws, h, w, CV, boxes, objectness,
                                                            spatial_scale, (T*)out, R, (int)nitems);
     } else {
-      // DRN_ROIPOOL_GATHER (measurement switch): 0 = the first, bin-major table kernel; 2 / 3 = row-major kernel compiled for
-      // 2 / 3 CTAs of 14 warps per SM
+      // DRN_ROIPOOL_GATHER=0 (measurement switch): the first, bin-major table kernel
       static int variant = -1;
       if (variant < 0) {
         const char* e = getenv("DRN_ROIPOOL_GATHER");
         variant = e ? atoi(e) : 2;
       }
-      const dim3 grid2(R, cdiv(CV, 32));
+      const dim3 grid2(R, cdiv(CV, 32)), gridn(cdiv(R, GATHER_NR), cdiv(CV, 32));
       if (variant == 0)
         roipool_gather_binmajor_kernel<V><<<grid2, 224, 0, st>>>((const T*)feat, (const T*)ws, h, w, CV, boxes, objectness,
                                                                   spatial_scale, (T*)out, R, (int)nitems);
-      else if (variant == 3)
-        roipool_gather_kernel<V, 3><<<grid2, GATHER_THREADS, 0, st>>>((const T*)feat, (const T*)ws, h, w, CV, boxes, objectness,
-                                                                       spatial_scale, (T*)out, R, (int)nitems);
       else
-        roipool_gather_kernel<V, 2><<<grid2, GATHER_THREADS, 0, st>>>((const T*)feat, (const T*)ws, h, w, CV, boxes, objectness,
+        roipool_gather_kernel<V, 2><<<gridn, GATHER_THREADS, 0, st>>>((const T*)feat, (const T*)ws, h, w, CV, boxes, objectness,
                                                                        spatial_scale, (T*)out, R, (int)nitems);
     }
     DRN_CHECK_LAUNCH("roipool gather");
@@ -829,9 +958,23 @@ int drn_conv3x3_c3_fwd(const float* img, int H, int W, int Hp, int Wp, const flo
   const int grid = (int)((threads + 127) / 128);
   const size_t smem = 27 * Cout * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
+// DRN_C3_TILED=0 (measurement switch) keeps the per-thread-normalising kernel for Cout == 64 too
+  static int tiled_env = -1;
+  if (tiled_env < 0) {
+    const char* e = getenv("DRN_C3_TILED");
+    tiled_env = (e && e[0] == '0') ? 0 : 1;
+  }
+  const bool tiled = tiled_env && Cout == 64;
+  const dim3 tgrid((Wo + C3_TW - 1) / C3_TW, (Ho + C3_TH - 1) / C3_TH);
 #define DRN_C3_LAUNCH(T, S)                                                                                          \
-  conv3x3_c3_kernel<T, S><<<grid, 128, smem, st>>>(img, H, W, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], \
-                                                   w_packed, scale, bias, Cout, relu, Ho, Wo, (T*)out)
+  do {                                                                                                               \
+    if (tiled)                                                                                                       \
+      conv3x3_c3_tile_kernel<T, S><<<tgrid, 128, 0, st>>>(img, H, W, mean3[0], mean3[1], mean3[2], std3[0], std3[1], \
+                                                          std3[2], w_packed, scale, bias, relu, Ho, Wo, (T*)out);    \
+    else                                                                                                             \
+      conv3x3_c3_kernel<T, S><<<grid, 128, smem, st>>>(img, H, W, mean3[0], mean3[1], mean3[2], std3[0], std3[1],    \
+                                                       std3[2], w_packed, scale, bias, Cout, relu, Ho, Wo, (T*)out); \
+  } while (0)
   if (out_dtype == DRN_F32) {
     if (stride == 1) DRN_C3_LAUNCH(float, 1); else DRN_C3_LAUNCH(float, 2);
   } else {

@@ -313,22 +313,56 @@ mil_pgt_fused_kernel(const float* __restrict__ logits, int ld, int R, int K, int
   __shared__ bool is_last;
   const int c = blockIdx.x;
   const float* det = logits + det_off + c;
-  float m = -INFINITY;
-  for (int r = threadIdx.x; r < R; r += blockDim.x) m = fmaxf(m, det[(long long)r * ld]);
-  m = block_max(m, sh);
-  float s = 0.f;
-  for (int r = threadIdx.x; r < R; r += blockDim.x) s += expf(det[(long long)r * ld] - m);
-  s = block_sum(s, sh);
-  float tot = 0.f, bv = -INFINITY;
-  int bi = 0x7fffffff;
   const float* cls = logits + cls_off + c;
-  for (int r = threadIdx.x; r < R; r += blockDim.x) {
-    const float pc = expf(cls[(long long)r * ld] - rowmax[r]) / rowsum[r];
-    const float pd = expf(det[(long long)r * ld] - m) / s;
-    const float sc = pc * pd;
-    scores[(long long)r * K + c] = sc;
-    tot += sc;
-    if (better(sc, r, bv, bi)) { bv = sc; bi = r; }
+  float m = -INFINITY, s = 0.f, tot = 0.f, bv = -INFINITY;
+  int bi = 0x7fffffff;
+  constexpr int MR = 8;  // rows per thread held in registers: R <= 8 * 512
+  if (R <= MR * (int)blockDim.x) {
+    // every operand of this thread's rows is loaded once, all loads in flight together (the generic form below walks the
+    // column three times: 3 x R / 512 dependent L2 round trips); per-thread visiting order and the block trees are unchanged
+    float dv[MR], cv[MR], rmx[MR], rsm[MR];
+#pragma unroll
+    for (int i = 0; i < MR; ++i) {
+      const int r = threadIdx.x + i * (int)blockDim.x;
+      const bool ok = r < R;
+      const long long off = (long long)(ok ? r : 0) * ld;
+      dv[i] = ok ? __ldg(det + off) : -INFINITY;
+      cv[i] = __ldg(cls + off);
+      rmx[i] = __ldg(rowmax + (ok ? r : 0));
+      rsm[i] = __ldg(rowsum + (ok ? r : 0));
+    }
+#pragma unroll
+    for (int i = 0; i < MR; ++i) m = fmaxf(m, dv[i]);
+    m = block_max(m, sh);
+#pragma unroll
+    for (int i = 0; i < MR; ++i)
+      if (threadIdx.x + i * (int)blockDim.x < R) { dv[i] = expf(dv[i] - m); s += dv[i]; }
+    s = block_sum(s, sh);
+#pragma unroll
+    for (int i = 0; i < MR; ++i) {
+      const int r = threadIdx.x + i * (int)blockDim.x;
+      if (r < R) {
+        const float pc = expf(cv[i] - rmx[i]) / rsm[i];
+        const float pd = dv[i] / s;
+        const float sc = pc * pd;
+        scores[(long long)r * K + c] = sc;
+        tot += sc;
+        if (better(sc, r, bv, bi)) { bv = sc; bi = r; }
+      }
+    }
+  } else {
+    for (int r = threadIdx.x; r < R; r += blockDim.x) m = fmaxf(m, det[(long long)r * ld]);
+    m = block_max(m, sh);
+    for (int r = threadIdx.x; r < R; r += blockDim.x) s += expf(det[(long long)r * ld] - m);
+    s = block_sum(s, sh);
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+      const float pc = expf(cls[(long long)r * ld] - rowmax[r]) / rowsum[r];
+      const float pd = expf(det[(long long)r * ld] - m) / s;
+      const float sc = pc * pd;
+      scores[(long long)r * K + c] = sc;
+      tot += sc;
+      if (better(sc, r, bv, bi)) { bv = sc; bi = r; }
+    }
   }
   tot = block_sum(tot, sh);
 #pragma unroll
@@ -415,6 +449,10 @@ __device__ __forceinline__ void match_row(const Box4& p, float ap, const float (
   if (ml == -1) lab_out = -1;
 }
 
+// CMAX = 32: rows of up to 32 logits are loaded ONCE into registers (all loads in flight together; the generic CMAX = 0 form
+// walks the row three times).  Sums keep the generic form's order (k ascending per row; block_sum tree over the rows, blocks
+// in order), the 0/1 counters are exact integer reductions: results are bit-identical to the per-function kernels.
+template <int CMAX>
 __global__ void __launch_bounds__(STAGE_THREADS)
 oicr_stage_fused_kernel(const StageFusedArgs a) {
   __shared__ float sg[MAX_G][5];
@@ -422,10 +460,12 @@ oicr_stage_fused_kernel(const StageFusedArgs a) {
   __shared__ float sg0[MAX_G][5];
   __shared__ int scl0[MAX_G];
   __shared__ float sh[32];
-  __shared__ float sv[8];
-  __shared__ int si[8];
+  __shared__ float sv[8][STAGE_THREADS / 32];
+  __shared__ int si[8][STAGE_THREADS / 32];
+  __shared__ int scnt[11];
   __shared__ bool is_last;
   const int C1 = a.K + 1, K = a.K, G = a.G, nb = gridDim.x;
+  if (threadIdx.x < 11) scnt[threadIdx.x] = 0;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     const float x1 = a.pgt_box[4 * g], y1 = a.pgt_box[4 * g + 1], x2 = a.pgt_box[4 * g + 2], y2 = a.pgt_box[4 * g + 3];
     sg[g][0] = x1; sg[g][1] = y1; sg[g][2] = x2; sg[g][3] = y2;
@@ -439,14 +479,18 @@ oicr_stage_fused_kernel(const StageFusedArgs a) {
     sg0[g][4] = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
     scl0[g] = (int)a.gt_classes[g];
   }
-  __syncthreads();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  float lw = 0.f, valid = 0.f, acc = 0.f, nfg = 0.f, fgacc = 0.f, fneg = 0.f;
-  float c_fg = 0.f, c_bg = 0.f, c_ig = 0.f, c0_fg = 0.f, c0_bg = 0.f, c0_ig = 0.f;
-  float myprob[1];
-  (void)myprob;
+  const float* x = a.logits + (long long)min(r, a.R - 1) * a.ld + a.col_off;
+  float xr[CMAX > 0 ? CMAX : 1];
+  if constexpr (CMAX > 0) {   // issued before the barrier: the row's loads fly while the GT tables are staged
+#pragma unroll
+    for (int k = 0; k < CMAX; ++k) xr[k] = (k < C1) ? __ldg(x + k) : -INFINITY;
+  }
+  __syncthreads();
+  float lw = 0.f;
+  int f_valid = 0, f_acc = 0, f_nfg = 0, f_fgacc = 0, f_fneg = 0;
+  int c_fg = 0, c_bg = 0, c_ig = 0, c0_fg = 0, c0_bg = 0, c0_ig = 0;
   float pbuf_m = 0.f, pbuf_s = 1.f;
-  const float* x = nullptr;
   if (r < a.R) {
     const float4 bb = __ldg(reinterpret_cast<const float4*>(a.boxes) + r);
     const Box4 p = {bb.x, bb.y, bb.z, bb.w};
@@ -456,77 +500,94 @@ oicr_stage_fused_kernel(const StageFusedArgs a) {
       match_row(p, ap, sg0, scl0, Gb, K, a.mc, l0, m0);
       a.labels0[r] = l0;
       a.matched0[r] = m0;
-      if (l0 == -1) c0_ig = 1.f; else if (l0 == K) c0_bg = 1.f; else c0_fg = 1.f;
+      if (l0 == -1) c0_ig = 1; else if (l0 == K) c0_bg = 1; else c0_fg = 1;
     }
     int lab, mi;
     match_row(p, ap, sg, scl, G, K, a.mc, lab, mi);
     a.labels[r] = lab;
     a.matched[r] = mi;
-    if (lab == -1) c_ig = 1.f; else if (lab == K) c_bg = 1.f; else c_fg = 1.f;
-    x = a.logits + (long long)r * a.ld + a.col_off;
+    if (lab == -1) c_ig = 1; else if (lab == K) c_bg = 1; else c_fg = 1;
     float m = -INFINITY;
     int am = 0;
-#pragma unroll 8
-    for (int k = 0; k < C1; ++k) {
-      const float v = __ldg(x + k);
-      if (v > m) { m = v; am = k; }
-    }
     float s = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < C1; ++k) s += expf(__ldg(x + k) - m);
     float* pr = a.probs + (long long)r * C1;
+    if constexpr (CMAX > 0) {
+#pragma unroll
+      for (int k = 0; k < CMAX; ++k)
+        if (k < C1 && xr[k] > m) { m = xr[k]; am = k; }
+#pragma unroll
+      for (int k = 0; k < CMAX; ++k)
+        if (k < C1) { xr[k] = expf(xr[k] - m); s += xr[k]; }
+#pragma unroll
+      for (int k = 0; k < CMAX; ++k)
+        if (k < C1) pr[k] = xr[k] / s;
+    } else {
 #pragma unroll 8
-    for (int k = 0; k < C1; ++k) pr[k] = expf(__ldg(x + k) - m) / s;
+      for (int k = 0; k < C1; ++k) {
+        const float v = __ldg(x + k);
+        if (v > m) { m = v; am = k; }
+      }
+#pragma unroll 8
+      for (int k = 0; k < C1; ++k) s += expf(__ldg(x + k) - m);
+#pragma unroll 8
+      for (int k = 0; k < C1; ++k) pr[k] = expf(__ldg(x + k) - m) / s;
+    }
     pbuf_m = m; pbuf_s = s;
     float w = a.pgt_weight[mi];
     if (lab == -1) w = 0.f;
     if (a.weights) a.weights[r] = w;
-    if (w > 1e-12f) valid = 1.f;
-    if (lab >= 0) lw = (-((x[lab] - m) - logf(s))) * w;
+    if (w > 1e-12f) f_valid = 1;
+    if (lab >= 0) lw = (-((__ldg(x + lab) - m) - logf(s))) * w;
     const bool fg = lab >= 0 && lab < K;
-    if (am == lab) acc = 1.f;
+    if (am == lab) f_acc = 1;
     if (fg) {
-      nfg = 1.f;
-      if (am == lab) fgacc = 1.f;
-      if (am == K) fneg = 1.f;
+      f_nfg = 1;
+      if (am == lab) f_fgacc = 1;
+      if (am == K) f_fneg = 1;
     }
   }
-  float v;
-  v = block_sum(lw, sh);    if (threadIdx.x == 0) a.part[0 * nb + blockIdx.x] = v;
-  v = block_sum(valid, sh); if (threadIdx.x == 0) a.part[1 * nb + blockIdx.x] = v;
-  v = block_sum(acc, sh);   if (threadIdx.x == 0) a.part[2 * nb + blockIdx.x] = v;
-  v = block_sum(nfg, sh);   if (threadIdx.x == 0) a.part[3 * nb + blockIdx.x] = v;
-  v = block_sum(fgacc, sh); if (threadIdx.x == 0) a.part[4 * nb + blockIdx.x] = v;
-  v = block_sum(fneg, sh);  if (threadIdx.x == 0) a.part[5 * nb + blockIdx.x] = v;
-  v = block_sum(c_fg, sh);  if (threadIdx.x == 0) a.part[6 * nb + blockIdx.x] = v;
-  v = block_sum(c_bg, sh);  if (threadIdx.x == 0) a.part[7 * nb + blockIdx.x] = v;
-  v = block_sum(c_ig, sh);  if (threadIdx.x == 0) a.part[8 * nb + blockIdx.x] = v;
-  if (Gb >= 0) {
-    v = block_sum(c0_fg, sh); if (threadIdx.x == 0) a.part[9 * nb + blockIdx.x] = v;
-    v = block_sum(c0_bg, sh); if (threadIdx.x == 0) a.part[10 * nb + blockIdx.x] = v;
-    v = block_sum(c0_ig, sh); if (threadIdx.x == 0) a.part[11 * nb + blockIdx.x] = v;
-  }
-  if (a.has_next) {
-    // block-partial argmax of the new probabilities for every image-level class (input of the next get_pgt)
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int g = 0; g < G; ++g) {
-      float bv = -INFINITY;
-      int bi = 0x7fffffff;
-      if (r < a.R) { bv = expf(x[scl[g]] - pbuf_m) / pbuf_s; bi = r; }  // == probs[r][class g], same expression
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  {
+    // the ten 0/1 counters: warp-level integer reductions + shared-memory atomics (exact, order-free)
+    const int fl[11] = {f_valid, f_acc, f_nfg, f_fgacc, f_fneg, c_fg, c_bg, c_ig, c0_fg, c0_bg, c0_ig};
+    const int nfl = Gb >= 0 ? 11 : 8;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    for (int j = 0; j < 11; ++j) {
+      if (j < nfl) {
+        const int v = __reduce_add_sync(0xffffffffu, fl[j]);
+        if (lane == 0 && v) atomicAdd(&scnt[j], v);
+      }
+    }
+  }
+  float v = block_sum(lw, sh);   // the only floating-point sum: same tree as oicr_stage_kernel (its barriers also publish scnt)
+  if (threadIdx.x == 0) a.part[0 * nb + blockIdx.x] = v;
+  if (threadIdx.x < (Gb >= 0 ? 11 : 8)) a.part[(1 + threadIdx.x) * nb + blockIdx.x] = (float)scnt[threadIdx.x];
+  if (a.has_next) {
+    // block-partial argmax of the new probabilities for every image-level class (input of the next get_pgt), 8 classes per barrier
+    for (int g0 = 0; g0 < G; g0 += 8) {
+      const int ng = min(8, G - g0);
+      if (g0 > 0) __syncthreads();
+      for (int gg = 0; gg < ng; ++gg) {
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        if (r < a.R) { bv = expf(__ldg(x + scl[g0 + gg]) - pbuf_m) / pbuf_s; bi = r; }  // == probs[r][class g], same expression
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { sv[gg][wid] = bv; si[gg][wid] = bi; }
       }
       __syncthreads();
-      if (lane == 0) { sv[wid] = bv; si[wid] = bi; }
-      __syncthreads();
-      if (threadIdx.x == 0) {
+      if (threadIdx.x < ng) {
+        const int gg = threadIdx.x;
+        float bv = sv[gg][0];
+        int bi = si[gg][0];
         for (int i = 1; i < (int)(blockDim.x >> 5); ++i)
-          if (better(sv[i], si[i], bv, bi)) { bv = sv[i]; bi = si[i]; }
-        a.part[(12 + g) * nb + blockIdx.x] = bv;
-        a.part_idx[g * nb + blockIdx.x] = bi;
+          if (better(sv[gg][i], si[gg][i], bv, bi)) { bv = sv[gg][i]; bi = si[gg][i]; }
+        a.part[(12 + g0 + gg) * nb + blockIdx.x] = bv;
+        a.part_idx[(g0 + gg) * nb + blockIdx.x] = bi;
       }
     }
   }
@@ -854,7 +915,8 @@ int drn_oicr_stage_fused_fwd(const float* logits, int ld, int col_off, int R, in
   a.part = part_ws;                                        // [(12 + G) * nb] floats ...
   a.part_idx = reinterpret_cast<int*>(part_ws + (size_t)(12 + G) * nb);  // ... followed by [G * nb] ints
   a.counter = counter;
-  oicr_stage_fused_kernel<<<nb, STAGE_THREADS, 0, (cudaStream_t)stream>>>(a);
+  if (K + 1 <= 32) oicr_stage_fused_kernel<32><<<nb, STAGE_THREADS, 0, (cudaStream_t)stream>>>(a);
+  else oicr_stage_fused_kernel<0><<<nb, STAGE_THREADS, 0, (cudaStream_t)stream>>>(a);
   DRN_CHECK_LAUNCH("oicr_stage_fused");
   return 0;
 }

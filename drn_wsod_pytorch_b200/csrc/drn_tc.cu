@@ -306,7 +306,20 @@ __device__ __forceinline__ uint32_t mix32(uint64_t x) {
   return (uint32_t)(x >> 32);
 }
 
+// DRN_TC_DEBUG & 256 (tools/timeline_probe.py): per-launch timeline in nanoseconds (%globaltimer), slot = launch ordinal since
+// drn_gemm_timeline_reset(): [0] earliest CTA start, [1] earliest "past griddepcontrol.wait", [2] earliest first-operand
+// arrival (MMA warp), [3] latest CTA end.  (The two dies' timers are offset by ~1.6 ms: min and max stamps are only
+// comparable among themselves.)
+constexpr int TL_SLOTS = 512;
+__device__ unsigned long long g_timeline[TL_SLOTS][4];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 struct Params {
+  int tl_slot;  // -1: no timeline
   // problem
   int M;        // GEMM mode: rows.  conv mode: unused
   int N;        // output channels
@@ -499,6 +512,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int unit = blockIdx.x / CG, num_units = gridDim.x / CG;   // a unit = one CTA (CG=1) or one CTA pair
   const int num_mp = (p.num_m_tiles + CG - 1) / CG;               // M tiles per unit step (pairs for CG=2)
   const int num_tiles = num_mp * p.num_n_tiles;
+  if (p.tl_slot >= 0 && threadIdx.x == 0) atomicMin(&g_timeline[p.tl_slot][0], gtime());
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
@@ -546,6 +560,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   // while the previous kernel of the stream is still draining; global memory is only touched after this point.
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (p.tl_slot >= 0 && threadIdx.x == 0) atomicMin(&g_timeline[p.tl_slot][1], gtime());
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (every CTA): all 32 lanes walk the
@@ -701,6 +716,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t dx_bytes = (uint32_t)p.dil * 128u;
           for (int cb = 0; cb < cblocks; ++cb) {
             mbar_wait(&hfull_bar[hs], hphase);
+            if (p.tl_slot >= 0 && cb == 0 && lane == 0) atomicMin(&g_timeline[p.tl_slot][2], gtime());
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t slot = smem_base + (uint32_t)(halo_smem - smem) + hs * HALO_SLOT_BYTES;
             uint32_t a_start = slot;
@@ -742,6 +758,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t accum = 0;
         for (int ki = 0; ki < nkb; ++ki) {
           mbar_wait_addr(full_addr, phase);
+          if (p.tl_slot >= 0 && ki == 0 && lane == 0) atomicMin(&g_timeline[p.tl_slot][2], gtime());
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (elect_one()) {
             umma_kblock<CG>(tmem_d, a_lo, a_lo + B_DESC_OFF, DESC_HI, idesc, accum);
@@ -1001,6 +1018,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (p.tl_slot >= 0 && threadIdx.x == 0) atomicMax(&g_timeline[p.tl_slot][3], gtime());
   if constexpr (CG == 2) cluster_sync_all();  // the leader's MMAs read the peer's smem: nobody leaves early
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1040,6 +1058,7 @@ static int make_map(CUtensorMap* map, const void* base, int rank, const cuuint64
   return 0;
 }
 
+static int g_tl_next = -1;  // next timeline slot (drn_gemm_timeline_reset arms it)
 static int g_max_sms = 0;  // drn_gemm_set_max_sms: leave SMs to a concurrently running kernel (NCCL)
 static int num_sms() {
   static int n = 0;
@@ -1214,6 +1233,26 @@ extern "C" int drn_gemm_set_max_sms(int max_sms) {
   drn::tc::g_max_sms = max_sms > 0 ? (max_sms & ~1) : 0;  // even: CTA pairs
   return prev;
 }
+// Profiling aid (DRN_TC_DEBUG & 256, tools/timeline_probe.py; not part of the drop-in ABI): arm / read the per-launch
+// device timeline of the GEMM kernel.
+extern "C" int drn_gemm_timeline_reset(drn_stream_t stream) {
+  using namespace drn::tc;
+  static unsigned long long init[TL_SLOTS][4];
+  for (int i = 0; i < TL_SLOTS; ++i) { init[i][0] = init[i][1] = init[i][2] = ~0ull; init[i][3] = 0ull; }
+  cudaError_t e = cudaMemcpyToSymbolAsync(g_timeline, init, sizeof(init), 0, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+  if (e != cudaSuccess) return set_err("timeline reset: %s", cudaGetErrorString(e));
+  g_tl_next = 0;
+  return 0;
+}
+extern "C" int drn_gemm_timeline_read(unsigned long long* out, int max_slots) {
+  using namespace drn::tc;
+  const int n = g_tl_next < 0 ? 0 : (g_tl_next < max_slots ? g_tl_next : max_slots);
+  if (n > 0) {
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_timeline, (size_t)n * 4 * sizeof(unsigned long long), 0, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return -1;
+  }
+  return n;
+}
 extern "C" int drn_gemm_set_tail_split(int enabled) {
   const int prev = drn::tc::g_tail_split;
   drn::tc::g_tail_split = enabled ? 1 : 0;
@@ -1265,6 +1304,8 @@ static int conv_igemm_bf16_tc_impl(const void* in, int N, int H, int W, int Cin,
     const char* e = getenv("DRN_TC_DEBUG");
     p.debug = e ? atoi(e) : 0;
   }
+  p.tl_slot = -1;
+  if ((p.debug & 256) && g_tl_next >= 0 && g_tl_next < TL_SLOTS) p.tl_slot = g_tl_next++;
   const int Ktot = ksize * ksize * Cin;
   p.KB = Ktot / BK;
   CUtensorMap ma, mb, mo, mr;

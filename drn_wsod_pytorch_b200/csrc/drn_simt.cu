@@ -113,70 +113,116 @@ conv3x3_c3_kernel(const float* __restrict__ img, int H, int W, float m0, float m
   }
 }
 
-// Tiled variant for Cout == 64 (every stem on the path): one CTA = C3_TH x C3_TW output pixels, 128 threads.  The input patch
-// under the tile is normalised ONCE into shared memory ((img - mean) / std with IEEE division, zero outside the valid image:
-// the same values the kernel above computes per thread) -- the kernel above normalises each input value 4 x ~3 times (once per
-// channel group and per overlapping pixel group, ~900 of its ~3100 instructions per thread) and re-stages the filter per 128
-// output pixels.  The FMA order per output (kh, c, kw) is unchanged: results are bit-identical.
-constexpr int C3_TW = 64, C3_TH = 4;  // tile: 16 pixel groups of 4 wide x 2 rows per pass, 2 passes
+// Tiled variant for Cout == 64 (every stem on the path): one CTA = th x C3_TW output pixels (th even, chosen by the host), 256
+// threads = 16 pixel groups x 2 rows x 8 channel groups, one thread = 4 adjacent pixels x 8 channels.  The input patch under the
+// tile is normalised ONCE into shared memory ((img - mean) / std with IEEE division, zero outside the valid image: the same
+// values the kernel above computes per thread).  The FMA order per output (kh, c, kw) is unchanged: results are bit-identical
+// to the kernel above.
+// History (ncu, 600x1000 image): v1 (16 channels per thread, 128 threads, 64 x 4 tile) 59 us -- patch staged one dependent
+// global load at a time, 168 registers -> 3 CTAs / SM, 600 CTAs = 1.35 waves; v2 (batched patch loads, <= 128 registers, tile
+// rows chosen so that the CTAs spread evenly: 64 x 6) 35 us -- 11 warps / SM, IPC 0.44 per scheduler, stalled on the shared-
+// memory loads of the FMA loop (short scoreboard 2.2 per issue; 47 % of the shared wavefronts were bank conflicts).  v3 (this):
+// half the accumulators per thread -> twice the warps (24 / SM), filter stored so that a quarter-warp's 128-bit loads are
+// contiguous, stride-2 patches stored as even | odd columns so that the pixel groups' 128-bit loads are contiguous.
+constexpr int C3_TW = 64;
+constexpr int C3_TH_MAX = 12;
+constexpr int C3_TILE_THREADS = 256;
+
+template <int STRIDE> struct C3Patch;
+template <> struct C3Patch<2> {
+  static constexpr int PC = (C3_TW - 1) * 2 + 3;  // 129 input columns under 64 outputs
+  static constexpr int NE = 68;                   // even columns 0, 2, .., 128 (65, padded to a 16-byte multiple)
+  static constexpr int PCP = NE + 64;             // then odd columns 1, 3, .., 127
+  static __device__ __forceinline__ int col_of_slot(int slot) { return slot < NE ? 2 * slot : 2 * (slot - NE) + 1; }
+  // input columns 2 p0 .. 2 p0 + 8 of the four pixels p0 .. p0 + 3 (p0 % 4 == 0): x[2 j + kw]
+  static __device__ __forceinline__ void load(const float* row, int p0, float (&x)[9]) {
+    const float4 e = *reinterpret_cast<const float4*>(row + p0);
+    const float e4 = row[p0 + 4];
+    const float4 o = *reinterpret_cast<const float4*>(row + NE + p0);
+    x[0] = e.x; x[1] = o.x; x[2] = e.y; x[3] = o.y; x[4] = e.z; x[5] = o.z; x[6] = e.w; x[7] = o.w; x[8] = e4;
+  }
+};
+template <> struct C3Patch<1> {
+  static constexpr int PC = (C3_TW - 1) + 3;      // 66
+  static constexpr int PCP = 68;
+  static __device__ __forceinline__ int col_of_slot(int slot) { return slot; }
+  static __device__ __forceinline__ void load(const float* row, int p0, float (&x)[6]) {
+    const float4 a = *reinterpret_cast<const float4*>(row + p0);
+    const float2 b = *reinterpret_cast<const float2*>(row + p0 + 4);
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y;
+  }
+};
 
 template <typename OutT, int STRIDE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(C3_TILE_THREADS, 3)
 conv3x3_c3_tile_kernel(const float* __restrict__ img, int H, int W, float m0, float m1, float m2, float s0, float s1, float s2,
                        const float* __restrict__ wp, const float* __restrict__ scale, const float* __restrict__ bias,
-                       int relu, int Ho, int Wo, OutT* __restrict__ out) {
-  constexpr int Cout = 64;
-  constexpr int PR = (C3_TH - 1) * STRIDE + 3, PC = (C3_TW - 1) * STRIDE + 3, PCP = (PC + 3) & ~3;
+                       int relu, int Ho, int Wo, int th, OutT* __restrict__ out) {
+  typedef C3Patch<STRIDE> P;
+  constexpr int Cout = 64, PC = P::PC, PCP = P::PCP;
   constexpr int NCOL = (C3_NPX - 1) * STRIDE + 3;
-  __shared__ __align__(16) float sw[27 * Cout];
-  __shared__ __align__(16) float sx[3][PR][PCP];
-  for (int i = threadIdx.x; i < 27 * Cout / 4; i += 128) reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(wp) + i);
-  const int oh_t = blockIdx.y * C3_TH, ow_t = blockIdx.x * C3_TW;
+  extern __shared__ __align__(16) float c3_smem[];
+  float* sw = c3_smem;             // [27 taps][2 halves][8 channel groups][4]: channel = 8 cg + 4 half + k
+  float* sx = c3_smem + 27 * Cout; // [3][PR][PCP] normalised input patch
+  const int PR = (th - 1) * STRIDE + 3;
+  for (int i = threadIdx.x; i < 27 * Cout; i += C3_TILE_THREADS) {
+    const int ch = i & 63;
+    sw[(i & ~63) + ((ch >> 2) & 1) * 32 + (ch >> 3) * 4 + (ch & 3)] = __ldg(wp + i);
+  }
+  const int oh_t = blockIdx.y * th, ow_t = blockIdx.x * C3_TW;
   const int ih0 = oh_t * STRIDE - 1, iw0 = ow_t * STRIDE - 1;
   const float mean[3] = {m0, m1, m2};
   const float stdv[3] = {s0, s1, s2};
-  for (int i = threadIdx.x; i < 3 * PR * PCP; i += 128) {
-    const int pc = i % PCP, pr = (i / PCP) % PR, c = i / (PCP * PR);
-    const int ih = ih0 + pr, iw = iw0 + pc;
-    float v = 0.f;  // rows / cols outside the valid H x W image are ImageList zero padding
-    if (pc < PC && ih >= 0 && ih < H && iw >= 0 && iw < W)
-      v = __fdiv_rn(__fsub_rn(__ldg(img + ((long long)c * H + ih) * W + iw), mean[c]), stdv[c]);
-    sx[c][pr][pc] = v;
+  const int plane = PR * PCP;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* src = img + (long long)c * H * W;
+    float* dst = sx + c * plane;
+    constexpr int U = 8;  // loads in flight per thread
+#pragma unroll 1
+    for (int base = threadIdx.x; base < plane; base += C3_TILE_THREADS * U) {
+      float raw[U];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = base + u * C3_TILE_THREADS;
+        const int pr = i / PCP, pc = P::col_of_slot(i - pr * PCP);
+        const int ih = ih0 + pr, iw = iw0 + pc;
+        ok[u] = i < plane && pc < PC && ih >= 0 && ih < H && iw >= 0 && iw < W;  // outside the valid H x W image: ImageList zero padding
+        raw[u] = ok[u] ? __ldg(src + (long long)ih * W + iw) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = base + u * C3_TILE_THREADS;
+        if (i < plane) dst[i] = ok[u] ? __fdiv_rn(__fsub_rn(raw[u], mean[c]), stdv[c]) : 0.f;
+      }
+    }
   }
   __syncthreads();
-  const int cg = threadIdx.x & 3, pg = threadIdx.x >> 2;   // 16 output channels; pixel group: 16 across x 2 rows
-  const int gx = pg & 15, gy = pg >> 4;
-  const float* wrow = sw + cg * 16;
-  float sc[16], bi[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    sc[j] = scale ? __ldg(scale + cg * 16 + j) : 1.f;
-    bi[j] = __ldg(bias + cg * 16 + j);
-  }
+  const int cg = threadIdx.x & 7, gx = (threadIdx.x >> 3) & 15, gy = threadIdx.x >> 7;  // 8 channels; pixel group: 16 across x 2 rows
+  const float* wrow = sw + cg * 4;
 #pragma unroll 1
-  for (int pass = 0; pass < C3_TH / 2; ++pass) {
+  for (int pass = 0; pass < th / 2; ++pass) {
     const int orow = pass * 2 + gy;                       // output row inside the tile
     const int oh = oh_t + orow, ow0 = ow_t + gx * C3_NPX;
     if (oh >= Ho || ow0 >= Wo) continue;
-    float acc[C3_NPX][16];
+    float acc[C3_NPX][8];
 #pragma unroll
     for (int p = 0; p < C3_NPX; ++p)
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[p][j] = 0.f;
+      for (int j = 0; j < 8; ++j) acc[p][j] = 0.f;
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         float x[NCOL];
-        const float* xr = &sx[c][orow * STRIDE + kh][gx * C3_NPX * STRIDE];
-#pragma unroll
-        for (int i = 0; i < NCOL; ++i) x[i] = xr[i];
+        P::load(sx + c * plane + (orow * STRIDE + kh) * PCP, gx * C3_NPX, x);
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
-          const float4* w4 = reinterpret_cast<const float4*>(wrow + ((kh * 3 + kw) * 3 + c) * Cout);
+          const float* wt = wrow + ((kh * 3 + kw) * 3 + c) * Cout;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 wv = w4[q];
+          for (int q = 0; q < 2; ++q) {
+            const float4 wv = *reinterpret_cast<const float4*>(wt + q * 32);
 #pragma unroll
             for (int p = 0; p < C3_NPX; ++p) {
               const float xv = x[p * STRIDE + kw];
@@ -189,31 +235,55 @@ conv3x3_c3_tile_kernel(const float* __restrict__ img, int H, int W, float m0, fl
         }
       }
     }
+    float sc[8], bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; j += 4) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + cg * 8 + j));
+      bi[j] = b4.x; bi[j + 1] = b4.y; bi[j + 2] = b4.z; bi[j + 3] = b4.w;
+      if (scale) {
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(scale + cg * 8 + j));
+        sc[j] = s4.x; sc[j + 1] = s4.y; sc[j + 2] = s4.z; sc[j + 3] = s4.w;
+      } else {
+        sc[j] = sc[j + 1] = sc[j + 2] = sc[j + 3] = 1.f;
+      }
+    }
 #pragma unroll
     for (int p = 0; p < C3_NPX; ++p) {
       const int ow = ow0 + p;
       if (ow >= Wo) break;
-      OutT* o = out + ((long long)oh * Wo + ow) * Cout + cg * 16;
-      float v[16];
+      OutT* o = out + ((long long)oh * Wo + ow) * Cout + cg * 8;
+      float v[8];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < 8; ++j) {
         float t = scale ? acc[p][j] * sc[j] : acc[p][j];  // same rounding sequence as the reference: conv, *scale, +bias
         t += bi[j];
         v[j] = relu ? fmaxf(t, 0.f) : t;
       }
       if constexpr (sizeof(OutT) == 4) {
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        for (int j = 0; j < 8; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       } else {
-        uint4 pk[2];
-        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(pk);
+        uint4 pk;
+        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) h2[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-        *reinterpret_cast<uint4*>(o) = pk[0];
-        *reinterpret_cast<uint4*>(o + 8) = pk[1];
+        for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        *reinterpret_cast<uint4*>(o) = pk;
       }
     }
   }
+}
+
+// Rows per tile of the kernel above: the launch is FMA-bound, so its time follows the SM with the most CTAs:
+// ceil(#CTAs / #SMs) x (th / 2 compute passes + ~half a pass of patch staging); smallest wins, ties to the smaller tile.
+static int c3_pick_th(int Ho, int Wo, int num_sms) {
+  int best = 2;
+  double best_cost = 1e30;
+  for (int th = 2; th <= C3_TH_MAX; th += 2) {
+    const long ctas = (long)((Wo + C3_TW - 1) / C3_TW) * ((Ho + th - 1) / th);
+    const double cost = (double)((ctas + num_sms - 1) / num_sms) * (th / 2 + 0.5);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = th; }
+  }
+  return best;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -965,12 +1035,24 @@ int drn_conv3x3_c3_fwd(const float* img, int H, int W, int Hp, int Wp, const flo
     tiled_env = (e && e[0] == '0') ? 0 : 1;
   }
   const bool tiled = tiled_env && Cout == 64;
-  const dim3 tgrid((Wo + C3_TW - 1) / C3_TW, (Ho + C3_TH - 1) / C3_TH);
+  // DRN_C3_TH (measurement switch): rows per tile of the tiled kernel; unset = c3_pick_th
+  static int th_env = -1, sms = 0;
+  if (th_env < 0) {
+    const char* e = getenv("DRN_C3_TH");
+    th_env = e ? atoi(e) : 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  int th = (th_env >= 2 && th_env <= C3_TH_MAX) ? (th_env & ~1) : c3_pick_th(Ho, Wo, sms);
+  const dim3 tgrid((Wo + C3_TW - 1) / C3_TW, (Ho + th - 1) / th);
+  const int pcp = stride == 2 ? C3Patch<2>::PCP : C3Patch<1>::PCP;
+  const size_t tsmem = (size_t)(27 * 64 + 3 * ((th - 1) * stride + 3) * pcp) * sizeof(float);  // <= 46.5 KB at th = 12, stride 2
 #define DRN_C3_LAUNCH(T, S)                                                                                          \
   do {                                                                                                               \
     if (tiled)                                                                                                       \
-      conv3x3_c3_tile_kernel<T, S><<<tgrid, 128, 0, st>>>(img, H, W, mean3[0], mean3[1], mean3[2], std3[0], std3[1], \
-                                                          std3[2], w_packed, scale, bias, relu, Ho, Wo, (T*)out);    \
+      conv3x3_c3_tile_kernel<T, S><<<tgrid, C3_TILE_THREADS, tsmem, st>>>(img, H, W, mean3[0], mean3[1], mean3[2], std3[0],      \
+                                                              std3[1], std3[2], w_packed, scale, bias, relu, Ho, Wo, \
+                                                              th, (T*)out);                                          \
     else                                                                                                             \
       conv3x3_c3_kernel<T, S><<<grid, 128, smem, st>>>(img, H, W, mean3[0], mean3[1], mean3[2], std3[0], std3[1],    \
                                                        std3[2], w_packed, scale, bias, Cout, relu, Ho, Wo, (T*)out); \

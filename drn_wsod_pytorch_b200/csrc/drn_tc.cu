@@ -470,6 +470,71 @@ __device__ __forceinline__ void epi_chunk(uint32_t taddr, uint32_t scale_s, uint
   }
 }
 
+// The same chunk without dropout (every conv layer, eval-mode fc6 / fc7): both 32-column TMEM loads are issued before the one
+// wait, scale / bias run as packed fp32 pairs (FFMA2 / FADD2: same IEEE results per lane as fmaf / +, half the issue slots) and
+// ReLU rides the conversion (cvt.rn.relu.bf16x2.f32 clamps the rounded value at +0: the value max(x, 0) rounds to).  Per
+// chunk and lane: 2 LDTM + 16 (32) LDS.64x2 + 32 FADD2 (FFMA2) + 32 F2FP + 8 STS, against 64 FADD + 64 FMNMX + 32 F2FP before.
+// The epilogue is a latency chain run by one or two warps per scheduler; the last tile's chain is the drain every launch pays.
+__device__ __forceinline__ void lds_2x64(uint32_t saddr, uint64_t& a, uint64_t& b) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(saddr));
+}
+__device__ __forceinline__ uint64_t pair_u32(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+template <bool RELU>
+__device__ __forceinline__ uint32_t pair_to_bf16x2(uint64_t v) {
+  uint32_t lo, hi, r;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+  if constexpr (RELU) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return r;
+}
+template <bool SCALE, bool RELU>
+__device__ __forceinline__ void epi_half_packed(const uint32_t (&v)[32], int c0, uint32_t scale_s, uint32_t bias_s, uint32_t row_s,
+                                                uint32_t sw_xor) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int cl = c0 + j;
+    uint64_t b[4], f[4];
+    lds_2x64(bias_s + cl * 4, b[0], b[1]);
+    lds_2x64(bias_s + cl * 4 + 16, b[2], b[3]);
+    if constexpr (SCALE) {
+      uint64_t sc[4];
+      lds_2x64(scale_s + cl * 4, sc[0], sc[1]);
+      lds_2x64(scale_s + cl * 4 + 16, sc[2], sc[3]);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) f[t] = fma_f32x2(pair_u32(v[j + 2 * t], v[j + 2 * t + 1]), sc[t], b[t]);
+    } else {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) f[t] = add_f32x2(pair_u32(v[j + 2 * t], v[j + 2 * t + 1]), b[t]);
+    }
+    const uint32_t q = (uint32_t)(cl >> 3);
+    sts128(row_s + ((q ^ sw_xor) << 4), pair_to_bf16x2<RELU>(f[0]), pair_to_bf16x2<RELU>(f[1]), pair_to_bf16x2<RELU>(f[2]),
+           pair_to_bf16x2<RELU>(f[3]));
+  }
+}
+template <bool SCALE, bool RELU>
+__device__ __forceinline__ void epi_chunk_packed(uint32_t taddr, uint32_t scale_s, uint32_t bias_s, uint32_t row_s, uint32_t sw_xor) {
+  uint32_t v0[32], v1[32];
+  tmem_ld32_nowait(taddr, v0);
+  tmem_ld32_nowait(taddr + 32, v1);
+  tmem_ld_wait();
+  epi_half_packed<SCALE, RELU>(v0, 0, scale_s, bias_s, row_s, sw_xor);
+  epi_half_packed<SCALE, RELU>(v1, 32, scale_s, bias_s, row_s, sw_xor);
+}
+
 // CG = 1: one CTA computes a 128 x BN tile.  CG = 2: a CTA pair (2-CTA cluster, tcgen05 cta_group::2)
 // computes a 256 x BN tile: each CTA stages its own 128 A rows and HALF of the B rows, the leader's MMA
 // reads both halves (the peer's through the pair's shared-memory path), so the per-SM operand feed drops
@@ -700,6 +765,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t acc_phase = 0;
       int hs = 0;
       uint32_t hphase = 0;
+      bool b_ready = false;
       const uint32_t smem_base = smem_u32(smem);
       const uint32_t full_base = smem_u32(full_bar);
       constexpr uint32_t EMPTY_OFF = STAGES * 8;  // empty_bar = full_bar + STAGES
@@ -714,6 +780,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if constexpr (HALO) {
           const int cblocks = p.Cin / BK;
           const uint32_t dx_bytes = (uint32_t)p.dil * 128u;
+          if (p.bres && !(p.debug & 1024)) {
+            // Resident weights (Cin = 64: one channel block, tap ti in ring slot ti for the whole kernel): the nine weight barriers
+            // are waited for once per CTA, and a tile is ONE elected block of 9 x 4 MMAs + two commits.  The general loop below
+            // spends ~55 issue-warp instructions per tap (barrier try_wait, election, descriptor rebuild, slot bookkeeping) for
+            // 128 clocks of N = 64 tensor work: the issue warp, not the tensor pipe, paced these layers (stem conv2 / conv3 at
+            // 300 x 500: 2.3 us per tile against 0.6 us of MMA work).
+            if (!b_ready) {
+              b_ready = true;
+#pragma unroll 1
+              for (int ti = 0; ti < 9; ++ti) mbar_wait(&full_bar[ti], 0u);
+            }
+            mbar_wait(&hfull_bar[hs], hphase);
+            if (p.tl_slot >= 0 && lane == 0) atomicMin(&g_timeline[p.tl_slot][2], gtime());
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t slot = smem_base + (uint32_t)(halo_smem - smem) + hs * HALO_SLOT_BYTES;
+            if (elect_one()) {
+#pragma unroll
+              for (int ti = 0; ti < 9; ++ti) {
+                const uint32_t a_start = slot + (uint32_t)(ti / 3) * HALO_ROW_BYTES + (uint32_t)(ti % 3) * dx_bytes;
+                const uint32_t a_hi = p.halo_bo ? (DESC_HI | (((a_start >> 7) & 7u) << 17)) : DESC_HI;
+                umma_kblock<CG>(tmem_d, smem_desc_lo(a_start), smem_desc_lo(smem_base + ti * STAGE_BYTES), a_hi, idesc, ti > 0 ? 1u : 0u);
+              }
+              umma_commit_addr<CG>(smem_u32(&hempty_bar[hs]));  // all nine taps have read the rows
+              umma_commit_addr<CG>(smem_u32(&tfull_bar[acc]));
+            }
+            __syncwarp();
+            if (++hs == HALO_SLOTS) { hs = 0; hphase ^= 1; }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            continue;
+          }
           for (int cb = 0; cb < cblocks; ++cb) {
             mbar_wait(&hfull_bar[hs], hphase);
             if (p.tl_slot >= 0 && cb == 0 && lane == 0) atomicMin(&g_timeline[p.tl_slot][2], gtime());
@@ -932,9 +1028,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (p.drop_keep_thresh) {
               if (p.scale) epi_chunk<true, true>(ta, sc_s, bi_s, row_s, sw_xor, relu_floor, dbase, p.drop_keep_thresh, p.drop_inv_keep);
               else epi_chunk<false, true>(ta, sc_s, bi_s, row_s, sw_xor, relu_floor, dbase, p.drop_keep_thresh, p.drop_inv_keep);
-            } else {
+            } else if (p.debug & 512) {  // measurement switch: the scalar epilogue math
               if (p.scale) epi_chunk<true, false>(ta, sc_s, bi_s, row_s, sw_xor, relu_floor, 0ull, 0u, 1.f);
               else epi_chunk<false, false>(ta, sc_s, bi_s, row_s, sw_xor, relu_floor, 0ull, 0u, 1.f);
+            } else if (p.relu) {
+              if (p.scale) epi_chunk_packed<true, true>(ta, sc_s, bi_s, row_s, sw_xor);
+              else epi_chunk_packed<false, true>(ta, sc_s, bi_s, row_s, sw_xor);
+            } else {
+              if (p.scale) epi_chunk_packed<true, false>(ta, sc_s, bi_s, row_s, sw_xor);
+              else epi_chunk_packed<false, false>(ta, sc_s, bi_s, row_s, sw_xor);
             }
           }
           fence_async_smem();

@@ -877,7 +877,7 @@ class _WSLROIHeads(nn.Module):
         if self.pcl:
             return self._train_device_pcl(features, boxes_l, obj_l, gtb_l, gtc_l, gt_int_l, gt_oh_l)
         nloss = 1 + S + sum(self.refine_reg)
-        loss_buf = torch.zeros((N, nloss), dtype=torch.float32, device=dev)
+        loss_buf = torch.empty((N, nloss), dtype=torch.float32, device=dev)  # every slot is ASSIGNED by its loss kernel (no fill launch)
         stage_stats = [[None] * N for _ in range(S)]
         label_counts = [[None] * N for _ in range(S + 1)]
         mil_scale = (1.0 / (N * N)) if self.box_predictor.mean_loss else (1.0 / N)
@@ -944,7 +944,8 @@ class _WSLROIHeads(nn.Module):
             midx0_l.append(midx0)
             tr["labels_gt"] = lab0
             traces.append(tr)
-        return {"loss_buf": loss_buf, "img_scores": torch.stack(img_scores, dim=0), "label_counts": label_counts,
+        img_scores_t = img_scores[0].unsqueeze(0) if N == 1 else torch.stack(img_scores, dim=0)  # one image: a view, no copy kernel
+        return {"loss_buf": loss_buf, "img_scores": img_scores_t, "label_counts": label_counts,
                 "stage_stats": stage_stats, "lab0": lab0_l, "midx0": midx0_l, "traces": traces}
 
     def _train_device_pcl(self, features, boxes_l, obj_l, gtb_l, gtc_l, gt_int_l, gt_oh_l):

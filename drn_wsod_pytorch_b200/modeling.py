@@ -103,6 +103,13 @@ def _f32tc_pack(w, bias, Cg):
             "groups": G, "cg": Cg}
 
 
+def _f32tc_operand(w2d):
+    """fp32 [N, K] (any strides, K a multiple of 64) -> the "weight" operands of one fp32_tc GEMM with zero bias."""
+    n, k = w2d.shape
+    w = w2d.contiguous().view(n, 1, k)
+    return _f32tc_pack(w, torch.zeros((n,), device=w.device, dtype=torch.float32), _kgroup(1, k))
+
+
 def _split_of(x, Cg):
     """(big, small) bf16 operands of an fp32 activation, computed once per tensor and group size."""
     cache = getattr(x, "_drn_split", None)
@@ -1061,6 +1068,8 @@ class _WSLROIHeads(nn.Module):
             n = w_op.shape[1]
             packed = {"w": w_op, "scale": None, "bias": torch.zeros((n,), device=dy.device, dtype=torch.float32), "cout": n}
             return ops.conv_f32(dy.view(1, R, 1, Kd), packed, 1, 1, False).view(R, n)
+        if self.precision == "fp32_tc":  # w_op: the pre-split operands of W^T ([in][out], see _f32tc_operand)
+            return _f32tc_layer(dy.view(1, R, 1, Kd), w_op, 1, 1, False).view(R, w_op["cout"])
         n = w_op.shape[0]
         packed = {"w": w_op, "scale": None, "bias": torch.zeros((n,), device=dy.device, dtype=torch.float32), "cout": n}
         return ops.conv_bf16_tc(dy.view(1, R, 1, Kd), packed, 1, 1, False, out_dtype=out_dtype).view(R, n)
@@ -1076,6 +1085,12 @@ class _WSLROIHeads(nn.Module):
         if self.precision == "fp32":
             xp = x if Rp == R else torch.cat([x, x.new_zeros(Rp - R, n)], 0)  # [K = Rp][N = in]
             dW = ops.conv_f32(dy_t.view(1, out_f, 1, Rp), {"w": xp, "scale": None, "bias": bias0, "cout": n}, 1, 1, False).view(out_f, n)
+            return ops.permute_cols49(dW, c49) if c49 else dW
+        if self.precision == "fp32_tc":
+            # fp32 accuracy on the bf16 tensor cores (csrc/drn_split.cu): dY^T [out][Rp] is the fp32 activation, X^T [in][Rp] the
+            # "weight" whose three bf16 terms are split here, once per step (K = Rp in groups of _kgroup)
+            xp = x if Rp == R else torch.cat([x, x.new_zeros(Rp - R, n)], 0)
+            dW = _f32tc_layer(dy_t.view(1, out_f, 1, Rp), _f32tc_operand(xp.t()), 1, 1, False).view(out_f, n)
             return ops.permute_cols49(dW, c49) if c49 else dW
         x_t, _ = ops.masked_transpose(x, c49=c49, ld_out=Rp)                    # [in][Rp], K-major
         if sharder is not None:  # distributed.ShardedLinearTrainer: the GEMM's epilogue reduce-scatters the tiles into the owners' windows
@@ -1106,15 +1121,14 @@ class _WSLROIHeads(nn.Module):
         as GEMMs on the forward's kernels -- dX = dY W, dW = dY^T X -- with drn_masked_transpose applying the
         ReLU/dropout mask and producing the K-major operands.  The backbone is frozen (FREEZE_AT 5), so the chain
         stops at the pooled features.  Returns {parameter: gradient (fp32, parameter layout)}."""
-        if self.precision == "fp32_tc":
-            raise NotImplementedError('B200.PRECISION "fp32_tc" covers forward+loss and inference; train with "bf16" or "fp32"')
         K, S = self.num_classes, self.refine_K
         traces = d["traces"]
         N = len(traces)
         heads = self._heads_packed()
         offs, ld = heads["offs"], heads["cout"]
         f32 = self.precision == "fp32"
-        wdt = torch.float32 if f32 else torch.bfloat16
+        tc32 = self.precision == "fp32_tc"  # fp32 operands and gradients, every GEMM as split-bf16 tensor-core GEMMs (_f32tc_layer)
+        wdt = torch.float32 if (f32 or tc32) else torch.bfloat16
         pad = 16 if f32 else 64
         mil_scale = (1.0 / (N * N)) if self.box_predictor.mean_loss else (1.0 / N)
         Rtot = sum(tr["logits"].shape[0] for tr in traces)
@@ -1131,11 +1145,17 @@ class _WSLROIHeads(nn.Module):
                 hook(grads[p])
 
         # input-gradient operands: heads W_h transposed (either mode), fc weights ([in][out] bf16 / the parameter itself fp32)
-        wh_op, _ = ops.masked_transpose(heads["w"])
-        w_op = [None] + [fc.weight.detach() if f32 else ops.masked_transpose(fc.packed(self.precision)["w"])[0] for fc in fcs[1:]]
         head_layers = [("cls", self.box_predictor.cls), ("det", self.box_predictor.det)]
         head_layers += [(f"cls_score_{k}", self.box_refinery[k].cls_score) for k in range(S)]
         head_layers += [(f"bbox_pred_{k}", self.box_refinery[k].bbox_pred) for k in range(S) if self.refine_reg[k]]
+        if tc32:
+            wh = torch.cat([l.weight.detach().float() for _, l in head_layers], 0)
+            wh = torch.cat([wh, wh.new_zeros(ld - wh.shape[0], wh.shape[1])], 0) if wh.shape[0] < ld else wh
+            wh_op = _f32tc_operand(wh.t())                                     # W_h^T [in][ld]
+            w_op = [None] + [_f32tc_operand(fc.weight.detach().float().t()) for fc in fcs[1:]]
+        else:
+            wh_op, _ = ops.masked_transpose(heads["w"])
+            w_op = [None] + [fc.weight.detach() if f32 else ops.masked_transpose(fc.packed(self.precision)["w"])[0] for fc in fcs[1:]]
         for tr in traces:
             logits, acts = tr["logits"], tr["acts"]
             R = logits.shape[0]
@@ -1176,12 +1196,12 @@ class _WSLROIHeads(nn.Module):
                 fc, y, x = fcs[li], acts[li + 1], acts[li]
                 dy_t, dy = ops.masked_transpose(dx, mask=y, mul=tr["dropout_mul"], ld_out=Rp, out_dtype=wdt, want_masked=li > 0)
                 blocks = self.wgrad_row_blocks if (li == 0 and hook is not None) else 1
-                sharder = self.fc6_sharder if (li == 0 and not f32) else None
+                sharder = self.fc6_sharder if (li == 0 and not f32 and not tc32) else None
                 if sharder is not None:
                     assert N == 1, "the sharded fc6 path takes one image per rank and step (IMS_PER_BATCH == world size)"
                 gw = self._wgrad(dy_t, x, R, c49=self.in_channels if li == 0 else 0, row_blocks=blocks, on_block=hook, sharder=sharder)
                 if gw is not None:  # (sharded: the gradient lives in the owners' windows, the optimizer steps it there)
-                    acc(fc.weight, gw, announced=blocks > 1 and not f32 and dy_t.shape[0] % (128 * blocks) == 0)
+                    acc(fc.weight, gw, announced=blocks > 1 and not f32 and not tc32 and dy_t.shape[0] % (128 * blocks) == 0)
                 acc(fc.bias, ops.rowsum(dy_t, cols=R))
                 if li > 0:
                     dx = self._dgrad(dy, w_op[li], wdt)

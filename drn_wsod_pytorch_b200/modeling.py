@@ -1543,9 +1543,12 @@ class GeneralizedRCNNWSL(nn.Module):
             self._seen[key] = (seen, first)
             after = self.CAPTURE_AFTER if kind == "train" else self.CAPTURE_AFTER_EVAL
             share = seen / float(self._calls - first + 1)
-            # dominant signature (fixed-shape training, a benchmark): capture at once; a recurring one among others (the 8 TTA
-            # scales): after 8 sightings; one of many (multi-scale training): never -- the eager path is GPU-bound anyway
-            worth = seen >= after and share >= self.CAPTURE_MIN_SHARE and (share >= 0.5 or seen >= 8)
+            # dominant signature (fixed-shape training, a benchmark): capture at once; a recurring one among others: after 8
+            # sightings in training, after 4 in eval (the 8 TTA scales of an image size show up twice per image: the second
+            # image of that size captures them -- with 8 the captures of a small eval set landed on its 4th image, 150 ms
+            # per image instead of 58 in tools/tta_bench.py); one of many (multi-scale training): never -- the eager path is
+            # GPU-bound anyway
+            worth = seen >= after and share >= self.CAPTURE_MIN_SHARE and (share >= 0.5 or seen >= (8 if kind == "train" else 4))
             if not worth and not force:
                 return None, flat
             if len(self._plans) >= self.MAX_PLANS:

@@ -312,6 +312,15 @@ __device__ __forceinline__ uint32_t mix32(uint64_t x) {
 // comparable among themselves.)
 constexpr int TL_SLOTS = 512;
 __device__ unsigned long long g_timeline[TL_SLOTS][4];
+// DRN_TC_DEBUG & 2048 (tools/tile_trace.py): per-tile pipeline trace of CTA 0, SM clock stamps.  Row = tile ordinal of the CTA,
+// column: 0 producer starts the tile, 1 producer has issued its last load, 2 MMA warp past the accumulator-free wait, 3 MMA warp
+// past the first operand wait, 4 MMA warp has issued the tile's last commit, 5 epilogue warp 0 past the accumulator-full wait,
+// 6 epilogue warp 0 has issued its last store of the tile, 7 (row 0 only) kernel start.
+constexpr int TR_TILES = 48;
+__device__ long long g_trace[TR_TILES][8];
+__device__ __forceinline__ void trace(bool on, int tile_ord, int col) {
+  if (on && tile_ord < TR_TILES && (threadIdx.x & 31) == 0) g_trace[tile_ord][col] = clock64();
+}
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -578,6 +587,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int num_mp = (p.num_m_tiles + CG - 1) / CG;               // M tiles per unit step (pairs for CG=2)
   const int num_tiles = num_mp * p.num_n_tiles;
   if (p.tl_slot >= 0 && threadIdx.x == 0) atomicMin(&g_timeline[p.tl_slot][0], gtime());
+  const bool tr_on = (p.debug & 2048) && blockIdx.x == 0;
+  if (threadIdx.x == 0) trace(tr_on, 0, 7);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
@@ -639,7 +650,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int hs = 0;
       uint32_t hphase = 0;
       bool b_loaded = false;
+      int tr_k = -1;
       while (sched.next(pc)) {
+        if (tr_k >= 0) trace(tr_on, tr_k, 1);  // the previous tile's loads are all issued
+        ++tr_k;
+        trace(tr_on, tr_k, 0);
         const int tile = pc.tile;
         const int mt = (tile % num_mp) * CG + cta_rank, nt = tile / num_mp;
         int img = 0, h0 = 0, w0 = 0;
@@ -751,6 +766,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
       }
+      if (tr_k >= 0) trace(tr_on, tr_k, 1);
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA): the whole warp walks the
@@ -771,10 +787,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       constexpr uint32_t EMPTY_OFF = STAGES * 8;  // empty_bar = full_bar + STAGES
       Sched sched(unit, num_units, num_tiles, p);
       Piece pc;
+      int tr_k = -1;
       while (sched.next(pc)) {
         const int tile = pc.tile;
         const bool with_res = p.has_residual && pc.kind != 1;
+        ++tr_k;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        trace(tr_on, tr_k, 2);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tmem_base + acc * BN;
         if constexpr (HALO) {
@@ -784,14 +803,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // Resident weights (Cin = 64: one channel block, tap ti in ring slot ti for the whole kernel): the nine weight barriers
             // are waited for once per CTA, and a tile is ONE elected block of 9 x 4 MMAs + two commits.  The general loop below
             // spends ~55 issue-warp instructions per tap (barrier try_wait, election, descriptor rebuild, slot bookkeeping) for
-            // 128 clocks of N = 64 tensor work: the issue warp, not the tensor pipe, paced these layers (stem conv2 / conv3 at
-            // 300 x 500: 2.3 us per tile against 0.6 us of MMA work).
+            // 128 clocks of N = 64 tensor work (stem conv2 / conv3 at 300 x 500: 18.8 -> 16.9 us).  What is left
+            // (tools/tile_trace.py, profiles/r2_tile_trace.txt): the 36 MMAs of a tile take ~2080 clocks = 58 per N = 64 MMA
+            // against 32 of tensor work -- every MMA reads its 128 x 16 A slice (4 KB) + 64 x 16 B slice (2 KB) from shared
+            // memory, ~48 clocks at 128 B/clk: narrow-N layers are bound by the operand read, not by issue or the tensor pipe.
             if (!b_ready) {
               b_ready = true;
 #pragma unroll 1
               for (int ti = 0; ti < 9; ++ti) mbar_wait(&full_bar[ti], 0u);
             }
             mbar_wait(&hfull_bar[hs], hphase);
+            trace(tr_on, tr_k, 3);
             if (p.tl_slot >= 0 && lane == 0) atomicMin(&g_timeline[p.tl_slot][2], gtime());
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t slot = smem_base + (uint32_t)(halo_smem - smem) + hs * HALO_SLOT_BYTES;
@@ -806,12 +828,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               umma_commit_addr<CG>(smem_u32(&tfull_bar[acc]));
             }
             __syncwarp();
+            trace(tr_on, tr_k, 4);
             if (++hs == HALO_SLOTS) { hs = 0; hphase ^= 1; }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             continue;
           }
           for (int cb = 0; cb < cblocks; ++cb) {
             mbar_wait(&hfull_bar[hs], hphase);
+            if (cb == 0) trace(tr_on, tr_k, 3);
             if (p.tl_slot >= 0 && cb == 0 && lane == 0) atomicMin(&g_timeline[p.tl_slot][2], gtime());
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t slot = smem_base + (uint32_t)(halo_smem - smem) + hs * HALO_SLOT_BYTES;
@@ -841,6 +865,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             if (++hs == HALO_SLOTS) { hs = 0; hphase ^= 1; }
           }
+          trace(tr_on, tr_k, 4);
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
           continue;
         }
@@ -854,6 +879,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t accum = 0;
         for (int ki = 0; ki < nkb; ++ki) {
           mbar_wait_addr(full_addr, phase);
+          if (ki == 0) trace(tr_on, tr_k, 3);
           if (p.tl_slot >= 0 && ki == 0 && lane == 0) atomicMin(&g_timeline[p.tl_slot][2], gtime());
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (elect_one()) {
@@ -886,6 +912,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
+        trace(tr_on, tr_k, 4);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -919,6 +946,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     Piece pc, pc_next;
     bool have = sched.next(pc);
     if (have) fetch_sb(pc.tile / num_mp);
+    int tr_e = 0;
 
     while (have) {
       const bool have_next = sched.next(pc_next);
@@ -955,6 +983,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (have_next) fetch_sb(pc_next.tile / num_mp);  // in flight while this tile is drained
 
       mbar_wait(&tfull_bar[acc], acc_phase);
+      if (warp == 2) trace(tr_on, tr_e, 5);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
 
@@ -1106,6 +1135,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
       }
+      if (warp == 2) trace(tr_on, tr_e, 6);
+      ++tr_e;
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) {
@@ -1355,6 +1386,21 @@ extern "C" int drn_gemm_timeline_read(unsigned long long* out, int max_slots) {
   }
   return n;
 }
+// Profiling aid (DRN_TC_DEBUG & 2048, tools/tile_trace.py; not part of the drop-in ABI): clear / read CTA 0's per-tile trace.
+extern "C" int drn_gemm_trace_reset(drn_stream_t stream) {
+  using namespace drn::tc;
+  void* addr = nullptr;
+  cudaError_t e = cudaGetSymbolAddress(&addr, g_trace);
+  if (e == cudaSuccess) e = cudaMemsetAsync(addr, 0, sizeof(long long) * TR_TILES * 8, (cudaStream_t)stream);
+  if (e != cudaSuccess) return set_err("trace reset: %s", cudaGetErrorString(e));
+  return 0;
+}
+extern "C" int drn_gemm_trace_read(long long* out, int max_tiles) {
+  using namespace drn::tc;
+  const int n = max_tiles < TR_TILES ? max_tiles : TR_TILES;
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_trace, (size_t)n * 8 * sizeof(long long), 0, cudaMemcpyDeviceToHost);
+  return e == cudaSuccess ? n : -1;
+}
 extern "C" int drn_gemm_set_tail_split(int enabled) {
   const int prev = drn::tc::g_tail_split;
   drn::tc::g_tail_split = enabled ? 1 : 0;
@@ -1526,7 +1572,7 @@ static int conv_igemm_bf16_tc_impl(const void* in, int N, int H, int W, int Cin,
       if (bn == 128) return launch<128, 5, 2, 2, 8>(ma, mb, mo, mr, p, st, workspace, workspace_bytes);
       return launch<64, 6, 2, 2, 8>(ma, mb, mo, mr, p, st, workspace, workspace_bytes);
     }
-    if (bn == 256) return launch<256, 3, 1, 1, 8>(ma, mb, mo, mr, p, st, workspace, workspace_bytes);
+    if (bn == 256) return launch<256, 3, 2, 1, 8>(ma, mb, mo, mr, p, st, workspace, workspace_bytes);  // two staging slots: a chunk's TMA store drains while the next is computed (tools/tile_trace.py: these tiles are epilogue-paced; 64->256+res 8.7 -> 8.0, 128->512+res 7.0 -> 6.5 us; 16 epilogue warps with one chunk each measured SLOWER, 9.8 / 7.2 us: profiles/r2_tile_trace.txt)
     if (bn == 128) return launch<128, 4, 2, 1, 8>(ma, mb, mo, mr, p, st, workspace, workspace_bytes);
     return launch<64, 5, 2, 1, 8>(ma, mb, mo, mr, p, st, workspace, workspace_bytes);
   }

@@ -315,7 +315,7 @@ __device__ unsigned long long g_timeline[TL_SLOTS][4];
 // DRN_TC_DEBUG & 2048 (tools/tile_trace.py): per-tile pipeline trace of CTA 0, SM clock stamps.  Row = tile ordinal of the CTA,
 // column: 0 producer starts the tile, 1 producer has issued its last load, 2 MMA warp past the accumulator-free wait, 3 MMA warp
 // past the first operand wait, 4 MMA warp has issued the tile's last commit, 5 epilogue warp 0 past the accumulator-full wait,
-// 6 epilogue warp 0 has issued its last store of the tile, 7 (row 0 only) kernel start.
+// 6 epilogue warp 0 has issued its last store of the tile, 7: row 0 = kernel start, row 1 = prologue done (past griddepcontrol.wait).
 constexpr int TR_TILES = 48;
 __device__ long long g_trace[TR_TILES][8];
 __device__ __forceinline__ void trace(bool on, int tile_ord, int col) {
@@ -590,16 +590,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const bool tr_on = (p.debug & 2048) && blockIdx.x == 0;
   if (threadIdx.x == 0) trace(tr_on, 0, 7);
 
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b) : "memory");
-    if (!p.out_f32) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_o) : "memory");
-    if (p.has_residual) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_r) : "memory");
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EW * CG); }
-    for (int s = 0; s < HALO_SLOTS; ++s) { mbar_init(&hfull_bar[s], 1); mbar_init(&hempty_bar[s], 1); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    // the barriers are one contiguous array (full | empty | tmem-full | tmem-empty | halo-full | halo-empty): lane i initialises
+    // barrier i (one lane doing all ~20-26 of them in turn sat on every launch's critical path)
+    constexpr int NBAR = 2 * STAGES + 4 + 2 * HALO_SLOTS;
+    static_assert(NBAR <= 32, "one barrier per lane");
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b) : "memory");
+      if (!p.out_f32) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_o) : "memory");
+      if (p.has_residual) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_r) : "memory");
+    }
+    if (lane < NBAR) {
+      const bool is_tempty = lane >= 2 * STAGES + 2 && lane < 2 * STAGES + 4;
+      mbar_init(&full_bar[lane], is_tempty ? (uint32_t)(EW * CG) : 1u);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
   }
   if (warp == 1) {
     if constexpr (CG == 2) {
@@ -637,6 +645,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (p.tl_slot >= 0 && threadIdx.x == 0) atomicMin(&g_timeline[p.tl_slot][1], gtime());
+  if (threadIdx.x == 0) trace(tr_on, 1, 7);  // prologue done (row 1, column 7)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (every CTA): all 32 lanes walk the

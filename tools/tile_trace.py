@@ -86,6 +86,7 @@ def main():
         t0 = t[0][7]
         print(f"== layer rows/HxW={key[0]} Cin={key[1]} Cout={key[2]} k={key[3]} dil={key[4]} res={int(key[5])}: "
               f"{e0.elapsed_time(e1) * 1e3:.1f} us for this single launch (cold pipeline, launch overhead included)")
+        print(f"prologue done (barriers, TMEM, griddepcontrol.wait) at {t[1][7] - t0} clocks")
         print("tile " + " ".join(f"{c:>13}" for c in COLS) + "   (SM clocks since kernel start; ~1.9 clocks per ns)")
         for i in range(min(n, args.tiles)):
             if not any(t[i][:7]):

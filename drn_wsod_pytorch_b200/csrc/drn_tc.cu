@@ -357,7 +357,10 @@ struct Params {
   int n_peers, my_rank, rows_per_peer;
   int bres;     // HALO mode, Cin = 64, one N tile: the nine weight tiles (72 KB) are loaded once per CTA and stay in the ring's nine slots
   int halo_bo;  // HALO mode: also set the descriptor's base-offset field to the start's 128 B row phase (hardware probe switch)
-  int debug;  // DRN_TC_DEBUG (profiling experiments only): 1 = skip TMA stores, 2 = skip epilogue math, 4 = skip tcgen05.ld
+  int debug;  // DRN_TC_DEBUG bit mask (profiling experiments only; every bit but 256 / 2048 gives WRONG results or a slower path):
+              //   1 skip the output stores, 2 skip the epilogue math, 32 skip the A-operand loads, 256 per-launch timeline
+              //   (tools/timeline_probe.py), 512 scalar instead of packed epilogue math, 1024 per-tap issue loop for
+              //   resident-weight HALO layers, 2048 per-tile pipeline trace of CTA 0 (tools/tile_trace.py)
   // stream-K (deep-K GEMMs whose tile count does not fill whole waves): every unit gets an equal share of the
   // tiles x K-blocks iteration space; a unit that starts inside a tile dumps that partial accumulator to sk_ws
   // and raises sk_flags[unit], the unit that began the tile (and reaches it last in time) adds it and runs the epilogue

@@ -639,6 +639,276 @@ oicr_stage_fused_kernel(const StageFusedArgs a) {
   }
 }
 
+// ---------------------------------------------------------------- all refinement stages of one image in TWO launches
+// The stage chain above runs S kernels one after the other because each one mines the NEXT stage's pseudo GT.  But the pseudo
+// GT of stage k+1 is the per-class argmax of stage k's softmax (roi_heads_oicr.py:491-567 get_pgt on
+// `prev_pred_scores = predict_probs(...)`, detached) -- it depends on the stage's LOGITS only, never on its labels or loss.
+// So: kernel A computes, for all stages side by side (blockIdx.y = stage), the softmax and the next pseudo GT; kernel B, again
+// for all stages side by side, labels the proposals against their stage's pseudo GT and reduces the weighted CE and the
+// counters.  Per-row arithmetic, block reductions and cross-block orders are those of oicr_stage_fused_kernel: results are
+// bit-identical; the tail's latency chain drops from S kernels to two (measured: profiles/r2_tail_stage_parallel.txt).
+constexpr int MAX_STAGES = 8;
+struct StagesArgs {
+  const float* logits; int ld, R, K, S;
+  int col_off[MAX_STAGES];      // class-logit columns of stage k
+  int delta_off[MAX_STAGES];    // bbox_pred columns of stage k (-1: none): re-derive the boxes of stage k+1's pseudo GT
+  float bw[MAX_STAGES][4];      // ... with the regression weights of refinery k+1
+  const float* boxes;
+  const int64_t* gt_img; int G;
+  const float* img_score; int agnostic;
+  float* probs;                 // [S][R][K+1]
+  int64_t* pgt_idx; float* pgt_score; float* pgt_box; float* pgt_weight;  // [S][G(,4)], entry k = pseudo GT of stage k; entry 0 is not touched
+  const float* pgt0_box; const float* pgt0_weight;                        // stage 0's pseudo GT (drn_wsddn_mil_pgt_fwd)
+  MatcherCfg mc; float loss_scale;
+  const float* gt_boxes; const int64_t* gt_classes; int Gb;   // real GT: first labelling, done by stage 0's blocks; Gb == -1: skip
+  int64_t* labels0; int64_t* matched0; int32_t* counts0;
+  int64_t* labels; int64_t* matched;   // [S][R]
+  int32_t* counts;                     // [S][3]
+  float* weights;                      // [S][R]
+  float* stats;                        // [S][6]
+  float* loss; int loss_col[MAX_STAGES];
+  float* partA; int* partA_idx;        // [S][G][nb]
+  float* partB;                        // [S][12][nb]
+  uint32_t* counters;                  // [2 S], zero on entry, left at zero
+};
+
+template <int CMAX>
+__global__ void __launch_bounds__(STAGE_THREADS)
+oicr_stages_probs_kernel(const StagesArgs a) {
+  __shared__ int scl[MAX_G];
+  __shared__ float sv[8][STAGE_THREADS / 32];
+  __shared__ int si[8][STAGE_THREADS / 32];
+  __shared__ bool is_last;
+  const int st = blockIdx.y, C1 = a.K + 1, G = a.G, nb = gridDim.x;
+  const bool has_next = st + 1 < a.S;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) scl[g] = (int)a.gt_img[g];
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* x = a.logits + (long long)min(r, a.R - 1) * a.ld + a.col_off[st];
+  float xr[CMAX > 0 ? CMAX : 1];
+  if constexpr (CMAX > 0) {
+#pragma unroll
+    for (int k = 0; k < CMAX; ++k) xr[k] = (k < C1) ? __ldg(x + k) : -INFINITY;
+  }
+  __syncthreads();
+  float pbuf_m = 0.f, pbuf_s = 1.f;
+  if (r < a.R) {
+    float m = -INFINITY;
+    float s = 0.f;
+    float* pr = a.probs + ((long long)st * a.R + r) * C1;
+    if constexpr (CMAX > 0) {
+#pragma unroll
+      for (int k = 0; k < CMAX; ++k)
+        if (k < C1 && xr[k] > m) m = xr[k];
+#pragma unroll
+      for (int k = 0; k < CMAX; ++k)
+        if (k < C1) { xr[k] = expf(xr[k] - m); s += xr[k]; }
+#pragma unroll
+      for (int k = 0; k < CMAX; ++k)
+        if (k < C1) pr[k] = xr[k] / s;
+    } else {
+#pragma unroll 8
+      for (int k = 0; k < C1; ++k) {
+        const float v = __ldg(x + k);
+        if (v > m) m = v;
+      }
+#pragma unroll 8
+      for (int k = 0; k < C1; ++k) s += expf(__ldg(x + k) - m);
+#pragma unroll 8
+      for (int k = 0; k < C1; ++k) pr[k] = expf(__ldg(x + k) - m) / s;
+    }
+    pbuf_m = m; pbuf_s = s;
+  }
+  if (!has_next) return;  // block-uniform
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float* part = a.partA + (long long)st * G * nb;
+  int* part_idx = a.partA_idx + (long long)st * G * nb;
+  // block-partial argmax of the new probabilities for every image-level class, 8 classes per barrier (as oicr_stage_fused_kernel)
+  for (int g0 = 0; g0 < G; g0 += 8) {
+    const int ng = min(8, G - g0);
+    if (g0 > 0) __syncthreads();
+    for (int gg = 0; gg < ng; ++gg) {
+      float bv = -INFINITY;
+      int bi = 0x7fffffff;
+      if (r < a.R) { bv = expf(__ldg(x + scl[g0 + gg]) - pbuf_m) / pbuf_s; bi = r; }  // == probs[r][class g], same expression
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) { sv[gg][wid] = bv; si[gg][wid] = bi; }
+    }
+    __syncthreads();
+    if (threadIdx.x < ng) {
+      const int gg = threadIdx.x;
+      float bv = sv[gg][0];
+      int bi = si[gg][0];
+      for (int i = 1; i < (int)(blockDim.x >> 5); ++i)
+        if (better(sv[gg][i], si[gg][i], bv, bi)) { bv = sv[gg][i]; bi = si[gg][i]; }
+      part[(g0 + gg) * nb + blockIdx.x] = bv;
+      part_idx[(g0 + gg) * nb + blockIdx.x] = bi;
+    }
+  }
+  __threadfence();
+  if (threadIdx.x == 0) is_last = (atomicAdd(a.counters + st, 1u) == (unsigned)(nb - 1));
+  __syncthreads();
+  if (!is_last) return;
+  if (threadIdx.x == 0) a.counters[st] = 0u;
+  if (threadIdx.x < G) {
+    const int g = threadIdx.x;
+    const volatile float* pv = part + g * nb;
+    const volatile int* pi = part_idx + g * nb;
+    float bv = pv[0];
+    int bi = pi[0];
+    for (int b = 1; b < nb; ++b) {
+      const float ov = pv[b];
+      const int oi = pi[b];
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (bi == 0x7fffffff) bi = 0;
+    const int c = scl[g];
+    const long long o = (long long)(st + 1) * G + g;   // the pseudo GT of the NEXT stage
+    a.pgt_idx[o] = bi;
+    a.pgt_score[o] = bv;
+    a.pgt_weight[o] = a.img_score[c];
+    Box4 b = {a.boxes[4 * bi + 0], a.boxes[4 * bi + 1], a.boxes[4 * bi + 2], a.boxes[4 * bi + 3]};
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+    if (a.delta_off[st] >= 0) {
+      const float* d = a.logits + (long long)bi * a.ld + a.delta_off[st] + (a.agnostic ? 0 : 4 * c);
+      d0 = d[0]; d1 = d[1]; d2 = d[2]; d3 = d[3];
+    }
+    b = apply_deltas_rn(b, d0, d1, d2, d3, a.bw[st][0], a.bw[st][1], a.bw[st][2], a.bw[st][3]);  // fast_rcnn.py:1511-1532
+    a.pgt_box[4 * o + 0] = b.x1; a.pgt_box[4 * o + 1] = b.y1;
+    a.pgt_box[4 * o + 2] = b.x2; a.pgt_box[4 * o + 3] = b.y2;
+  }
+}
+
+template <int CMAX>
+__global__ void __launch_bounds__(STAGE_THREADS)
+oicr_stages_label_ce_kernel(const StagesArgs a) {
+  __shared__ float sg[MAX_G][5];
+  __shared__ int scl[MAX_G];
+  __shared__ float sg0[MAX_G][5];
+  __shared__ int scl0[MAX_G];
+  __shared__ float sh[32];
+  __shared__ int scnt[11];
+  __shared__ bool is_last;
+  const int st = blockIdx.y, C1 = a.K + 1, K = a.K, G = a.G, nb = gridDim.x;
+  const float* pgt_box = st == 0 ? a.pgt0_box : a.pgt_box + (long long)st * G * 4;
+  const float* pgt_weight = st == 0 ? a.pgt0_weight : a.pgt_weight + (long long)st * G;
+  if (threadIdx.x < 11) scnt[threadIdx.x] = 0;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    const float x1 = pgt_box[4 * g], y1 = pgt_box[4 * g + 1], x2 = pgt_box[4 * g + 2], y2 = pgt_box[4 * g + 3];
+    sg[g][0] = x1; sg[g][1] = y1; sg[g][2] = x2; sg[g][3] = y2;
+    sg[g][4] = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
+    scl[g] = (int)a.gt_img[g];
+  }
+  const int Gb = st == 0 ? a.Gb : -1;
+  for (int g = threadIdx.x; g < Gb; g += blockDim.x) {
+    const float x1 = a.gt_boxes[4 * g], y1 = a.gt_boxes[4 * g + 1], x2 = a.gt_boxes[4 * g + 2], y2 = a.gt_boxes[4 * g + 3];
+    sg0[g][0] = x1; sg0[g][1] = y1; sg0[g][2] = x2; sg0[g][3] = y2;
+    sg0[g][4] = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
+    scl0[g] = (int)a.gt_classes[g];
+  }
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* x = a.logits + (long long)min(r, a.R - 1) * a.ld + a.col_off[st];
+  float xr[CMAX > 0 ? CMAX : 1];
+  if constexpr (CMAX > 0) {
+#pragma unroll
+    for (int k = 0; k < CMAX; ++k) xr[k] = (k < C1) ? __ldg(x + k) : -INFINITY;
+  }
+  __syncthreads();
+  float lw = 0.f;
+  int f_valid = 0, f_acc = 0, f_nfg = 0, f_fgacc = 0, f_fneg = 0;
+  int c_fg = 0, c_bg = 0, c_ig = 0, c0_fg = 0, c0_bg = 0, c0_ig = 0;
+  if (r < a.R) {
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(a.boxes) + r);
+    const Box4 p = {bb.x, bb.y, bb.z, bb.w};
+    const float ap = __fmul_rn(__fsub_rn(p.x2, p.x1), __fsub_rn(p.y2, p.y1));
+    if (Gb >= 0) {  // roi_heads_oicr.py:266: labelling against the real GT (logging + proposals' gt fields)
+      int l0, m0;
+      match_row(p, ap, sg0, scl0, Gb, K, a.mc, l0, m0);
+      a.labels0[r] = l0;
+      a.matched0[r] = m0;
+      if (l0 == -1) c0_ig = 1; else if (l0 == K) c0_bg = 1; else c0_fg = 1;
+    }
+    int lab, mi;
+    match_row(p, ap, sg, scl, G, K, a.mc, lab, mi);
+    a.labels[(long long)st * a.R + r] = lab;
+    a.matched[(long long)st * a.R + r] = mi;
+    if (lab == -1) c_ig = 1; else if (lab == K) c_bg = 1; else c_fg = 1;
+    float m = -INFINITY;
+    int am = 0;
+    float s = 0.f;
+    if constexpr (CMAX > 0) {   // the row's softmax statistics, in the order of the kernel that stored the probabilities
+#pragma unroll
+      for (int k = 0; k < CMAX; ++k)
+        if (k < C1 && xr[k] > m) { m = xr[k]; am = k; }
+#pragma unroll
+      for (int k = 0; k < CMAX; ++k)
+        if (k < C1) s += expf(xr[k] - m);
+    } else {
+#pragma unroll 8
+      for (int k = 0; k < C1; ++k) {
+        const float v = __ldg(x + k);
+        if (v > m) { m = v; am = k; }
+      }
+#pragma unroll 8
+      for (int k = 0; k < C1; ++k) s += expf(__ldg(x + k) - m);
+    }
+    float w = pgt_weight[mi];
+    if (lab == -1) w = 0.f;
+    a.weights[(long long)st * a.R + r] = w;
+    if (w > 1e-12f) f_valid = 1;
+    if (lab >= 0) lw = (-((__ldg(x + lab) - m) - logf(s))) * w;
+    const bool fg = lab >= 0 && lab < K;
+    if (am == lab) f_acc = 1;
+    if (fg) {
+      f_nfg = 1;
+      if (am == lab) f_fgacc = 1;
+      if (am == K) f_fneg = 1;
+    }
+  }
+  const int lane = threadIdx.x & 31;
+  {
+    const int fl[11] = {f_valid, f_acc, f_nfg, f_fgacc, f_fneg, c_fg, c_bg, c_ig, c0_fg, c0_bg, c0_ig};
+    const int nfl = Gb >= 0 ? 11 : 8;
+#pragma unroll
+    for (int j = 0; j < 11; ++j) {
+      if (j < nfl) {
+        const int v = __reduce_add_sync(0xffffffffu, fl[j]);
+        if (lane == 0 && v) atomicAdd(&scnt[j], v);
+      }
+    }
+  }
+  float* part = a.partB + (long long)st * 12 * nb;
+  float v = block_sum(lw, sh);   // same tree as oicr_stage_kernel (its barriers also publish scnt)
+  if (threadIdx.x == 0) part[0 * nb + blockIdx.x] = v;
+  if (threadIdx.x < (Gb >= 0 ? 11 : 8)) part[(1 + threadIdx.x) * nb + blockIdx.x] = (float)scnt[threadIdx.x];
+  __threadfence();
+  if (threadIdx.x == 0) is_last = (atomicAdd(a.counters + a.S + st, 1u) == (unsigned)(nb - 1));
+  __syncthreads();
+  if (!is_last) return;
+  const int nsum = Gb >= 0 ? 12 : 9;
+  if (threadIdx.x < nsum) {
+    float s = 0.f;
+    const volatile float* pp = part + threadIdx.x * nb;
+    for (int b = 0; b < nb; ++b) s += pp[b];  // fixed order
+    sh[threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a.loss[a.loss_col[st]] = (sh[0] / sh[1]) * a.loss_scale;
+    float* stats = a.stats + 6 * st;
+    stats[0] = sh[2]; stats[1] = sh[3]; stats[2] = sh[4]; stats[3] = sh[5];
+    stats[4] = sh[0]; stats[5] = sh[1];
+    int32_t* counts = a.counts + 3 * st;
+    counts[0] = (int)sh[6]; counts[1] = (int)sh[7]; counts[2] = (int)sh[8];
+    if (Gb >= 0) { a.counts0[0] = (int)sh[9]; a.counts0[1] = (int)sh[10]; a.counts0[2] = (int)sh[11]; }
+    a.counters[a.S + st] = 0u;
+  }
+}
+
 // ---------------------------------------------------------------- box-regression loss (reg/ configs)
 __global__ void __launch_bounds__(STAGE_THREADS)
 oicr_boxreg_kernel(const float* __restrict__ deltas, int ld, int col_off, int R, int K, int agnostic,
@@ -918,6 +1188,62 @@ int drn_oicr_stage_fused_fwd(const float* logits, int ld, int col_off, int R, in
   if (K + 1 <= 32) oicr_stage_fused_kernel<32><<<nb, STAGE_THREADS, 0, (cudaStream_t)stream>>>(a);
   else oicr_stage_fused_kernel<0><<<nb, STAGE_THREADS, 0, (cudaStream_t)stream>>>(a);
   DRN_CHECK_LAUNCH("oicr_stage_fused");
+  return 0;
+}
+
+int drn_oicr_stages_fwd(const float* logits, int ld, int R, int K, int S, const int* col_offs, const int* delta_offs,
+                        const float* bbox_w, const float* boxes, const int64_t* gt_classes_img, int G,
+                        const float* img_score, int cls_agnostic, const float* pgt0_box, const float* pgt0_weight,
+                        const float* thresholds, const int* labels_cfg, int nthr, float loss_scale,
+                        const float* gt_boxes, const int64_t* gt_classes, int Gb, int64_t* labels0, int64_t* matched0,
+                        int32_t* counts0, float* probs, int64_t* pgt_idx, float* pgt_score, float* pgt_box,
+                        float* pgt_weight, int64_t* labels, int64_t* matched_idx, int32_t* counts, float* weights,
+                        float* stats, float* loss, const int* loss_cols, float* part_ws, uint32_t* counters,
+                        drn_stream_t stream) {
+  DRN_CHECK_ARG(logits && col_offs && boxes && gt_classes_img && img_score && pgt0_box && pgt0_weight && probs && labels &&
+                    matched_idx && counts && weights && stats && loss && loss_cols && part_ws && counters,
+                "oicr_stages: null pointer");
+  DRN_CHECK_ARG(S >= 1 && S <= MAX_STAGES, "oicr_stages: S=%d (1..%d)", S, MAX_STAGES);
+  DRN_CHECK_ARG(R > 0 && G > 0 && G <= MAX_G, "oicr_stages: R=%d G=%d (max %d)", R, G, MAX_G);
+  DRN_CHECK_ARG(nthr >= 0 && nthr <= 4, "oicr_stages: %d thresholds (max 4)", nthr);
+  DRN_CHECK_ARG(Gb <= MAX_G, "oicr_stages: Gb=%d exceeds %d", Gb, MAX_G);
+  DRN_CHECK_ARG(Gb < 0 || (labels0 && matched0 && counts0 && (Gb == 0 || (gt_boxes && gt_classes))),
+                "oicr_stages: first-labelling buffers missing");
+  DRN_CHECK_ARG(S == 1 || (pgt_idx && pgt_score && pgt_box && pgt_weight && bbox_w), "oicr_stages: pseudo-GT buffers missing");
+  StagesArgs a;
+  a.logits = logits; a.ld = ld; a.R = R; a.K = K; a.S = S;
+  for (int k = 0; k < S; ++k) {
+    DRN_CHECK_ARG(col_offs[k] >= 0 && col_offs[k] + K + 1 <= ld, "oicr_stages: columns of stage %d exceed ld=%d", k, ld);
+    a.col_off[k] = col_offs[k];
+    a.delta_off[k] = delta_offs ? delta_offs[k] : -1;
+    a.loss_col[k] = loss_cols[k];
+    for (int j = 0; j < 4; ++j) a.bw[k][j] = bbox_w ? bbox_w[4 * k + j] : 1.f;
+  }
+  a.boxes = boxes; a.gt_img = gt_classes_img; a.G = G; a.img_score = img_score; a.agnostic = cls_agnostic;
+  a.probs = probs; a.pgt_idx = pgt_idx; a.pgt_score = pgt_score; a.pgt_box = pgt_box; a.pgt_weight = pgt_weight;
+  a.pgt0_box = pgt0_box; a.pgt0_weight = pgt0_weight;
+  a.mc.nthr = nthr;
+  for (int i = 0; i < nthr; ++i) a.mc.thr[i] = thresholds[i];
+  for (int i = 0; i <= nthr; ++i) a.mc.lab[i] = labels_cfg[i];
+  a.loss_scale = loss_scale;
+  a.gt_boxes = gt_boxes; a.gt_classes = gt_classes; a.Gb = Gb;
+  a.labels0 = labels0; a.matched0 = matched0; a.counts0 = counts0;
+  a.labels = labels; a.matched = matched_idx; a.counts = counts; a.weights = weights; a.stats = stats; a.loss = loss;
+  const int nb = cdiv(R, STAGE_THREADS);
+  a.partA = part_ws;                                                   // [S][G][nb] floats
+  a.partA_idx = reinterpret_cast<int*>(part_ws + (size_t)S * G * nb);  // [S][G][nb] ints
+  a.partB = part_ws + (size_t)2 * S * G * nb;                          // [S][12][nb] floats
+  a.counters = counters;
+  const dim3 grid(nb, S);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (K + 1 <= 32) {
+    oicr_stages_probs_kernel<32><<<grid, STAGE_THREADS, 0, st>>>(a);
+    oicr_stages_label_ce_kernel<32><<<grid, STAGE_THREADS, 0, st>>>(a);
+  } else {
+    oicr_stages_probs_kernel<0><<<grid, STAGE_THREADS, 0, st>>>(a);
+    oicr_stages_label_ce_kernel<0><<<grid, STAGE_THREADS, 0, st>>>(a);
+  }
+  DRN_CHECK_LAUNCH("oicr_stages");
   return 0;
 }
 

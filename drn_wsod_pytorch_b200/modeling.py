@@ -703,6 +703,9 @@ class _WSLROIHeads(nn.Module):
         self.output_dir, self.vis_test, self.vis_period = cfg.OUTPUT_DIR, cfg.WSL.VIS_TEST, cfg.VIS_PERIOD
         self._heads_cache = None
         self._counter = None
+        self._counters = None
+        # DRN_B200_STAGE_PARALLEL=0 (measurement switch): one fused kernel per refinement stage, one after the other
+        self.stage_parallel = os.environ.get("DRN_B200_STAGE_PARALLEL", "1") != "0"
         self.fused_tail = os.environ.get("DRN_B200_FUSED_TAIL", "1") != "0"
         # opt-in: measured gain 0.02-0.05 ms of 2.7 (the GEMM is SM<-L2 feed bound, a co-resident gather starves:
         # profiles/r1_overlap_negative_result.txt), less than the tail split-K schedule of the one-piece fc6 saves
@@ -881,6 +884,7 @@ class _WSLROIHeads(nn.Module):
         dev = boxes_l[0].device
         if self._counter is None or self._counter.device != dev:
             self._counter = torch.zeros((1,), dtype=torch.int32, device=dev)
+            self._counters = torch.zeros((16,), dtype=torch.int32, device=dev)  # drn_oicr_stages_fwd: 2 per stage, self-resetting
         if self.pcl:
             return self._train_device_pcl(features, boxes_l, obj_l, gtb_l, gtc_l, gt_int_l, gt_oh_l)
         nloss = 1 + S + sum(self.refine_reg)
@@ -909,7 +913,32 @@ class _WSLROIHeads(nn.Module):
             tr = {"scores": scores, "img_score": img_score, "logits": logits, "feat": feat, "stages": [], "acts": self._acts,
                   "boxes": boxes, "gt_onehot": gt_oh, "dropout_mul": 2.0 if self.box_head.training else 1.0}
             prev, prev_ld_deltas, prev_deltas, col = scores, 0, None, 1
-            for k in range(S):
+            if pgt is not None and self.stage_parallel:
+                # all S stages in two launches: the pseudo GT of stage k+1 depends on stage k's logits only (ops.oicr_stages)
+                doffs = [offs[f"bbox_pred_{k}"] if self.refine_reg[k] else -1 for k in range(S)]
+                bws = [self.box_refinery[min(k + 1, S - 1)].bbox_w for k in range(S)]
+                lcols, c = [], 1
+                for k in range(S):
+                    lcols.append(c)
+                    c += 2 if doffs[k] >= 0 else 1
+                sts, first = ops.oicr_stages(logits, [offs[f"cls_score_{k}"] for k in range(S)], doffs, bws, K, boxes, gt_int,
+                                             img_score, self.cls_agnostic_bbox_reg, pgt, self.iou_thresholds, self.iou_labels, 1.0,
+                                             loss_buf[i], lcols, self._counters, first_gt=(gtb_l[i], gtc_l[i]))
+                lab0, midx0, cnt0 = first
+                for k in range(S):
+                    o = sts[k]
+                    pgt_idx, pgt_score, pgt_box, pgt_w = o["pgt"]
+                    label_counts[k + 1][i] = o["counts"]
+                    stage_stats[k][i] = o["stats"]
+                    if doffs[k] >= 0:
+                        lw = self.box_refinery[k].loss_weight.get("loss_box_reg", 1.0)
+                        ops.oicr_boxreg_loss(logits, doffs[k], K, self.cls_agnostic_bbox_reg, boxes, pgt_box, o["labels"], o["matched"],
+                                             self.box_refinery[k].bbox_w, self.box_refinery[k].smooth_l1_beta, lw,
+                                             loss_buf[i, lcols[k] + 1:lcols[k] + 2], self._counter)
+                    tr["stages"].append(dict(pgt_idx=pgt_idx, pgt_scores=pgt_score, pgt_boxes=pgt_box, pgt_weights=pgt_w,
+                                             labels=o["labels"], matched=o["matched"], probs=o["probs"], weights=o["weights"],
+                                             stats=o["stats"]))
+            for k in range(S if not (pgt is not None and self.stage_parallel) else 0):
                 bw = self.box_refinery[k].bbox_w
                 doff = offs[f"bbox_pred_{k}"] if self.refine_reg[k] else -1
                 if pgt is None:

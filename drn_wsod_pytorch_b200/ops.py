@@ -261,6 +261,45 @@ def oicr_stage_fused(logits, col_off, K, boxes, gt_int, pgt_box, pgt_weight, thr
     return out
 
 
+def oicr_stages(logits, col_offs, delta_offs, bbox_ws, K, boxes, gt_int, img_score, cls_agnostic, pgt0, thresholds, labels_cfg,
+                loss_scale, loss_row, loss_cols, counters, first_gt=None):
+    """All S refinement stages of one image in two launches (drn_oicr_stages_fwd): every stage's softmax + the next stage's
+    pseudo GT, then every stage's labelling + weighted CE.  pgt0 = (idx, score, box, weight) of stage 0 (wsddn_mil_pgt);
+    bbox_ws[k] = the regression weights that turn stage k's deltas (delta_offs[k], -1: none) into stage k+1's pseudo-GT boxes;
+    stage k's loss is written to loss_row[loss_cols[k]]; counters: >= 2 S zeroed int32.  Returns a list of S dicts
+    (labels, matched, counts, probs, stats, weights, pgt=(idx, score, box, weight)) + the first labelling (or None)."""
+    R, ld = logits.shape
+    dev = logits.device
+    S, G = len(col_offs), gt_int.numel()
+    nb = (R + 255) // 256
+    assert counters.numel() >= 2 * S
+    i64 = lambda *s: torch.empty(s, device=dev, dtype=torch.int64)
+    f32 = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
+    probs, labels, matched, weights = f32(S, R, K + 1), i64(S, R), i64(S, R), f32(S, R)
+    counts, stats = torch.empty((S, 3), device=dev, dtype=torch.int32), f32(S, 6)
+    pgt_idx, pgt_score, pgt_box, pgt_w = i64(S, G), f32(S, G), f32(S, G, 4), f32(S, G)
+    part = f32(S * (12 + 2 * G) * nb)
+    if first_gt is not None:
+        gtb, gtc = first_gt
+        Gb = gtc.numel()
+        first = (i64(R), i64(R), torch.empty((3,), device=dev, dtype=torch.int32))
+        f_args = (gtb if Gb else None, gtc if Gb else None, Gb) + first
+    else:
+        first = None
+        f_args = (None, None, -1, None, None, None)
+    bw = [float(v) for w in bbox_ws for v in w]
+    call("drn_oicr_stages_fwd", logits, ld, R, K, S, ivec(col_offs), ivec(delta_offs), fvec(bw), boxes, gt_int, G, img_score,
+         int(cls_agnostic), pgt0[2], pgt0[3], fvec(thresholds), ivec(labels_cfg), len(thresholds), float(loss_scale), *f_args,
+         probs, pgt_idx, pgt_score, pgt_box, pgt_w, labels, matched, counts, weights, stats, loss_row, ivec(loss_cols), part,
+         counters, current_stream())
+    out = []
+    for k in range(S):
+        pgt = tuple(pgt0) if k == 0 else (pgt_idx[k], pgt_score[k], pgt_box[k], pgt_w[k])
+        out.append(dict(labels=labels[k], matched=matched[k], counts=counts[k], probs=probs[k], stats=stats[k], weights=weights[k],
+                        pgt=pgt))
+    return out, first
+
+
 def oicr_boxreg_loss(logits, col_off, K, cls_agnostic, boxes, pgt_box, labels, matched, bbox_w, beta, loss_scale,
                      loss_out, counter):
     R, ld = logits.shape

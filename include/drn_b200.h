@@ -189,6 +189,28 @@ int drn_oicr_stage_fused_fwd(const float* logits, int ld, int col_off, int R, in
                              float* next_pgt_box, float* next_pgt_weight, float* part_ws, uint32_t* counter,
                              drn_stream_t stream);
 
+/* Fused tail, part 2 for ALL S refinement stages of one image in two launches (the default training path).  The pseudo GT of
+ * stage k+1 is the per-class argmax of stage k's softmax (WSL/roi_heads/roi_heads_oicr.py:359-394, :491-567: get_pgt on the
+ * detached predict_probs of the previous stage) -- a function of the LOGITS only -- so the S stages need not run one after
+ * the other: launch 1 computes every stage's probabilities and the next stage's pseudo GT (grid.y = stage), launch 2 labels
+ * the proposals against their stage's pseudo GT and reduces the weighted CE, #valid and the accuracy counters (grid.y = stage;
+ * stage 0 also does the first labelling vs the real GT when Gb >= 0).  Same per-row arithmetic and reduction orders as S calls
+ * of drn_oicr_stage_fused_fwd: bit-identical outputs.
+ * Stage-major outputs: probs [S][R][K+1], labels / matched_idx / weights [S][R], counts [S][3], stats [S][6]; pgt_* [S][G(,4)]:
+ * entry k = pseudo GT of stage k, entries 1.. are written, entry 0 is not touched (stage 0's comes in as pgt0_box / pgt0_weight
+ * from drn_wsddn_mil_pgt_fwd).  Host arrays: col_offs / delta_offs (-1: no bbox_pred) / loss_cols [S] (stage k's loss goes to
+ * loss[loss_cols[k]]), bbox_w [S][4] (row k = the weights that turn stage k's deltas into stage k+1's pseudo-GT boxes).
+ * part_ws: [S * (12 + 2 * G) * ceil(R/256)] 4-byte words; counters: [2 * S] uint32 zero-initialised, self-resetting. */
+int drn_oicr_stages_fwd(const float* logits, int ld, int R, int K, int S, const int* col_offs, const int* delta_offs,
+                        const float* bbox_w_host, const float* boxes, const int64_t* gt_classes_img, int G,
+                        const float* img_score, int cls_agnostic, const float* pgt0_box, const float* pgt0_weight,
+                        const float* thresholds_host, const int* labels_host, int nthr, float loss_scale,
+                        const float* gt_boxes, const int64_t* gt_classes, int Gb, int64_t* labels0, int64_t* matched0,
+                        int32_t* counts0, float* probs, int64_t* pgt_idx, float* pgt_score, float* pgt_box,
+                        float* pgt_weight, int64_t* labels, int64_t* matched_idx, int32_t* counts, float* weights,
+                        float* stats, float* loss, const int* loss_cols, float* part_ws, uint32_t* counters,
+                        drn_stream_t stream);
+
 /* Box regression loss of a refinement stage with REFINE_REG[k] (reg/ configs).
  * Replaces WSL/roi_heads/fast_rcnn.py:1146-1211 with smooth_l1(beta) and
  * detectron2/modeling/box_regression.py:38-71 (get_deltas).  deltas: [R][ld] at col_off, 4K wide

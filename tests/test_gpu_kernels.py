@@ -395,6 +395,22 @@ def test_fused_tail_is_bit_identical_to_the_per_function_kernels(R, K, G):
             assert torch.equal(o["first"][0], lab0) and torch.equal(o["first"][1], midx0) and torch.equal(o["first"][2], cnt0)
         pgt = o["next"]
     assert torch.equal(la, lb) and counter.item() == 0
+    # --- all stages in two launches (drn_oicr_stages_fwd): the next pseudo GT depends on a stage's logits only
+    lc = torch.zeros(1 + S, device=DEV)
+    counters = torch.zeros(16, dtype=torch.int32, device=DEV)
+    scores_c, img_c, pgt0 = ops.wsddn_mil_pgt(d_logits, K, 0, K, oh, True, 1.0, lc[0:1], boxes, gt_int, counter)
+    for rep in range(2):  # twice: the counters reset themselves
+        sts, first = ops.oicr_stages(d_logits, [2 * K + k * (K + 1) for k in range(S)], [-1] * S, [bw] * S, K, boxes, gt_int, img_c,
+                                     False, pgt0, thr, labs, 1.0, lc, [1 + k for k in range(S)], counters, first_gt=(gtb, gtc))
+        for k in range(S):
+            rp, lab, mi, cnt, probs, stats, wts = ref_stages[k]
+            o = sts[k]
+            for a, b in zip(o["pgt"], rp):
+                assert torch.equal(a, b), f"stage {k} pseudo GT differs (two-launch form)"
+            assert torch.equal(o["labels"], lab) and torch.equal(o["matched"], mi) and torch.equal(o["counts"], cnt)
+            assert torch.equal(o["probs"], probs) and torch.equal(o["stats"], stats) and torch.equal(o["weights"], wts)
+        assert torch.equal(first[0], lab0) and torch.equal(first[1], midx0) and torch.equal(first[2], cnt0)
+        assert torch.equal(la, lc) and int(counters.abs().sum()) == 0
 
 
 def test_label_proposals_no_gt_and_ignore_band():

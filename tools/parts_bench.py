@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 
-OPS = ("first_conv", "conv_bf16_tc", "maxpool2x2", "roipool", "wsddn_mil_pgt", "oicr_stage_fused", "wsddn_mil", "oicr_pgt",
+OPS = ("first_conv", "conv_bf16_tc", "maxpool2x2", "roipool", "wsddn_mil_pgt", "oicr_stage_fused", "oicr_stages", "wsddn_mil", "oicr_pgt",
        "label_proposals", "oicr_stage", "oicr_boxreg_loss")
 
 

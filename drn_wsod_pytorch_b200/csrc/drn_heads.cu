@@ -770,7 +770,6 @@ oicr_stages_probs_kernel(const StagesArgs a) {
     const long long o = (long long)(st + 1) * G + g;   // the pseudo GT of the NEXT stage
     a.pgt_idx[o] = bi;
     a.pgt_score[o] = bv;
-    a.pgt_weight[o] = a.img_score[c];
     Box4 b = {a.boxes[4 * bi + 0], a.boxes[4 * bi + 1], a.boxes[4 * bi + 2], a.boxes[4 * bi + 3]};
     float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
     if (a.delta_off[st] >= 0) {
@@ -794,8 +793,16 @@ oicr_stages_label_ce_kernel(const StagesArgs a) {
   __shared__ int scnt[11];
   __shared__ bool is_last;
   const int st = blockIdx.y, C1 = a.K + 1, K = a.K, G = a.G, nb = gridDim.x;
+  __shared__ float spw[MAX_G];
   const float* pgt_box = st == 0 ? a.pgt0_box : a.pgt_box + (long long)st * G * 4;
-  const float* pgt_weight = st == 0 ? a.pgt0_weight : a.pgt_weight + (long long)st * G;
+  // pseudo-GT weight = the image score of its class (get_pgt): stage 0's comes with its pseudo GT, the later stages' are taken
+  // from the MIL image scores here -- kernel A, which mined their pseudo GT, depends on the logits only and may run beside the
+  // MIL kernels -- and published by block 0
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    const float w = st == 0 ? a.pgt0_weight[g] : a.img_score[(int)a.gt_img[g]];
+    spw[g] = w;
+    if (st > 0 && blockIdx.x == 0) a.pgt_weight[(long long)st * G + g] = w;
+  }
   if (threadIdx.x < 11) scnt[threadIdx.x] = 0;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     const float x1 = pgt_box[4 * g], y1 = pgt_box[4 * g + 1], x2 = pgt_box[4 * g + 2], y2 = pgt_box[4 * g + 3];
@@ -856,7 +863,7 @@ oicr_stages_label_ce_kernel(const StagesArgs a) {
 #pragma unroll 8
       for (int k = 0; k < C1; ++k) s += expf(__ldg(x + k) - m);
     }
-    float w = pgt_weight[mi];
+    float w = spw[mi];
     if (lab == -1) w = 0.f;
     a.weights[(long long)st * a.R + r] = w;
     if (w > 1e-12f) f_valid = 1;
@@ -1198,11 +1205,12 @@ int drn_oicr_stages_fwd(const float* logits, int ld, int R, int K, int S, const 
                         const float* gt_boxes, const int64_t* gt_classes, int Gb, int64_t* labels0, int64_t* matched0,
                         int32_t* counts0, float* probs, int64_t* pgt_idx, float* pgt_score, float* pgt_box,
                         float* pgt_weight, int64_t* labels, int64_t* matched_idx, int32_t* counts, float* weights,
-                        float* stats, float* loss, const int* loss_cols, float* part_ws, uint32_t* counters,
+                        float* stats, float* loss, const int* loss_cols, float* part_ws, uint32_t* counters, int phases,
                         drn_stream_t stream) {
-  DRN_CHECK_ARG(logits && col_offs && boxes && gt_classes_img && img_score && pgt0_box && pgt0_weight && probs && labels &&
-                    matched_idx && counts && weights && stats && loss && loss_cols && part_ws && counters,
-                "oicr_stages: null pointer");
+  DRN_CHECK_ARG(phases >= 1 && phases <= 3, "oicr_stages: phases=%d (1 = probabilities + pseudo GT, 2 = labelling + CE, 3 = both)", phases);
+  DRN_CHECK_ARG(logits && col_offs && boxes && gt_classes_img && probs && labels && matched_idx && counts && weights && stats &&
+                    loss_cols && part_ws && counters, "oicr_stages: null pointer");
+  DRN_CHECK_ARG(!(phases & 2) || (img_score && pgt0_box && pgt0_weight && loss), "oicr_stages: launch 2 needs img_score, pgt0_*, loss");
   DRN_CHECK_ARG(S >= 1 && S <= MAX_STAGES, "oicr_stages: S=%d (1..%d)", S, MAX_STAGES);
   DRN_CHECK_ARG(R > 0 && G > 0 && G <= MAX_G, "oicr_stages: R=%d G=%d (max %d)", R, G, MAX_G);
   DRN_CHECK_ARG(nthr >= 0 && nthr <= 4, "oicr_stages: %d thresholds (max 4)", nthr);
@@ -1237,11 +1245,11 @@ int drn_oicr_stages_fwd(const float* logits, int ld, int R, int K, int S, const 
   const dim3 grid(nb, S);
   cudaStream_t st = (cudaStream_t)stream;
   if (K + 1 <= 32) {
-    oicr_stages_probs_kernel<32><<<grid, STAGE_THREADS, 0, st>>>(a);
-    oicr_stages_label_ce_kernel<32><<<grid, STAGE_THREADS, 0, st>>>(a);
+    if (phases & 1) oicr_stages_probs_kernel<32><<<grid, STAGE_THREADS, 0, st>>>(a);
+    if (phases & 2) oicr_stages_label_ce_kernel<32><<<grid, STAGE_THREADS, 0, st>>>(a);
   } else {
-    oicr_stages_probs_kernel<0><<<grid, STAGE_THREADS, 0, st>>>(a);
-    oicr_stages_label_ce_kernel<0><<<grid, STAGE_THREADS, 0, st>>>(a);
+    if (phases & 1) oicr_stages_probs_kernel<0><<<grid, STAGE_THREADS, 0, st>>>(a);
+    if (phases & 2) oicr_stages_label_ce_kernel<0><<<grid, STAGE_THREADS, 0, st>>>(a);
   }
   DRN_CHECK_LAUNCH("oicr_stages");
   return 0;

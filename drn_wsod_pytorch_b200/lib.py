@@ -39,7 +39,7 @@ _PROTOS = {
     "drn_oicr_stage_fused_fwd": [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _FP, _IP, c_int, c_float, _P, _P, c_int,
                                  _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _FP, _P, _P, _P, _P, _P, _P, _P],
     "drn_oicr_stages_fwd": [_P, c_int, c_int, c_int, c_int, _IP, _IP, _FP, _P, _P, c_int, _P, c_int, _P, _P, _FP, _IP, c_int, c_float,
-                            _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _IP, _P, _P, _P],
+                            _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _IP, _P, _P, c_int, _P],
     "drn_oicr_boxreg_loss": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _FP, c_float, c_float, _P, _P, _P, _P],
     "drn_oicr_infer": [_P, c_int, c_int, c_int, c_int, c_int, _IP, _IP, _P, _FP, _P, _P, _P],
     "drn_detections_fwd": [_P, _P, c_int, c_int, c_int, c_float, c_float, c_float, c_double, c_int, _P, _P, _P, _P, _P, _P, c_size_t,

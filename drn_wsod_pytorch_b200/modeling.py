@@ -704,6 +704,7 @@ class _WSLROIHeads(nn.Module):
         self._heads_cache = None
         self._counter = None
         self._counters = None
+        self._tail_stream = None
         # DRN_B200_STAGE_PARALLEL=0 (measurement switch): one fused kernel per refinement stage, one after the other
         self.stage_parallel = os.environ.get("DRN_B200_STAGE_PARALLEL", "1") != "0"
         self.fused_tail = os.environ.get("DRN_B200_FUSED_TAIL", "1") != "0"
@@ -906,24 +907,34 @@ class _WSLROIHeads(nn.Module):
                                                   mil_scale, loss_buf[i, 0:1])
                 pgt = None
             else:
+                stages_ctx = None
+                if self.stage_parallel:
+                    # all S stages in two launches (ops.oicr_stages_*): the pseudo GT of stage k+1 depends on stage k's logits
+                    # only, so launch 1 (every stage's softmax + next pseudo GT) runs on a second stream beside the MIL kernels
+                    doffs = [offs[f"bbox_pred_{k}"] if self.refine_reg[k] else -1 for k in range(S)]
+                    bws = [self.box_refinery[min(k + 1, S - 1)].bbox_w for k in range(S)]
+                    cur = torch.cuda.current_stream(dev)
+                    if self._tail_stream is None or self._tail_stream.device != dev:
+                        self._tail_stream = torch.cuda.Stream(dev)
+                    self._tail_stream.wait_stream(cur)
+                    stages_ctx = ops.oicr_stages_launch1(logits, [offs[f"cls_score_{k}"] for k in range(S)], doffs, bws, K, boxes, gt_int,
+                                                         self.cls_agnostic_bbox_reg, self.iou_thresholds, self.iou_labels, self._counters,
+                                                         first_gt=(gtb_l[i], gtc_l[i]), stream=self._tail_stream)
                 scores, img_score, pgt = ops.wsddn_mil_pgt(logits, K, offs["cls"], offs["det"], gt_oh, self.box_predictor.mean_loss,
                                                            mil_scale, loss_buf[i, 0:1], boxes, gt_int, self._counter)
+                if stages_ctx is not None:
+                    torch.cuda.current_stream(dev).wait_stream(self._tail_stream)
                 lab0 = midx0 = cnt0 = None
             img_scores.append(img_score)
             tr = {"scores": scores, "img_score": img_score, "logits": logits, "feat": feat, "stages": [], "acts": self._acts,
                   "boxes": boxes, "gt_onehot": gt_oh, "dropout_mul": 2.0 if self.box_head.training else 1.0}
             prev, prev_ld_deltas, prev_deltas, col = scores, 0, None, 1
             if pgt is not None and self.stage_parallel:
-                # all S stages in two launches: the pseudo GT of stage k+1 depends on stage k's logits only (ops.oicr_stages)
-                doffs = [offs[f"bbox_pred_{k}"] if self.refine_reg[k] else -1 for k in range(S)]
-                bws = [self.box_refinery[min(k + 1, S - 1)].bbox_w for k in range(S)]
                 lcols, c = [], 1
                 for k in range(S):
                     lcols.append(c)
                     c += 2 if doffs[k] >= 0 else 1
-                sts, first = ops.oicr_stages(logits, [offs[f"cls_score_{k}"] for k in range(S)], doffs, bws, K, boxes, gt_int,
-                                             img_score, self.cls_agnostic_bbox_reg, pgt, self.iou_thresholds, self.iou_labels, 1.0,
-                                             loss_buf[i], lcols, self._counters, first_gt=(gtb_l[i], gtc_l[i]))
+                sts, first = ops.oicr_stages_launch2(stages_ctx, img_score, pgt, 1.0, loss_buf[i], lcols)
                 lab0, midx0, cnt0 = first
                 for k in range(S):
                     o = sts[k]

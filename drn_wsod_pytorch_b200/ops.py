@@ -261,13 +261,11 @@ def oicr_stage_fused(logits, col_off, K, boxes, gt_int, pgt_box, pgt_weight, thr
     return out
 
 
-def oicr_stages(logits, col_offs, delta_offs, bbox_ws, K, boxes, gt_int, img_score, cls_agnostic, pgt0, thresholds, labels_cfg,
-                loss_scale, loss_row, loss_cols, counters, first_gt=None):
-    """All S refinement stages of one image in two launches (drn_oicr_stages_fwd): every stage's softmax + the next stage's
-    pseudo GT, then every stage's labelling + weighted CE.  pgt0 = (idx, score, box, weight) of stage 0 (wsddn_mil_pgt);
-    bbox_ws[k] = the regression weights that turn stage k's deltas (delta_offs[k], -1: none) into stage k+1's pseudo-GT boxes;
-    stage k's loss is written to loss_row[loss_cols[k]]; counters: >= 2 S zeroed int32.  Returns a list of S dicts
-    (labels, matched, counts, probs, stats, weights, pgt=(idx, score, box, weight)) + the first labelling (or None)."""
+def oicr_stages_launch1(logits, col_offs, delta_offs, bbox_ws, K, boxes, gt_int, cls_agnostic, thresholds, labels_cfg, counters,
+                        first_gt=None, stream=None):
+    """Launch 1 of drn_oicr_stages_fwd (every stage's softmax + the next stage's pseudo GT): needs the logits only, so a
+    caller may run it on `stream` (a torch.cuda.Stream that has waited for the logits) beside the MIL kernels.  Allocates every
+    output of both launches (on the current stream) and returns the context for oicr_stages_launch2."""
     R, ld = logits.shape
     dev = logits.device
     S, G = len(col_offs), gt_int.numel()
@@ -275,29 +273,52 @@ def oicr_stages(logits, col_offs, delta_offs, bbox_ws, K, boxes, gt_int, img_sco
     assert counters.numel() >= 2 * S
     i64 = lambda *s: torch.empty(s, device=dev, dtype=torch.int64)
     f32 = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
-    probs, labels, matched, weights = f32(S, R, K + 1), i64(S, R), i64(S, R), f32(S, R)
-    counts, stats = torch.empty((S, 3), device=dev, dtype=torch.int32), f32(S, 6)
-    pgt_idx, pgt_score, pgt_box, pgt_w = i64(S, G), f32(S, G), f32(S, G, 4), f32(S, G)
-    part = f32(S * (12 + 2 * G) * nb)
+    c = dict(S=S, G=G, K=K, logits=logits, boxes=boxes, gt_int=gt_int, cls_agnostic=int(cls_agnostic), counters=counters,
+             col_offs=ivec(col_offs), delta_offs=ivec(delta_offs), bw=fvec([float(v) for w in bbox_ws for v in w]),
+             thr=fvec(thresholds), labs=ivec(labels_cfg), nthr=len(thresholds),
+             probs=f32(S, R, K + 1), labels=i64(S, R), matched=i64(S, R), weights=f32(S, R),
+             counts=torch.empty((S, 3), device=dev, dtype=torch.int32), stats=f32(S, 6),
+             pgt_idx=i64(S, G), pgt_score=f32(S, G), pgt_box=f32(S, G, 4), pgt_w=f32(S, G), part=f32(S * (12 + 2 * G) * nb))
     if first_gt is not None:
         gtb, gtc = first_gt
         Gb = gtc.numel()
-        first = (i64(R), i64(R), torch.empty((3,), device=dev, dtype=torch.int32))
-        f_args = (gtb if Gb else None, gtc if Gb else None, Gb) + first
+        c["first"] = (i64(R), i64(R), torch.empty((3,), device=dev, dtype=torch.int32))
+        c["f_args"] = (gtb if Gb else None, gtc if Gb else None, Gb) + c["first"]
     else:
-        first = None
-        f_args = (None, None, -1, None, None, None)
-    bw = [float(v) for w in bbox_ws for v in w]
-    call("drn_oicr_stages_fwd", logits, ld, R, K, S, ivec(col_offs), ivec(delta_offs), fvec(bw), boxes, gt_int, G, img_score,
-         int(cls_agnostic), pgt0[2], pgt0[3], fvec(thresholds), ivec(labels_cfg), len(thresholds), float(loss_scale), *f_args,
-         probs, pgt_idx, pgt_score, pgt_box, pgt_w, labels, matched, counts, weights, stats, loss_row, ivec(loss_cols), part,
-         counters, current_stream())
+        c["first"] = None
+        c["f_args"] = (None, None, -1, None, None, None)
+    _oicr_stages_call(c, None, None, 1.0, None, ivec([0] * S), 1, current_stream() if stream is None else stream.cuda_stream)
+    return c
+
+
+def _oicr_stages_call(c, img_score, pgt0, loss_scale, loss_row, loss_cols, phases, stream):
+    R, ld = c["logits"].shape
+    call("drn_oicr_stages_fwd", c["logits"], ld, R, c["K"], c["S"], c["col_offs"], c["delta_offs"], c["bw"], c["boxes"], c["gt_int"],
+         c["G"], img_score, c["cls_agnostic"], None if pgt0 is None else pgt0[2], None if pgt0 is None else pgt0[3], c["thr"],
+         c["labs"], c["nthr"], float(loss_scale), *c["f_args"], c["probs"], c["pgt_idx"], c["pgt_score"], c["pgt_box"], c["pgt_w"],
+         c["labels"], c["matched"], c["counts"], c["weights"], c["stats"], loss_row, loss_cols, c["part"], c["counters"],
+         int(phases), stream)
+
+
+def oicr_stages_launch2(c, img_score, pgt0, loss_scale, loss_row, loss_cols):
+    """Launch 2 (every stage's labelling + weighted CE) on the current stream, which must have joined launch 1's.
+    pgt0 = (idx, score, box, weight) of stage 0 (wsddn_mil_pgt); stage k's loss goes to loss_row[loss_cols[k]].
+    Returns (list of S dicts: labels, matched, counts, probs, stats, weights, pgt=(idx, score, box, weight); first labelling)."""
+    _oicr_stages_call(c, img_score, pgt0, loss_scale, loss_row, ivec(loss_cols), 2, current_stream())
     out = []
-    for k in range(S):
-        pgt = tuple(pgt0) if k == 0 else (pgt_idx[k], pgt_score[k], pgt_box[k], pgt_w[k])
-        out.append(dict(labels=labels[k], matched=matched[k], counts=counts[k], probs=probs[k], stats=stats[k], weights=weights[k],
-                        pgt=pgt))
-    return out, first
+    for k in range(c["S"]):
+        pgt = tuple(pgt0) if k == 0 else (c["pgt_idx"][k], c["pgt_score"][k], c["pgt_box"][k], c["pgt_w"][k])
+        out.append(dict(labels=c["labels"][k], matched=c["matched"][k], counts=c["counts"][k], probs=c["probs"][k],
+                        stats=c["stats"][k], weights=c["weights"][k], pgt=pgt))
+    return out, c["first"]
+
+
+def oicr_stages(logits, col_offs, delta_offs, bbox_ws, K, boxes, gt_int, img_score, cls_agnostic, pgt0, thresholds, labels_cfg,
+                loss_scale, loss_row, loss_cols, counters, first_gt=None):
+    """All S refinement stages of one image in two launches on the current stream (drn_oicr_stages_fwd)."""
+    c = oicr_stages_launch1(logits, col_offs, delta_offs, bbox_ws, K, boxes, gt_int, cls_agnostic, thresholds, labels_cfg, counters,
+                            first_gt=first_gt)
+    return oicr_stages_launch2(c, img_score, pgt0, loss_scale, loss_row, loss_cols)
 
 
 def oicr_boxreg_loss(logits, col_off, K, cls_agnostic, boxes, pgt_box, labels, matched, bbox_w, beta, loss_scale,

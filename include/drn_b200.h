@@ -200,7 +200,9 @@ int drn_oicr_stage_fused_fwd(const float* logits, int ld, int col_off, int R, in
  * entry k = pseudo GT of stage k, entries 1.. are written, entry 0 is not touched (stage 0's comes in as pgt0_box / pgt0_weight
  * from drn_wsddn_mil_pgt_fwd).  Host arrays: col_offs / delta_offs (-1: no bbox_pred) / loss_cols [S] (stage k's loss goes to
  * loss[loss_cols[k]]), bbox_w [S][4] (row k = the weights that turn stage k's deltas into stage k+1's pseudo-GT boxes).
- * part_ws: [S * (12 + 2 * G) * ceil(R/256)] 4-byte words; counters: [2 * S] uint32 zero-initialised, self-resetting. */
+ * part_ws: [S * (12 + 2 * G) * ceil(R/256)] 4-byte words; counters: [2 * S] uint32 zero-initialised, self-resetting.
+ * phases: 1 = launch 1 only, 2 = launch 2 only, 3 = both.  Launch 1 reads logits, boxes and gt_classes_img only (not img_score,
+ * not pgt0_*): a caller may issue it on a second stream beside drn_wsddn_mil_pgt_fwd and join before launch 2. */
 int drn_oicr_stages_fwd(const float* logits, int ld, int R, int K, int S, const int* col_offs, const int* delta_offs,
                         const float* bbox_w_host, const float* boxes, const int64_t* gt_classes_img, int G,
                         const float* img_score, int cls_agnostic, const float* pgt0_box, const float* pgt0_weight,
@@ -208,7 +210,7 @@ int drn_oicr_stages_fwd(const float* logits, int ld, int R, int K, int S, const 
                         const float* gt_boxes, const int64_t* gt_classes, int Gb, int64_t* labels0, int64_t* matched0,
                         int32_t* counts0, float* probs, int64_t* pgt_idx, float* pgt_score, float* pgt_box,
                         float* pgt_weight, int64_t* labels, int64_t* matched_idx, int32_t* counts, float* weights,
-                        float* stats, float* loss, const int* loss_cols, float* part_ws, uint32_t* counters,
+                        float* stats, float* loss, const int* loss_cols, float* part_ws, uint32_t* counters, int phases,
                         drn_stream_t stream);
 
 /* Box regression loss of a refinement stage with REFINE_REG[k] (reg/ configs).

@@ -33,6 +33,30 @@ def test_cabi_library_exports_every_header_symbol():
     assert handle.drn_version() >= 100
 
 
+def test_cabi_prototypes_have_the_header_argument_counts():
+    """Every ctypes prototype in lib.py takes exactly as many arguments as the header declares for that entry point."""
+    import re
+
+    with open(lib.HEADER_PATH) as f:
+        src = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    decls = {m.group(1): m.group(2) for m in re.finditer(r"\b(drn_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)}
+    for name, argtypes in lib._PROTOS.items():
+        assert name in decls, name
+        params = decls[name].strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(argtypes), f"{name}: header declares {n} parameters, lib.py binds {len(argtypes)}"
+
+
+def test_cabi_stage_pair_rejects_bad_arguments_without_a_gpu():
+    handle = lib.load()
+    f3 = (ctypes.c_float * 4)(1, 1, 1, 1)
+    i1 = (ctypes.c_int * 1)(0)
+    args = [None, 128, 10, 20, 1, i1, i1, f3, None, None, 1, None, 0, None, None, f3, i1, 1, ctypes.c_float(1.0), None, None, -1, None,
+            None, None, None, None, None, None, None, None, None, None, None, None, None, i1, None, None]
+    assert handle.drn_oicr_stages_fwd(*args, 0, None) != 0 and b"phases" in handle.drn_last_error()
+    assert handle.drn_oicr_stages_fwd(*args, 3, None) != 0 and b"null pointer" in handle.drn_last_error()
+
+
 def test_cabi_argument_errors_are_reported_not_crashed():
     handle = lib.load()
     rc = handle.drn_roipool_fwd(None, 4, 4, 64, None, None, 3, ctypes.c_float(0.125), 0, None, None, 0, None)
